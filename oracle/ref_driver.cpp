@@ -1,0 +1,209 @@
+/*
+ * TEST INFRASTRUCTURE — not part of the shipped product.
+ *
+ * Headless host for ONE macproject3 module call. It links against the *unmodified* reference
+ * libraries that oracle/Makefile builds from /root/reference into oracle/_ref/, fills the
+ * reference's own sparse grids (array3 / macarray3) from a dense scene file, calls
+ * macproject3_interface::project() on whichever module `Projection=<name>` selects
+ * (default: the reference's macpressuresolver3) and dumps dense results.
+ *
+ * It replaces src/ui/ui.cpp (which needs boost posix_time + GL) with the same
+ * load -> configure -> initialize sequence (ui.cpp:632-702) and mirrors what the simulators do
+ * before their first project() call:
+ *   - level sets: activate |phi| < band, set_as_levelset(band), flood_fill()
+ *       (src/utility/macutility3.cpp:336-374)
+ *   - smoke: fluid = constant -1 background, no actives (src/smoke/macsmoke3.cpp:106)
+ *   - accuracy test: solid = cell-shaped constant +1 (src/examples/accuracytest3-example.cpp:90)
+ *
+ * File formats are documented in oracle/refio.py (the only reader/writer on the Python side).
+ */
+#include <shiokaze/core/cmdparser.h>
+#include <shiokaze/core/console.h>
+#include <shiokaze/array/array3.h>
+#include <shiokaze/array/macarray3.h>
+#include <shiokaze/array/shared_array_core3.h>
+#include <shiokaze/projection/macproject3_interface.h>
+#include <shiokaze/utility/macutility3_interface.h>
+#include <shiokaze/utility/utility.h>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+//
+SHKZ_USING_NAMESPACE
+//
+namespace {
+//
+struct scene_header {
+	char magic[8];
+	int32_t nx, ny, nz;
+	int32_t solid_mode; // 0: nodal, nothing active   1: nodal narrow band from raw values   2: cell-shaped constant +1
+	int32_t fluid_mode; // 0: constant -1 background (all fluid)   1: narrow band from raw values
+	int32_t repeat;     // number of project() calls on the same inputs (timing); results are from the last
+	int32_t pad0, pad1;
+	double dx, dt, surface_tension, band, current_volume, target_volume;
+};
+//
+struct host : public recursive_configurable {
+	array3<Real> fluid{this};
+	array3<Real> solid{this};
+	macarray3<Real> velocity{this};
+	macproject3_driver proj{this,"macpressuresolver3"};
+	macutility3_driver util{this,"macutility3"};
+	shape3 shape;
+	double dx;
+	host( const scene_header &h ) {
+		shape = shape3(h.nx,h.ny,h.nz);
+		dx = h.dx;
+		set_environment("shape",&shape);
+		set_environment("dx",&dx);
+	}
+};
+//
+template <class T> std::vector<T> read_block( FILE *fp, size_t count ) {
+	std::vector<T> buf(count);
+	if( count && std::fread(buf.data(),sizeof(T),count,fp) != count ) {
+		std::fprintf(stderr,"ref_driver: short read\n");
+		std::exit(2);
+	}
+	return buf;
+}
+template <class T> void write_block( FILE *fp, const std::vector<T> &buf ) {
+	if( buf.size() && std::fwrite(buf.data(),sizeof(T),buf.size(),fp) != buf.size() ) {
+		std::fprintf(stderr,"ref_driver: short write\n");
+		std::exit(2);
+	}
+}
+// Dense read exactly as a bridge would do it: array3::operator() = active value / fill value / background
+// (include/shiokaze/array/array3.h:796-801).
+void dump_dense( FILE *fp, const array3<Real> &a, bool with_active ) {
+	const shape3 s = a.shape();
+	std::vector<double> values(s.count());
+	std::vector<uint8_t> active(with_active ? s.count() : 0);
+	size_t n (0);
+	for( int k=0; k<(int)s.d; ++k ) for( int j=0; j<(int)s.h; ++j ) for( int i=0; i<(int)s.w; ++i, ++n ) {
+		values[n] = a(i,j,k);
+		if( with_active ) active[n] = a.active(i,j,k) ? 1 : 0;
+	}
+	int32_t dims[4] = {(int32_t)s.w,(int32_t)s.h,(int32_t)s.d,with_active ? 1 : 0};
+	std::fwrite(dims,sizeof(int32_t),4,fp);
+	write_block(fp,values);
+	write_block(fp,active);
+}
+//
+} // namespace
+//
+int main( int argc, const char *argv[] ) {
+	//
+	std::string in_path, out_path;
+	bool dump_fractions (false);
+	for( int i=1; i<argc; ++i ) {
+		if( ! std::strncmp(argv[i],"in=",3)) in_path = argv[i]+3;
+		if( ! std::strncmp(argv[i],"out=",4)) out_path = argv[i]+4;
+		if( ! std::strcmp(argv[i],"DumpFractions=1")) dump_fractions = true;
+	}
+	if( in_path.empty() || out_path.empty()) {
+		std::fprintf(stderr,"usage: ref_driver in=<scene> out=<result> [DumpFractions=1] [Projection=<module>] [flag=value ...]\n");
+		return 2;
+	}
+	FILE *fp = std::fopen(in_path.c_str(),"rb");
+	if( ! fp ) { std::perror(in_path.c_str()); return 2; }
+	scene_header h;
+	if( std::fread(&h,sizeof(h),1,fp) != 1 || std::memcmp(h.magic,"SHKZIN02",8)) {
+		std::fprintf(stderr,"ref_driver: bad scene header\n");
+		return 2;
+	}
+	//
+	cmdparser parser(argc,argv);
+	configuration &config = configurable::set_global_configuration(parser);
+	config.push_group("Root","Root");
+	host H(h);
+	H.setup_now(config);
+	//
+	const shape3 shape = H.shape;
+	const int repeat = h.repeat > 0 ? h.repeat : 1;
+	//
+	std::vector<float> vel[DIM3];
+	std::vector<uint8_t> vel_active[DIM3];
+	for( int dim : DIMS3 ) vel[dim] = read_block<float>(fp,shape.face(dim).count());
+	for( int dim : DIMS3 ) vel_active[dim] = read_block<uint8_t>(fp,shape.face(dim).count());
+	//
+	if( h.solid_mode == 2 ) {
+		H.solid.initialize(shape,1.0);
+	} else {
+		H.solid.initialize(shape.nodal());
+		if( h.solid_mode == 1 ) {
+			std::vector<float> raw = read_block<float>(fp,shape.nodal().count());
+			const shape3 ns = shape.nodal();
+			H.solid.parallel_all([&]( int i, int j, int k, auto &it ) {
+				double value = raw[ns.encode(i,j,k)];
+				if( std::abs(value) < h.band ) it.set(value);
+			});
+		}
+		H.solid.set_as_levelset(h.band);
+		H.solid.flood_fill();
+	}
+	if( h.fluid_mode == 0 ) {
+		H.fluid.initialize(shape,-1.0);
+	} else {
+		std::vector<float> raw = read_block<float>(fp,shape.count());
+		H.fluid.initialize(shape);
+		H.fluid.set_as_levelset(h.band);
+		H.fluid.parallel_all([&]( int i, int j, int k, auto &it ) {
+			double value = raw[shape.encode(i,j,k)];
+			if( std::abs(value) < h.band ) it.set(value);
+			else it.set_off();
+		});
+		H.fluid.flood_fill();
+	}
+	std::fclose(fp);
+	//
+	double ms_last (0.0), ms_sum (0.0);
+	for( int rep=0; rep<repeat; ++rep ) {
+		H.velocity.initialize(shape);
+		for( int dim : DIMS3 ) {
+			const shape3 fs = shape.face(dim);
+			const std::vector<float> &src = vel[dim];
+			const std::vector<uint8_t> &act = vel_active[dim];
+			H.velocity[dim].parallel_all([&]( int i, int j, int k, auto &it ) {
+				size_t n = fs.encode(i,j,k);
+				if( act[n] ) it.set(src[n]);
+			});
+		}
+		if( h.target_volume ) H.proj->set_target_volume(h.current_volume,h.target_volume);
+		double t0 = utility::get_milliseconds();
+		H.proj->project(h.dt,H.velocity,H.solid,H.fluid,h.surface_tension);
+		ms_last = utility::get_milliseconds()-t0;
+		ms_sum += ms_last;
+	}
+	std::printf("REFDRIVER project_ms_last=%.3f project_ms_mean=%.3f repeat=%d sizeof_Real=%d\n",ms_last,ms_sum/repeat,repeat,(int)sizeof(Real));
+	//
+	FILE *out = std::fopen(out_path.c_str(),"wb");
+	if( ! out ) { std::perror(out_path.c_str()); return 2; }
+	const char magic[8] = {'S','H','K','Z','O','U','T','2'};
+	std::fwrite(magic,1,8,out);
+	int32_t info[4] = {h.nx,h.ny,h.nz,(int32_t)sizeof(Real)};
+	std::fwrite(info,sizeof(int32_t),4,out);
+	double ms[2] = {ms_last,ms_sum/repeat};
+	std::fwrite(ms,sizeof(double),2,out);
+	for( int dim : DIMS3 ) dump_dense(out,H.velocity[dim],true);
+	dump_dense(out,*H.proj->get_pressure(),true);
+	dump_dense(out,H.fluid,true);
+	dump_dense(out,H.solid,true);
+	int32_t has_fractions = dump_fractions ? 1 : 0;
+	std::fwrite(&has_fractions,sizeof(int32_t),1,out);
+	if( dump_fractions ) {
+		// The two macutility3 methods on the path, called directly (src/utility/macutility3.cpp:94-194).
+		macarray3<Real> areas(shape), rhos(shape);
+		H.util->compute_area_fraction(H.solid,areas);
+		H.util->compute_fluid_fraction(H.fluid,rhos);
+		for( int dim : DIMS3 ) dump_dense(out,areas[dim],false);
+		for( int dim : DIMS3 ) dump_dense(out,rhos[dim],false);
+	}
+	std::fclose(out);
+	shared_array_core3::clear();
+	return 0;
+}
