@@ -1,0 +1,170 @@
+/*
+ * shkz_b200.h — thin C-ABI of the B200 pressure-projection library (libshkz_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of ryichando/shiokaze: the 3D MAC-grid pressure
+ * projection `macproject3_interface::project()` as implemented by
+ *     src/projection/macpressuresolver3.cpp:50-272   (orchestration, assembly, velocity update)
+ *     src/utility/macutility3.cpp:94-194             (solid area / liquid fractions)
+ *     src/math/RCMatrix.cpp + src/linsolver/pcg.cpp:45-73 + local/include/pcgsolver/pcg_solver.h:246-295
+ *                                                     (matrix + conjugate-gradient solve)
+ * The C++ module that a Shiokaze host loads (shiokaze_b200/plugin/b200pressure3.cpp, selected with
+ * `Projection=b200pressure3`) gathers dense buffers from the host's array3 / macarray3 grids and calls
+ * the functions below; nothing else crosses the boundary. Plain pointers and sizes only, no C++ or
+ * torch types, no exceptions; every function returns an error code and records a message retrievable
+ * with shkz_b200_last_error(). There is no CPU fallback: without a usable CUDA device every compute
+ * entry point fails with SHKZ_B200_ERR_NO_DEVICE.
+ *
+ * Dense layouts (the reference's own index order, include/shiokaze/math/shape.h:883-888: x fastest):
+ *     cell grid   nx * ny * nzl               index i + nx*(j + ny*k)
+ *     x faces     (nx+1) * ny * nzl           y faces  nx * (ny+1) * nzl        z faces  nx * ny * (nzl+1)
+ *     nodal grid  (nx+1) * (ny+1) * (nzl+1)
+ * nzl = number of z planes held by this solver (= nz for a whole grid, = k1-k0 for a z-slab).
+ * Values are what array3::operator() returns (active value / flood-fill value / background,
+ * include/shiokaze/array/array3.h:796-801); face activity is array3::active().
+ */
+#ifndef SHKZ_B200_H
+#define SHKZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHKZ_B200_ABI_VERSION 1
+
+enum shkz_b200_status {
+	SHKZ_B200_OK = 0,
+	SHKZ_B200_ERR_ARG = 1,       /* bad argument / unsupported combination */
+	SHKZ_B200_ERR_NO_DEVICE = 2, /* no CUDA device: the library never falls back to the CPU */
+	SHKZ_B200_ERR_CUDA = 3,      /* a CUDA runtime call failed */
+	SHKZ_B200_ERR_COMM = 4,      /* slab communicator (NCCL / IPC) failure */
+	SHKZ_B200_ERR_STATE = 5      /* call sequence error */
+};
+
+enum shkz_b200_precond {
+	SHKZ_B200_PRECOND_NONE = 0, /* plain CG == what the reference's "pcg" computes (pcg_solver.h:383 discards MIC(0)) */
+	SHKZ_B200_PRECOND_MG = 1    /* aggregation-multigrid V-cycle, red-black Gauss-Seidel smoothing */
+};
+
+enum shkz_b200_precision {
+	SHKZ_B200_PREC_FP64 = 0,  /* CG vectors and operator coefficients double (the reference's FLOAT_TYPE=double) */
+	SHKZ_B200_PREC_MIXED = 1, /* CG vectors double, operator coefficients float */
+	SHKZ_B200_PREC_FP32 = 2   /* everything float */
+};
+
+enum shkz_b200_real {
+	SHKZ_B200_REAL_F32 = 0, /* host built with Real=float (include/shiokaze/core/config.h:34, the default) */
+	SHKZ_B200_REAL_F64 = 1  /* host built with Real=double */
+};
+
+/* Flags of the reference module and its children, same meaning and defaults
+ * (macpressuresolver3.cpp:274-280,296-305; macutility3.cpp:408-412,417-421; pcg.cpp:39-44,75-80). */
+typedef struct shkz_b200_params {
+	uint32_t struct_size;         /* = sizeof(shkz_b200_params), for forward compatibility */
+	int32_t second_order_fluid;   /* SecondOrderAccurateFluid (Yes) */
+	int32_t second_order_solid;   /* SecondOrderAccurateSolid (Yes) */
+	int32_t apply_rhs_correct;    /* nonzero: add rhs_correct to every row (Gain && target volume set) */
+	double eps_fluid;             /* MacUtility.EpsFluid (1e-2) */
+	double eps_solid;             /* MacUtility.EpsSolid (1e-2) */
+	double surface_tension;       /* project()'s surface_tension argument */
+	double rhs_correct;           /* volume-correction constant, macpressuresolver3.cpp:204-214 (host computes the PI controller) */
+	double residual;              /* LinSolver.Residual (1e-4): stop when |r|_inf <= residual * |b|_inf */
+	uint32_t max_iterations;      /* LinSolver.MaxIterations (30000) */
+	/* additive flags of this implementation */
+	int32_t precond;              /* shkz_b200_precond (default MG) */
+	int32_t precision;            /* shkz_b200_precision (default MIXED) */
+	int32_t mg_pre_sweeps;        /* red-black sweeps before coarse correction (default 2) */
+	int32_t mg_post_sweeps;       /* and after, reversed colour order (default 2) */
+	int32_t mg_coarse_sweeps;     /* sweeps on the coarsest level, each direction (default 8) */
+	int32_t mg_min_size;          /* stop coarsening when the largest extent is <= this (default 4) */
+	int32_t check_every;          /* host reads the convergence flag every this many iterations (default 4) */
+	double mg_coarse_scale;       /* coarse operator = scale * (P^T A P), piecewise-constant P (default 0.5) */
+} shkz_b200_params;
+
+typedef struct shkz_b200_stats {
+	uint64_t n_rows;        /* number of unknowns (cells in the row set) on this solver's slab */
+	uint64_t n_rows_global; /* ... over all slabs */
+	uint32_t iterations;    /* as the reference counts them (pcg_solver.h:282) */
+	int32_t converged;
+	double reresid;         /* |r|_inf / |b|_inf at exit */
+	double rhs_absmax;      /* |b|_inf */
+	int32_t has_dirichlet;  /* 0: pure Neumann (singular) system, pressure mean removed */
+	int32_t mg_levels;
+	uint64_t kernel_launches; /* kernels of this library launched by the call */
+	float ms_h2d, ms_assemble, ms_setup, ms_solve, ms_update, ms_d2h, ms_total; /* CUDA-event times */
+} shkz_b200_stats;
+
+typedef struct shkz_b200_solver shkz_b200_solver; /* opaque */
+
+int shkz_b200_abi_version(void);
+const char *shkz_b200_last_error(void);
+void shkz_b200_default_params(shkz_b200_params *params);
+
+/* Number of CUDA devices visible (0 when there is none; never an error). */
+int shkz_b200_device_count(void);
+
+/*
+ * Create a solver for a whole nx*ny*nz grid on CUDA device `device`.
+ * Replaces macpressuresolver3::initialize(shape,dx) + post_initialize() (macpressuresolver3.cpp:281-291).
+ * real: shkz_b200_real — the element type of every grid buffer passed to project().
+ */
+int shkz_b200_create(int nx, int ny, int nz, double dx, int real, int device, shkz_b200_solver **out);
+
+/*
+ * Create a solver for the z-slab [k0,k1) of an nx*ny*nz grid (one solver per GPU / rank).
+ * All grid buffers then hold nzl = k1-k0 cell planes (z faces / nodes: nzl+1, the shared plane duplicated).
+ * Until shkz_b200_slab_connect() succeeds the solver refuses to project when (k0,k1) != (0,nz).
+ */
+int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int real, int device, shkz_b200_solver **out);
+
+void shkz_b200_destroy(shkz_b200_solver *solver);
+
+/*
+ * project(): replaces macproject3_interface::project (macproject3_interface.h:67-72).
+ *   dt               time step
+ *   vel[3]           in/out face velocities; only ACTIVE faces are modified (macpressuresolver3.cpp:252-268)
+ *   vel_active[3]    in/out face activity (1/0); faces the reference would set_off() become 0
+ *   solid            nodal solid level set, or NULL when the host's levelset_exist(solid) is false
+ *                    (include/shiokaze/array/array_utility3.h:112-122)
+ *   fluid            cell liquid level set (dense read, smoke passes its constant -1 grid)
+ *   fluid_levelset   host's levelset_exist(fluid): 0 => every liquid fraction is 1 (macutility3.cpp:191-193)
+ *   pressure         out, cell grid, 0 outside the row set        (get_pressure(), macproject3_interface.h:79)
+ *   pressure_active  out, 1 on the row set (the reference activates exactly these cells, :245-248); may be NULL
+ * Grid element type is float or double as chosen at creation. `_host` takes host pointers and does
+ * the H2D / D2H copies itself; `_device` takes device pointers on the solver's GPU and runs on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream), returning after the stream has been synchronised.
+ */
+int shkz_b200_project_host(shkz_b200_solver *solver, double dt, void *const vel[3], uint8_t *const vel_active[3],
+                           const void *solid, const void *fluid, int fluid_levelset, const shkz_b200_params *params,
+                           void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats);
+
+int shkz_b200_project_device(shkz_b200_solver *solver, double dt, void *const vel[3], uint8_t *const vel_active[3],
+                             const void *solid, const void *fluid, int fluid_levelset, const shkz_b200_params *params,
+                             void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats, void *cuda_stream);
+
+/*
+ * Re-run only the linear solve of the last project() (same matrix, same right-hand side, x = 0):
+ * the timed unit of the solver benchmark. Velocity and pressure outputs are not touched.
+ */
+int shkz_b200_resolve(shkz_b200_solver *solver, const shkz_b200_params *params, shkz_b200_stats *stats, void *cuda_stream);
+
+/* ---- z-slab communicator (one process per GPU; NVLink peer access through CUDA IPC + NCCL scalars) ---- */
+#define SHKZ_B200_NCCL_ID_BYTES 128
+#define SHKZ_B200_IPC_BYTES 128
+/* rank 0 fills a fresh NCCL unique id that the host broadcasts to every rank */
+int shkz_b200_comm_unique_id(uint8_t id[SHKZ_B200_NCCL_ID_BYTES]);
+/* this rank's exported halo window + interprocess event (opaque bytes to hand to the z-neighbours) */
+int shkz_b200_slab_export(shkz_b200_solver *solver, uint8_t ipc[SHKZ_B200_IPC_BYTES]);
+/* connect: NCCL communicator over `world` ranks + the neighbours' exports (NULL at the domain ends) */
+int shkz_b200_slab_connect(shkz_b200_solver *solver, int rank, int world, const uint8_t id[SHKZ_B200_NCCL_ID_BYTES],
+                           const uint8_t *lower_ipc, const uint8_t *upper_ipc);
+
+/* ---- test hook: copy an internal device array to the host (names: see DESIGN.md, e.g. "diag","rhs") ---- */
+int shkz_b200_debug_fetch(shkz_b200_solver *solver, const char *name, void *dst, size_t dst_bytes, size_t *needed_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,92 @@
+"""ctypes binding of include/shkz_b200.h (the C-ABI of libshkz_b200.so). Fails loudly when the library
+is missing or cannot be loaded; nothing here computes on the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libshkz_b200.so")
+
+OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_COMM, ERR_STATE = range(6)
+PRECOND_NONE, PRECOND_MG = 0, 1
+PREC_FP64, PREC_MIXED, PREC_FP32 = 0, 1, 2
+REAL_F32, REAL_F64 = 0, 1
+NCCL_ID_BYTES = 128
+IPC_BYTES = 128
+
+EXPORTS = [
+    "shkz_b200_abi_version", "shkz_b200_last_error", "shkz_b200_default_params", "shkz_b200_device_count",
+    "shkz_b200_create", "shkz_b200_create_slab", "shkz_b200_destroy", "shkz_b200_project_host",
+    "shkz_b200_project_device", "shkz_b200_resolve", "shkz_b200_comm_unique_id", "shkz_b200_slab_export",
+    "shkz_b200_slab_connect", "shkz_b200_debug_fetch",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("second_order_fluid", C.c_int32), ("second_order_solid", C.c_int32),
+                ("apply_rhs_correct", C.c_int32), ("eps_fluid", C.c_double), ("eps_solid", C.c_double),
+                ("surface_tension", C.c_double), ("rhs_correct", C.c_double), ("residual", C.c_double),
+                ("max_iterations", C.c_uint32), ("precond", C.c_int32), ("precision", C.c_int32),
+                ("mg_pre_sweeps", C.c_int32), ("mg_post_sweeps", C.c_int32), ("mg_coarse_sweeps", C.c_int32),
+                ("mg_min_size", C.c_int32), ("check_every", C.c_int32), ("mg_coarse_scale", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("n_rows_global", C.c_uint64), ("iterations", C.c_uint32), ("converged", C.c_int32),
+                ("reresid", C.c_double), ("rhs_absmax", C.c_double), ("has_dirichlet", C.c_int32), ("mg_levels", C.c_int32),
+                ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_float), ("ms_assemble", C.c_float), ("ms_setup", C.c_float),
+                ("ms_solve", C.c_float), ("ms_update", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class ShkzError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libshkz_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libshkz_b200.so (built in-tree by `make -C shiokaze_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C shiokaze_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u8p = C.c_void_p, C.POINTER(C.c_uint8)
+    L.shkz_b200_abi_version.restype = C.c_int
+    L.shkz_b200_last_error.restype = C.c_char_p
+    L.shkz_b200_default_params.argtypes = [C.POINTER(Params)]
+    L.shkz_b200_default_params.restype = None
+    L.shkz_b200_device_count.restype = C.c_int
+    L.shkz_b200_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(vp)]
+    L.shkz_b200_create_slab.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(vp)]
+    L.shkz_b200_destroy.argtypes = [vp]
+    L.shkz_b200_destroy.restype = None
+    proj = [vp, C.c_double, C.POINTER(vp), C.POINTER(vp), vp, vp, C.c_int, C.POINTER(Params), vp, vp, C.POINTER(Stats)]
+    L.shkz_b200_project_host.argtypes = proj
+    L.shkz_b200_project_device.argtypes = proj + [vp]
+    L.shkz_b200_resolve.argtypes = [vp, C.POINTER(Params), C.POINTER(Stats), vp]
+    L.shkz_b200_comm_unique_id.argtypes = [u8p]
+    L.shkz_b200_slab_export.argtypes = [vp, u8p]
+    L.shkz_b200_slab_connect.argtypes = [vp, C.c_int, C.c_int, u8p, u8p, u8p]
+    L.shkz_b200_debug_fetch.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != OK:
+        raise ShkzError(code, lib().shkz_b200_last_error().decode(errors="replace"))
+
+
+def default_params() -> Params:
+    p = Params()
+    lib().shkz_b200_default_params(C.byref(p))
+    return p

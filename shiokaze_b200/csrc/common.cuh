@@ -1,0 +1,115 @@
+// Shared device-side definitions of libshkz_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace shkz {
+
+// Local z-slab of a global nx*ny*nzg cell grid: planes [k0, k0+nzl). Every internal cell array is
+// allocated with one ghost plane below and above and addressed through a pointer to plane 0, so
+// indices -plane .. ncell+plane-1 are valid. Walls and non-row cells are encoded as ZERO coefficients,
+// which is why no kernel in the solve needs (i,j,k) bounds logic for its neighbour reads.
+struct Dims {
+	int nx, ny, nzl; // local extent
+	int k0, nzg;     // first global plane, global z extent
+	long long plane; // nx*ny
+	long long ncell; // plane*nzl
+};
+
+// Device-resident CG control block: the host never needs a value from here inside the loop.
+struct CGState {
+	double rho;     // z.r of the current iteration
+	double sz;      // s.(A s)
+	double alpha, beta;
+	double rnorm;   // |r|_inf
+	double rr;      // r.r (plain CG) or z.r (MG) for the next rho
+	double bnorm;   // |b|_inf
+	double tol;     // residual * |b|_inf
+	double sum_x;   // sum of x over rows (singular systems: mean removal)
+	unsigned long long n_rows;
+	int iter;       // completed iterations, counted like pcg_solver.h:282
+	int max_iter;
+	int done;       // 1: converged, max_iter reached, or trivial rhs — later kernels become no-ops
+	int converged;
+	int has_dirichlet;
+	int pad;
+};
+
+struct RedBuf {
+	double *partials;      // [blocks][N]
+	unsigned int *counter; // zero between kernels
+};
+
+__device__ __forceinline__ unsigned linear_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+__device__ __forceinline__ unsigned linear_bid() { return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); }
+
+template <int N, unsigned MAXMASK>
+__device__ __forceinline__ void warp_combine(double (&v)[N]) {
+#pragma unroll
+	for (int n = 0; n < N; ++n) {
+#pragma unroll
+		for (int off = 16; off > 0; off >>= 1) {
+			double o = __shfl_xor_sync(0xffffffffu, v[n], off);
+			v[n] = ((MAXMASK >> n) & 1u) ? fmax(v[n], o) : v[n] + o;
+		}
+	}
+}
+
+template <int N, unsigned MAXMASK>
+__device__ __forceinline__ void block_combine(double (&v)[N], double (*sm)[32]) {
+	const unsigned tid = linear_tid(), lane = tid & 31u, wid = tid >> 5;
+	const unsigned nwarps = (blockDim.x * blockDim.y * blockDim.z + 31u) >> 5;
+	warp_combine<N, MAXMASK>(v);
+	__syncthreads(); // sm may still be read from a previous use
+	if (lane == 0) {
+#pragma unroll
+		for (int n = 0; n < N; ++n) sm[n][wid] = v[n];
+	}
+	__syncthreads();
+	if (wid == 0) {
+#pragma unroll
+		for (int n = 0; n < N; ++n) v[n] = lane < nwarps ? sm[n][lane] : 0.0;
+		warp_combine<N, MAXMASK>(v);
+	}
+}
+
+// Grid-wide reduction with a deterministic combine order: every block stores its partial, the block
+// that arrives last folds all partials in a fixed order and runs `fin(total)` on one thread.
+// All values reduced here are sums, or maxima of non-negative numbers (identity 0 for both).
+template <int N, unsigned MAXMASK, class Fin>
+__device__ __forceinline__ void grid_reduce(double (&v)[N], RedBuf rb, Fin fin) {
+	__shared__ double sm[N][32];
+	__shared__ int is_last;
+	const unsigned tid = linear_tid();
+	const unsigned nthreads = blockDim.x * blockDim.y * blockDim.z;
+	const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+	block_combine<N, MAXMASK>(v, sm);
+	if (tid == 0) {
+		const unsigned bid = linear_bid();
+#pragma unroll
+		for (int n = 0; n < N; ++n) __stcg(&rb.partials[(size_t)bid * N + n], v[n]);
+		__threadfence();
+		const unsigned ticket = atomicAdd(rb.counter, 1u);
+		is_last = (ticket == nblocks - 1);
+	}
+	__syncthreads();
+	if (!is_last) return;
+	__threadfence();
+	double acc[N];
+#pragma unroll
+	for (int n = 0; n < N; ++n) acc[n] = 0.0;
+	for (unsigned b = tid; b < nblocks; b += nthreads) {
+#pragma unroll
+		for (int n = 0; n < N; ++n) {
+			const double p = __ldcg(&rb.partials[(size_t)b * N + n]);
+			acc[n] = ((MAXMASK >> n) & 1u) ? fmax(acc[n], p) : acc[n] + p;
+		}
+	}
+	block_combine<N, MAXMASK>(acc, sm);
+	if (tid == 0) {
+		fin(acc);
+		*rb.counter = 0u;
+	}
+}
+
+} // namespace shkz

@@ -1,0 +1,328 @@
+// Coefficient assembly and velocity update kernels (replace the reference's CPU loops K1-K6, K12-K14
+// of SURVEY.md section 2d). Arithmetic that must agree bit-for-bit with the reference (fractions,
+// matrix entries, right-hand side) uses the explicit round-to-nearest intrinsics so that nvcc never
+// contracts it into FMAs; the operation order is the reference's.
+#pragma once
+#include <float.h>
+#include "common.cuh"
+
+namespace shkz {
+
+struct AsmParams {
+	double dt, dx;
+	double eps_fluid, eps_solid;
+	double surface_tension;
+	double rhs_correct;
+	int second_order_fluid, second_order_solid;
+	int have_solid, fluid_levelset;
+	int apply_rhs_correct;
+	int pad;
+};
+
+template <class RealT>
+struct FaceGrids { // face-shaped, no ghost planes: x (nx+1,ny,nzl)  y (nx,ny+1,nzl)  z (nx,ny,nzl+1)
+	RealT *p[3];
+};
+template <class RealT>
+struct ConstFaceGrids {
+	const RealT *p[3];
+};
+struct FaceMasks {
+	uint8_t *p[3];
+};
+
+__device__ __forceinline__ long long face_index(const Dims &d, int dim, int i, int j, int k) {
+	const long long w = d.nx + (dim == 0), h = d.ny + (dim == 1);
+	return i + w * (j + h * (long long)k);
+}
+__device__ __forceinline__ int clampi(int v, int n) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); }
+
+// include/shiokaze/utility/utility.h:162-170
+__device__ __forceinline__ double fraction(double phi0, double phi1) {
+	if (__dmul_rn(phi0, phi1) >= 0.0) {
+		if (phi0 < 0.0 || phi1 < 0.0) return 1.0;
+		return 0.0;
+	}
+	const double denom = fmax(fabs(__dsub_rn(phi1, phi0)), DBL_MIN);
+	return __ddiv_rn(-fmin(phi0, phi1), denom);
+}
+
+// include/shiokaze/utility/utility.h:179-214 — polygon of {phi<0} on the unit square, shoelace area.
+// Corner order (0,0),(1,0),(1,1),(0,1).
+__device__ __forceinline__ double get_area(double v0, double v1, double v2, double v3) {
+	const double qx[4] = {0.0, 1.0, 1.0, 0.0}, qy[4] = {0.0, 0.0, 1.0, 1.0};
+	const double v[4] = {v0, v1, v2, v3};
+	double px[8], py[8];
+	int pnum = 0;
+#pragma unroll
+	for (int n = 0; n < 4; ++n) {
+		const int m = (n + 1) & 3;
+		if (v[n] < 0.0) {
+			px[pnum] = qx[n];
+			py[pnum] = qy[n];
+			pnum++;
+		}
+		if (__dmul_rn(v[n], v[m]) < 0.0) {
+			const double y0 = v[n], y1 = v[m];
+			const double den = __dsub_rn(y0, y1);
+			if (den != 0.0) {
+				const double a = __ddiv_rn(y0, den);
+				const double na = __dsub_rn(1.0, a);
+				px[pnum] = __dadd_rn(__dmul_rn(na, qx[n]), __dmul_rn(a, qx[m]));
+				py[pnum] = __dadd_rn(__dmul_rn(na, qy[n]), __dmul_rn(a, qy[m]));
+				pnum++;
+			}
+		}
+	}
+	double sum = 0.0;
+	for (int m = 0; m < pnum; ++m) {
+		const int m1 = (m + 1 == pnum) ? 0 : m + 1;
+		sum = __dadd_rn(sum, __dsub_rn(__dmul_rn(px[m], py[m1]), __dmul_rn(py[m], px[m1])));
+	}
+	return __dmul_rn(0.5, sum);
+}
+
+// K1 + K2 (+ first-order toggles): src/utility/macutility3.cpp:94-194, macpressuresolver3.cpp:70-80.
+// One thread per (i,j,k) in [0,nx] x [0,ny] x [0,nzl]; it owns the three lower faces of that slot.
+template <class RealT>
+__global__ void __launch_bounds__(256) k_face_fractions(Dims d, AsmParams P, const RealT *__restrict__ solid,
+                                                       const RealT *__restrict__ phi, FaceGrids<RealT> areas, FaceGrids<RealT> rhos) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = blockIdx.z;
+	if (i > d.nx || j > d.ny) return;
+	const int kg = k + d.k0;
+	const long long sw = d.nx + 1, sh = d.ny + 1;
+#pragma unroll
+	for (int dim = 0; dim < 3; ++dim) {
+		if (i >= d.nx + (dim == 0) || j >= d.ny + (dim == 1) || k >= d.nzl + (dim == 2)) continue;
+		const int pd = dim == 0 ? i : (dim == 1 ? j : kg);
+		const int n_dim = dim == 0 ? d.nx : (dim == 1 ? d.ny : d.nzg);
+		double area;
+		if (!P.have_solid) {
+			area = (pd == 0 || pd == n_dim) ? 0.0 : 1.0; // macutility3.cpp:149-164
+		} else {
+			if (pd == 0) area = 0.0; // :120 (a nodal solid never matches the far wall)
+			else {
+#define SOLID(a, b, c) (double)solid[(a) + sw * ((b) + sh * (long long)(c))]
+				double q00, q10, q11, q01;
+				if (dim == 0) { q00 = SOLID(i, j, k); q10 = SOLID(i, j + 1, k); q11 = SOLID(i, j + 1, k + 1); q01 = SOLID(i, j, k + 1); }
+				else if (dim == 1) { q00 = SOLID(i, j, k); q10 = SOLID(i + 1, j, k); q11 = SOLID(i + 1, j, k + 1); q01 = SOLID(i, j, k + 1); }
+				else { q00 = SOLID(i, j, k); q10 = SOLID(i + 1, j, k); q11 = SOLID(i + 1, j + 1, k); q01 = SOLID(i, j + 1, k); }
+#undef SOLID
+				area = __dsub_rn(1.0, get_area(q00, q10, q11, q01));
+			}
+			if (area != 0.0 && area < P.eps_solid) area = P.eps_solid; // :141
+		}
+		RealT area_r = (RealT)area;
+		if (!P.second_order_solid && area_r != (RealT)0) area_r = (RealT)1;
+		double rho;
+		if (!P.fluid_levelset) rho = 1.0; // :191-193
+		else {
+			// :179-182 with shape3::clamp (shape.h:790-798); the z clamp is global, ghost planes carry the neighbour slab
+			const int ia = clampi(i, d.nx), ja = clampi(j, d.ny), ka = clampi(kg, d.nzg) - d.k0;
+			const int ib = clampi(i - (dim == 0), d.nx), jb = clampi(j - (dim == 1), d.ny), kb = clampi(kg - (dim == 2), d.nzg) - d.k0;
+			const double a = (double)phi[ia + (long long)d.nx * (ja + (long long)d.ny * ka)];
+			const double b = (double)phi[ib + (long long)d.nx * (jb + (long long)d.ny * kb)];
+			rho = fraction(a, b);
+			if (rho != 0.0 && rho < P.eps_fluid) rho = P.eps_fluid; // :183
+		}
+		RealT rho_r = (RealT)rho;
+		if (!P.second_order_fluid && rho_r != (RealT)0) rho_r = (RealT)1;
+		const long long f = face_index(d, dim, i, j, k);
+		areas.p[dim][f] = area_r;
+		rhos.p[dim][f] = rho_r;
+	}
+}
+
+// K3a: curvature = 7-point Laplacian of phi with clamped neighbours / dx^2 (macpressuresolver3.cpp:92-102)
+template <class RealT>
+__global__ void __launch_bounds__(256) k_curvature(Dims d, AsmParams P, const RealT *__restrict__ phi, RealT *__restrict__ curv) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = blockIdx.z;
+	if (i >= d.nx || j >= d.ny) return;
+	const int kg = k + d.k0;
+#define PHI(a, b, c) (double)phi[clampi(a, d.nx) + (long long)d.nx * (clampi(b, d.ny) + (long long)d.ny * (clampi(c, d.nzg) - d.k0))]
+	double s = PHI(i - 1, j, kg);
+	s = __dadd_rn(s, PHI(i + 1, j, kg));
+	s = __dadd_rn(s, PHI(i, j - 1, kg));
+	s = __dadd_rn(s, PHI(i, j + 1, kg));
+	s = __dadd_rn(s, PHI(i, j, kg - 1));
+	s = __dadd_rn(s, PHI(i, j, kg + 1));
+	s = __dsub_rn(s, __dmul_rn(6.0, PHI(i, j, kg)));
+#undef PHI
+	curv[i + (long long)d.nx * (j + (long long)d.ny * k)] = (RealT)__ddiv_rn(s, __dmul_rn(P.dx, P.dx));
+}
+
+// K3b: surface-tension increment on ACTIVE faces with 0 < rho < 1 (macpressuresolver3.cpp:104-113)
+template <class RealT>
+__global__ void __launch_bounds__(256) k_surface_tension(Dims d, AsmParams P, const RealT *__restrict__ phi, const RealT *__restrict__ curv,
+                                                        ConstFaceGrids<RealT> rhos, FaceGrids<RealT> vel, FaceMasks active) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = blockIdx.z;
+	if (i > d.nx || j > d.ny) return;
+	const int kg = k + d.k0;
+#pragma unroll
+	for (int dim = 0; dim < 3; ++dim) {
+		if (i >= d.nx + (dim == 0) || j >= d.ny + (dim == 1) || k >= d.nzl + (dim == 2)) continue;
+		const long long f = face_index(d, dim, i, j, k);
+		if (!active.p[dim][f]) continue;
+		const double rho = (double)rhos.p[dim][f];
+		if (rho != 0.0 && rho < 1.0) {
+			const long long ca = clampi(i, d.nx) + (long long)d.nx * (clampi(j, d.ny) + (long long)d.ny * (clampi(kg, d.nzg) - d.k0));
+			const long long cb = clampi(i - (dim == 0), d.nx) + (long long)d.nx * (clampi(j - (dim == 1), d.ny) + (long long)d.ny * (clampi(kg - (dim == 2), d.nzg) - d.k0));
+			const double sgn = (double)phi[ca] < 0.0 ? -1.0 : 1.0;
+			const double theta = sgn < 0 ? __dsub_rn(1.0, rho) : rho;
+			const double face_c = __dadd_rn(__dmul_rn(theta, (double)curv[ca]), __dmul_rn(__dsub_rn(1.0, theta), (double)curv[cb]));
+			// -sgn * dt / (dx*rho) * kappa * face_c, left to right
+			double inc = __ddiv_rn(__dmul_rn(-sgn, P.dt), __dmul_rn(P.dx, rho));
+			inc = __dmul_rn(__dmul_rn(inc, P.surface_tension), face_c);
+			vel.p[dim][f] = vel.p[dim][f] + (RealT)inc; // array3::increment in Real arithmetic (array3.h:631-639)
+		}
+	}
+}
+
+// K4: row labelling (macpressuresolver3.cpp:121-156) as a dense mask. in_rows has ghost planes.
+template <class RealT>
+__global__ void __launch_bounds__(256) k_label_rows(Dims d, const RealT *__restrict__ phi, ConstFaceGrids<RealT> areas,
+                                                   ConstFaceGrids<RealT> rhos, uint8_t *__restrict__ in_rows) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = blockIdx.z;
+	if (i >= d.nx || j >= d.ny) return;
+	const int kg = k + d.k0;
+	const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+	bool inside = false;
+	if (phi[c] < (RealT)0) {
+		const int qo[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+#pragma unroll
+		for (int nq = 0; nq < 6; ++nq) {
+			const int dim = nq >> 1;
+			const int qi = i + qo[nq][0], qj = j + qo[nq][1], qkg = kg + qo[nq][2];
+			if (qi < 0 || qj < 0 || qkg < 0 || qi >= d.nx || qj >= d.ny || qkg >= d.nzg) continue;
+			const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
+			if (phi[q] < (RealT)0) {
+				const int up = (nq & 1) ? 0 : 1;
+				const long long f = face_index(d, dim, i + (dim == 0) * up, j + (dim == 1) * up, k + (dim == 2) * up);
+				if (areas.p[dim][f] != (RealT)0 && rhos.p[dim][f] != (RealT)0) inside = true;
+			}
+		}
+	}
+	in_rows[c] = inside ? 1 : 0;
+}
+
+// K5 + K6: matrix-free coefficients and right-hand side (macpressuresolver3.cpp:163-217).
+//   w{x,y,z}[c] = dt*A/(dx^2*theta) of the LOWER face of c when both cells are rows, else 0
+//   diag[c]     = sum over the open in-grid faces of c (air neighbours included: ghost-fluid Dirichlet)
+//   rhs[c]      = sum -sgn*A*u/dx (+ volume-correction constant); 0 outside the row set
+// CoefT/VecT copies feed the CG operator; the float copies feed multigrid level 0 (may alias).
+template <class RealT, class CoefT, class VecT>
+__global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const RealT *__restrict__ phi, const uint8_t *__restrict__ in_rows,
+                                                     ConstFaceGrids<RealT> areas, ConstFaceGrids<RealT> rhos, ConstFaceGrids<RealT> vel,
+                                                     CoefT *__restrict__ wx, CoefT *__restrict__ wy, CoefT *__restrict__ wz, CoefT *__restrict__ diag,
+                                                     float *__restrict__ mwx, float *__restrict__ mwy, float *__restrict__ mwz, float *__restrict__ mdiag,
+                                                     VecT *__restrict__ rhs, RedBuf rb, CGState *st) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = blockIdx.z;
+	double red[3] = {0.0, 0.0, 0.0}; // |b|_inf, row count, dirichlet flag
+	if (i < d.nx && j < d.ny) {
+		const int kg = k + d.k0;
+		const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+		double diagonal = 0.0, b = 0.0, lower[3] = {0.0, 0.0, 0.0};
+		if (in_rows[c]) {
+			const int qo[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+			const double dx2 = __dmul_rn(P.dx, P.dx);
+#pragma unroll
+			for (int nq = 0; nq < 6; ++nq) {
+				const int dim = nq >> 1;
+				const int qi = i + qo[nq][0], qj = j + qo[nq][1], qkg = kg + qo[nq][2];
+				if (qi < 0 || qj < 0 || qkg < 0 || qi >= d.nx || qj >= d.ny || qkg >= d.nzg) continue;
+				const int up = (nq & 1) ? 0 : 1;
+				const long long f = face_index(d, dim, i + (dim == 0) * up, j + (dim == 1) * up, k + (dim == 2) * up);
+				const double area = (double)areas.p[dim][f];
+				if (area != 0.0) {
+					const double rho = (double)rhos.p[dim][f];
+					if (rho != 0.0) {
+						const double value = __ddiv_rn(__dmul_rn(P.dt, area), __dmul_rn(dx2, rho));
+						const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
+						if (phi[q] < (RealT)0) {
+							if (!up) lower[dim] = value;
+						} else red[2] = 1.0;
+						diagonal = __dadd_rn(diagonal, value);
+					}
+					const double sgn = up ? -1.0 : 1.0; // -sgn[nq]
+					b = __dadd_rn(b, __ddiv_rn(__dmul_rn(__dmul_rn(sgn, area), (double)vel.p[dim][f]), P.dx));
+				}
+			}
+			if (P.apply_rhs_correct) b = __dadd_rn(b, P.rhs_correct);
+			red[0] = fabs(b);
+			red[1] = 1.0;
+		}
+		wx[c] = (CoefT)lower[0]; wy[c] = (CoefT)lower[1]; wz[c] = (CoefT)lower[2]; diag[c] = (CoefT)diagonal;
+		if ((void *)mwx != (void *)wx) { mwx[c] = (float)lower[0]; mwy[c] = (float)lower[1]; mwz[c] = (float)lower[2]; mdiag[c] = (float)diagonal; }
+		rhs[c] = (VecT)b;
+	}
+	grid_reduce<3, 0x5u>(red, rb, [&](double (&t)[3]) {
+		st->bnorm = t[0];
+		st->n_rows = (unsigned long long)(t[1] + 0.5);
+		st->has_dirichlet = t[2] > 0.0 ? 1 : 0;
+	});
+}
+
+// K12: pressure scatter to the Real grid (macpressuresolver3.cpp:245-248); singular systems lose their mean.
+template <class RealT, class VecT>
+__global__ void __launch_bounds__(256) k_store_pressure(Dims d, const VecT *__restrict__ x, const uint8_t *__restrict__ in_rows,
+                                                       const CGState *__restrict__ st, RealT *__restrict__ pressure) {
+	const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (c >= d.ncell) return;
+	double shift = 0.0;
+	if (!st->has_dirichlet && st->n_rows) shift = st->sum_x / (double)st->n_rows;
+	pressure[c] = in_rows[c] ? (RealT)((double)x[c] - shift) : (RealT)0;
+}
+
+template <class VecT>
+__global__ void __launch_bounds__(256) k_sum_rows(Dims d, const VecT *__restrict__ x, const uint8_t *__restrict__ in_rows, RedBuf rb, CGState *st) {
+	double red[1] = {0.0};
+	for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < d.ncell; c += (long long)gridDim.x * blockDim.x)
+		if (in_rows[c]) red[0] += (double)x[c];
+	grid_reduce<1, 0u>(red, rb, [&](double (&t)[1]) { st->sum_x = t[0]; });
+}
+
+// K13: velocity update on ACTIVE faces (macpressuresolver3.cpp:252-268). pressure has ghost planes.
+template <class RealT>
+__global__ void __launch_bounds__(256) k_update_velocity(Dims d, AsmParams P, const RealT *__restrict__ phi, const RealT *__restrict__ pressure,
+                                                        ConstFaceGrids<RealT> areas, ConstFaceGrids<RealT> rhos, FaceGrids<RealT> vel, FaceMasks active) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = blockIdx.z;
+	if (i > d.nx || j > d.ny) return;
+	const int kg = k + d.k0;
+#pragma unroll
+	for (int dim = 0; dim < 3; ++dim) {
+		if (i >= d.nx + (dim == 0) || j >= d.ny + (dim == 1) || k >= d.nzl + (dim == 2)) continue;
+		const long long f = face_index(d, dim, i, j, k);
+		if (!active.p[dim][f]) continue;
+		const int pd = dim == 0 ? i : (dim == 1 ? j : kg);
+		const int n_dim = dim == 0 ? d.nx : (dim == 1 ? d.ny : d.nzg);
+		const RealT rho = rhos.p[dim][f];
+		const long long c = i + (long long)d.nx * (j + (long long)d.ny * k); // may be a ghost / out-of-row slot for the far faces
+		const long long cm = c - (dim == 0 ? 1 : (dim == 1 ? d.nx : d.plane));
+		if (areas.p[dim][f] != (RealT)0 && rho != (RealT)0) {
+			if (pd == 0 || pd == n_dim) vel.p[dim][f] = (RealT)0;
+			else {
+				const RealT diff = pressure[c] - pressure[cm]; // Real arithmetic, as the reference's expression
+				const RealT delta = (RealT)__ddiv_rn(__dmul_rn(P.dt, (double)diff), __dmul_rn((double)rho, P.dx));
+				vel.p[dim][f] = vel.p[dim][f] - delta; // array3::subtract (array3.h:663-671)
+			}
+		} else {
+			if (pd == 0 && phi[c] < (RealT)0) vel.p[dim][f] = (RealT)0;
+			else if (pd == n_dim && phi[cm] < (RealT)0) vel.p[dim][f] = (RealT)0;
+			else { active.p[dim][f] = 0; vel.p[dim][f] = (RealT)0; } // set_off(): reads back as the background 0
+		}
+	}
+}
+
+} // namespace shkz

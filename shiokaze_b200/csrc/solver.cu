@@ -1,0 +1,728 @@
+// Host side of libshkz_b200: device memory, launch sequences, and the C-ABI of include/shkz_b200.h.
+// No CPU compute path exists in this file: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/shkz_b200.h"
+#include "common.cuh"
+#include "kernels_assemble.cuh"
+#include "kernels_cg.cuh"
+#include "kernels_mg.cuh"
+#include "slab_comm.h"
+
+using namespace shkz;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...) {
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_error = buf;
+	return code;
+}
+
+#define CK(call)                                                                                              \
+	do {                                                                                                      \
+		cudaError_t e_ = (call);                                                                              \
+		if (e_ != cudaSuccess) return fail(SHKZ_B200_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+#define CKR(call)                     \
+	do {                              \
+		int r_ = (call);              \
+		if (r_ != SHKZ_B200_OK) return r_; \
+	} while (0)
+
+// A cell-shaped device array with one ghost plane on each side; `p` points at plane 0.
+struct CellArray {
+	void *base = nullptr;
+	size_t bytes = 0;
+	int alloc(const Dims &d, size_t elem) {
+		bytes = (size_t)(d.nzl + 2) * (size_t)d.plane * elem;
+		CK(cudaMalloc(&base, bytes));
+		CK(cudaMemset(base, 0, bytes));
+		return SHKZ_B200_OK;
+	}
+	void release() {
+		if (base) cudaFree(base);
+		base = nullptr;
+		bytes = 0;
+	}
+	template <class T> T *ptr(const Dims &d) const { return base ? static_cast<T *>(base) + d.plane : nullptr; }
+};
+
+struct PlainArray {
+	void *base = nullptr;
+	size_t bytes = 0;
+	int alloc(size_t n) {
+		bytes = n ? n : 1;
+		CK(cudaMalloc(&base, bytes));
+		CK(cudaMemset(base, 0, bytes));
+		return SHKZ_B200_OK;
+	}
+	void release() {
+		if (base) cudaFree(base);
+		base = nullptr;
+		bytes = 0;
+	}
+};
+
+Dims make_dims(int nx, int ny, int nzl, int k0, int nzg) {
+	Dims d;
+	d.nx = nx; d.ny = ny; d.nzl = nzl; d.k0 = k0; d.nzg = nzg;
+	d.plane = (long long)nx * ny;
+	d.ncell = d.plane * nzl;
+	return d;
+}
+
+size_t face_count(const Dims &d, int dim) {
+	return (size_t)(d.nx + (dim == 0)) * (size_t)(d.ny + (dim == 1)) * (size_t)(d.nzl + (dim == 2));
+}
+
+struct HostLevel {
+	Dims d;
+	CellArray wx, wy, wz, diag, x, b, r;
+	bool own_coef = true, own_x = true, own_b = true; // level 0 may alias CG arrays
+	MGLevel view;
+};
+
+} // namespace
+
+struct shkz_b200_solver {
+	Dims d;
+	double dx = 0;
+	int real = SHKZ_B200_REAL_F32;
+	int device = 0;
+	size_t real_bytes = 4;
+	bool whole_grid = true;
+	// geometry / assembly products (RealT)
+	CellArray phi, pressure, curv;
+	CellArray in_rows;
+	PlainArray areas[3], rhos[3];
+	// operator + CG vectors; element sizes depend on the precision mode they were allocated for
+	int alloc_precision = -1;
+	CellArray wx, wy, wz, diag; // CoefT
+	CellArray b, x, r, s, z;    // VecT
+	std::vector<HostLevel> levels;
+	int mg_min_size_built = -1;
+	// reductions / control
+	PlainArray partials, counter, state;
+	CGState *h_state = nullptr; // pinned
+	size_t max_blocks = 0;
+	// host-call staging (device)
+	PlainArray st_vel[3], st_act[3], st_solid, st_fluid, st_pressure, st_pact;
+	// slab communicator
+	SlabComm *comm = nullptr;
+	// bookkeeping
+	uint64_t launches = 0;
+	bool have_system = false;
+	AsmParams last_asm{};
+	cudaEvent_t ev[8]{};
+	bool events = false;
+
+	RedBuf redbuf() const { return RedBuf{static_cast<double *>(partials.base), static_cast<unsigned int *>(counter.base)}; }
+	CGState *dstate() const { return static_cast<CGState *>(state.base); }
+};
+
+namespace {
+
+void release_precision_arrays(shkz_b200_solver *S) {
+	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->diag, &S->b, &S->x, &S->r, &S->s, &S->z}) a->release();
+	for (HostLevel &L : S->levels) {
+		if (L.own_coef) { L.wx.release(); L.wy.release(); L.wz.release(); L.diag.release(); }
+		if (L.own_x) L.x.release();
+		if (L.own_b) L.b.release();
+		L.r.release();
+	}
+	S->levels.clear();
+	S->alloc_precision = -1;
+	S->have_system = false;
+}
+
+template <class VecT, class CoefT>
+int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_params &P) {
+	const int min_size = P.mg_min_size < 2 ? 2 : P.mg_min_size;
+	if (S->alloc_precision == precision && S->mg_min_size_built == min_size) return SHKZ_B200_OK;
+	release_precision_arrays(S);
+	const Dims &d = S->d;
+	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->diag}) CKR(a->alloc(d, sizeof(CoefT)));
+	for (CellArray *a : {&S->b, &S->x, &S->r, &S->s, &S->z}) CKR(a->alloc(d, sizeof(VecT)));
+	// multigrid hierarchy (always allocated: switching the preconditioner must not reallocate)
+	Dims cur = d;
+	for (int l = 0;; ++l) {
+		HostLevel L;
+		L.d = cur;
+		if (l == 0 && sizeof(CoefT) == sizeof(float)) {
+			L.own_coef = false;
+			L.wx = S->wx; L.wy = S->wy; L.wz = S->wz; L.diag = S->diag;
+		} else {
+			for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.diag}) CKR(a->alloc(cur, sizeof(float)));
+		}
+		if (l == 0 && sizeof(VecT) == sizeof(float)) {
+			L.own_x = L.own_b = false;
+			L.x = S->z; // the V-cycle writes z directly
+			L.b = S->r; // and smooths against r directly
+		} else {
+			CKR(L.x.alloc(cur, sizeof(float)));
+			CKR(L.b.alloc(cur, sizeof(float)));
+		}
+		CKR(L.r.alloc(cur, sizeof(float)));
+		L.view.d = cur;
+		L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.diag = L.diag.ptr<float>(cur);
+		L.view.x = L.x.ptr<float>(cur); L.view.b = L.b.ptr<float>(cur); L.view.r = L.r.ptr<float>(cur);
+		S->levels.push_back(L);
+		const int big = cur.nx > cur.ny ? (cur.nx > cur.nzg ? cur.nx : cur.nzg) : (cur.ny > cur.nzg ? cur.ny : cur.nzg);
+		if (big <= min_size) break;
+		// slabs: keep aggregates inside one rank (even local extent and even first plane)
+		if (!S->whole_grid && ((cur.nzl & 1) || (cur.k0 & 1) || cur.nzl < 2)) break;
+		cur = make_dims((cur.nx + 1) / 2, (cur.ny + 1) / 2, (cur.nzl + 1) / 2, cur.k0 / 2, (cur.nzg + 1) / 2);
+	}
+	S->alloc_precision = precision;
+	S->mg_min_size_built = min_size;
+	return SHKZ_B200_OK;
+}
+
+dim3 cell_block() { return dim3(32, 8, 1); }
+dim3 cell_grid(const Dims &d, int ex, int ey, int ez) { return dim3((d.nx + ex + 31) / 32, (d.ny + ey + 7) / 8, d.nzl + ez); }
+int flat_blocks(long long n) {
+	long long b = (n + 255) / 256;
+	const long long cap = 148 * 16;
+	return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+#define LAUNCH(S, kernel, grid, block, stream, ...)   \
+	do {                                              \
+		kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); \
+		(S)->launches++;                              \
+	} while (0)
+
+// ---- halo exchange of one cell array (ghost planes), a no-op on a whole grid ----
+template <class T>
+int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
+	if (S->whole_grid || !S->comm) return SHKZ_B200_OK;
+	return S->comm->exchange(p, d.plane, d.nzl, sizeof(T), st) ? fail(SHKZ_B200_ERR_COMM, "halo exchange failed: %s", S->comm->error()) : SHKZ_B200_OK;
+}
+
+// ---- multigrid ----
+void rbgs(shkz_b200_solver *S, const MGLevel &L, int color, bool zero_x, const CGState *st, cudaStream_t stream) {
+	const dim3 block(32, 8, 1);
+	const dim3 grid(((L.d.nx + 1) / 2 + 31) / 32, (L.d.ny + 7) / 8, L.d.nzl);
+	if (zero_x) LAUNCH(S, k_rbgs<true>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.diag, L.b, L.x, color, st);
+	else LAUNCH(S, k_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.diag, L.b, L.x, color, st);
+}
+
+int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, const CGState *st, cudaStream_t stream) {
+	const MGLevel &L = S->levels[l].view;
+	const bool last = (l + 1 == S->levels.size());
+	const int pre = last ? (P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps) : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
+	const int post = last ? pre : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
+	for (int sw = 0; sw < pre; ++sw) {
+		rbgs(S, L, 0, sw == 0, st, stream);
+		CKR(halo(S, L.d, L.x, stream));
+		rbgs(S, L, 1, false, st, stream);
+		CKR(halo(S, L.d, L.x, stream));
+	}
+	if (!last) {
+		const MGLevel &C = S->levels[l + 1].view;
+		LAUNCH(S, k_residual, stencil_grid(L.d), stencil_block(), stream, L.d, L.wx, L.wy, L.wz, L.diag, L.b, L.x, L.r, st);
+		LAUNCH(S, k_restrict, cell_grid(C.d, 0, 0, 0), cell_block(), stream, L.d, C.d, L.r, C.b, st);
+		CKR(vcycle(S, l + 1, P, st, stream));
+		LAUNCH(S, k_prolong_add, cell_grid(L.d, 0, 0, 0), cell_block(), stream, L.d, C.d, C.x, L.x, st);
+		CKR(halo(S, L.d, L.x, stream));
+	}
+	for (int sw = 0; sw < post; ++sw) {
+		rbgs(S, L, 1, false, st, stream);
+		CKR(halo(S, L.d, L.x, stream));
+		rbgs(S, L, 0, false, st, stream);
+		if (sw + 1 < post || l > 0) CKR(halo(S, L.d, L.x, stream));
+	}
+	return SHKZ_B200_OK;
+}
+
+int build_hierarchy(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
+	for (size_t l = 0; l + 1 < S->levels.size(); ++l) {
+		const MGLevel &F = S->levels[l].view, &C = S->levels[l + 1].view;
+		LAUNCH(S, k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, (float)P.mg_coarse_scale, F.wx, F.wy, F.wz, F.diag, C.wx,
+		       C.wy, C.wz, C.diag);
+		CKR(halo(S, C.d, C.wz, stream));
+	}
+	CK(cudaGetLastError());
+	return SHKZ_B200_OK;
+}
+
+// ---- the CG driver (pcg_solver.h:246-295 with the loop control on the device) ----
+template <class VecT, class CoefT>
+int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
+	const Dims &d = S->d;
+	const long long n = d.ncell;
+	const RedBuf rb = S->redbuf();
+	CGState *st = S->dstate();
+	VecT *b = S->b.ptr<VecT>(d), *x = S->x.ptr<VecT>(d), *r = S->r.ptr<VecT>(d), *s = S->s.ptr<VecT>(d), *z = S->z.ptr<VecT>(d);
+	const CoefT *wx = S->wx.ptr<CoefT>(d), *wy = S->wy.ptr<CoefT>(d), *wz = S->wz.ptr<CoefT>(d), *diag = S->diag.ptr<CoefT>(d);
+	const bool mg = P.precond == SHKZ_B200_PRECOND_MG;
+	const int fb = flat_blocks(n);
+	const bool alias = sizeof(VecT) == sizeof(float);
+
+	if (S->comm && !S->whole_grid) CKR(S->comm->allreduce_begin_state(st, stream) ? fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error()) : SHKZ_B200_OK);
+	LAUNCH(S, k_cg_begin<VecT>, 1, 32, stream, n, P.residual, (int)P.max_iterations, st);
+	CK(cudaMemsetAsync(x, 0, sizeof(VecT) * (size_t)n, stream));
+	CK(cudaMemcpyAsync(r, b, sizeof(VecT) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+
+	auto precondition = [&]() -> int {
+		const MGLevel &L0 = S->levels[0].view;
+		if (!alias) LAUNCH(S, k_to_mg<VecT>, fb, 256, stream, n, r, L0.b, st);
+		CKR(vcycle(S, 0, P, st, stream));
+		LAUNCH(S, k_from_mg<VecT>, fb, 256, stream, n, L0.x, r, z, rb, st);
+		return SHKZ_B200_OK;
+	};
+
+	if (mg) {
+		CKR(precondition());
+		LAUNCH(S, k_copy_dot<VecT>, fb, 256, stream, n, z, r, s, rb, st);
+	} else {
+		LAUNCH(S, k_copy_dot<VecT>, fb, 256, stream, n, r, r, s, rb, st);
+	}
+	const int check = P.check_every < 1 ? 1 : P.check_every;
+	unsigned it = 0;
+	while (it < P.max_iterations) {
+		for (int c = 0; c < check && it < P.max_iterations; ++c, ++it) {
+			CKR(halo(S, d, s, stream));
+			LAUNCH(S, (k_spmv_dot<VecT, CoefT>), stencil_grid(d), stencil_block(), stream, d, wx, wy, wz, diag, s, z, rb, st);
+			if (mg) {
+				LAUNCH(S, (k_axpy2_norm<VecT, false>), fb, 256, stream, n, s, z, x, r, rb, st);
+				CKR(precondition());
+				LAUNCH(S, k_beta_from_zr, 1, 1, stream, st);
+				LAUNCH(S, k_xpay<VecT>, fb, 256, stream, n, z, s, st);
+			} else {
+				LAUNCH(S, (k_axpy2_norm<VecT, true>), fb, 256, stream, n, s, z, x, r, rb, st);
+				LAUNCH(S, k_xpay<VecT>, fb, 256, stream, n, r, s, st);
+			}
+		}
+		CK(cudaMemcpyAsync(S->h_state, st, sizeof(CGState), cudaMemcpyDeviceToHost, stream));
+		CK(cudaStreamSynchronize(stream));
+		if (S->h_state->done) break;
+	}
+	CK(cudaMemcpyAsync(S->h_state, st, sizeof(CGState), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaGetLastError());
+	return SHKZ_B200_OK;
+}
+
+void fill_stats(const shkz_b200_solver *S, shkz_b200_stats *out) {
+	if (!out) return;
+	const CGState &h = *S->h_state;
+	out->n_rows = h.n_rows;
+	out->n_rows_global = h.n_rows;
+	out->iterations = (uint32_t)h.iter;
+	out->converged = h.converged;
+	out->rhs_absmax = h.bnorm;
+	out->reresid = h.bnorm > 0 ? h.rnorm / h.bnorm : 0.0;
+	out->has_dirichlet = h.has_dirichlet;
+	out->mg_levels = (int)S->levels.size();
+	out->kernel_launches = S->launches;
+}
+
+template <class RealT, class VecT, class CoefT>
+int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *const act[3], const void *solid_v, const void *fluid_v, int fluid_levelset,
+                 const shkz_b200_params &P, void *pressure_v, uint8_t *pressure_active, shkz_b200_stats *stats, cudaStream_t stream) {
+	const Dims &d = S->d;
+	CKR((ensure_precision_arrays<VecT, CoefT>(S, P.precision, P)));
+	RealT *phi = S->phi.ptr<RealT>(d);
+	RealT *pres = S->pressure.ptr<RealT>(d);
+	uint8_t *in_rows = S->in_rows.ptr<uint8_t>(d);
+	const RealT *solid = static_cast<const RealT *>(solid_v);
+	FaceGrids<RealT> vel, areas, rhos;
+	ConstFaceGrids<RealT> cvel, careas, crhos;
+	FaceMasks masks;
+	for (int dim = 0; dim < 3; ++dim) {
+		vel.p[dim] = static_cast<RealT *>(vel_v[dim]); cvel.p[dim] = vel.p[dim];
+		areas.p[dim] = static_cast<RealT *>(S->areas[dim].base); careas.p[dim] = areas.p[dim];
+		rhos.p[dim] = static_cast<RealT *>(S->rhos[dim].base); crhos.p[dim] = rhos.p[dim];
+		masks.p[dim] = act[dim];
+	}
+	AsmParams A{};
+	A.dt = dt; A.dx = S->dx;
+	A.eps_fluid = P.eps_fluid; A.eps_solid = P.eps_solid;
+	A.surface_tension = P.surface_tension; A.rhs_correct = P.rhs_correct;
+	A.second_order_fluid = P.second_order_fluid; A.second_order_solid = P.second_order_solid;
+	A.have_solid = solid != nullptr; A.fluid_levelset = fluid_levelset;
+	A.apply_rhs_correct = P.apply_rhs_correct;
+	S->last_asm = A;
+	const RedBuf rb = S->redbuf();
+	CGState *st = S->dstate();
+
+	CK(cudaEventRecord(S->ev[0], stream));
+	// fluid -> internal array with ghost planes (neighbour slabs fill them)
+	CK(cudaMemcpyAsync(phi, fluid_v, sizeof(RealT) * (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
+	CKR(halo(S, d, phi, stream));
+	LAUNCH(S, k_face_fractions<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, solid, (const RealT *)phi, areas, rhos);
+	if (P.surface_tension != 0.0) {
+		RealT *curv = S->curv.ptr<RealT>(d);
+		if (!curv) { CKR(S->curv.alloc(d, sizeof(RealT))); curv = S->curv.ptr<RealT>(d); }
+		LAUNCH(S, k_curvature<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, curv);
+		CKR(halo(S, d, curv, stream));
+		LAUNCH(S, k_surface_tension<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)curv, crhos, vel, masks);
+	}
+	LAUNCH(S, k_label_rows<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, (const RealT *)phi, careas, crhos, in_rows);
+	CKR(halo(S, d, in_rows, stream));
+	{
+		const bool share = sizeof(CoefT) == sizeof(float);
+		const MGLevel &L0 = S->levels[0].view;
+		LAUNCH(S, (k_build_system<RealT, CoefT, VecT>), cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, (const uint8_t *)in_rows, careas,
+		       crhos, cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->diag.ptr<CoefT>(d), share ? nullptr : L0.wx,
+		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.diag, S->b.ptr<VecT>(d), rb, st);
+		CKR(halo(S, d, S->wz.ptr<CoefT>(d), stream));
+		if (!share) CKR(halo(S, d, L0.wz, stream));
+	}
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(S->ev[1], stream));
+	if (P.precond == SHKZ_B200_PRECOND_MG) CKR(build_hierarchy(S, P, stream));
+	CK(cudaEventRecord(S->ev[2], stream));
+	S->have_system = true;
+	CKR((solve<VecT, CoefT>(S, P, stream)));
+	CK(cudaEventRecord(S->ev[3], stream));
+	// pressure scatter + velocity update
+	if (!S->h_state->has_dirichlet && S->h_state->n_rows) {
+		LAUNCH(S, k_sum_rows<VecT>, flat_blocks(d.ncell), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows, rb, st);
+		if (S->comm && !S->whole_grid) CKR(S->comm->allreduce_sum_x(st, stream) ? fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error()) : SHKZ_B200_OK);
+	}
+	LAUNCH(S, (k_store_pressure<RealT, VecT>), (unsigned)((d.ncell + 255) / 256), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows,
+	       (const CGState *)st, pres);
+	CKR(halo(S, d, pres, stream));
+	LAUNCH(S, k_update_velocity<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)pres, careas, crhos, vel, masks);
+	if (pressure_v) CK(cudaMemcpyAsync(pressure_v, pres, sizeof(RealT) * (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
+	if (pressure_active) CK(cudaMemcpyAsync(pressure_active, in_rows, (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
+	CK(cudaEventRecord(S->ev[4], stream));
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaGetLastError());
+	if (stats) {
+		fill_stats(S, stats);
+		cudaEventElapsedTime(&stats->ms_assemble, S->ev[0], S->ev[1]);
+		cudaEventElapsedTime(&stats->ms_setup, S->ev[1], S->ev[2]);
+		cudaEventElapsedTime(&stats->ms_solve, S->ev[2], S->ev[3]);
+		cudaEventElapsedTime(&stats->ms_update, S->ev[3], S->ev[4]);
+		cudaEventElapsedTime(&stats->ms_total, S->ev[0], S->ev[4]);
+	}
+	return SHKZ_B200_OK;
+}
+
+typedef int (*project_fn)(shkz_b200_solver *, double, void *const[3], uint8_t *const[3], const void *, const void *, int, const shkz_b200_params &, void *,
+                          uint8_t *, shkz_b200_stats *, cudaStream_t);
+
+project_fn pick_project(int real, int precision) {
+	if (real == SHKZ_B200_REAL_F32) {
+		if (precision == SHKZ_B200_PREC_FP64) return project_impl<float, double, double>;
+		if (precision == SHKZ_B200_PREC_MIXED) return project_impl<float, double, float>;
+		if (precision == SHKZ_B200_PREC_FP32) return project_impl<float, float, float>;
+	} else if (real == SHKZ_B200_REAL_F64) {
+		if (precision == SHKZ_B200_PREC_FP64) return project_impl<double, double, double>;
+		if (precision == SHKZ_B200_PREC_MIXED) return project_impl<double, double, float>;
+		if (precision == SHKZ_B200_PREC_FP32) return project_impl<double, float, float>;
+	}
+	return nullptr;
+}
+
+int check_params(const shkz_b200_params *p, shkz_b200_params &out) {
+	if (!p) {
+		shkz_b200_default_params(&out);
+		return SHKZ_B200_OK;
+	}
+	if (p->struct_size != sizeof(shkz_b200_params)) return fail(SHKZ_B200_ERR_ARG, "params.struct_size %u != %zu", p->struct_size, sizeof(shkz_b200_params));
+	out = *p;
+	if (out.precond != SHKZ_B200_PRECOND_NONE && out.precond != SHKZ_B200_PRECOND_MG) return fail(SHKZ_B200_ERR_ARG, "unknown precond %d", out.precond);
+	if (out.precision < 0 || out.precision > 2) return fail(SHKZ_B200_ERR_ARG, "unknown precision %d", out.precision);
+	if (!(out.mg_coarse_scale > 0.0)) return fail(SHKZ_B200_ERR_ARG, "mg_coarse_scale must be > 0");
+	return SHKZ_B200_OK;
+}
+
+int device_ready(int device) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		cudaGetLastError();
+		return fail(SHKZ_B200_ERR_NO_DEVICE, "no CUDA device available (%s); libshkz_b200 has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+	}
+	if (device < 0 || device >= n) return fail(SHKZ_B200_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+	return SHKZ_B200_OK;
+}
+
+} // namespace
+
+// =============================================== C-ABI ===============================================
+extern "C" {
+
+int shkz_b200_abi_version(void) { return SHKZ_B200_ABI_VERSION; }
+
+const char *shkz_b200_last_error(void) { return g_error.c_str(); }
+
+void shkz_b200_default_params(shkz_b200_params *p) {
+	if (!p) return;
+	memset(p, 0, sizeof *p);
+	p->struct_size = sizeof *p;
+	p->second_order_fluid = 1;
+	p->second_order_solid = 1;
+	p->eps_fluid = 1e-2;
+	p->eps_solid = 1e-2;
+	p->residual = 1e-4;
+	p->max_iterations = 30000;
+	p->precond = SHKZ_B200_PRECOND_MG;
+	p->precision = SHKZ_B200_PREC_MIXED;
+	p->mg_pre_sweeps = 2;
+	p->mg_post_sweeps = 2;
+	p->mg_coarse_sweeps = 8;
+	p->mg_min_size = 4;
+	p->check_every = 4;
+	p->mg_coarse_scale = 0.5;
+}
+
+int shkz_b200_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int real, int device, shkz_b200_solver **out) {
+	if (!out) return fail(SHKZ_B200_ERR_ARG, "out is NULL");
+	*out = nullptr;
+	if (nx < 1 || ny < 1 || nz < 1 || k0 < 0 || k1 > nz || k1 <= k0) return fail(SHKZ_B200_ERR_ARG, "bad grid %dx%dx%d slab [%d,%d)", nx, ny, nz, k0, k1);
+	if (!(dx > 0.0)) return fail(SHKZ_B200_ERR_ARG, "dx must be positive");
+	if (real != SHKZ_B200_REAL_F32 && real != SHKZ_B200_REAL_F64) return fail(SHKZ_B200_ERR_ARG, "unknown real type %d", real);
+	if ((long long)nz + 2 > 65535) return fail(SHKZ_B200_ERR_ARG, "nz too large for the launch geometry");
+	CKR(device_ready(device));
+	CK(cudaSetDevice(device));
+	shkz_b200_solver *S = new shkz_b200_solver();
+	S->d = make_dims(nx, ny, k1 - k0, k0, nz);
+	S->dx = dx;
+	S->real = real;
+	S->device = device;
+	S->real_bytes = real == SHKZ_B200_REAL_F64 ? 8 : 4;
+	S->whole_grid = (k0 == 0 && k1 == nz);
+	const Dims &d = S->d;
+	int rc = SHKZ_B200_OK;
+	auto tryalloc = [&](int r) { if (rc == SHKZ_B200_OK) rc = r; };
+	tryalloc(S->phi.alloc(d, S->real_bytes));
+	tryalloc(S->pressure.alloc(d, S->real_bytes));
+	tryalloc(S->in_rows.alloc(d, 1));
+	for (int dim = 0; dim < 3; ++dim) {
+		tryalloc(S->areas[dim].alloc(face_count(d, dim) * S->real_bytes));
+		tryalloc(S->rhos[dim].alloc(face_count(d, dim) * S->real_bytes));
+	}
+	// reduction scratch: the largest grid any reducing kernel uses
+	{
+		const dim3 g1 = stencil_grid(d), g2 = cell_grid(d, 1, 1, 1);
+		size_t m = (size_t)g1.x * g1.y * g1.z, m2 = (size_t)g2.x * g2.y * g2.z;
+		S->max_blocks = (m > m2 ? m : m2) + 148 * 16;
+		tryalloc(S->partials.alloc(S->max_blocks * 4 * sizeof(double)));
+		tryalloc(S->counter.alloc(64));
+		tryalloc(S->state.alloc(sizeof(CGState)));
+	}
+	if (rc == SHKZ_B200_OK && cudaMallocHost((void **)&S->h_state, sizeof(CGState)) != cudaSuccess) rc = fail(SHKZ_B200_ERR_CUDA, "cudaMallocHost failed");
+	if (rc == SHKZ_B200_OK) {
+		memset(S->h_state, 0, sizeof(CGState));
+		for (auto &e : S->ev)
+			if (cudaEventCreate(&e) != cudaSuccess) rc = fail(SHKZ_B200_ERR_CUDA, "cudaEventCreate failed");
+		S->events = true;
+	}
+	if (rc != SHKZ_B200_OK) {
+		shkz_b200_destroy(S);
+		return rc;
+	}
+	*out = S;
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_create(int nx, int ny, int nz, double dx, int real, int device, shkz_b200_solver **out) {
+	return shkz_b200_create_slab(nx, ny, nz, 0, nz, dx, real, device, out);
+}
+
+void shkz_b200_destroy(shkz_b200_solver *S) {
+	if (!S) return;
+	cudaSetDevice(S->device);
+	cudaDeviceSynchronize();
+	if (S->comm) { delete S->comm; S->comm = nullptr; }
+	release_precision_arrays(S);
+	S->phi.release(); S->pressure.release(); S->curv.release(); S->in_rows.release();
+	for (int dim = 0; dim < 3; ++dim) {
+		S->areas[dim].release(); S->rhos[dim].release(); S->st_vel[dim].release(); S->st_act[dim].release();
+	}
+	S->st_solid.release(); S->st_fluid.release(); S->st_pressure.release(); S->st_pact.release();
+	S->partials.release(); S->counter.release(); S->state.release();
+	if (S->h_state) cudaFreeHost(S->h_state);
+	if (S->events) for (auto &e : S->ev) if (e) cudaEventDestroy(e);
+	delete S;
+}
+
+int shkz_b200_project_device(shkz_b200_solver *S, double dt, void *const vel[3], uint8_t *const vel_active[3], const void *solid, const void *fluid,
+                             int fluid_levelset, const shkz_b200_params *params, void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats,
+                             void *cuda_stream) {
+	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	if (!vel || !vel_active || !fluid) return fail(SHKZ_B200_ERR_ARG, "vel / vel_active / fluid must not be NULL");
+	for (int dim = 0; dim < 3; ++dim)
+		if (!vel[dim] || !vel_active[dim]) return fail(SHKZ_B200_ERR_ARG, "vel[%d] / vel_active[%d] is NULL", dim, dim);
+	if (!S->whole_grid && !S->comm) return fail(SHKZ_B200_ERR_STATE, "slab solver is not connected (call shkz_b200_slab_connect)");
+	shkz_b200_params P;
+	CKR(check_params(params, P));
+	CKR(device_ready(S->device));
+	CK(cudaSetDevice(S->device));
+	project_fn fn = pick_project(S->real, P.precision);
+	if (!fn) return fail(SHKZ_B200_ERR_ARG, "unsupported real/precision combination");
+	if (stats) memset(stats, 0, sizeof *stats);
+	S->launches = 0;
+	return fn(S, dt, vel, vel_active, solid, fluid, fluid_levelset, P, pressure, pressure_active, stats, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int shkz_b200_project_host(shkz_b200_solver *S, double dt, void *const vel[3], uint8_t *const vel_active[3], const void *solid, const void *fluid,
+                           int fluid_levelset, const shkz_b200_params *params, void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats) {
+	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	if (!vel || !vel_active || !fluid) return fail(SHKZ_B200_ERR_ARG, "vel / vel_active / fluid must not be NULL");
+	CKR(device_ready(S->device));
+	CK(cudaSetDevice(S->device));
+	const Dims &d = S->d;
+	const size_t rb = S->real_bytes;
+	const size_t nodal = (size_t)(d.nx + 1) * (d.ny + 1) * (d.nzl + 1);
+	cudaStream_t stream = nullptr;
+	void *dvel[3];
+	uint8_t *dact[3];
+	CK(cudaEventRecord(S->ev[5], stream));
+	for (int dim = 0; dim < 3; ++dim) {
+		if (!vel[dim] || !vel_active[dim]) return fail(SHKZ_B200_ERR_ARG, "vel[%d] / vel_active[%d] is NULL", dim, dim);
+		const size_t nf = face_count(d, dim);
+		if (!S->st_vel[dim].base) { CKR(S->st_vel[dim].alloc(nf * rb)); CKR(S->st_act[dim].alloc(nf)); }
+		CK(cudaMemcpyAsync(S->st_vel[dim].base, vel[dim], nf * rb, cudaMemcpyHostToDevice, stream));
+		CK(cudaMemcpyAsync(S->st_act[dim].base, vel_active[dim], nf, cudaMemcpyHostToDevice, stream));
+		dvel[dim] = S->st_vel[dim].base;
+		dact[dim] = static_cast<uint8_t *>(S->st_act[dim].base);
+	}
+	if (!S->st_fluid.base) { CKR(S->st_fluid.alloc((size_t)d.ncell * rb)); CKR(S->st_pressure.alloc((size_t)d.ncell * rb)); CKR(S->st_pact.alloc((size_t)d.ncell)); }
+	CK(cudaMemcpyAsync(S->st_fluid.base, fluid, (size_t)d.ncell * rb, cudaMemcpyHostToDevice, stream));
+	if (solid) {
+		if (!S->st_solid.base) CKR(S->st_solid.alloc(nodal * rb));
+		CK(cudaMemcpyAsync(S->st_solid.base, solid, nodal * rb, cudaMemcpyHostToDevice, stream));
+	}
+	CK(cudaEventRecord(S->ev[6], stream));
+	int rc = shkz_b200_project_device(S, dt, dvel, dact, solid ? S->st_solid.base : nullptr, S->st_fluid.base, fluid_levelset, params, S->st_pressure.base,
+	                                  static_cast<uint8_t *>(S->st_pact.base), stats, stream);
+	if (rc != SHKZ_B200_OK) return rc;
+	CK(cudaEventRecord(S->ev[6 + 1], stream));
+	for (int dim = 0; dim < 3; ++dim) {
+		const size_t nf = face_count(d, dim);
+		CK(cudaMemcpyAsync(vel[dim], S->st_vel[dim].base, nf * rb, cudaMemcpyDeviceToHost, stream));
+		CK(cudaMemcpyAsync(vel_active[dim], S->st_act[dim].base, nf, cudaMemcpyDeviceToHost, stream));
+	}
+	if (pressure) CK(cudaMemcpyAsync(pressure, S->st_pressure.base, (size_t)d.ncell * rb, cudaMemcpyDeviceToHost, stream));
+	if (pressure_active) CK(cudaMemcpyAsync(pressure_active, S->st_pact.base, (size_t)d.ncell, cudaMemcpyDeviceToHost, stream));
+	CK(cudaEventRecord(S->ev[0], stream));
+	CK(cudaStreamSynchronize(stream));
+	if (stats) {
+		cudaEventElapsedTime(&stats->ms_h2d, S->ev[5], S->ev[6]);
+		cudaEventElapsedTime(&stats->ms_d2h, S->ev[7], S->ev[0]);
+		stats->ms_total += stats->ms_h2d + stats->ms_d2h;
+	}
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_resolve(shkz_b200_solver *S, const shkz_b200_params *params, shkz_b200_stats *stats, void *cuda_stream) {
+	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	if (!S->have_system) return fail(SHKZ_B200_ERR_STATE, "resolve() needs a prior project()");
+	shkz_b200_params P;
+	CKR(check_params(params, P));
+	if (P.precision != S->alloc_precision) return fail(SHKZ_B200_ERR_STATE, "resolve() precision differs from the assembled system");
+	CKR(device_ready(S->device));
+	CK(cudaSetDevice(S->device));
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	if (stats) memset(stats, 0, sizeof *stats);
+	S->launches = 0;
+	CK(cudaEventRecord(S->ev[1], stream));
+	if (P.precond == SHKZ_B200_PRECOND_MG) CKR(build_hierarchy(S, P, stream));
+	CK(cudaEventRecord(S->ev[2], stream));
+	int rc;
+	if (P.precision == SHKZ_B200_PREC_FP64) rc = solve<double, double>(S, P, stream);
+	else if (P.precision == SHKZ_B200_PREC_MIXED) rc = solve<double, float>(S, P, stream);
+	else rc = solve<float, float>(S, P, stream);
+	if (rc != SHKZ_B200_OK) return rc;
+	CK(cudaEventRecord(S->ev[3], stream));
+	CK(cudaStreamSynchronize(stream));
+	if (stats) {
+		fill_stats(S, stats);
+		cudaEventElapsedTime(&stats->ms_setup, S->ev[1], S->ev[2]);
+		cudaEventElapsedTime(&stats->ms_solve, S->ev[2], S->ev[3]);
+		stats->ms_total = stats->ms_setup + stats->ms_solve;
+	}
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_debug_fetch(shkz_b200_solver *S, const char *name, void *dst, size_t dst_bytes, size_t *needed) {
+	if (!S || !name) return fail(SHKZ_B200_ERR_ARG, "solver / name is NULL");
+	CK(cudaSetDevice(S->device));
+	const Dims &d = S->d;
+	const std::string n(name);
+	const void *src = nullptr;
+	size_t bytes = 0;
+	const size_t vec = S->alloc_precision == SHKZ_B200_PREC_FP32 ? 4 : 8;
+	const size_t coef = S->alloc_precision == SHKZ_B200_PREC_FP64 ? 8 : 4;
+	auto cell = [&](const CellArray &a, size_t elem) { src = a.base ? static_cast<const char *>(a.base) + (size_t)d.plane * elem : nullptr; bytes = (size_t)d.ncell * elem; };
+	if (n == "diag") cell(S->diag, coef);
+	else if (n == "wx") cell(S->wx, coef);
+	else if (n == "wy") cell(S->wy, coef);
+	else if (n == "wz") cell(S->wz, coef);
+	else if (n == "rhs") cell(S->b, vec);
+	else if (n == "x") cell(S->x, vec);
+	else if (n == "in_rows") cell(S->in_rows, 1);
+	else if (n == "phi") cell(S->phi, S->real_bytes);
+	else if (n.size() == 6 && n.compare(0, 5, "areas") == 0 && n[5] >= '0' && n[5] <= '2') { src = S->areas[n[5] - '0'].base; bytes = face_count(d, n[5] - '0') * S->real_bytes; }
+	else if (n.size() == 5 && n.compare(0, 4, "rhos") == 0 && n[4] >= '0' && n[4] <= '2') { src = S->rhos[n[4] - '0'].base; bytes = face_count(d, n[4] - '0') * S->real_bytes; }
+	else if (n.compare(0, 3, "mg_") == 0) { // mg_<level>_<diag|wx|wy|wz>
+		int l = -1;
+		char what[16] = {0};
+		if (sscanf(name, "mg_%d_%15s", &l, what) == 2 && l >= 0 && (size_t)l < S->levels.size()) {
+			const HostLevel &L = S->levels[l];
+			const std::string w(what);
+			const CellArray *a = w == "diag" ? &L.diag : w == "wx" ? &L.wx : w == "wy" ? &L.wy : w == "wz" ? &L.wz : nullptr;
+			if (a) { src = a->base ? static_cast<const char *>(a->base) + (size_t)L.d.plane * 4 : nullptr; bytes = (size_t)L.d.ncell * 4; }
+		}
+	}
+	if (needed) *needed = bytes;
+	if (!src) return fail(SHKZ_B200_ERR_ARG, "unknown or unallocated array '%s'", name);
+	if (!dst) return SHKZ_B200_OK;
+	if (dst_bytes < bytes) return fail(SHKZ_B200_ERR_ARG, "buffer too small for '%s': %zu < %zu", name, dst_bytes, bytes);
+	CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_comm_unique_id(uint8_t id[SHKZ_B200_NCCL_ID_BYTES]) {
+	if (!id) return fail(SHKZ_B200_ERR_ARG, "id is NULL");
+	std::string err;
+	if (SlabComm::unique_id(id, err)) return fail(SHKZ_B200_ERR_COMM, "%s", err.c_str());
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_slab_export(shkz_b200_solver *S, uint8_t ipc[SHKZ_B200_IPC_BYTES]) {
+	if (!S || !ipc) return fail(SHKZ_B200_ERR_ARG, "solver / ipc is NULL");
+	CK(cudaSetDevice(S->device));
+	if (!S->comm) S->comm = new SlabComm(S->d.plane, S->device);
+	if (S->comm->export_window(ipc)) return fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error());
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_slab_connect(shkz_b200_solver *S, int rank, int world, const uint8_t id[SHKZ_B200_NCCL_ID_BYTES], const uint8_t *lower_ipc,
+                           const uint8_t *upper_ipc) {
+	if (!S || !id) return fail(SHKZ_B200_ERR_ARG, "solver / id is NULL");
+	CK(cudaSetDevice(S->device));
+	if (!S->comm) return fail(SHKZ_B200_ERR_STATE, "call shkz_b200_slab_export first");
+	if (S->comm->connect(rank, world, id, lower_ipc, upper_ipc)) return fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error());
+	return SHKZ_B200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,180 @@
+"""Python host mirror of the reference module `macpressuresolver3` (src/projection/macpressuresolver3.cpp)
+on top of the C-ABI. Flag names and defaults are the reference's (macpressuresolver3.cpp:274-280,296-305;
+macutility3.cpp:408-421; pcg.cpp:39-44,75-80); the `set_target_volume` / volume-correction PI state lives
+here on the host exactly as it does in the reference module (:204-217,316-320).
+
+Device memory is PyTorch's (plumbing only); all arithmetic happens in libshkz_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+
+_PRECOND = {"none": capi.PRECOND_NONE, "cg": capi.PRECOND_NONE, "mg": capi.PRECOND_MG}
+_PRECISION = {"fp64": capi.PREC_FP64, "mixed": capi.PREC_MIXED, "fp32": capi.PREC_FP32}
+
+
+@dataclass
+class ProjectionResult:
+    iterations: int
+    reresid: float
+    converged: bool
+    n_rows: int
+    stats: dict
+
+
+class MacPressureSolver3:
+    """project(dt, velocity, solid, fluid, surface_tension) with the reference's configurable parameters.
+
+    Reference flags: SecondOrderAccurateFluid, SecondOrderAccurateSolid, Gain, WarmStart (not supported: see
+    DESIGN.md), EpsFluid, EpsSolid, Residual, MaxIterations. Additive flags: Precond ("mg"|"none"),
+    Precision ("mixed"|"fp64"|"fp32"), MGPreSweeps, MGPostSweeps, MGCoarseSweeps, MGMinSize, CheckEvery.
+    """
+
+    def __init__(self, shape: Sequence[int], dx: float, real: str = "f32", device: int = 0, zrange=None, **flags):
+        self.nx, self.ny, self.nz = (int(v) for v in shape)
+        self.dx = float(dx)
+        self.real = real
+        self.np_real = np.float32 if real == "f32" else np.float64
+        self.device = device
+        self.zrange = (0, self.nz) if zrange is None else (int(zrange[0]), int(zrange[1]))
+        self.nzl = self.zrange[1] - self.zrange[0]
+        self.params = capi.default_params()
+        self.gain = 1.0
+        self._target_volume = self._current_volume = self._y_prev = 0.0
+        self.configure(**flags)
+        h = C.c_void_p()
+        capi.check(capi.lib().shkz_b200_create_slab(self.nx, self.ny, self.nz, self.zrange[0], self.zrange[1], self.dx,
+                                                     capi.REAL_F32 if real == "f32" else capi.REAL_F64, device, C.byref(h)))
+        self._h = h
+        self.last_rhs_correct = 0.0
+
+    # -- reference interface ----------------------------------------------------------------------
+    def configure(self, **flags):
+        p = self.params
+        for key, value in flags.items():
+            if key == "SecondOrderAccurateFluid": p.second_order_fluid = int(bool(value))
+            elif key == "SecondOrderAccurateSolid": p.second_order_solid = int(bool(value))
+            elif key == "Gain": self.gain = float(value)
+            elif key == "WarmStart":
+                if value:
+                    raise NotImplementedError("WarmStart=Yes is not supported (reference default is No)")
+            elif key == "EpsFluid": p.eps_fluid = float(value)
+            elif key == "EpsSolid": p.eps_solid = float(value)
+            elif key == "Residual": p.residual = float(value)
+            elif key == "MaxIterations": p.max_iterations = int(value)
+            elif key == "Precond": p.precond = _PRECOND[str(value).lower()]
+            elif key == "Precision": p.precision = _PRECISION[str(value).lower()]
+            elif key == "MGPreSweeps": p.mg_pre_sweeps = int(value)
+            elif key == "MGPostSweeps": p.mg_post_sweeps = int(value)
+            elif key == "MGCoarseSweeps": p.mg_coarse_sweeps = int(value)
+            elif key == "MGMinSize": p.mg_min_size = int(value)
+            elif key == "MGCoarseScale": p.mg_coarse_scale = float(value)
+            elif key == "CheckEvery": p.check_every = int(value)
+            else:
+                raise KeyError(f"unknown flag {key}")
+
+    def set_target_volume(self, current_volume: float, target_volume: float):
+        self._current_volume, self._target_volume = float(current_volume), float(target_volume)
+
+    def _volume_correction(self, dt: float):
+        """PI controller of macpressuresolver3.cpp:204-214 (host-side scalar state)."""
+        p = self.params
+        p.apply_rhs_correct = 0
+        p.rhs_correct = 0.0
+        if self.gain and self._target_volume:
+            x = (self._current_volume - self._target_volume) / self._target_volume
+            y = self._y_prev + x * dt
+            self._y_prev = y
+            kp = self.gain * 2.3 / (25.0 * 0.01)
+            ki = kp * kp / 16.0
+            p.rhs_correct = -(kp * x + ki * y) / (x + 1.0)
+            p.apply_rhs_correct = 1
+        self.last_rhs_correct = p.rhs_correct
+
+    # -- shapes -----------------------------------------------------------------------------------
+    def face_shapes(self):
+        nx, ny, nzl = self.nx, self.ny, self.nzl
+        return [(nzl, ny, nx + 1), (nzl, ny + 1, nx), (nzl + 1, ny, nx)]
+
+    def _finish(self, st: capi.Stats) -> ProjectionResult:
+        return ProjectionResult(int(st.iterations), float(st.reresid), bool(st.converged), int(st.n_rows), st.asdict())
+
+    # -- host buffers (numpy): the call the Shiokaze plugin makes ------------------------------------
+    def project(self, dt, velocity, velocity_active, solid, fluid, fluid_levelset: bool, surface_tension: float = 0.0):
+        """In place on numpy arrays (velocity: 3 face arrays, velocity_active: 3 uint8). Returns
+        (pressure, pressure_active, ProjectionResult)."""
+        rt = self.np_real
+        for v, a, shp in zip(velocity, velocity_active, self.face_shapes()):
+            assert v.dtype == rt and v.flags.c_contiguous and v.shape == shp, (v.dtype, v.shape, shp)
+            assert a.dtype == np.uint8 and a.flags.c_contiguous and a.shape == shp
+        assert fluid.dtype == rt and fluid.flags.c_contiguous and fluid.shape == (self.nzl, self.ny, self.nx)
+        if solid is not None:
+            assert solid.dtype == rt and solid.flags.c_contiguous and solid.shape == (self.nzl + 1, self.ny + 1, self.nx + 1)
+        self._volume_correction(dt)
+        self.params.surface_tension = float(surface_tension)
+        pressure = np.zeros((self.nzl, self.ny, self.nx), dtype=rt)
+        pact = np.zeros((self.nzl, self.ny, self.nx), dtype=np.uint8)
+        vp = (C.c_void_p * 3)(*[v.ctypes.data for v in velocity])
+        ap = (C.c_void_p * 3)(*[a.ctypes.data for a in velocity_active])
+        st = capi.Stats()
+        capi.check(capi.lib().shkz_b200_project_host(self._h, float(dt), vp, ap, solid.ctypes.data if solid is not None else None,
+                                                     fluid.ctypes.data, int(bool(fluid_levelset)), C.byref(self.params),
+                                                     pressure.ctypes.data, pact.ctypes.data, C.byref(st)))
+        return pressure, pact, self._finish(st)
+
+    def project_scene(self, scene, surface_tension: Optional[float] = None):
+        """Convenience for tests: run a scenes.Scene through project() on copies; returns dict of outputs."""
+        rt = self.np_real
+        vel = [np.ascontiguousarray(v, dtype=rt).copy() for v in scene.vel]
+        act = [np.ascontiguousarray(a, dtype=np.uint8).copy() for a in scene.vel_active]
+        solid = np.ascontiguousarray(scene.solid, dtype=rt) if scene.solid is not None else None
+        fluid = np.ascontiguousarray(scene.fluid, dtype=rt)
+        p, pa, res = self.project(scene.dt, vel, act, solid, fluid, scene.fluid_levelset,
+                                  scene.surface_tension if surface_tension is None else surface_tension)
+        return dict(vel=vel, vel_active=act, pressure=p, pressure_active=pa, result=res)
+
+    # -- device buffers (torch tensors on this solver's GPU) ----------------------------------------
+    def project_device(self, dt, velocity, velocity_active, solid, fluid, fluid_levelset: bool, pressure=None,
+                       pressure_active=None, surface_tension: float = 0.0, stream: int = 0):
+        self._volume_correction(dt)
+        self.params.surface_tension = float(surface_tension)
+        vp = (C.c_void_p * 3)(*[v.data_ptr() for v in velocity])
+        ap = (C.c_void_p * 3)(*[a.data_ptr() for a in velocity_active])
+        st = capi.Stats()
+        capi.check(capi.lib().shkz_b200_project_device(self._h, float(dt), vp, ap, solid.data_ptr() if solid is not None else None,
+                                                       fluid.data_ptr(), int(bool(fluid_levelset)), C.byref(self.params),
+                                                       pressure.data_ptr() if pressure is not None else None,
+                                                       pressure_active.data_ptr() if pressure_active is not None else None,
+                                                       C.byref(st), stream or None))
+        return self._finish(st)
+
+    def resolve(self, stream: int = 0) -> ProjectionResult:
+        """Repeat only the linear solve of the last project() (same matrix and right-hand side)."""
+        st = capi.Stats()
+        capi.check(capi.lib().shkz_b200_resolve(self._h, C.byref(self.params), C.byref(st), stream or None))
+        return self._finish(st)
+
+    # -- test hook ----------------------------------------------------------------------------------
+    def debug_fetch(self, name: str) -> np.ndarray:
+        need = C.c_size_t()
+        capi.check(capi.lib().shkz_b200_debug_fetch(self._h, name.encode(), None, 0, C.byref(need)))
+        buf = np.empty(need.value, dtype=np.uint8)
+        capi.check(capi.lib().shkz_b200_debug_fetch(self._h, name.encode(), buf.ctypes.data, buf.nbytes, None))
+        return buf
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().shkz_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

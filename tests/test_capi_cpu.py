@@ -1,0 +1,69 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/shkz_b200.h declares,
+and refuses to compute without a CUDA device (no CPU fallback). No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from shiokaze_b200 import capi
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "shkz_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(shkz_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    names = declared_symbols()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(L, name), name
+    assert sorted(capi.EXPORTS) == names
+    assert L.shkz_b200_abi_version() == 1
+
+
+def test_default_params_are_the_reference_defaults():
+    p = capi.default_params()
+    assert p.struct_size == C.sizeof(capi.Params)
+    assert (p.second_order_fluid, p.second_order_solid) == (1, 1)          # macpressuresolver3.cpp:300-301
+    assert (p.eps_fluid, p.eps_solid) == (1e-2, 1e-2)                      # macutility3.cpp:419-420
+    assert p.residual == 1e-4 and p.max_iterations == 30000                # pcg.cpp:76-77
+    assert p.precond == capi.PRECOND_MG and p.precision == capi.PREC_MIXED
+
+
+def test_argument_errors_do_not_need_a_device():
+    L = capi.lib()
+    h = C.c_void_p()
+    assert L.shkz_b200_create(0, 8, 8, 0.1, capi.REAL_F32, 0, C.byref(h)) == capi.ERR_ARG
+    assert L.shkz_b200_create(8, 8, 8, -1.0, capi.REAL_F32, 0, C.byref(h)) == capi.ERR_ARG
+    assert L.shkz_b200_create_slab(8, 8, 8, 4, 2, 0.1, capi.REAL_F32, 0, C.byref(h)) == capi.ERR_ARG
+    assert L.shkz_b200_create(8, 8, 8, 0.1, 7, 0, C.byref(h)) == capi.ERR_ARG
+    assert b"real type" in L.shkz_b200_last_error()
+    assert L.shkz_b200_resolve(None, None, None, None) == capi.ERR_ARG
+
+
+def test_no_cpu_fallback():
+    L = capi.lib()
+    if L.shkz_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    assert L.shkz_b200_create(8, 8, 8, 0.125, capi.REAL_F32, 0, C.byref(h)) == capi.ERR_NO_DEVICE
+    assert not h.value
+    assert b"no CPU fallback" in L.shkz_b200_last_error()
+    from shiokaze_b200 import MacPressureSolver3
+    with pytest.raises(capi.ShkzError):
+        MacPressureSolver3((8, 8, 8), 0.125)
+
+
+def test_product_never_imports_the_oracle():
+    """The shipped package must not reach into oracle/ (test infrastructure)."""
+    pkg = os.path.join(ROOT, "shiokaze_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(base, f), errors="replace").read()
+                assert "dense_oracle" not in src and "oracle." not in src.replace("oracle/", ""), os.path.join(base, f)
