@@ -190,10 +190,11 @@ typedef struct {
 	size_t *col;
 	double *val;
 	double *rhs;
+	double *dirichlet; /* part of the diagonal that comes from air neighbours (ghost-fluid Dirichlet faces) */
 } csr_system;
 
 static void csr_free(csr_system *A) {
-	free(A->rowstart); free(A->col); free(A->val); free(A->rhs);
+	free(A->rowstart); free(A->col); free(A->val); free(A->rhs); free(A->dirichlet);
 	memset(A, 0, sizeof *A);
 }
 
@@ -230,13 +231,14 @@ static void assemble(const oracle_params *P, const double *fluid, double *const 
 	A->col = (size_t *)malloc(sizeof(size_t) * 7 * (index ? index : 1));
 	A->val = (double *)malloc(sizeof(double) * 7 * (index ? index : 1));
 	A->rhs = (double *)calloc(index ? index : 1, sizeof(double));
+	A->dirichlet = (double *)calloc(index ? index : 1, sizeof(double));
 	size_t nnz = 0;
 	for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
 		size_t c = cell_index(P, i, j, k);
 		size_t n_index = index_map[c];
 		if (n_index == SIZE_MAX) continue;
 		size_t cols[7]; double vals[7]; int cnt = 0;
-		double diagonal = 0.0, rhs = 0.0;
+		double diagonal = 0.0, rhs = 0.0, dirichlet = 0.0;
 		for (int nq = 0; nq < 6; ++nq) {
 			int dim = direction[nq];
 			int qi = i + qoff[nq][0], qj = j + qoff[nq][1], qk = k + qoff[nq][2];
@@ -250,7 +252,7 @@ static void assemble(const oracle_params *P, const double *fluid, double *const 
 					size_t q = cell_index(P, qi, qj, qk);
 					if (fluid[q] < 0.0) {
 						cols[cnt] = index_map[q]; vals[cnt] = -value; cnt++;
-					}
+					} else dirichlet += value;
 					diagonal += value;
 				}
 				rhs += -sgn[nq] * area * vel[dim][f] / dx;
@@ -266,6 +268,7 @@ static void assemble(const oracle_params *P, const double *fluid, double *const 
 		A->rowstart[n_index] = nnz;
 		for (int a = 0; a < cnt; ++a) { A->col[nnz] = cols[a]; A->val[nnz] = vals[a]; nnz++; }
 		A->rhs[n_index] = rhs + P->rhs_correct; /* :204-217 */
+		A->dirichlet[n_index] = dirichlet;
 	}
 	A->rowstart[index] = nnz;
 }
@@ -327,11 +330,12 @@ done:
  * Whole project() call (src/projection/macpressuresolver3.cpp:50-272).
  *   vel[3], vel_active[3]: in/out, face-shaped; pressure / in_rows: out, cell-shaped.
  *   areas_out / rhos_out / rhs_out / diag_out: optional dumps (may be NULL) for kernel-level tests:
- *   rhs_out and diag_out are cell-shaped (0 outside the row set).
+ *   rhs_out, diag_out and dirichlet_out are cell-shaped (0 outside the row set); dirichlet_out is the
+ *   part of the diagonal contributed by air neighbours (diag = sum of couplings + dirichlet).
  */
 int oracle_project(const oracle_params *P, double *vel[3], uint8_t *vel_active[3], const double *solid, const double *fluid,
                    double *pressure, uint8_t *in_rows, double *areas_out[3], double *rhos_out[3],
-                   double *rhs_out, double *diag_out, oracle_stats *st) {
+                   double *rhs_out, double *diag_out, double *dirichlet_out, oracle_stats *st) {
 	const int nx = P->nx, ny = P->ny, nz = P->nz;
 	const size_t ncell = (size_t)nx * ny * nz;
 	double *areas[3], *rhos[3];
@@ -356,6 +360,7 @@ int oracle_project(const oracle_params *P, double *vel[3], uint8_t *vel_active[3
 		in_rows[c] = (uint8_t)in;
 		pressure[c] = in ? RR(P, x[index_map[c]]) : 0.0;
 		if (rhs_out) rhs_out[c] = in ? A.rhs[index_map[c]] : 0.0;
+		if (dirichlet_out) dirichlet_out[c] = in ? A.dirichlet[index_map[c]] : 0.0;
 		if (diag_out) {
 			double dg = 0.0;
 			if (in) for (size_t e = A.rowstart[index_map[c]]; e < A.rowstart[index_map[c] + 1]; ++e) if (A.col[e] == index_map[c]) dg = A.val[e];

@@ -58,6 +58,7 @@ class OracleResult:
     rhos: list
     rhs: np.ndarray
     diag: np.ndarray
+    dirichlet: np.ndarray
     iterations: int
     reresid: float
     n_rows: int
@@ -94,15 +95,17 @@ def project(scene, residual=1e-4, max_iterations=30000, eps_fluid=1e-2, eps_soli
     rhos = [np.zeros(v.shape, dtype=np.float64) for v in vel]
     rhs = np.zeros((nz, ny, nx), dtype=np.float64)
     diag = np.zeros((nz, ny, nx), dtype=np.float64)
+    dirichlet = np.zeros((nz, ny, nx), dtype=np.float64)
     st = Stats()
     rc = lib().oracle_project(C.byref(P), _dptr3(vel), _bptr3(act),
                               solid.ctypes.data_as(C.POINTER(C.c_double)) if solid is not None else None,
                               fluid.ctypes.data_as(C.POINTER(C.c_double)),
                               pressure.ctypes.data_as(C.POINTER(C.c_double)), in_rows.ctypes.data_as(C.POINTER(C.c_uint8)),
                               _dptr3(areas), _dptr3(rhos), rhs.ctypes.data_as(C.POINTER(C.c_double)),
-                              diag.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st))
+                              diag.ctypes.data_as(C.POINTER(C.c_double)),
+                              dirichlet.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st))
     assert rc == 0
-    return OracleResult(vel, act, pressure, in_rows, areas, rhos, rhs, diag, int(st.iterations), float(st.reresid),
+    return OracleResult(vel, act, pressure, in_rows, areas, rhos, rhs, diag, dirichlet, int(st.iterations), float(st.reresid),
                         int(st.n_rows), int(st.nnz), bool(st.converged), float(st.rhs_absmax))
 
 

@@ -215,14 +215,18 @@ __global__ void __launch_bounds__(256) k_label_rows(Dims d, const RealT *__restr
 
 // K5 + K6: matrix-free coefficients and right-hand side (macpressuresolver3.cpp:163-217).
 //   w{x,y,z}[c] = dt*A/(dx^2*theta) of the LOWER face of c when both cells are rows, else 0
-//   diag[c]     = sum over the open in-grid faces of c (air neighbours included: ghost-fluid Dirichlet)
+//   dd[c]       = the part of the reference's diagonal that comes from AIR neighbours (ghost-fluid
+//                 Dirichlet faces); the full diagonal is dd + the six couplings, which the solver
+//                 kernels re-form on the fly so that the operator annihilates constants exactly on
+//                 pure-Neumann rows whatever the coefficient precision ("difference form")
 //   rhs[c]      = sum -sgn*A*u/dx (+ volume-correction constant); 0 outside the row set
-// CoefT/VecT copies feed the CG operator; the float copies feed multigrid level 0 (may alias).
+// CoefT/VecT copies feed the CG operator; the float copies feed multigrid level 0 (NULL when CoefT is
+// float and level 0 shares the operator arrays).
 template <class RealT, class CoefT, class VecT>
 __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const RealT *__restrict__ phi, const uint8_t *__restrict__ in_rows,
                                                      ConstFaceGrids<RealT> areas, ConstFaceGrids<RealT> rhos, ConstFaceGrids<RealT> vel,
-                                                     CoefT *__restrict__ wx, CoefT *__restrict__ wy, CoefT *__restrict__ wz, CoefT *__restrict__ diag,
-                                                     float *__restrict__ mwx, float *__restrict__ mwy, float *__restrict__ mwz, float *__restrict__ mdiag,
+                                                     CoefT *__restrict__ wx, CoefT *__restrict__ wy, CoefT *__restrict__ wz, CoefT *__restrict__ dd,
+                                                     float *__restrict__ mwx, float *__restrict__ mwy, float *__restrict__ mwz, float *__restrict__ mdd,
                                                      VecT *__restrict__ rhs, RedBuf rb, CGState *st) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
 	if (i < d.nx && j < d.ny) {
 		const int kg = k + d.k0;
 		const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-		double diagonal = 0.0, b = 0.0, lower[3] = {0.0, 0.0, 0.0};
+		double dirichlet = 0.0, b = 0.0, lower[3] = {0.0, 0.0, 0.0};
 		if (in_rows[c]) {
 			const int qo[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 			const double dx2 = __dmul_rn(P.dx, P.dx);
@@ -250,8 +254,10 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
 						const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
 						if (phi[q] < (RealT)0) {
 							if (!up) lower[dim] = value;
-						} else red[2] = 1.0;
-						diagonal = __dadd_rn(diagonal, value);
+						} else {
+							dirichlet = __dadd_rn(dirichlet, value);
+							red[2] = 1.0;
+						}
 					}
 					const double sgn = up ? -1.0 : 1.0; // -sgn[nq]
 					b = __dadd_rn(b, __ddiv_rn(__dmul_rn(__dmul_rn(sgn, area), (double)vel.p[dim][f]), P.dx));
@@ -261,8 +267,8 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
 			red[0] = fabs(b);
 			red[1] = 1.0;
 		}
-		wx[c] = (CoefT)lower[0]; wy[c] = (CoefT)lower[1]; wz[c] = (CoefT)lower[2]; diag[c] = (CoefT)diagonal;
-		if ((void *)mwx != (void *)wx) { mwx[c] = (float)lower[0]; mwy[c] = (float)lower[1]; mwz[c] = (float)lower[2]; mdiag[c] = (float)diagonal; }
+		wx[c] = (CoefT)lower[0]; wy[c] = (CoefT)lower[1]; wz[c] = (CoefT)lower[2]; dd[c] = (CoefT)dirichlet;
+		if (mwx != nullptr) { mwx[c] = (float)lower[0]; mwy[c] = (float)lower[1]; mwz[c] = (float)lower[2]; mdd[c] = (float)dirichlet; }
 		rhs[c] = (VecT)b;
 	}
 	grid_reduce<3, 0x5u>(red, rb, [&](double (&t)[3]) {

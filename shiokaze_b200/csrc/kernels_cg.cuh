@@ -1,10 +1,12 @@
 // Conjugate-gradient kernels on the dense matrix-free 7-point operator (replace K9/K10 of SURVEY.md 2d:
 // local/include/pcgsolver/sparse_matrix.h:264-275 and the BLAS-1 calls of pcg_solver.h:277-289).
 //
-//   (A p)[c] = diag[c] p[c] - wx[c] p[c-1] - wx[c+1] p[c+1] - wy[c] p[c-nx] - wy[c+nx] p[c+nx]
-//                           - wz[c] p[c-plane] - wz[c+plane] p[c+plane]
-// with w = 0 on walls / towards non-row cells and diag = 0 off the row set, so the flat neighbour
-// offsets never need bounds logic (wrapped reads hit finite values times a zero coefficient).
+//   (A p)[c] = dd[c] p[c] + wx[c] (p[c]-p[c-1]) + wx[c+1] (p[c]-p[c+1]) + wy[c] (p[c]-p[c-nx]) + wy[c+nx] (p[c]-p[c+nx])
+//                         + wz[c] (p[c]-p[c-plane]) + wz[c+plane] (p[c]-p[c+plane])
+// ("difference form": w = face coupling between two row cells, dd = Dirichlet part of the diagonal).
+// w = 0 on walls / towards non-row cells and dd = 0 off the row set, so the flat neighbour offsets
+// never need bounds logic (wrapped reads hit finite values times a zero coefficient), and constants are
+// annihilated exactly on pure-Neumann rows even with float coefficients.
 //
 // Thread layout for stencil kernels: a CTA owns a TX x TY column of cells and marches ZC planes in z
 // keeping the z-neighbours in registers; x/y neighbours are re-read through L1.
@@ -21,7 +23,7 @@ inline dim3 stencil_block() { return dim3(TX, TY, 1); }
 // z = A s,  sz = s.z ; last block: alpha = rho / sz            (pcg_solver.h:276-277)
 template <class VecT, class CoefT>
 __global__ void __launch_bounds__(TX *TY) k_spmv_dot(Dims d, const CoefT *__restrict__ wx, const CoefT *__restrict__ wy, const CoefT *__restrict__ wz,
-                                                    const CoefT *__restrict__ diag, const VecT *__restrict__ s, VecT *__restrict__ z, RedBuf rb, CGState *st) {
+                                                    const CoefT *__restrict__ dd, const VecT *__restrict__ s, VecT *__restrict__ z, RedBuf rb, CGState *st) {
 	if (st->done) return;
 	const int i = blockIdx.x * TX + threadIdx.x, j = blockIdx.y * TY + threadIdx.y;
 	const int kbeg = blockIdx.z * ZC, kend = min(kbeg + ZC, d.nzl);
@@ -33,13 +35,13 @@ __global__ void __launch_bounds__(TX *TY) k_spmv_dot(Dims d, const CoefT *__rest
 		for (int k = kbeg; k < kend; ++k, c += d.plane) {
 			const VecT sp = s[c + d.plane];
 			const CoefT wzp = wz[c + d.plane];
-			VecT v = (VecT)diag[c] * sc;
-			v -= (VecT)wx[c] * s[c - 1];
-			v -= (VecT)wx[c + 1] * s[c + 1];
-			v -= (VecT)wy[c] * s[c - d.nx];
-			v -= (VecT)wy[c + d.nx] * s[c + d.nx];
-			v -= (VecT)wzc * sm;
-			v -= (VecT)wzp * sp;
+			VecT v = (VecT)dd[c] * sc;
+			v += (VecT)wx[c] * (sc - s[c - 1]);
+			v += (VecT)wx[c + 1] * (sc - s[c + 1]);
+			v += (VecT)wy[c] * (sc - s[c - d.nx]);
+			v += (VecT)wy[c + d.nx] * (sc - s[c + d.nx]);
+			v += (VecT)wzc * (sc - sm);
+			v += (VecT)wzp * (sc - sp);
 			z[c] = v;
 			red[0] += (double)sc * (double)v;
 			sm = sc; sc = sp; wzc = wzp;

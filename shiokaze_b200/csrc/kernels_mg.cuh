@@ -4,8 +4,9 @@
 // Hierarchy: 2x2x2 cell aggregates, piecewise-constant prolongation P, restriction P^T, coarse
 // operator scale * P^T A P. With this P the Galerkin product of a face-coefficient 7-point operator is
 // again one (coarse face coefficient = sum of the 4 fine faces crossing the coarse face), so every
-// level uses the same four arrays (wx, wy, wz, diag) and the same kernels; cut cells, ghost-fluid
-// Dirichlet faces and Neumann walls are carried algebraically. scale = 1/2 restores the h^-2 scaling
+// level uses the same four arrays (wx, wy, wz, dd) and the same kernels; cut cells, ghost-fluid
+// Dirichlet faces and Neumann walls are carried algebraically (coarse dd = sum of the children's dd,
+// couplings inside an aggregate drop out). scale = 1/2 restores the h^-2 scaling
 // that piecewise-constant transfer loses (the usual over-correction of unsmoothed aggregation).
 // Smoother: red-black Gauss-Seidel, colours by (i+j+k_global) parity, reversed order after the
 // coarse correction so that the V-cycle is a symmetric operator for CG.
@@ -17,7 +18,7 @@ namespace shkz {
 
 struct MGLevel {
 	Dims d;
-	float *wx, *wy, *wz, *diag; // with ghost planes, pointing at plane 0
+	float *wx, *wy, *wz, *dd; // with ghost planes, pointing at plane 0
 	float *x, *b, *r;
 };
 
@@ -25,7 +26,7 @@ struct MGLevel {
 // one whose parity matches. x == 0 on entry of the very first half sweep is exploited by ZERO_X.
 template <bool ZERO_X>
 __global__ void __launch_bounds__(256) k_rbgs(Dims d, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
-                                             const float *__restrict__ diag, const float *__restrict__ b, float *__restrict__ x, int color,
+                                             const float *__restrict__ dd, const float *__restrict__ b, float *__restrict__ x, int color,
                                              const CGState *__restrict__ st) {
 	if (st && st->done) return;
 	const int ip = blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,17 +35,18 @@ __global__ void __launch_bounds__(256) k_rbgs(Dims d, const float *__restrict__ 
 	const int i = 2 * ip + ((j + k + d.k0 + color) & 1);
 	if (i >= d.nx || j >= d.ny) return;
 	const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-	const float dg = diag[c];
+	const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + d.nx], w4 = wz[c], w5 = wz[c + d.plane];
+	const float dg = dd[c] + ((w0 + w1) + (w2 + w3) + (w4 + w5));
 	float v = 0.f;
 	if (dg > 0.f) {
 		float acc = b[c];
 		if (!ZERO_X) {
-			acc += wx[c] * x[c - 1];
-			acc += wx[c + 1] * x[c + 1];
-			acc += wy[c] * x[c - d.nx];
-			acc += wy[c + d.nx] * x[c + d.nx];
-			acc += wz[c] * x[c - d.plane];
-			acc += wz[c + d.plane] * x[c + d.plane];
+			acc += w0 * x[c - 1];
+			acc += w1 * x[c + 1];
+			acc += w2 * x[c - d.nx];
+			acc += w3 * x[c + d.nx];
+			acc += w4 * x[c - d.plane];
+			acc += w5 * x[c + d.plane];
 		}
 		v = __fdividef(acc, dg);
 	}
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) k_rbgs(Dims d, const float *__restrict__ 
 
 // r = b - A x
 __global__ void __launch_bounds__(TX *TY) k_residual(Dims d, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
-                                                    const float *__restrict__ diag, const float *__restrict__ b, const float *__restrict__ x,
+                                                    const float *__restrict__ dd, const float *__restrict__ b, const float *__restrict__ x,
                                                     float *__restrict__ r, const CGState *__restrict__ st) {
 	if (st && st->done) return;
 	const int i = blockIdx.x * TX + threadIdx.x, j = blockIdx.y * TY + threadIdx.y;
@@ -63,13 +65,13 @@ __global__ void __launch_bounds__(TX *TY) k_residual(Dims d, const float *__rest
 	float xm = x[c - d.plane], xc = x[c], wzc = wz[c];
 	for (int k = kbeg; k < kend; ++k, c += d.plane) {
 		const float xp = x[c + d.plane], wzp = wz[c + d.plane];
-		float v = b[c] - diag[c] * xc;
-		v += wx[c] * x[c - 1];
-		v += wx[c + 1] * x[c + 1];
-		v += wy[c] * x[c - d.nx];
-		v += wy[c + d.nx] * x[c + d.nx];
-		v += wzc * xm;
-		v += wzp * xp;
+		float v = b[c] - dd[c] * xc;
+		v += wx[c] * (x[c - 1] - xc);
+		v += wx[c + 1] * (x[c + 1] - xc);
+		v += wy[c] * (x[c - d.nx] - xc);
+		v += wy[c + d.nx] * (x[c + d.nx] - xc);
+		v += wzc * (xm - xc);
+		v += wzp * (xp - xc);
 		r[c] = v;
 		xm = xc; xc = xp; wzc = wzp;
 	}
@@ -105,15 +107,16 @@ __global__ void __launch_bounds__(256) k_prolong_add(Dims df, Dims dc, const flo
 	x[i + (long long)df.nx * (j + (long long)df.ny * k)] += ec[(i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1))];
 }
 
-// Coarse operator = scale * P^T A P (setup, once per projection).
+// Coarse operator = scale * P^T A P (setup, once per projection): coarse face coupling = sum of the four
+// fine couplings crossing the coarse face, coarse dd = sum of the children's dd.
 __global__ void __launch_bounds__(256) k_coarsen_operator(Dims df, Dims dc, float scale, const float *__restrict__ wx, const float *__restrict__ wy,
-                                                         const float *__restrict__ wz, const float *__restrict__ diag, float *__restrict__ cwx,
-                                                         float *__restrict__ cwy, float *__restrict__ cwz, float *__restrict__ cdiag) {
+                                                         const float *__restrict__ wz, const float *__restrict__ dd, float *__restrict__ cwx,
+                                                         float *__restrict__ cwy, float *__restrict__ cwz, float *__restrict__ cdd) {
 	const int I = blockIdx.x * blockDim.x + threadIdx.x;
 	const int J = blockIdx.y * blockDim.y + threadIdx.y;
 	const int K = blockIdx.z;
 	if (I >= dc.nx || J >= dc.ny) return;
-	float sx = 0.f, sy = 0.f, sz = 0.f, sd = 0.f, internal = 0.f;
+	float sx = 0.f, sy = 0.f, sz = 0.f, sd = 0.f;
 #pragma unroll
 	for (int dk = 0; dk < 2; ++dk)
 #pragma unroll
@@ -123,19 +126,16 @@ __global__ void __launch_bounds__(256) k_coarsen_operator(Dims df, Dims dc, floa
 				const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
 				if (i >= df.nx || j >= df.ny || k >= df.nzl) continue;
 				const long long c = i + (long long)df.nx * (j + (long long)df.ny * k);
-				sd += diag[c];
-				const float a = wx[c], b = wy[c], e = wz[c];
-				if (di) internal += a; else sx += a;
-				if (dj) internal += b; else sy += b;
-				if (dk) internal += e; else sz += e;
+				sd += dd[c];
+				if (!di) sx += wx[c];
+				if (!dj) sy += wy[c];
+				if (!dk) sz += wz[c];
 			}
-	float D = sd - 2.f * internal;
-	if (!(D > 1e-6f * sd)) D = 0.f; // aggregate without any outside coupling: not a coarse unknown
 	const long long C = I + (long long)dc.nx * (J + (long long)dc.ny * K);
-	cwx[C] = D > 0.f ? scale * sx : 0.f;
-	cwy[C] = D > 0.f ? scale * sy : 0.f;
-	cwz[C] = D > 0.f ? scale * sz : 0.f;
-	cdiag[C] = scale * D;
+	cwx[C] = scale * sx;
+	cwy[C] = scale * sy;
+	cwz[C] = scale * sz;
+	cdd[C] = scale * sd;
 }
 
 // Hand-off CG -> MG: b0 = float(r)

@@ -90,7 +90,7 @@ size_t face_count(const Dims &d, int dim) {
 
 struct HostLevel {
 	Dims d;
-	CellArray wx, wy, wz, diag, x, b, r;
+	CellArray wx, wy, wz, dd, x, b, r;
 	bool own_coef = true, own_x = true, own_b = true; // level 0 may alias CG arrays
 	MGLevel view;
 };
@@ -110,7 +110,7 @@ struct shkz_b200_solver {
 	PlainArray areas[3], rhos[3];
 	// operator + CG vectors; element sizes depend on the precision mode they were allocated for
 	int alloc_precision = -1;
-	CellArray wx, wy, wz, diag; // CoefT
+	CellArray wx, wy, wz, dd; // CoefT
 	CellArray b, x, r, s, z;    // VecT
 	std::vector<HostLevel> levels;
 	int mg_min_size_built = -1;
@@ -136,9 +136,9 @@ struct shkz_b200_solver {
 namespace {
 
 void release_precision_arrays(shkz_b200_solver *S) {
-	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->diag, &S->b, &S->x, &S->r, &S->s, &S->z}) a->release();
+	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd, &S->b, &S->x, &S->r, &S->s, &S->z}) a->release();
 	for (HostLevel &L : S->levels) {
-		if (L.own_coef) { L.wx.release(); L.wy.release(); L.wz.release(); L.diag.release(); }
+		if (L.own_coef) { L.wx.release(); L.wy.release(); L.wz.release(); L.dd.release(); }
 		if (L.own_x) L.x.release();
 		if (L.own_b) L.b.release();
 		L.r.release();
@@ -154,7 +154,7 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 	if (S->alloc_precision == precision && S->mg_min_size_built == min_size) return SHKZ_B200_OK;
 	release_precision_arrays(S);
 	const Dims &d = S->d;
-	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->diag}) CKR(a->alloc(d, sizeof(CoefT)));
+	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd}) CKR(a->alloc(d, sizeof(CoefT)));
 	for (CellArray *a : {&S->b, &S->x, &S->r, &S->s, &S->z}) CKR(a->alloc(d, sizeof(VecT)));
 	// multigrid hierarchy (always allocated: switching the preconditioner must not reallocate)
 	Dims cur = d;
@@ -163,9 +163,9 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 		L.d = cur;
 		if (l == 0 && sizeof(CoefT) == sizeof(float)) {
 			L.own_coef = false;
-			L.wx = S->wx; L.wy = S->wy; L.wz = S->wz; L.diag = S->diag;
+			L.wx = S->wx; L.wy = S->wy; L.wz = S->wz; L.dd = S->dd;
 		} else {
-			for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.diag}) CKR(a->alloc(cur, sizeof(float)));
+			for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.dd}) CKR(a->alloc(cur, sizeof(float)));
 		}
 		if (l == 0 && sizeof(VecT) == sizeof(float)) {
 			L.own_x = L.own_b = false;
@@ -177,7 +177,7 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 		}
 		CKR(L.r.alloc(cur, sizeof(float)));
 		L.view.d = cur;
-		L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.diag = L.diag.ptr<float>(cur);
+		L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.dd = L.dd.ptr<float>(cur);
 		L.view.x = L.x.ptr<float>(cur); L.view.b = L.b.ptr<float>(cur); L.view.r = L.r.ptr<float>(cur);
 		S->levels.push_back(L);
 		const int big = cur.nx > cur.ny ? (cur.nx > cur.nzg ? cur.nx : cur.nzg) : (cur.ny > cur.nzg ? cur.ny : cur.nzg);
@@ -216,8 +216,8 @@ int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
 void rbgs(shkz_b200_solver *S, const MGLevel &L, int color, bool zero_x, const CGState *st, cudaStream_t stream) {
 	const dim3 block(32, 8, 1);
 	const dim3 grid(((L.d.nx + 1) / 2 + 31) / 32, (L.d.ny + 7) / 8, L.d.nzl);
-	if (zero_x) LAUNCH(S, k_rbgs<true>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.diag, L.b, L.x, color, st);
-	else LAUNCH(S, k_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.diag, L.b, L.x, color, st);
+	if (zero_x) LAUNCH(S, k_rbgs<true>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, color, st);
+	else LAUNCH(S, k_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, color, st);
 }
 
 int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, const CGState *st, cudaStream_t stream) {
@@ -233,7 +233,7 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, const CGSta
 	}
 	if (!last) {
 		const MGLevel &C = S->levels[l + 1].view;
-		LAUNCH(S, k_residual, stencil_grid(L.d), stencil_block(), stream, L.d, L.wx, L.wy, L.wz, L.diag, L.b, L.x, L.r, st);
+		LAUNCH(S, k_residual, stencil_grid(L.d), stencil_block(), stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, L.r, st);
 		LAUNCH(S, k_restrict, cell_grid(C.d, 0, 0, 0), cell_block(), stream, L.d, C.d, L.r, C.b, st);
 		CKR(vcycle(S, l + 1, P, st, stream));
 		LAUNCH(S, k_prolong_add, cell_grid(L.d, 0, 0, 0), cell_block(), stream, L.d, C.d, C.x, L.x, st);
@@ -251,8 +251,8 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, const CGSta
 int build_hierarchy(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	for (size_t l = 0; l + 1 < S->levels.size(); ++l) {
 		const MGLevel &F = S->levels[l].view, &C = S->levels[l + 1].view;
-		LAUNCH(S, k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, (float)P.mg_coarse_scale, F.wx, F.wy, F.wz, F.diag, C.wx,
-		       C.wy, C.wz, C.diag);
+		LAUNCH(S, k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, (float)P.mg_coarse_scale, F.wx, F.wy, F.wz, F.dd, C.wx,
+		       C.wy, C.wz, C.dd);
 		CKR(halo(S, C.d, C.wz, stream));
 	}
 	CK(cudaGetLastError());
@@ -267,7 +267,7 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	const RedBuf rb = S->redbuf();
 	CGState *st = S->dstate();
 	VecT *b = S->b.ptr<VecT>(d), *x = S->x.ptr<VecT>(d), *r = S->r.ptr<VecT>(d), *s = S->s.ptr<VecT>(d), *z = S->z.ptr<VecT>(d);
-	const CoefT *wx = S->wx.ptr<CoefT>(d), *wy = S->wy.ptr<CoefT>(d), *wz = S->wz.ptr<CoefT>(d), *diag = S->diag.ptr<CoefT>(d);
+	const CoefT *wx = S->wx.ptr<CoefT>(d), *wy = S->wy.ptr<CoefT>(d), *wz = S->wz.ptr<CoefT>(d), *dd = S->dd.ptr<CoefT>(d);
 	const bool mg = P.precond == SHKZ_B200_PRECOND_MG;
 	const int fb = flat_blocks(n);
 	const bool alias = sizeof(VecT) == sizeof(float);
@@ -296,7 +296,7 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	while (it < P.max_iterations) {
 		for (int c = 0; c < check && it < P.max_iterations; ++c, ++it) {
 			CKR(halo(S, d, s, stream));
-			LAUNCH(S, (k_spmv_dot<VecT, CoefT>), stencil_grid(d), stencil_block(), stream, d, wx, wy, wz, diag, s, z, rb, st);
+			LAUNCH(S, (k_spmv_dot<VecT, CoefT>), stencil_grid(d), stencil_block(), stream, d, wx, wy, wz, dd, s, z, rb, st);
 			if (mg) {
 				LAUNCH(S, (k_axpy2_norm<VecT, false>), fb, 256, stream, n, s, z, x, r, rb, st);
 				CKR(precondition());
@@ -378,8 +378,8 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		const bool share = sizeof(CoefT) == sizeof(float);
 		const MGLevel &L0 = S->levels[0].view;
 		LAUNCH(S, (k_build_system<RealT, CoefT, VecT>), cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, (const uint8_t *)in_rows, careas,
-		       crhos, cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->diag.ptr<CoefT>(d), share ? nullptr : L0.wx,
-		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.diag, S->b.ptr<VecT>(d), rb, st);
+		       crhos, cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->dd.ptr<CoefT>(d), share ? nullptr : L0.wx,
+		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.dd, S->b.ptr<VecT>(d), rb, st);
 		CKR(halo(S, d, S->wz.ptr<CoefT>(d), stream));
 		if (!share) CKR(halo(S, d, L0.wz, stream));
 	}
@@ -673,7 +673,7 @@ int shkz_b200_debug_fetch(shkz_b200_solver *S, const char *name, void *dst, size
 	const size_t vec = S->alloc_precision == SHKZ_B200_PREC_FP32 ? 4 : 8;
 	const size_t coef = S->alloc_precision == SHKZ_B200_PREC_FP64 ? 8 : 4;
 	auto cell = [&](const CellArray &a, size_t elem) { src = a.base ? static_cast<const char *>(a.base) + (size_t)d.plane * elem : nullptr; bytes = (size_t)d.ncell * elem; };
-	if (n == "diag") cell(S->diag, coef);
+	if (n == "dd") cell(S->dd, coef);
 	else if (n == "wx") cell(S->wx, coef);
 	else if (n == "wy") cell(S->wy, coef);
 	else if (n == "wz") cell(S->wz, coef);
@@ -683,13 +683,13 @@ int shkz_b200_debug_fetch(shkz_b200_solver *S, const char *name, void *dst, size
 	else if (n == "phi") cell(S->phi, S->real_bytes);
 	else if (n.size() == 6 && n.compare(0, 5, "areas") == 0 && n[5] >= '0' && n[5] <= '2') { src = S->areas[n[5] - '0'].base; bytes = face_count(d, n[5] - '0') * S->real_bytes; }
 	else if (n.size() == 5 && n.compare(0, 4, "rhos") == 0 && n[4] >= '0' && n[4] <= '2') { src = S->rhos[n[4] - '0'].base; bytes = face_count(d, n[4] - '0') * S->real_bytes; }
-	else if (n.compare(0, 3, "mg_") == 0) { // mg_<level>_<diag|wx|wy|wz>
+	else if (n.compare(0, 3, "mg_") == 0) { // mg_<level>_<dd|wx|wy|wz>
 		int l = -1;
 		char what[16] = {0};
 		if (sscanf(name, "mg_%d_%15s", &l, what) == 2 && l >= 0 && (size_t)l < S->levels.size()) {
 			const HostLevel &L = S->levels[l];
 			const std::string w(what);
-			const CellArray *a = w == "diag" ? &L.diag : w == "wx" ? &L.wx : w == "wy" ? &L.wy : w == "wz" ? &L.wz : nullptr;
+			const CellArray *a = w == "dd" ? &L.dd : w == "wx" ? &L.wx : w == "wy" ? &L.wy : w == "wz" ? &L.wz : nullptr;
 			if (a) { src = a->base ? static_cast<const char *>(a->base) + (size_t)L.d.plane * 4 : nullptr; bytes = (size_t)L.d.ncell * 4; }
 		}
 	}
