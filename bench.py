@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the pressure-projection hot path.
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    the reference's CPU implementation, bounded sample
+
+A "step" is ONE project() call — fractions, coefficient assembly, multigrid hierarchy, MG-preconditioned CG
+to the reference's default tolerance (Residual=1e-4 relative inf-norm), pressure scatter, velocity update —
+on the workload BASELINE.json quotes the metric on: configs[1], the macsmoke3 buoyant plume on a 256^3
+all-fluid Neumann box (16.8 M unknowns). `value` is grid cells projected per second with the inputs
+resident in HBM (restored from pristine device copies inside the timed region), `e2e` is the same through
+the host-buffer C-ABI call a Shiokaze plugin makes (pinned host buffers, H2D and D2H inside the timed region).
+For N > 1 every rank owns a 256x256x256 z-slab of a 256x256x(256 N) box (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "projection_throughput"
+UNIT = "Mcells/s"
+
+# plain-CG iteration counts of the reference at full size (Residual=1e-4). The reference's "pcg" is plain CG
+# (pcg_solver.h:383) and our fp64 Precond=none path tracks it iteration for iteration (tests/test_gpu_parity.py);
+# the 256^3 entry was also confirmed by a full run of the unmodified reference build (measurement).
+REFERENCE_ITERATIONS = {("smoke_plume", 256): 888}
+
+
+# ------------------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(self.NAMES, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, levels_rows):
+    """Algorithmic (minimum necessary) bytes one launch of `kernel` moves, counted on unknown rows
+    (DESIGN.md 'Kernels and their rooflines'). V = CG vector bytes, C = operator coefficient bytes, MG is fp32."""
+    V = 4 if precision == "fp32" else 8
+    Cc = 8 if precision == "fp64" else 4
+    name, _, lvl = kernel.partition("@")
+    n = levels_rows[int(lvl)] if lvl else n_rows
+    per_row = {
+        "spmv_dot": 2 * V + 4 * Cc,          # read s, wx wy wz dd ; write z (s.z fused)
+        "axpy2_norm": 6 * V,                  # read s x z r ; write x r (norms fused)
+        "xpay": 3 * V,                        # read z s ; write s
+        "copy_dot": 3 * V,
+        "to_mg": V + 4,
+        "from_mg": (4 + 2 * V) if V == 8 else 8,
+        # one colour: b, other-colour x, own x written (4 B each on n/2 cells) + 7 coefficient values per updated cell
+        "rbgs": (3 * 4 + 7 * 4) / 2.0,
+        "residual": 4 * 3 + 4 * 4,            # b, x, r + 4 coefficient arrays
+        "restrict": 4 + 0.5,
+        "prolong_add": 8 + 0.5,
+    }.get(name)
+    return None if per_row is None else per_row * n
+
+
+def build_scene(workload, n, zrange=None):
+    from shiokaze_b200 import scenes
+    return scenes.BENCH_SCENES[workload](n, zrange=zrange) if zrange else scenes.BENCH_SCENES[workload](n)
+
+
+# ------------------------------------------------------------------------------------------------------
+def reference_sample(workload, n, budget_s, threads):
+    """One bounded sample of the reference's CPU implementation of the path, scaled to the full workload.
+
+    The reference cannot finish the full workload in minutes (256^3: ~16 min, one core in the solve), so a step
+    runs the unmodified reference build (oracle/_ref) on a thin slab of the same scene — n x n x nzs cells around
+    the plume — twice: MaxIterations=0 (every fixed cost: fractions, RCMatrix assembly, the SparseMatrix copy and
+    the dead MIC(0) factorisation) and MaxIterations=m (adds m CG iterations). Cost per cell and per
+    cell-iteration are then scaled to n^3 cells and the reference's full iteration count."""
+    from oracle import refio
+    from shiokaze_b200 import scenes
+    nzs = 8 if budget_s < 20 else 16
+    m = 6
+    z0 = n // 2 - nzs // 2
+    slab = build_scene(workload, n, zrange=(z0, z0 + nzs))
+    sc = scenes.standalone(slab)
+    t0 = time.time()
+    kind = "reference" if refio.ref_available("f32") else "port"
+    if kind == "reference":
+        r0 = refio.run_reference(sc, "f32", flags={"MaxIterations": 0}, threads=threads)
+        r1 = refio.run_reference(sc, "f32", flags={"MaxIterations": m}, threads=threads)
+        fixed_ms = r0.phase_ms.get("projection", r0.ms_project)
+        iter_ms = max(r1.phase_ms.get("linsolve", 0.0) - r0.phase_ms.get("linsolve", 0.0), 1e-9) / m
+        cores = threads
+    else:  # the dense C port of the same algorithm (single thread)
+        from oracle import dense_oracle
+        t = time.time(); dense_oracle.project(sc, max_iterations=0); fixed_ms = (time.time() - t) * 1e3
+        t = time.time(); dense_oracle.project(sc, max_iterations=m); iter_ms = max((time.time() - t) * 1e3 - fixed_ms, 1e-9) / m
+        cores = 1
+    scale = n / float(nzs)
+    iters_full = REFERENCE_ITERATIONS.get((workload, n), int(round(888 * n / 256.0)))
+    full_ms = scale * (fixed_ms + iters_full * iter_ms)
+    cells = float(n) ** 3
+    return {
+        "ms_per_solve": full_ms, "value": cells / (full_ms * 1e-3) / 1e6, "kind": kind, "cores": cores,
+        "sample": (f"{workload} {n}x{n}x{nzs} slab of the {n}^3 scene through {'the unmodified reference build (oracle/_ref)' if kind == 'reference' else 'the dense C port (oracle/dense_oracle.c)'}: "
+                   f"fixed cost {fixed_ms:.0f} ms + {iter_ms:.1f} ms per CG iteration on the slab (solve phase is single-threaded in the reference), "
+                   f"scaled x{scale:.0f} cells and to the reference's {iters_full} iterations at {n}^3"),
+        "wall_s": time.time() - t0,
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    budget = max(8.0, 150.0 / max(1, args.steps + args.warmup))
+    for _ in range(args.warmup):
+        reference_sample(args.workload, args.n, budget, threads)
+    samples = [reference_sample(args.workload, args.n, budget, threads) for _ in range(args.steps)]
+    ms = float(np.mean([s["ms_per_solve"] for s in samples]))
+    cells = float(args.n) ** 3 * args.gpus
+    value = cells / (ms * args.gpus * 1e-3) / 1e6  # the reference has no multi-GPU path: N slabs take N times as long
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms * args.gpus, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, "cpu"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": samples[0]["cores"], "kind": samples[0]["kind"], "sample": samples[0]["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def config_dict(args, where):
+    return {"workload": f"{args.workload} {args.n}^3 per GPU ({'macsmoke3 buoyant plume, all-fluid Neumann box' if args.workload == 'smoke_plume' else args.workload}), "
+                        f"one project() call: assembly + MG-PCG solve to Residual={args.residual:g} + velocity update",
+            "grid": [args.n, args.n, args.n * args.gpus], "slab_per_gpu": [args.n, args.n, args.n], "parallelism": f"z-slab x{args.gpus}",
+            "precision": args.precision, "precond": args.precond, "mg_sweeps": [args.pre, args.post], "residual": args.residual,
+            "l2_policy": "inputs (318 MB per step) and solver working set (>1 GB) exceed the 126 MB L2; no explicit flush",
+            "where": where}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from shiokaze_b200 import MacPressureSolver3, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if capi.lib().shkz_b200_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: libshkz_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.n
+    nzg = n * world
+    zr = (rank * n, (rank + 1) * n)
+    if world > 1:
+        from shiokaze_b200 import dist as sdist
+        sc = sdist.slab_scene(args.workload, n, nzg, zr)
+    else:
+        sc = build_scene(args.workload, n)
+    flags = dict(Precision=args.precision, Precond=args.precond, Residual=args.residual, MGPreSweeps=args.pre, MGPostSweeps=args.post,
+                 CheckEvery=args.check_every)
+    S = MacPressureSolver3((sc.nx, sc.ny, nzg), sc.dx, device=local, zrange=zr, **flags)
+    if world > 1:
+        sdist.connect(S, rank, world)
+
+    # pristine device copies + working set (PyTorch is only the allocator here)
+    def dev_t(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    vel0 = [dev_t(v) for v in sc.vel]
+    act0 = [dev_t(a) for a in sc.vel_active]
+    fluid = dev_t(sc.fluid)
+    solid = dev_t(sc.solid) if sc.solid is not None else None
+    vel = [torch.empty_like(v) for v in vel0]
+    act = [torch.empty_like(a) for a in act0]
+    pres = torch.zeros(sc.fluid.shape, dtype=torch.float32, device=dev)
+    pact = torch.zeros(sc.fluid.shape, dtype=torch.uint8, device=dev)
+
+    def step():
+        for d in range(3):
+            vel[d].copy_(vel0[d]); act[d].copy_(act0[d])
+        return S.project_device(sc.dt, vel, act, solid, fluid, sc.fluid_levelset, pres, pact)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        res = step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, iters = 0, []
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+        launches += res.stats["kernel_launches"] + 6  # + the six restore copies
+        iters.append(res.iterations)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    cells_global = float(n) * n * nzg
+    value = cells_global / (ms_step * 1e-3) / 1e6
+    n_rows = res.stats["n_rows_global"] if world > 1 else res.n_rows
+    phase = {k: res.stats[k] for k in ("ms_assemble", "ms_setup", "ms_solve", "ms_update")}
+
+    # ---- end to end through the host-buffer C-ABI (what the Shiokaze plugin calls), pinned host memory ----
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(np.zeros(1, a.dtype)).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    hv0 = [np.ascontiguousarray(v) for v in sc.vel]
+    ha0 = [np.ascontiguousarray(a) for a in sc.vel_active]
+    hv = [pinned(v) for v in hv0]
+    ha = [pinned(a) for a in ha0]
+    hfluid = pinned(sc.fluid)
+    hsolid = pinned(sc.solid) if sc.solid is not None else None
+    h2d = sum(v.nbytes for v in hv0) + sum(a.nbytes for a in ha0) + sc.fluid.nbytes + (sc.solid.nbytes if sc.solid is not None else 0)
+    d2h = sum(v.nbytes for v in hv0) + sum(a.nbytes for a in ha0) + sc.fluid.nbytes + sc.fluid.size
+    e2e_s = 0.0
+    e2e_steps = args.steps if world == 1 else 0   # slab e2e goes through the same call; measured on one GPU
+    for it in range(min(2, args.warmup) + e2e_steps):
+        for d in range(3):
+            hv[d].numpy()[...] = hv0[d]; ha[d].numpy()[...] = ha0[d]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        S.project(sc.dt, [t.numpy() for t in hv], [t.numpy() for t in ha], hsolid.numpy() if hsolid is not None else None,
+                  hfluid.numpy(), sc.fluid_levelset)
+        t1 = time.perf_counter()
+        if it >= min(2, args.warmup):
+            e2e_s += t1 - t0
+    e2e_value = (cells_global * e2e_steps / e2e_s / 1e6) if e2e_s > 0 else None
+
+    # ---- roofline of the dominant kernel: CUDA events around every launch of one extra solve ----
+    roofline = None
+    table = {}
+    if rank == 0 or world > 1:
+        S.profile(True)
+        for d in range(3):
+            vel[d].copy_(vel0[d]); act[d].copy_(act0[d])
+        S.project_device(sc.dt, vel, act, solid, fluid, sc.fluid_levelset, pres, pact)
+        table = S.profile_table()
+        S.profile(False)
+    if rank == 0 and table:
+        peak, how = measured_peak()
+        levels_rows = [n_rows / (8 ** l) for l in range(16)]
+        solve_kernels = {k: v for k, v in table.items() if algorithmic_bytes_per_launch(k, n_rows, args.precision, levels_rows)}
+        dom = max(solve_kernels, key=lambda k: solve_kernels[k][1])
+        cnt, tot = solve_kernels[dom]
+        per_launch = algorithmic_bytes_per_launch(dom, res.n_rows, args.precision, [res.n_rows / (8 ** l) for l in range(16)])
+        achieved = per_launch / (tot / cnt * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(dom.split("@")[0] + ("@" + dom.split("@")[1] if "@" in dom else ""), None)
+        except Exception:
+            pass
+        total_profiled = sum(v[1] for v in table.values())
+        alg_total = sum((algorithmic_bytes_per_launch(k, res.n_rows, args.precision, [res.n_rows / (8 ** l) for l in range(16)]) or 0) * v[0]
+                        for k, v in table.items())
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": how, "launches": cnt, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_launch": per_launch,
+                    "share_of_step": tot / total_profiled if total_profiled else None,
+                    "solve_whole": {"algorithmic_GB": alg_total / 1e9, "ms": res.stats["ms_solve"], "achieved": alg_total / 1e9 / (res.stats["ms_solve"] * 1e-3),
+                                    "frac": alg_total / 1e9 / (res.stats["ms_solve"] * 1e-3) / peak},
+                    "by_kernel_ms": {k: round(v[1], 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])[:12]}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s = reference_sample(args.workload, n, 30.0, os.cpu_count() or 1)
+        cpu_baseline = {"value": s["value"], "unit": UNIT, "cores": s["cores"], "kind": s["kind"], "sample": s["sample"],
+                        "ms_per_solve": s["ms_per_solve"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"mixed": "f64", "fp64": "f64", "fp32": "f32"}[args.precision], "data": "synthetic", "config": config_dict(args, "gpu"),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": (e2e_s / e2e_steps * 1e3) if e2e_steps else None},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "solve": {"iterations": iters[-1], "reresid": res.reresid, "converged": res.converged, "n_rows": int(n_rows),
+                      "cell_iters_per_s": n_rows * iters[-1] / (phase["ms_solve"] * 1e-3), **phase},
+        }
+        print(json.dumps(line))
+    S.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="smoke_plume")
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "fp64", "fp32"])
+    ap.add_argument("--precond", default="mg", choices=["mg", "none"])
+    ap.add_argument("--pre", type=int, default=2)
+    ap.add_argument("--post", type=int, default=2)
+    ap.add_argument("--residual", type=float, default=1e-4)
+    ap.add_argument("--check-every", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least three warm-up steps
+    return run_reference_arm(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

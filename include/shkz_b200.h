@@ -161,6 +161,12 @@ int shkz_b200_slab_export(shkz_b200_solver *solver, uint8_t ipc[SHKZ_B200_IPC_BY
 int shkz_b200_slab_connect(shkz_b200_solver *solver, int rank, int world, const uint8_t id[SHKZ_B200_NCCL_ID_BYTES],
                            const uint8_t *lower_ipc, const uint8_t *upper_ipc);
 
+/* ---- per-kernel timing (CUDA events around every launch; slows the call down, never on by default) ----
+ * enable(1) resets the accumulators; entries are "<kernel>" or "<kernel>@<multigrid level>". */
+int shkz_b200_profile_enable(shkz_b200_solver *solver, int on);
+int shkz_b200_profile_count(shkz_b200_solver *solver);
+int shkz_b200_profile_get(shkz_b200_solver *solver, int index, char *name, size_t name_bytes, uint64_t *launches, double *total_ms);
+
 /* ---- test hook: copy an internal device array to the host (names: see DESIGN.md, e.g. "diag","rhs") ---- */
 int shkz_b200_debug_fetch(shkz_b200_solver *solver, const char *name, void *dst, size_t dst_bytes, size_t *needed_bytes);
 

@@ -19,7 +19,8 @@ EXPORTS = [
     "shkz_b200_abi_version", "shkz_b200_last_error", "shkz_b200_default_params", "shkz_b200_device_count",
     "shkz_b200_create", "shkz_b200_create_slab", "shkz_b200_destroy", "shkz_b200_project_host",
     "shkz_b200_project_device", "shkz_b200_resolve", "shkz_b200_comm_unique_id", "shkz_b200_slab_export",
-    "shkz_b200_slab_connect", "shkz_b200_debug_fetch",
+    "shkz_b200_slab_connect", "shkz_b200_debug_fetch", "shkz_b200_profile_enable", "shkz_b200_profile_count",
+    "shkz_b200_profile_get",
 ]
 
 
@@ -77,6 +78,9 @@ def lib():
     L.shkz_b200_slab_export.argtypes = [vp, u8p]
     L.shkz_b200_slab_connect.argtypes = [vp, C.c_int, C.c_int, u8p, u8p, u8p]
     L.shkz_b200_debug_fetch.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.shkz_b200_profile_enable.argtypes = [vp, C.c_int]
+    L.shkz_b200_profile_count.argtypes = [vp]
+    L.shkz_b200_profile_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     _lib = L
     return L
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -88,8 +89,55 @@ size_t face_count(const Dims &d, int dim) {
 	return (size_t)(d.nx + (dim == 0)) * (size_t)(d.ny + (dim == 1)) * (size_t)(d.nzl + (dim == 2));
 }
 
+struct Profiler {
+	bool on = false;
+	std::vector<cudaEvent_t> ev; // pairs
+	std::vector<int> id;         // entry index per pair
+	size_t used = 0;
+	std::vector<std::string> names;
+	std::vector<uint64_t> count;
+	std::vector<double> ms;
+	std::map<std::string, int> index;
+	static constexpr size_t kMaxPairs = 16384;
+	int entry(const char *tag) {
+		auto it = index.find(tag);
+		if (it != index.end()) return it->second;
+		const int n = (int)names.size();
+		names.push_back(tag); count.push_back(0); ms.push_back(0.0);
+		index[tag] = n;
+		return n;
+	}
+	int begin(const char *tag, cudaStream_t stream) {
+		if (!on || used >= kMaxPairs) return -1;
+		if (ev.size() < 2 * (used + 1)) {
+			cudaEvent_t a, b;
+			if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+			ev.push_back(a); ev.push_back(b);
+			id.push_back(0);
+		}
+		id[used] = entry(tag);
+		cudaEventRecord(ev[2 * used], stream);
+		return (int)used;
+	}
+	void end(int slot, cudaStream_t stream) {
+		if (slot < 0) return;
+		cudaEventRecord(ev[2 * slot + 1], stream);
+		used = slot + 1;
+	}
+	void collect() { // after the stream has been synchronised
+		for (size_t n = 0; n < used; ++n) {
+			float t = 0.f;
+			if (cudaEventElapsedTime(&t, ev[2 * n], ev[2 * n + 1]) == cudaSuccess) { ms[id[n]] += t; count[id[n]] += 1; }
+		}
+		used = 0;
+	}
+	void reset() { used = 0; names.clear(); count.clear(); ms.clear(); index.clear(); }
+	void destroy() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); id.clear(); reset(); }
+};
+
 struct HostLevel {
 	Dims d;
+	std::string tag_rbgs, tag_residual, tag_restrict, tag_prolong, tag_coarsen;
 	CellArray wx, wy, wz, dd, x, b, r;
 	bool own_coef = true, own_x = true, own_b = true; // level 0 may alias CG arrays
 	MGLevel view;
@@ -124,6 +172,7 @@ struct shkz_b200_solver {
 	SlabComm *comm = nullptr;
 	// bookkeeping
 	uint64_t launches = 0;
+	Profiler prof;
 	bool have_system = false;
 	AsmParams last_asm{};
 	cudaEvent_t ev[8]{};
@@ -176,6 +225,8 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 			CKR(L.b.alloc(cur, sizeof(float)));
 		}
 		CKR(L.r.alloc(cur, sizeof(float)));
+		L.tag_rbgs = "rbgs@" + std::to_string(l); L.tag_residual = "residual@" + std::to_string(l); L.tag_restrict = "restrict@" + std::to_string(l);
+		L.tag_prolong = "prolong_add@" + std::to_string(l); L.tag_coarsen = "coarsen_operator@" + std::to_string(l);
 		L.view.d = cur;
 		L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.dd = L.dd.ptr<float>(cur);
 		L.view.x = L.x.ptr<float>(cur); L.view.b = L.b.ptr<float>(cur); L.view.r = L.r.ptr<float>(cur);
@@ -199,10 +250,12 @@ int flat_blocks(long long n) {
 	return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-#define LAUNCH(S, kernel, grid, block, stream, ...)   \
-	do {                                              \
+#define LAUNCH(S, tag, kernel, grid, block, stream, ...)  \
+	do {                                                 \
+		const int slot_ = (S)->prof.begin(tag, stream);  \
 		kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); \
-		(S)->launches++;                              \
+		(S)->prof.end(slot_, stream);                    \
+		(S)->launches++;                                 \
 	} while (0)
 
 // ---- halo exchange of one cell array (ghost planes), a no-op on a whole grid ----
@@ -213,36 +266,38 @@ int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
 }
 
 // ---- multigrid ----
-void rbgs(shkz_b200_solver *S, const MGLevel &L, int color, bool zero_x, const CGState *st, cudaStream_t stream) {
+void rbgs(shkz_b200_solver *S, const HostLevel &H, int color, bool zero_x, const CGState *st, cudaStream_t stream) {
+	const MGLevel &L = H.view;
 	const dim3 block(32, 8, 1);
 	const dim3 grid(((L.d.nx + 1) / 2 + 31) / 32, (L.d.ny + 7) / 8, L.d.nzl);
-	if (zero_x) LAUNCH(S, k_rbgs<true>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, color, st);
-	else LAUNCH(S, k_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, color, st);
+	if (zero_x) LAUNCH(S, H.tag_rbgs.c_str(), k_rbgs<true>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, color, st);
+	else LAUNCH(S, H.tag_rbgs.c_str(), k_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, color, st);
 }
 
 int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, const CGState *st, cudaStream_t stream) {
-	const MGLevel &L = S->levels[l].view;
+	const HostLevel &H = S->levels[l];
+	const MGLevel &L = H.view;
 	const bool last = (l + 1 == S->levels.size());
 	const int pre = last ? (P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps) : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
 	const int post = last ? pre : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
 	for (int sw = 0; sw < pre; ++sw) {
-		rbgs(S, L, 0, sw == 0, st, stream);
+		rbgs(S, H, 0, sw == 0, st, stream);
 		CKR(halo(S, L.d, L.x, stream));
-		rbgs(S, L, 1, false, st, stream);
+		rbgs(S, H, 1, false, st, stream);
 		CKR(halo(S, L.d, L.x, stream));
 	}
 	if (!last) {
 		const MGLevel &C = S->levels[l + 1].view;
-		LAUNCH(S, k_residual, stencil_grid(L.d), stencil_block(), stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, L.r, st);
-		LAUNCH(S, k_restrict, cell_grid(C.d, 0, 0, 0), cell_block(), stream, L.d, C.d, L.r, C.b, st);
+		LAUNCH(S, H.tag_residual.c_str(), k_residual, stencil_grid(L.d), stencil_block(), stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, L.r, st);
+		LAUNCH(S, H.tag_restrict.c_str(), k_restrict, cell_grid(C.d, 0, 0, 0), cell_block(), stream, L.d, C.d, L.r, C.b, st);
 		CKR(vcycle(S, l + 1, P, st, stream));
-		LAUNCH(S, k_prolong_add, cell_grid(L.d, 0, 0, 0), cell_block(), stream, L.d, C.d, C.x, L.x, st);
+		LAUNCH(S, H.tag_prolong.c_str(), k_prolong_add, cell_grid(L.d, 0, 0, 0), cell_block(), stream, L.d, C.d, C.x, L.x, st);
 		CKR(halo(S, L.d, L.x, stream));
 	}
 	for (int sw = 0; sw < post; ++sw) {
-		rbgs(S, L, 1, false, st, stream);
+		rbgs(S, H, 1, false, st, stream);
 		CKR(halo(S, L.d, L.x, stream));
-		rbgs(S, L, 0, false, st, stream);
+		rbgs(S, H, 0, false, st, stream);
 		if (sw + 1 < post || l > 0) CKR(halo(S, L.d, L.x, stream));
 	}
 	return SHKZ_B200_OK;
@@ -251,7 +306,7 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, const CGSta
 int build_hierarchy(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	for (size_t l = 0; l + 1 < S->levels.size(); ++l) {
 		const MGLevel &F = S->levels[l].view, &C = S->levels[l + 1].view;
-		LAUNCH(S, k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, (float)P.mg_coarse_scale, F.wx, F.wy, F.wz, F.dd, C.wx,
+		LAUNCH(S, S->levels[l].tag_coarsen.c_str(), k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, (float)P.mg_coarse_scale, F.wx, F.wy, F.wz, F.dd, C.wx,
 		       C.wy, C.wz, C.dd);
 		CKR(halo(S, C.d, C.wz, stream));
 	}
@@ -273,42 +328,43 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	const bool alias = sizeof(VecT) == sizeof(float);
 
 	if (S->comm && !S->whole_grid) CKR(S->comm->allreduce_begin_state(st, stream) ? fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error()) : SHKZ_B200_OK);
-	LAUNCH(S, k_cg_begin<VecT>, 1, 32, stream, n, P.residual, (int)P.max_iterations, st);
+	LAUNCH(S, "cg_begin", k_cg_begin<VecT>, 1, 32, stream, n, P.residual, (int)P.max_iterations, st);
 	CK(cudaMemsetAsync(x, 0, sizeof(VecT) * (size_t)n, stream));
 	CK(cudaMemcpyAsync(r, b, sizeof(VecT) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
 
 	auto precondition = [&]() -> int {
 		const MGLevel &L0 = S->levels[0].view;
-		if (!alias) LAUNCH(S, k_to_mg<VecT>, fb, 256, stream, n, r, L0.b, st);
+		if (!alias) LAUNCH(S, "to_mg", k_to_mg<VecT>, fb, 256, stream, n, r, L0.b, st);
 		CKR(vcycle(S, 0, P, st, stream));
-		LAUNCH(S, k_from_mg<VecT>, fb, 256, stream, n, L0.x, r, z, rb, st);
+		LAUNCH(S, "from_mg", k_from_mg<VecT>, fb, 256, stream, n, L0.x, r, z, rb, st);
 		return SHKZ_B200_OK;
 	};
 
 	if (mg) {
 		CKR(precondition());
-		LAUNCH(S, k_copy_dot<VecT>, fb, 256, stream, n, z, r, s, rb, st);
+		LAUNCH(S, "copy_dot", k_copy_dot<VecT>, fb, 256, stream, n, z, r, s, rb, st);
 	} else {
-		LAUNCH(S, k_copy_dot<VecT>, fb, 256, stream, n, r, r, s, rb, st);
+		LAUNCH(S, "copy_dot", k_copy_dot<VecT>, fb, 256, stream, n, r, r, s, rb, st);
 	}
 	const int check = P.check_every < 1 ? 1 : P.check_every;
 	unsigned it = 0;
 	while (it < P.max_iterations) {
 		for (int c = 0; c < check && it < P.max_iterations; ++c, ++it) {
 			CKR(halo(S, d, s, stream));
-			LAUNCH(S, (k_spmv_dot<VecT, CoefT>), stencil_grid(d), stencil_block(), stream, d, wx, wy, wz, dd, s, z, rb, st);
+			LAUNCH(S, "spmv_dot", (k_spmv_dot<VecT, CoefT>), stencil_grid(d), stencil_block(), stream, d, wx, wy, wz, dd, s, z, rb, st);
 			if (mg) {
-				LAUNCH(S, (k_axpy2_norm<VecT, false>), fb, 256, stream, n, s, z, x, r, rb, st);
+				LAUNCH(S, "axpy2_norm", (k_axpy2_norm<VecT, false>), fb, 256, stream, n, s, z, x, r, rb, st);
 				CKR(precondition());
-				LAUNCH(S, k_beta_from_zr, 1, 1, stream, st);
-				LAUNCH(S, k_xpay<VecT>, fb, 256, stream, n, z, s, st);
+				LAUNCH(S, "beta_from_zr", k_beta_from_zr, 1, 1, stream, st);
+				LAUNCH(S, "xpay", k_xpay<VecT>, fb, 256, stream, n, z, s, st);
 			} else {
-				LAUNCH(S, (k_axpy2_norm<VecT, true>), fb, 256, stream, n, s, z, x, r, rb, st);
-				LAUNCH(S, k_xpay<VecT>, fb, 256, stream, n, r, s, st);
+				LAUNCH(S, "axpy2_norm", (k_axpy2_norm<VecT, true>), fb, 256, stream, n, s, z, x, r, rb, st);
+				LAUNCH(S, "xpay", k_xpay<VecT>, fb, 256, stream, n, r, s, st);
 			}
 		}
 		CK(cudaMemcpyAsync(S->h_state, st, sizeof(CGState), cudaMemcpyDeviceToHost, stream));
 		CK(cudaStreamSynchronize(stream));
+		S->prof.collect();
 		if (S->h_state->done) break;
 	}
 	CK(cudaMemcpyAsync(S->h_state, st, sizeof(CGState), cudaMemcpyDeviceToHost, stream));
@@ -364,20 +420,20 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	// fluid -> internal array with ghost planes (neighbour slabs fill them)
 	CK(cudaMemcpyAsync(phi, fluid_v, sizeof(RealT) * (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
 	CKR(halo(S, d, phi, stream));
-	LAUNCH(S, k_face_fractions<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, solid, (const RealT *)phi, areas, rhos);
+	LAUNCH(S, "face_fractions", k_face_fractions<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, solid, (const RealT *)phi, areas, rhos);
 	if (P.surface_tension != 0.0) {
 		RealT *curv = S->curv.ptr<RealT>(d);
 		if (!curv) { CKR(S->curv.alloc(d, sizeof(RealT))); curv = S->curv.ptr<RealT>(d); }
-		LAUNCH(S, k_curvature<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, curv);
+		LAUNCH(S, "curvature", k_curvature<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, curv);
 		CKR(halo(S, d, curv, stream));
-		LAUNCH(S, k_surface_tension<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)curv, crhos, vel, masks);
+		LAUNCH(S, "surface_tension", k_surface_tension<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)curv, crhos, vel, masks);
 	}
-	LAUNCH(S, k_label_rows<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, (const RealT *)phi, careas, crhos, in_rows);
+	LAUNCH(S, "label_rows", k_label_rows<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, (const RealT *)phi, careas, crhos, in_rows);
 	CKR(halo(S, d, in_rows, stream));
 	{
 		const bool share = sizeof(CoefT) == sizeof(float);
 		const MGLevel &L0 = S->levels[0].view;
-		LAUNCH(S, (k_build_system<RealT, CoefT, VecT>), cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, (const uint8_t *)in_rows, careas,
+		LAUNCH(S, "build_system", (k_build_system<RealT, CoefT, VecT>), cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, (const uint8_t *)in_rows, careas,
 		       crhos, cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->dd.ptr<CoefT>(d), share ? nullptr : L0.wx,
 		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.dd, S->b.ptr<VecT>(d), rb, st);
 		CKR(halo(S, d, S->wz.ptr<CoefT>(d), stream));
@@ -392,18 +448,19 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	CK(cudaEventRecord(S->ev[3], stream));
 	// pressure scatter + velocity update
 	if (!S->h_state->has_dirichlet && S->h_state->n_rows) {
-		LAUNCH(S, k_sum_rows<VecT>, flat_blocks(d.ncell), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows, rb, st);
+		LAUNCH(S, "sum_rows", k_sum_rows<VecT>, flat_blocks(d.ncell), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows, rb, st);
 		if (S->comm && !S->whole_grid) CKR(S->comm->allreduce_sum_x(st, stream) ? fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error()) : SHKZ_B200_OK);
 	}
-	LAUNCH(S, (k_store_pressure<RealT, VecT>), (unsigned)((d.ncell + 255) / 256), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows,
+	LAUNCH(S, "store_pressure", (k_store_pressure<RealT, VecT>), (unsigned)((d.ncell + 255) / 256), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows,
 	       (const CGState *)st, pres);
 	CKR(halo(S, d, pres, stream));
-	LAUNCH(S, k_update_velocity<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)pres, careas, crhos, vel, masks);
+	LAUNCH(S, "update_velocity", k_update_velocity<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)pres, careas, crhos, vel, masks);
 	if (pressure_v) CK(cudaMemcpyAsync(pressure_v, pres, sizeof(RealT) * (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
 	if (pressure_active) CK(cudaMemcpyAsync(pressure_active, in_rows, (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
 	CK(cudaEventRecord(S->ev[4], stream));
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
+	S->prof.collect();
 	if (stats) {
 		fill_stats(S, stats);
 		cudaEventElapsedTime(&stats->ms_assemble, S->ev[0], S->ev[1]);
@@ -561,6 +618,7 @@ void shkz_b200_destroy(shkz_b200_solver *S) {
 	S->partials.release(); S->counter.release(); S->state.release();
 	if (S->h_state) cudaFreeHost(S->h_state);
 	if (S->events) for (auto &e : S->ev) if (e) cudaEventDestroy(e);
+	S->prof.destroy();
 	delete S;
 }
 
@@ -654,12 +712,30 @@ int shkz_b200_resolve(shkz_b200_solver *S, const shkz_b200_params *params, shkz_
 	if (rc != SHKZ_B200_OK) return rc;
 	CK(cudaEventRecord(S->ev[3], stream));
 	CK(cudaStreamSynchronize(stream));
+	S->prof.collect();
 	if (stats) {
 		fill_stats(S, stats);
 		cudaEventElapsedTime(&stats->ms_setup, S->ev[1], S->ev[2]);
 		cudaEventElapsedTime(&stats->ms_solve, S->ev[2], S->ev[3]);
 		stats->ms_total = stats->ms_setup + stats->ms_solve;
 	}
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_profile_enable(shkz_b200_solver *S, int on) {
+	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	S->prof.reset();
+	S->prof.on = on != 0;
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_profile_count(shkz_b200_solver *S) { return S ? (int)S->prof.names.size() : 0; }
+
+int shkz_b200_profile_get(shkz_b200_solver *S, int index, char *name, size_t name_bytes, uint64_t *launches, double *total_ms) {
+	if (!S || index < 0 || (size_t)index >= S->prof.names.size()) return fail(SHKZ_B200_ERR_ARG, "profile index out of range");
+	if (name && name_bytes) { strncpy(name, S->prof.names[index].c_str(), name_bytes - 1); name[name_bytes - 1] = 0; }
+	if (launches) *launches = S->prof.count[index];
+	if (total_ms) *total_ms = S->prof.ms[index];
 	return SHKZ_B200_OK;
 }
 

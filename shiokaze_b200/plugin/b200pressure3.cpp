@@ -1,0 +1,215 @@
+/*
+ * b200pressure3 — Shiokaze module that replaces `macpressuresolver3` with the B200 CUDA path.
+ *
+ * Built as libshiokaze_b200pressure3.so against the reference's own headers and selected at run time with
+ *     Projection=b200pressure3
+ * through the reference's module loader (src/core/module.cpp:103-170: "lib"+"shiokaze_"+name+".so" via dlopen,
+ * then extern "C" create_instance()). It implements macproject3_interface
+ * (include/shiokaze/projection/macproject3_interface.h:38-101) with the same flags, console records and
+ * timer names as src/projection/macpressuresolver3.cpp, and delegates every computation to the C-ABI of
+ * include/shkz_b200.h. It contains no numerical code of its own and no CPU fallback: if the CUDA library
+ * reports an error the module prints it and exits, which is the reference's own fatal-error convention
+ * (src/core/module.cpp:67,114,142).
+ *
+ * Bridge contract: dense reads are array3::linearize() semantics
+ * (include/shiokaze/array/array3.h:198-208), velocity writes touch ACTIVE faces only (set / set_off),
+ * the pressure grid is cleared and then set exactly on the row set.
+ */
+#include <shiokaze/array/array3.h>
+#include <shiokaze/array/array_utility3.h>
+#include <shiokaze/array/macarray3.h>
+#include <shiokaze/core/console.h>
+#include <shiokaze/core/timer.h>
+#include <shiokaze/projection/macproject3_interface.h>
+#include <cstdint>
+#include <cstdlib>
+#include <string>
+#include <vector>
+//
+#include "../../include/shkz_b200.h"
+//
+SHKZ_USING_NAMESPACE
+//
+class b200pressure3 : public macproject3_interface {
+protected:
+	//
+	LONG_NAME("B200 MAC Pressure Solver 3D")
+	//
+	virtual void set_target_volume( double current_volume, double target_volume ) override {
+		m_current_volume = current_volume;
+		m_target_volume = target_volume;
+	}
+	//
+	static void fatal( const char *what ) {
+		console::dump( "<Red>b200pressure3: %s failed: %s<Default>\n", what, shkz_b200_last_error());
+		exit(-1);
+	}
+	// array3::linearize() with the activity mask alongside
+	static void gather( const array3<Real> &a, std::vector<Real> &values, std::vector<uint8_t> *active ) {
+		const shape3 s = a.shape();
+		values.assign(s.count(),a.get_background_value());
+		if( active ) active->assign(s.count(),0);
+		a.const_parallel_actives([&]( int i, int j, int k, const auto &it ) {
+			const size_t n = i + s.w * (j + s.h * (size_t)k);
+			values[n] = it();
+			if( active ) (*active)[n] = 1;
+		});
+		a.const_parallel_inside([&]( int i, int j, int k, const auto &it ) {
+			if( ! it.active()) values[i + s.w * (j + s.h * (size_t)k)] = it();
+		});
+	}
+	//
+	virtual void project( double dt,
+				macarray3<Real> &velocity,
+				const array3<Real> &solid,
+				const array3<Real> &fluid,
+				double surface_tension,
+				const std::vector<signed_rigidbody3_interface *> *rigidbodies ) override {
+		//
+		scoped_timer timer(this);
+		timer.tick(); console::dump( ">>> Pressure Projection (B200) started...\n" );
+		//
+		// Host -> dense buffers
+		timer.tick(); console::dump( "Gathering dense buffers..." );
+		std::vector<Real> vel[DIM3], solid_dense, fluid_dense;
+		std::vector<uint8_t> vel_active[DIM3];
+		for( int dim : DIMS3 ) gather(velocity[dim],vel[dim],&vel_active[dim]);
+		gather(fluid,fluid_dense,nullptr);
+		const bool fluid_levelset = array_utility3::levelset_exist(fluid);
+		bool have_solid = array_utility3::levelset_exist(solid);
+		if( have_solid && solid.shape() != m_shape.nodal()) {
+			console::dump( "<Red>b200pressure3: a solid level set must be nodal (shape+1).<Default>\n" );
+			exit(-1);
+		}
+		if( have_solid ) gather(solid,solid_dense,nullptr);
+		console::dump( "Done. Took %s\n", timer.stock("gather").c_str());
+		//
+		// Volume correction: the PI controller is host state, as in macpressuresolver3.cpp:204-217
+		shkz_b200_params params = m_cuda_param;
+		params.surface_tension = surface_tension;
+		params.apply_rhs_correct = 0;
+		params.rhs_correct = 0.0;
+		if( m_param.gain && m_target_volume ) {
+			double x = (m_current_volume-m_target_volume)/m_target_volume;
+			double y = m_y_prev + x*dt; m_y_prev = y;
+			double kp = m_param.gain * 2.3/(25.0*0.01);
+			double ki = kp*kp/16.0;
+			params.rhs_correct = -(kp*x+ki*y)/(x+1.0);
+			params.apply_rhs_correct = 1;
+			console::write(get_argument_name()+"_volume_correct_rhs", params.rhs_correct);
+		}
+		//
+		// The CUDA path
+		timer.tick(); console::dump( "Solving on the GPU...");
+		std::vector<Real> pressure(m_shape.count());
+		std::vector<uint8_t> pressure_active(m_shape.count());
+		void *vel_ptr[3] = { vel[0].data(), vel[1].data(), vel[2].data() };
+		uint8_t *act_ptr[3] = { vel_active[0].data(), vel_active[1].data(), vel_active[2].data() };
+		shkz_b200_stats stats;
+		if( shkz_b200_project_host(m_solver,dt,vel_ptr,act_ptr,have_solid ? solid_dense.data() : nullptr,fluid_dense.data(),
+				fluid_levelset,&params,pressure.data(),pressure_active.data(),&stats) != SHKZ_B200_OK ) fatal("shkz_b200_project_host");
+		console::write(get_argument_name()+"_number_projection_iteration", stats.iterations);
+		console::write(get_argument_name()+"_solid_fluid_fractions", stats.ms_assemble);
+		console::write(get_argument_name()+"_build_highres_linsystem", stats.ms_setup);
+		console::write(get_argument_name()+"_update_velocity", stats.ms_update);
+		console::dump( "Done. Took %d iterations, Reresid=%e. Took %s\n", stats.iterations, stats.reresid, timer.stock("linsolve").c_str());
+		//
+		// Dense buffers -> host grids
+		timer.tick(); console::dump( "Scattering results...");
+		m_pressure.clear();
+		for( int k=0; k<(int)m_shape.d; ++k ) for( int j=0; j<(int)m_shape.h; ++j ) for( int i=0; i<(int)m_shape.w; ++i ) {
+			const size_t n = i + m_shape.w * (j + m_shape.h * (size_t)k);
+			if( pressure_active[n] ) m_pressure.set(i,j,k,pressure[n]);
+		}
+		velocity.parallel_actives([&]( int dim, int i, int j, int k, auto &it, int tn ) {
+			const shape3 s = velocity[dim].shape();
+			const size_t n = i + s.w * (j + s.h * (size_t)k);
+			if( vel_active[dim][n] ) it.set(vel[dim][n]);
+			else it.set_off();
+		});
+		console::dump( "Done. Took %s\n", timer.stock("scatter").c_str());
+		console::dump( "<<< Projection done. Took %s.\n", timer.stock("projection").c_str());
+	}
+	//
+	virtual void configure( configuration &config ) override {
+		// the reference module's flags (macpressuresolver3.cpp:274-280)
+		bool second_order_fluid (true), second_order_solid (true), warm_start (false);
+		config.get_bool("SecondOrderAccurateFluid",second_order_fluid,"Whether to enforce second order accuracy");
+		config.get_bool("SecondOrderAccurateSolid",second_order_solid,"Whether to enforce second order accuracy for solid surfaces");
+		config.get_double("Gain",m_param.gain,"Rate for volume correction");
+		config.get_bool("WarmStart",warm_start,"Start from the solution of previous pressure");
+		config.set_default_bool("ReportProgress",false);
+		if( warm_start ) {
+			console::dump( "<Red>b200pressure3: WarmStart=Yes is not supported.<Default>\n" );
+			exit(-1);
+		}
+		shkz_b200_default_params(&m_cuda_param);
+		m_cuda_param.second_order_fluid = second_order_fluid;
+		m_cuda_param.second_order_solid = second_order_solid;
+		// the children's flags, under the groups the reference uses (macutility3.cpp:408-409, pcg.cpp:39-44)
+		{
+			configuration::auto_group group(config,"MAC Utility 3D","MacUtility");
+			config.get_double("EpsFluid",m_cuda_param.eps_fluid,"Minimal bound for fluid fraction");
+			config.get_double("EpsSolid",m_cuda_param.eps_solid,"Minimal bound for solid fraction");
+		}
+		{
+			configuration::auto_group group(config,"Linear System Solver","LinSolver");
+			double modified_ic (0.97), min_diag_ratio (0.25);
+			config.get_double("Residual",m_cuda_param.residual,"Tolerable residual");
+			config.get_unsigned("MaxIterations",m_cuda_param.max_iterations,"Maximal iteration count");
+			config.get_double("ModifiedIC",modified_ic,"Accepted for compatibility (the reference discards its MIC(0) result)");
+			config.get_double("MinDiagRatio",min_diag_ratio,"Accepted for compatibility");
+		}
+		// additive flags
+		std::string precision ("mixed"), precond ("mg");
+		config.get_string("Precision",precision,"CG arithmetic: mixed, fp64 or fp32");
+		config.get_string("Precond",precond,"Preconditioner: mg (multigrid V-cycle) or none (the reference's plain CG)");
+		config.get_integer("MGPreSweeps",m_cuda_param.mg_pre_sweeps,"Red-black sweeps before the coarse correction");
+		config.get_integer("MGPostSweeps",m_cuda_param.mg_post_sweeps,"Red-black sweeps after the coarse correction");
+		config.get_integer("GPU",m_device,"CUDA device index");
+		m_cuda_param.precision = precision == "fp64" ? SHKZ_B200_PREC_FP64 : (precision == "fp32" ? SHKZ_B200_PREC_FP32 : SHKZ_B200_PREC_MIXED);
+		m_cuda_param.precond = precond == "none" ? SHKZ_B200_PRECOND_NONE : SHKZ_B200_PRECOND_MG;
+	}
+	virtual void initialize( const shape3 &shape, double dx ) override {
+		m_shape = shape;
+		m_dx = dx;
+	}
+	virtual void post_initialize() override {
+		m_pressure.initialize(m_shape);
+		m_target_volume = m_current_volume = m_y_prev = 0.0;
+		if( m_solver ) { shkz_b200_destroy(m_solver); m_solver = nullptr; }
+		const int real = sizeof(Real) == sizeof(double) ? SHKZ_B200_REAL_F64 : SHKZ_B200_REAL_F32;
+		if( shkz_b200_create(m_shape.w,m_shape.h,m_shape.d,m_dx,real,m_device,&m_solver) != SHKZ_B200_OK ) fatal("shkz_b200_create");
+	}
+	virtual const array3<Real> * get_pressure() const override {
+		return &m_pressure;
+	}
+	virtual ~b200pressure3() {
+		if( m_solver ) shkz_b200_destroy(m_solver);
+	}
+	//
+	struct Parameters {
+		double gain {1.0};
+	};
+	Parameters m_param;
+	shkz_b200_params m_cuda_param;
+	shkz_b200_solver *m_solver {nullptr};
+	int m_device {0};
+	//
+	shape3 m_shape;
+	double m_dx {0.0};
+	array3<Real> m_pressure{this};
+	//
+	double m_target_volume {0.0};
+	double m_current_volume {0.0};
+	double m_y_prev {0.0};
+};
+//
+extern "C" module * create_instance() {
+	return new b200pressure3();
+}
+//
+extern "C" const char *license() {
+	return "MIT";
+}
+//

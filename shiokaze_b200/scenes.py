@@ -310,3 +310,14 @@ BENCH_SCENES = {
     "flip_splash": flip_splash,
     "liquid_box": liquid_box,
 }
+
+
+def standalone(slab: Scene) -> Scene:
+    """Re-label a z-slab as a whole grid of its own (nx x ny x nzl, same dx): the slab's top and bottom
+    planes become walls. Used to cut bounded CPU-baseline samples out of a large workload."""
+    import copy
+    s = copy.copy(slab)
+    s.nz = slab.nzl
+    s.zrange = (0, slab.nzl)
+    s.name = slab.name + "_slab"
+    return s

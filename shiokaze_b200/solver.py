@@ -160,6 +160,21 @@ class MacPressureSolver3:
         capi.check(capi.lib().shkz_b200_resolve(self._h, C.byref(self.params), C.byref(st), stream or None))
         return self._finish(st)
 
+    # -- per-kernel timing ---------------------------------------------------------------------------
+    def profile(self, on: bool = True):
+        capi.check(capi.lib().shkz_b200_profile_enable(self._h, int(on)))
+
+    def profile_table(self) -> dict:
+        """name -> (launches, total ms) accumulated since profile(True)."""
+        out = {}
+        L = capi.lib()
+        for i in range(L.shkz_b200_profile_count(self._h)):
+            name = C.create_string_buffer(64)
+            n, ms = C.c_uint64(), C.c_double()
+            capi.check(L.shkz_b200_profile_get(self._h, i, name, 64, C.byref(n), C.byref(ms)))
+            out[name.value.decode()] = (int(n.value), float(ms.value))
+        return out
+
     # -- test hook ----------------------------------------------------------------------------------
     def debug_fetch(self, name: str) -> np.ndarray:
         need = C.c_size_t()

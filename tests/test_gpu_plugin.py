@@ -1,0 +1,46 @@
+"""Drop-in test: the SAME headless Shiokaze host (oracle/ref_driver, the reference's own libraries and module
+loader) runs one project() with `Projection=macpressuresolver3` (the reference) and with
+`Projection=b200pressure3` (this repository's module -> C-ABI -> CUDA), on the same sparse grids."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import refio
+from shiokaze_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def have_plugin(real):
+    import os
+    return refio.ref_available(real) and os.path.isfile(os.path.join(refio.ref_dir(real), "libshiokaze_b200pressure3.so"))
+
+
+@pytest.mark.parametrize("real,tol", [("f32", 1e-3), ("f64", 1e-5)])
+@pytest.mark.parametrize("scene", ["dambreak_solid", "smoke", "flip"])
+def test_module_is_a_drop_in(cuda_device, real, tol, scene):
+    if not have_plugin(real):
+        pytest.skip("oracle/_ref (reference build + module) was not shipped to this box")
+    sc = {"dambreak_solid": lambda: scenes.dambreak(32, True), "smoke": lambda: scenes.smoke_plume(24),
+          "flip": lambda: scenes.flip_splash(40)}[scene]()
+    flags = {"Residual": 1e-10}
+    ref = refio.run_reference(sc, real, flags=flags)
+    ours = refio.run_reference(sc, real, flags={**flags, "Precision": "fp64"}, projection="b200pressure3")
+    assert "b200pressure3.so" in ours.stdout
+    assert np.array_equal(ours.pressure_active, ref.pressure_active)       # get_pressure() activity == row set
+    for d in range(3):
+        assert np.array_equal(ours.vel_active[d], ref.vel_active[d])       # set_off() on the same faces
+    assert rel_l2(ours.vel, ref.vel) < tol
+    assert 0 < ours.iterations < ref.iterations                            # MG-PCG needs far fewer iterations
+
+
+def test_module_reference_flags_and_volume_correction(cuda_device):
+    if not have_plugin("f32"):
+        pytest.skip("oracle/_ref (reference build + module) was not shipped to this box")
+    sc = scenes.dambreak(24, True)
+    flags = {"Residual": 1e-10, "SecondOrderAccurateFluid": "No", "SecondOrderAccurateSolid": "No", "EpsFluid": 0.05}
+    ref = refio.run_reference(sc, "f32", flags=flags, current_volume=1.05, target_volume=1.0)
+    ours = refio.run_reference(sc, "f32", flags={**flags, "Precond": "none", "Precision": "fp64"}, projection="b200pressure3",
+                               current_volume=1.05, target_volume=1.0)
+    assert rel_l2(ours.vel, ref.vel) < 1e-5
+    assert abs(ours.iterations - ref.iterations) <= max(3, 0.06 * ref.iterations)   # Precond=none is the reference's CG
