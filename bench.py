@@ -96,24 +96,28 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, levels_rows):
+def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, levels_rows, precond: str = "mg", sweeps=(2, 2)):
     """Algorithmic (minimum necessary) bytes one launch of `kernel` moves, counted on unknown rows
     (DESIGN.md 'Kernels and their rooflines'). V = CG vector bytes, C = operator coefficient bytes, MG is fp32."""
     V = 4 if precision == "fp32" else 8
     Cc = 8 if precision == "fp64" else 4
+    mg = precond == "mg"
+    b0 = 4 if (mg and V == 8) else 0          # float copy of r handed to multigrid
     name, _, lvl = kernel.partition("@")
     n = levels_rows[int(lvl)] if lvl else n_rows
+    pre, post = max(1, sweeps[0]), max(0, sweeps[1])
+    # one launch = one FULL red-black sweep: 4 coefficient arrays + b + x_old read, x_new written (fp32);
+    # the first pre-sweep does not read x_old, the first post-sweep also reads the coarse correction (1/8 value per cell)
+    sweep_avg = ((24.0 + 28.0 * (pre - 1)) + ((28.5 + 28.0 * (post - 1)) if post else 0.0)) / (pre + post)
     per_row = {
-        "spmv_dot": 2 * V + 4 * Cc,          # read s, wx wy wz dd ; write z (s.z fused)
-        "axpy2_norm": 6 * V,                  # read s x z r ; write x r (norms fused)
-        "xpay": 3 * V,                        # read z s ; write s
-        "copy_dot": 3 * V,
-        "to_mg": V + 4,
-        "from_mg": (4 + 2 * V) if V == 8 else 8,
-        # one colour: b, other-colour x, own x written (4 B each on n/2 cells) + 7 coefficient values per updated cell
-        "rbgs": (3 * 4 + 7 * 4) / 2.0,
-        "residual": 4 * 3 + 4 * 4,            # b, x, r + 4 coefficient arrays
-        "restrict": 4 + 0.5,
+        "cg_init": 4 * V + b0,                # read b ; write x r s (+ b0)
+        "spmv_dot": 2 * V + 4 * Cc,           # read s, wx wy wz dd ; write q (s.q fused)
+        "axpy2_norm": 6 * V + b0,             # read s q x r ; write x r (+ b0) (norms fused)
+        "xpay": (2 * V + 4) if mg else 3 * V, # read z s ; write s
+        "dot_rr": V,
+        "dot_zb": 8,
+        "sweep": sweep_avg,
+        "residual_restrict": 4 * 4 + 4 + 4 + 0.5,   # coefficients, b, x ; coarse b written
         "prolong_add": 8 + 0.5,
     }.get(name)
     return None if per_row is None else per_row * n
@@ -321,10 +325,11 @@ def run_ours(args):
     if rank == 0 and table:
         peak, how = measured_peak()
         levels_rows = [n_rows / (8 ** l) for l in range(16)]
-        solve_kernels = {k: v for k, v in table.items() if algorithmic_bytes_per_launch(k, n_rows, args.precision, levels_rows)}
+        ab = lambda k: algorithmic_bytes_per_launch(k, res.n_rows, args.precision, [res.n_rows / (8 ** l) for l in range(16)], args.precond, (args.pre, args.post))
+        solve_kernels = {k: v for k, v in table.items() if ab(k)}
         dom = max(solve_kernels, key=lambda k: solve_kernels[k][1])
         cnt, tot = solve_kernels[dom]
-        per_launch = algorithmic_bytes_per_launch(dom, res.n_rows, args.precision, [res.n_rows / (8 ** l) for l in range(16)])
+        per_launch = ab(dom)
         achieved = per_launch / (tot / cnt * 1e-3) / 1e9
         traffic = None
         try:
@@ -333,8 +338,7 @@ def run_ours(args):
         except Exception:
             pass
         total_profiled = sum(v[1] for v in table.values())
-        alg_total = sum((algorithmic_bytes_per_launch(k, res.n_rows, args.precision, [res.n_rows / (8 ** l) for l in range(16)]) or 0) * v[0]
-                        for k, v in table.items())
+        alg_total = sum((ab(k) or 0) * v[0] for k, v in table.items())
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": how, "launches": cnt, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_launch": per_launch,
                     "share_of_step": tot / total_profiled if total_profiled else None,

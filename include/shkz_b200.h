@@ -170,6 +170,12 @@ int shkz_b200_profile_get(shkz_b200_solver *solver, int index, char *name, size_
 /* ---- test hook: copy an internal device array to the host (names: see DESIGN.md, e.g. "diag","rhs") ---- */
 int shkz_b200_debug_fetch(shkz_b200_solver *solver, const char *name, void *dst, size_t dst_bytes, size_t *needed_bytes);
 
+
+/* ---- test hook: apply ONE multigrid V-cycle to the right-hand side of the last project() and keep the result for
+ * debug_fetch("vcycle"). legacy != 0 runs the unfused one-launch-per-colour kernels on dense grids instead of the
+ * fused tile kernels; the two must agree bit for bit (tests/test_gpu_parity.py). */
+int shkz_b200_debug_vcycle(shkz_b200_solver *solver, const shkz_b200_params *params, int legacy);
+
 #ifdef __cplusplus
 }
 #endif

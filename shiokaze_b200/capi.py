@@ -20,7 +20,7 @@ EXPORTS = [
     "shkz_b200_create", "shkz_b200_create_slab", "shkz_b200_destroy", "shkz_b200_project_host",
     "shkz_b200_project_device", "shkz_b200_resolve", "shkz_b200_comm_unique_id", "shkz_b200_slab_export",
     "shkz_b200_slab_connect", "shkz_b200_debug_fetch", "shkz_b200_profile_enable", "shkz_b200_profile_count",
-    "shkz_b200_profile_get",
+    "shkz_b200_profile_get", "shkz_b200_debug_vcycle",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
     L.shkz_b200_profile_enable.argtypes = [vp, C.c_int]
     L.shkz_b200_profile_count.argtypes = [vp]
     L.shkz_b200_profile_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    L.shkz_b200_debug_vcycle.argtypes = [vp, C.POINTER(Params), C.c_int]
     _lib = L
     return L
 

@@ -35,6 +35,29 @@ struct CGState {
 	int pad;
 };
 
+// Work decomposition of every solve kernel: the cell grid of a level is cut into TX x TY x bz tiles and
+// only tiles that hold at least one unknown are visited (compacted, ascending list built at assembly
+// time on the device). Kernels are persistent: a fixed grid strides over the list, whose length is read
+// from device memory, so launch geometry (and a captured CUDA graph) never depends on the scene.
+constexpr int TX = 64, TY = 16;
+
+struct Tiles {
+	const int *ids;    // active tile ids, ascending
+	const int *count;  // number of active tiles
+	int ntx, nty, ntz; // tile grid of the level
+	int bz;            // planes per tile (even)
+};
+
+__device__ __forceinline__ void tile_origin(const Tiles &T, int id, int &i0, int &j0, int &kb) {
+	const int tx = id % T.ntx;
+	const int r = id / T.ntx;
+	i0 = tx * TX;
+	j0 = (r % T.nty) * TY;
+	kb = (r / T.nty) * T.bz;
+}
+
+__device__ __forceinline__ int tile_of(const Tiles &T, int i, int j, int k) { return (i / TX) + T.ntx * ((j / TY) + T.nty * (k / T.bz)); }
+
 struct RedBuf {
 	double *partials;      // [blocks][N]
 	unsigned int *counter; // zero between kernels

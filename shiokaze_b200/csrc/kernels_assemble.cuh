@@ -221,13 +221,14 @@ __global__ void __launch_bounds__(256) k_label_rows(Dims d, const RealT *__restr
 //                 pure-Neumann rows whatever the coefficient precision ("difference form")
 //   rhs[c]      = sum -sgn*A*u/dx (+ volume-correction constant); 0 outside the row set
 // CoefT/VecT copies feed the CG operator; the float copies feed multigrid level 0 (NULL when CoefT is
-// float and level 0 shares the operator arrays).
+// float and level 0 shares the operator arrays). tile_flags (zeroed by the caller) marks the level-0 tiles
+// that hold at least one unknown.
 template <class RealT, class CoefT, class VecT>
 __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const RealT *__restrict__ phi, const uint8_t *__restrict__ in_rows,
                                                      ConstFaceGrids<RealT> areas, ConstFaceGrids<RealT> rhos, ConstFaceGrids<RealT> vel,
                                                      CoefT *__restrict__ wx, CoefT *__restrict__ wy, CoefT *__restrict__ wz, CoefT *__restrict__ dd,
                                                      float *__restrict__ mwx, float *__restrict__ mwy, float *__restrict__ mwz, float *__restrict__ mdd,
-                                                     VecT *__restrict__ rhs, RedBuf rb, CGState *st) {
+                                                     VecT *__restrict__ rhs, Tiles T, unsigned char *__restrict__ tile_flags, RedBuf rb, CGState *st) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	const int j = blockIdx.y * blockDim.y + threadIdx.y;
 	const int k = blockIdx.z;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
 			if (P.apply_rhs_correct) b = __dadd_rn(b, P.rhs_correct);
 			red[0] = fabs(b);
 			red[1] = 1.0;
+			tile_flags[tile_of(T, i, j, k)] = 1; // the solve only visits tiles that hold an unknown
 		}
 		wx[c] = (CoefT)lower[0]; wy[c] = (CoefT)lower[1]; wz[c] = (CoefT)lower[2]; dd[c] = (CoefT)dirichlet;
 		if (mwx != nullptr) { mwx[c] = (float)lower[0]; mwy[c] = (float)lower[1]; mwz[c] = (float)lower[2]; mdd[c] = (float)dirichlet; }

@@ -8,88 +8,41 @@
 // never need bounds logic (wrapped reads hit finite values times a zero coefficient), and constants are
 // annihilated exactly on pure-Neumann rows even with float coefficients.
 //
-// Thread layout for stencil kernels: a CTA owns a TX x TY column of cells and marches ZC planes in z
-// keeping the z-neighbours in registers; x/y neighbours are re-read through L1.
+// Every kernel is persistent over the level-0 list of active tiles (common.cuh): cells of tiles without
+// an unknown are never touched, so a liquid scene costs what its wet tiles cost. Block shape is
+// (TX, 8): a thread owns a cell column of the tile, two y sub-rows per tile.
 #pragma once
 #include "common.cuh"
 
 namespace shkz {
 
-constexpr int TX = 64, TY = 4, ZC = 16;
+constexpr int CG_BY = 8; // block = (TX, CG_BY)
+inline dim3 cg_block() { return dim3(TX, CG_BY, 1); }
 
-inline dim3 stencil_grid(const Dims &d) { return dim3((d.nx + TX - 1) / TX, (d.ny + TY - 1) / TY, (d.nzl + ZC - 1) / ZC); }
-inline dim3 stencil_block() { return dim3(TX, TY, 1); }
-
-// z = A s,  sz = s.z ; last block: alpha = rho / sz            (pcg_solver.h:276-277)
-template <class VecT, class CoefT>
-__global__ void __launch_bounds__(TX *TY) k_spmv_dot(Dims d, const CoefT *__restrict__ wx, const CoefT *__restrict__ wy, const CoefT *__restrict__ wz,
-                                                    const CoefT *__restrict__ dd, const VecT *__restrict__ s, VecT *__restrict__ z, RedBuf rb, CGState *st) {
-	if (st->done) return;
-	const int i = blockIdx.x * TX + threadIdx.x, j = blockIdx.y * TY + threadIdx.y;
-	const int kbeg = blockIdx.z * ZC, kend = min(kbeg + ZC, d.nzl);
-	double red[1] = {0.0};
-	if (i < d.nx && j < d.ny) {
-		long long c = i + (long long)d.nx * (j + (long long)d.ny * kbeg);
-		VecT sm = s[c - d.plane], sc = s[c];
-		CoefT wzc = wz[c];
-		for (int k = kbeg; k < kend; ++k, c += d.plane) {
-			const VecT sp = s[c + d.plane];
-			const CoefT wzp = wz[c + d.plane];
-			VecT v = (VecT)dd[c] * sc;
-			v += (VecT)wx[c] * (sc - s[c - 1]);
-			v += (VecT)wx[c + 1] * (sc - s[c + 1]);
-			v += (VecT)wy[c] * (sc - s[c - d.nx]);
-			v += (VecT)wy[c + d.nx] * (sc - s[c + d.nx]);
-			v += (VecT)wzc * (sc - sm);
-			v += (VecT)wzp * (sc - sp);
-			z[c] = v;
-			red[0] += (double)sc * (double)v;
-			sm = sc; sc = sp; wzc = wzp;
-		}
+// start of the solve: x = 0, r = b, s = 0 (and the float copy of r that feeds multigrid)    (pcg_solver.h:249-251)
+template <class VecT, bool WRITE_B0>
+__global__ void __launch_bounds__(TX *CG_BY) k_cg_init(Dims d, Tiles T, const VecT *__restrict__ b, VecT *__restrict__ x, VecT *__restrict__ r,
+                                                      VecT *__restrict__ s, float *__restrict__ b0) {
+	const int ntiles = *T.count;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+		if (i >= d.nx) continue;
+		for (int k = kb; k < ke; ++k)
+			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
+				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+				const VecT bv = b[c];
+				x[c] = (VecT)0;
+				s[c] = (VecT)0;
+				r[c] = bv;
+				if (WRITE_B0) b0[c] = (float)bv;
+			}
 	}
-	grid_reduce<1, 0u>(red, rb, [&](double (&t)[1]) {
-		st->sz = t[0];
-		st->alpha = st->rho / t[0];
-	});
 }
 
-// x += alpha s ; r -= alpha z ; |r|_inf ; r.r            (pcg_solver.h:278-285)
-// last block: convergence test, iteration count; for plain CG also beta and the new rho.
-template <class VecT, bool PLAIN>
-__global__ void __launch_bounds__(256) k_axpy2_norm(long long n, const VecT *__restrict__ s, const VecT *__restrict__ z, VecT *__restrict__ x, VecT *__restrict__ r,
-                                                   RedBuf rb, CGState *st) {
-	if (st->done) return;
-	const VecT alpha = (VecT)st->alpha;
-	double red[2] = {0.0, 0.0};
-	for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
-		x[c] += alpha * s[c];
-		const VecT rv = r[c] - alpha * z[c];
-		r[c] = rv;
-		red[0] = fmax(red[0], fabs((double)rv));
-		if (PLAIN) red[1] += (double)rv * (double)rv;
-	}
-	grid_reduce<2, 0x1u>(red, rb, [&](double (&t)[2]) {
-		st->rnorm = t[0];
-		st->iter += 1;
-		if (t[0] <= st->tol) { st->done = 1; st->converged = 1; }
-		else if (st->iter >= st->max_iter) st->done = 1;
-		if (PLAIN) { st->beta = t[1] / st->rho; st->rho = t[1]; }
-	});
-}
-
-// s = z + beta s   (pcg_solver.h:289; plain CG passes z = r)
-template <class VecT>
-__global__ void __launch_bounds__(256) k_xpay(long long n, const VecT *__restrict__ z, VecT *__restrict__ s, const CGState *__restrict__ st) {
-	if (st->done) return;
-	const VecT beta = (VecT)st->beta;
-	for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
-		s[c] = z[c] + beta * s[c];
-}
-
-// start of the solve: x = 0, s = z (= r for plain CG), rho = z.r         (pcg_solver.h:249-272)
-// r already holds b. FIRST: tol and the trivial-rhs exit.
-template <class VecT>
-__global__ void __launch_bounds__(256) k_cg_begin(long long n, double residual, int max_iter, CGState *st) {
+// FIRST scalar step: tol and the trivial-rhs exit                                         (pcg_solver.h:251-258)
+__global__ void k_cg_begin(double residual, int max_iter, CGState *st) {
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		const double factor = residual < 1e-30 ? 1e-30 : residual; // pcg_solver.h:239
 		st->tol = factor * st->bnorm;
@@ -98,30 +51,149 @@ __global__ void __launch_bounds__(256) k_cg_begin(long long n, double residual, 
 		st->converged = st->bnorm == 0.0 ? 1 : 0;
 		st->done = (st->bnorm == 0.0 || max_iter <= 0) ? 1 : 0;
 		st->rnorm = st->bnorm;
-		st->alpha = st->beta = st->sz = 0.0;
+		st->alpha = st->beta = st->sz = st->rho = 0.0;
 	}
 }
 
+// plain CG only: rho = r.r before the first iteration                                      (pcg_solver.h:262)
 template <class VecT>
-__global__ void __launch_bounds__(256) k_copy_dot(long long n, const VecT *__restrict__ z, const VecT *__restrict__ r, VecT *__restrict__ s, RedBuf rb, CGState *st) {
+__global__ void __launch_bounds__(TX *CG_BY) k_dot_rr(Dims d, Tiles T, const VecT *__restrict__ r, RedBuf rb, CGState *st) {
 	if (st->done) return;
 	double red[1] = {0.0};
-	for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
-		const VecT zv = z[c];
-		s[c] = zv;
-		red[0] += (double)zv * (double)r[c];
+	const int ntiles = *T.count;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+		if (i >= d.nx) continue;
+		for (int k = kb; k < ke; ++k)
+			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
+				const double v = (double)r[i + (long long)d.nx * (j + (long long)d.ny * k)];
+				red[0] += v * v;
+			}
 	}
 	grid_reduce<1, 0u>(red, rb, [&](double (&t)[1]) {
 		st->rho = t[0];
+		st->beta = 0.0;
 		if (t[0] == 0.0 || t[0] != t[0]) st->done = 1; // pcg_solver.h:263-271
 	});
 }
 
-// After a preconditioner application: beta = (z.r)_new / rho, rho = (z.r)_new   (pcg_solver.h:287-290)
-__global__ void k_beta_from_zr(CGState *st) {
+// multigrid path when the last V-cycle kernel could not fuse it: rho' = z.b0, beta = rho'/rho  (pcg_solver.h:286-288)
+__device__ __forceinline__ void finish_zr(CGState *st, double zr) {
+	st->beta = st->iter == 0 ? 0.0 : zr / st->rho;
+	st->rho = zr;
+	if (zr == 0.0 || zr != zr) st->done = 1; // pcg_solver.h:263-271
+}
+
+__global__ void __launch_bounds__(TX *CG_BY) k_dot_zb(Dims d, Tiles T, const float *__restrict__ z, const float *__restrict__ b0, RedBuf rb, CGState *st) {
 	if (st->done) return;
-	st->beta = st->rr / st->rho;
-	st->rho = st->rr;
+	double red[1] = {0.0};
+	const int ntiles = *T.count;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+		if (i >= d.nx) continue;
+		for (int k = kb; k < ke; ++k)
+			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
+				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+				red[0] += (double)z[c] * (double)b0[c];
+			}
+	}
+	grid_reduce<1, 0u>(red, rb, [&](double (&t)[1]) { finish_zr(st, t[0]); });
+}
+
+// s = z + beta s   (pcg_solver.h:289; plain CG passes z = r; the first iteration has beta = 0, s = 0)
+template <class VecT, class ZT>
+__global__ void __launch_bounds__(TX *CG_BY) k_xpay(Dims d, Tiles T, const ZT *__restrict__ z, VecT *__restrict__ s, const CGState *__restrict__ st) {
+	if (st->done) return;
+	const VecT beta = (VecT)st->beta;
+	const int ntiles = *T.count;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+		if (i >= d.nx) continue;
+		for (int k = kb; k < ke; ++k)
+			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
+				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+				s[c] = (VecT)z[c] + beta * s[c];
+			}
+	}
+}
+
+// q = A s,  sq = s.q ; last block: alpha = rho / sq            (pcg_solver.h:276-277)
+// A thread marches its cell column through the tile's planes keeping the z neighbours in registers.
+template <class VecT, class CoefT>
+__global__ void __launch_bounds__(TX *CG_BY) k_spmv_dot(Dims d, Tiles T, const CoefT *__restrict__ wx, const CoefT *__restrict__ wy, const CoefT *__restrict__ wz,
+                                                       const CoefT *__restrict__ dd, const VecT *__restrict__ s, VecT *__restrict__ q, RedBuf rb, CGState *st) {
+	if (st->done) return;
+	double red[1] = {0.0};
+	const int ntiles = *T.count;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+		if (i >= d.nx) continue;
+		for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
+			long long c = i + (long long)d.nx * (j + (long long)d.ny * kb);
+			VecT sm = s[c - d.plane], sc = s[c];
+			CoefT wzc = wz[c];
+			for (int k = kb; k < ke; ++k, c += d.plane) {
+				const VecT sp = s[c + d.plane];
+				const CoefT wzp = wz[c + d.plane];
+				VecT v = (VecT)dd[c] * sc;
+				v += (VecT)wx[c] * (sc - s[c - 1]);
+				v += (VecT)wx[c + 1] * (sc - s[c + 1]);
+				v += (VecT)wy[c] * (sc - s[c - d.nx]);
+				v += (VecT)wy[c + d.nx] * (sc - s[c + d.nx]);
+				v += (VecT)wzc * (sc - sm);
+				v += (VecT)wzp * (sc - sp);
+				q[c] = v;
+				red[0] += (double)sc * (double)v;
+				sm = sc; sc = sp; wzc = wzp;
+			}
+		}
+	}
+	grid_reduce<1, 0u>(red, rb, [&](double (&t)[1]) {
+		st->sz = t[0];
+		st->alpha = st->rho / t[0];
+	});
+}
+
+// x += alpha s ; r -= alpha q ; |r|_inf ; (plain CG: r.r) ; float copy of r for multigrid      (pcg_solver.h:278-285)
+// last block: convergence test, iteration count; for plain CG also beta and the new rho.
+template <class VecT, bool PLAIN, bool WRITE_B0>
+__global__ void __launch_bounds__(TX *CG_BY) k_axpy2_norm(Dims d, Tiles T, const VecT *__restrict__ s, const VecT *__restrict__ q, VecT *__restrict__ x,
+                                                         VecT *__restrict__ r, float *__restrict__ b0, RedBuf rb, CGState *st) {
+	if (st->done) return;
+	const VecT alpha = (VecT)st->alpha;
+	double red[2] = {0.0, 0.0};
+	const int ntiles = *T.count;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+		if (i >= d.nx) continue;
+		for (int k = kb; k < ke; ++k)
+			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
+				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+				x[c] += alpha * s[c];
+				const VecT rv = r[c] - alpha * q[c];
+				r[c] = rv;
+				if (WRITE_B0) b0[c] = (float)rv;
+				red[0] = fmax(red[0], fabs((double)rv));
+				if (PLAIN) red[1] += (double)rv * (double)rv;
+			}
+	}
+	grid_reduce<2, 0x1u>(red, rb, [&](double (&t)[2]) {
+		st->rnorm = t[0];
+		st->iter += 1;
+		if (t[0] <= st->tol) { st->done = 1; st->converged = 1; }
+		else if (st->iter >= st->max_iter) st->done = 1;
+		if (PLAIN) { st->beta = t[1] / st->rho; st->rho = t[1]; }
+	});
 }
 
 } // namespace shkz

@@ -10,113 +10,334 @@
 // that piecewise-constant transfer loses (the usual over-correction of unsmoothed aggregation).
 // Smoother: red-black Gauss-Seidel, colours by (i+j+k_global) parity, reversed order after the
 // coarse correction so that the V-cycle is a symmetric operator for CG.
+//
+// Kernels (all persistent over the level's list of active tiles, common.cuh):
+//   k_sweep             ONE launch = one full red-black sweep (both colours), out of place x_old -> x_new.
+//                       A CTA marches a TX x TY tile through its planes: the first colour of plane p+1 is
+//                       relaxed from x_old into a three-slot shared-memory ring of half-updated planes (with a
+//                       one-cell halo relaxed redundantly), then the second colour of plane p is relaxed from
+//                       the half-updated planes p-1, p, p+1. Every array is read once and x written once per
+//                       sweep (28 B/cell) instead of once per colour (56 B/cell). Options fold the neighbouring
+//                       V-cycle steps in: ZERO_X (first pre-sweep, x_old = 0 not read), PROLONG (first
+//                       post-sweep reads x_old + P e_coarse), DOT (last sweep on level 0 also reduces z.r).
+//   k_residual_restrict coarse b = P^T (b - A x) in one pass, no residual array.
+//   k_vcycle_tail       all levels small enough to live in shared memory run their part of the V-cycle in ONE
+//                       single-CTA launch (dozens of launch-latency-bound kernels otherwise).
 #pragma once
 #include "common.cuh"
-#include "kernels_cg.cuh"
 
 namespace shkz {
 
+// ---- the two arithmetic atoms; every smoother / residual in the library goes through these, with explicit
+// ---- fused multiply-adds so that fused, tail and legacy kernels agree bit for bit
+__device__ __forceinline__ float gs_diag(float w0, float w1, float w2, float w3, float w4, float w5, float dd) {
+	return dd + ((w0 + w1) + (w2 + w3) + (w4 + w5));
+}
+__device__ __forceinline__ float gs_relax(float w0, float w1, float w2, float w3, float w4, float w5, float dd, float b, float x0, float x1, float x2,
+                                          float x3, float x4, float x5) {
+	const float dg = gs_diag(w0, w1, w2, w3, w4, w5, dd);
+	float acc = b;
+	acc = __fmaf_rn(w0, x0, acc);
+	acc = __fmaf_rn(w1, x1, acc);
+	acc = __fmaf_rn(w2, x2, acc);
+	acc = __fmaf_rn(w3, x3, acc);
+	acc = __fmaf_rn(w4, x4, acc);
+	acc = __fmaf_rn(w5, x5, acc);
+	return dg > 0.f ? __fdividef(acc, dg) : 0.f;
+}
+__device__ __forceinline__ float gs_relax0(float w0, float w1, float w2, float w3, float w4, float w5, float dd, float b) {
+	const float dg = gs_diag(w0, w1, w2, w3, w4, w5, dd);
+	return dg > 0.f ? __fdividef(b, dg) : 0.f;
+}
+// b - A x at one cell; 0 on cells without an equation (their b may be stale)
+__device__ __forceinline__ float residual7(float w0, float w1, float w2, float w3, float w4, float w5, float dd, float b, float xc, float x0, float x1,
+                                           float x2, float x3, float x4, float x5) {
+	float v = __fmaf_rn(-dd, xc, b);
+	v = __fmaf_rn(w0, x0 - xc, v);
+	v = __fmaf_rn(w1, x1 - xc, v);
+	v = __fmaf_rn(w2, x2 - xc, v);
+	v = __fmaf_rn(w3, x3 - xc, v);
+	v = __fmaf_rn(w4, x4 - xc, v);
+	v = __fmaf_rn(w5, x5 - xc, v);
+	return gs_diag(w0, w1, w2, w3, w4, w5, dd) > 0.f ? v : 0.f;
+}
+
 struct MGLevel {
 	Dims d;
+	Tiles tiles;
 	float *wx, *wy, *wz, *dd; // with ghost planes, pointing at plane 0
-	float *x, *b, *r;
+	float *b;                 // right-hand side of the level
+	float *xa, *xb;           // ping-pong solution buffers
 };
 
-// One colour of a Gauss-Seidel sweep. Each thread owns a pair of x-adjacent cells and updates the
-// one whose parity matches. x == 0 on entry of the very first half sweep is exploited by ZERO_X.
-template <bool ZERO_X>
-__global__ void __launch_bounds__(256) k_rbgs(Dims d, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
-                                             const float *__restrict__ dd, const float *__restrict__ b, float *__restrict__ x, int color,
-                                             const CGState *__restrict__ st) {
+constexpr int SWEEP_THREADS = (TX / 2) * TY; // a thread owns two x-adjacent cells of the tile footprint
+constexpr int RING_CELLS = 2 * TX + 2 * TY;
+static_assert(RING_CELLS <= SWEEP_THREADS && (RING_CELLS % 32) == 0, "ring threads must be whole warps");
+inline dim3 sweep_block() { return dim3(TX / 2, TY, 1); }
+
+// One full red-black Gauss-Seidel sweep, colour FIRST then the other one, x_old -> x_new.
+template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
+__global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
+                                                        const float *__restrict__ dd, const float *__restrict__ b, const float *__restrict__ xo,
+                                                        float *__restrict__ xn, const float *__restrict__ ec, Dims dc, RedBuf rb, CGState *st) {
 	if (st && st->done) return;
-	const int ip = blockIdx.x * blockDim.x + threadIdx.x;
-	const int j = blockIdx.y * blockDim.y + threadIdx.y;
-	const int k = blockIdx.z;
-	const int i = 2 * ip + ((j + k + d.k0 + color) & 1);
-	if (i >= d.nx || j >= d.ny) return;
-	const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-	const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + d.nx], w4 = wz[c], w5 = wz[c + d.plane];
-	const float dg = dd[c] + ((w0 + w1) + (w2 + w3) + (w4 + w5));
-	float v = 0.f;
-	if (dg > 0.f) {
-		float acc = b[c];
-		if (!ZERO_X) {
-			acc += w0 * x[c - 1];
-			acc += w1 * x[c + 1];
-			acc += w2 * x[c - d.nx];
-			acc += w3 * x[c + d.nx];
-			acc += w4 * x[c - d.plane];
-			acc += w5 * x[c + d.plane];
+	__shared__ float H[3][TY + 2][TX + 2];
+	const int px = threadIdx.x, ty = threadIdx.y;
+	const int tid = px + (TX / 2) * ty;
+	const int ntiles = *T.count;
+	const long long nx = d.nx, ny = d.ny, plane = d.plane;
+	double red[1] = {0.0};
+
+	// x_old at (i,j,k) / flat index c (k may be a ghost plane; i, j may be one step outside the grid: such reads
+	// wrap to another finite slot of the allocation and only ever meet a zero coefficient)
+	auto XO = [&](long long c, int i, int j, int k) -> float {
+		if (ZERO_X) return 0.f;
+		float v = xo[c];
+		if (PROLONG) v += ec[(i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1))];
+		return v;
+	};
+	// value of cell (i,j) in the half-updated plane p: first-colour cells of in-slab planes relaxed from x_old
+	auto half_update = [&](int i, int j, int p, bool in_slab) -> float {
+		const long long c = i + nx * (j + ny * p);
+		if (in_slab && ((i + j + p + d.k0) & 1) == FIRST) {
+			const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
+			if (ZERO_X) return gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c]);
+			return gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], XO(c - 1, i - 1, j, p), XO(c + 1, i + 1, j, p), XO(c - nx, i, j - 1, p),
+			                XO(c + nx, i, j + 1, p), XO(c - plane, i, j, p - 1), XO(c + plane, i, j, p + 1));
 		}
-		v = __fdividef(acc, dg);
-	}
-	x[c] = v;
-}
+		return XO(c, i, j, p);
+	};
 
-// r = b - A x
-__global__ void __launch_bounds__(TX *TY) k_residual(Dims d, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
-                                                    const float *__restrict__ dd, const float *__restrict__ b, const float *__restrict__ x,
-                                                    float *__restrict__ r, const CGState *__restrict__ st) {
-	if (st && st->done) return;
-	const int i = blockIdx.x * TX + threadIdx.x, j = blockIdx.y * TY + threadIdx.y;
-	const int kbeg = blockIdx.z * ZC, kend = min(kbeg + ZC, d.nzl);
-	if (i >= d.nx || j >= d.ny) return;
-	long long c = i + (long long)d.nx * (j + (long long)d.ny * kbeg);
-	float xm = x[c - d.plane], xc = x[c], wzc = wz[c];
-	for (int k = kbeg; k < kend; ++k, c += d.plane) {
-		const float xp = x[c + d.plane], wzp = wz[c + d.plane];
-		float v = b[c] - dd[c] * xc;
-		v += wx[c] * (x[c - 1] - xc);
-		v += wx[c + 1] * (x[c + 1] - xc);
-		v += wy[c] * (x[c - d.nx] - xc);
-		v += wy[c + d.nx] * (x[c + d.nx] - xc);
-		v += wzc * (xm - xc);
-		v += wzp * (xp - xc);
-		r[c] = v;
-		xm = xc; xc = xp; wzc = wzp;
-	}
-}
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int ke = min(kb + T.bz, d.nzl);
+		const int i = i0 + 2 * px, j = j0 + ty;
+		const bool v0 = i < d.nx && j < d.ny, v1 = i + 1 < d.nx && j < d.ny;
+		// halo ring cell of this thread (first RING_CELLS threads = whole warps)
+		const bool ring = tid < RING_CELLS;
+		int ri, rj, rlx, rly;
+		if (tid < TX) { ri = i0 + tid; rj = j0 - 1; rlx = tid + 1; rly = 0; }
+		else if (tid < 2 * TX) { ri = i0 + tid - TX; rj = j0 + TY; rlx = tid - TX + 1; rly = TY + 1; }
+		else if (tid < 2 * TX + TY) { ri = i0 - 1; rj = j0 + tid - 2 * TX; rlx = 0; rly = tid - 2 * TX + 1; }
+		else { ri = i0 + TX; rj = j0 + tid - 2 * TX - TY; rlx = TX + 1; rly = tid - 2 * TX - TY + 1; }
+		const bool rv = ring && ri >= 0 && ri < d.nx && rj >= 0 && rj < d.ny;
 
-// coarse b = P^T r (sum over the 2x2x2 children that exist)
-__global__ void __launch_bounds__(256) k_restrict(Dims df, Dims dc, const float *__restrict__ r, float *__restrict__ bc, const CGState *__restrict__ st) {
-	if (st && st->done) return;
-	const int I = blockIdx.x * blockDim.x + threadIdx.x;
-	const int J = blockIdx.y * blockDim.y + threadIdx.y;
-	const int K = blockIdx.z;
-	if (I >= dc.nx || J >= dc.ny) return;
-	float acc = 0.f;
+		float hm0 = 0.f, hm1 = 0.f, hc0 = 0.f, hc1 = 0.f;
+		for (int p = kb - 1; p <= ke; ++p) {
+			const int slot = (p + 3) % 3;
+			const bool in_slab = p >= 0 && p < d.nzl;
+			// phase 1: half-updated plane p (own pair + ring)
+			const float hp0 = v0 ? half_update(i, j, p, in_slab) : 0.f;
+			const float hp1 = v1 ? half_update(i + 1, j, p, in_slab) : 0.f;
+			H[slot][ty + 1][2 * px + 1] = hp0;
+			H[slot][ty + 1][2 * px + 2] = hp1;
+			if (ring) H[slot][rly][rlx] = rv ? half_update(ri, rj, p, in_slab) : 0.f;
+			__syncthreads();
+			// phase 2: finish plane k = p - 1 from the half-updated planes k-1 (hm), k (hc, shared memory), k+1 (hp)
+			const int k = p - 1;
+			if (k >= kb) {
+				const int ks = (k + 3) % 3;
+				const int par = (i + j + k + d.k0) & 1; // colour of the even cell of the pair
 #pragma unroll
-	for (int dk = 0; dk < 2; ++dk)
-#pragma unroll
-		for (int dj = 0; dj < 2; ++dj)
-#pragma unroll
-			for (int di = 0; di < 2; ++di) {
-				const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
-				if (i < df.nx && j < df.ny && k < df.nzl) acc += r[i + (long long)df.nx * (j + (long long)df.ny * k)];
+				for (int e = 0; e < 2; ++e) {
+					if (!(e ? v1 : v0)) continue;
+					const long long c = (i + e) + nx * (j + ny * k);
+					const int lx = 2 * px + e + 1, ly = ty + 1;
+					float xnew = e ? hc1 : hc0;
+					if (((par + e) & 1) != FIRST) {
+						const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
+						xnew = gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], H[ks][ly][lx - 1], H[ks][ly][lx + 1], H[ks][ly - 1][lx], H[ks][ly + 1][lx],
+						                e ? hm1 : hm0, e ? hp1 : hp0);
+					}
+					xn[c] = xnew;
+					if (DOT) red[0] += (double)xnew * (double)b[c];
+				}
 			}
-	bc[I + (long long)dc.nx * (J + (long long)dc.ny * K)] = acc;
+			hm0 = hc0; hm1 = hc1; hc0 = hp0; hc1 = hp1;
+		}
+		__syncthreads(); // the next tile's first slot may be one this tile's last phase 2 still reads
+	}
+	if (DOT) {
+		grid_reduce<1, 0u>(red, rb, [&](double (&tot)[1]) {
+			const double zr = tot[0];
+			st->beta = st->iter == 0 ? 0.0 : zr / st->rho; // pcg_solver.h:286-288
+			st->rho = zr;
+			if (zr == 0.0 || zr != zr) st->done = 1;        // pcg_solver.h:263-271
+		});
+	}
 }
 
-// x += P e
-__global__ void __launch_bounds__(256) k_prolong_add(Dims df, Dims dc, const float *__restrict__ ec, float *__restrict__ x, const CGState *__restrict__ st) {
+// coarse b = P^T (b - A x): block (TX/2, TY/2), one coarse column per thread, aggregates never straddle tiles
+inline dim3 restrict_block() { return dim3(TX / 2, TY / 2, 1); }
+__global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_residual_restrict(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy,
+                                                                          const float *__restrict__ wz, const float *__restrict__ dd, const float *__restrict__ b,
+                                                                          const float *__restrict__ x, Dims dc, float *__restrict__ bc,
+                                                                          const CGState *__restrict__ st) {
 	if (st && st->done) return;
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const int j = blockIdx.y * blockDim.y + threadIdx.y;
-	const int k = blockIdx.z;
-	if (i >= df.nx || j >= df.ny) return;
-	x[i + (long long)df.nx * (j + (long long)df.ny * k)] += ec[(i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1))];
+	const int ntiles = *T.count;
+	const long long nx = d.nx, ny = d.ny, plane = d.plane;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int ke = min(kb + T.bz, d.nzl);
+		const int I = (i0 >> 1) + threadIdx.x, J = (j0 >> 1) + threadIdx.y;
+		if (I >= dc.nx || J >= dc.ny) continue;
+		for (int k = kb; k < ke; k += 2) {
+			float acc = 0.f;
+#pragma unroll
+			for (int dk = 0; dk < 2; ++dk)
+#pragma unroll
+				for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+					for (int di = 0; di < 2; ++di) {
+						const int i = 2 * I + di, j = 2 * J + dj, kk = k + dk;
+						if (i < d.nx && j < d.ny && kk < d.nzl) {
+							const long long c = i + nx * (j + ny * kk);
+							acc += residual7(wx[c], wx[c + 1], wy[c], wy[c + nx], wz[c], wz[c + plane], dd[c], b[c], x[c], x[c - 1], x[c + 1], x[c - nx],
+							                 x[c + nx], x[c - plane], x[c + plane]);
+						}
+					}
+			bc[I + (long long)dc.nx * (J + (long long)dc.ny * (k >> 1))] = acc;
+		}
+	}
 }
 
-// Coarse operator = scale * P^T A P (setup, once per projection): coarse face coupling = sum of the four
-// fine couplings crossing the coarse face, coarse dd = sum of the children's dd.
-__global__ void __launch_bounds__(256) k_coarsen_operator(Dims df, Dims dc, float scale, const float *__restrict__ wx, const float *__restrict__ wy,
+// x_new = x_old + P e (only used when MGPostSweeps = 0; otherwise the first post-sweep folds it in)
+__global__ void __launch_bounds__(TX *8) k_prolong_add(Dims d, Tiles T, Dims dc, const float *__restrict__ ec, const float *__restrict__ xo, float *__restrict__ xn,
+                                                      const CGState *__restrict__ st) {
+	if (st && st->done) return;
+	const int ntiles = *T.count;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+		if (i >= d.nx) continue;
+		for (int k = kb; k < ke; ++k)
+			for (int j = j0 + threadIdx.y; j < je; j += 8) {
+				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+				xn[c] = xo[c] + ec[(i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1))];
+			}
+	}
+}
+
+// ---- the shared-memory tail of the V-cycle ----------------------------------------------------------------
+constexpr int TAIL_MAX_LEVELS = 12;
+constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_ARRAYS = 6; // wx wy wz dd x b
+
+struct TailLevel {
+	Dims d;
+	const float *wx, *wy, *wz, *dd; // global, pointing at plane 0 (ghost planes allocated)
+	int offset;                     // first float of this level's block in shared memory
+	int stride;                     // ncell + 2*plane: floats per array
+};
+struct TailArgs {
+	int nlev;
+	int pre, post, coarse;
+	const float *b_in; // right-hand side of the first tail level (global)
+	float *x_out;      // its solution (global)
+	TailLevel L[TAIL_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(TAIL_THREADS) k_vcycle_tail(TailArgs A, const CGState *__restrict__ st) {
+	if (st && st->done) return;
+	extern __shared__ float sm[];
+	const int tid = threadIdx.x;
+	auto arr = [&](int l, int which) -> float * { return sm + A.L[l].offset + which * A.L[l].stride + (int)A.L[l].d.plane; };
+	// stage the operators; x and the ghost planes of b start at zero
+	for (int l = 0; l < A.nlev; ++l) {
+		const TailLevel &L = A.L[l];
+		const int plane = (int)L.d.plane, n = L.stride;
+		float *wx = arr(l, 0), *wy = arr(l, 1), *wz = arr(l, 2), *dd = arr(l, 3), *x = arr(l, 4), *b = arr(l, 5);
+		for (int c = tid - plane; c < n - plane; c += TAIL_THREADS) {
+			wx[c] = L.wx[c]; wy[c] = L.wy[c]; wz[c] = L.wz[c]; dd[c] = L.dd[c];
+			x[c] = 0.f;
+			b[c] = (l == 0 && c >= 0 && c < (int)L.d.ncell) ? A.b_in[c] : 0.f;
+		}
+	}
+	__syncthreads();
+	auto half = [&](int l, int color, bool zero_x) {
+		const Dims &d = A.L[l].d;
+		const int nx = d.nx, plane = (int)d.plane, n = (int)d.ncell;
+		const float *wx = arr(l, 0), *wy = arr(l, 1), *wz = arr(l, 2), *dd = arr(l, 3), *b = arr(l, 5);
+		float *x = arr(l, 4);
+		for (int c = tid; c < n; c += TAIL_THREADS) {
+			const int k = c / plane, rem = c - k * plane, j = rem / nx, i = rem - j * nx;
+			if (((i + j + k + d.k0) & 1) != color) continue;
+			const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
+			x[c] = zero_x ? gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c])
+			              : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], x[c - 1], x[c + 1], x[c - nx], x[c + nx], x[c - plane], x[c + plane]);
+		}
+		__syncthreads();
+	};
+	for (int l = 0; l < A.nlev; ++l) { // descend
+		const bool last = l + 1 == A.nlev;
+		const int sweeps = last ? A.coarse : A.pre;
+		for (int sw = 0; sw < sweeps; ++sw) {
+			half(l, 0, sw == 0);
+			half(l, 1, false);
+		}
+		if (last) break;
+		const Dims &d = A.L[l].d, &dc = A.L[l + 1].d;
+		const int nx = d.nx, ny = d.ny, plane = (int)d.plane;
+		const float *wx = arr(l, 0), *wy = arr(l, 1), *wz = arr(l, 2), *dd = arr(l, 3), *x = arr(l, 4), *b = arr(l, 5);
+		float *bc = arr(l + 1, 5);
+		const int cplane = (int)dc.plane;
+		for (int C = tid; C < (int)dc.ncell; C += TAIL_THREADS) {
+			const int K = C / cplane, rem = C - K * cplane, J = rem / dc.nx, I = rem - J * dc.nx;
+			float acc = 0.f;
+			for (int dk = 0; dk < 2; ++dk)
+				for (int dj = 0; dj < 2; ++dj)
+					for (int di = 0; di < 2; ++di) {
+						const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
+						if (i < nx && j < ny && k < d.nzl) {
+							const int c = i + nx * (j + ny * k);
+							acc += residual7(wx[c], wx[c + 1], wy[c], wy[c + nx], wz[c], wz[c + plane], dd[c], b[c], x[c], x[c - 1], x[c + 1], x[c - nx],
+							                 x[c + nx], x[c - plane], x[c + plane]);
+						}
+					}
+			bc[C] = acc;
+		}
+		__syncthreads();
+	}
+	for (int l = A.nlev - 1; l >= 0; --l) { // ascend
+		const bool last = l + 1 == A.nlev;
+		if (!last) {
+			const Dims &d = A.L[l].d, &dc = A.L[l + 1].d;
+			const int nx = d.nx, plane = (int)d.plane;
+			float *x = arr(l, 4);
+			const float *ec = arr(l + 1, 4);
+			for (int c = tid; c < (int)d.ncell; c += TAIL_THREADS) {
+				const int k = c / plane, rem = c - k * plane, j = rem / nx, i = rem - j * nx;
+				x[c] += ec[(i >> 1) + dc.nx * ((j >> 1) + dc.ny * (k >> 1))];
+			}
+			__syncthreads();
+		}
+		const int sweeps = last ? A.coarse : A.post;
+		for (int sw = 0; sw < sweeps; ++sw) {
+			half(l, 1, false);
+			half(l, 0, false);
+		}
+	}
+	const float *x = arr(0, 4);
+	for (int c = tid; c < (int)A.L[0].d.ncell; c += TAIL_THREADS) A.x_out[c] = x[c];
+}
+
+// ---- hierarchy setup -----------------------------------------------------------------------------------------
+// Coarse operator = scale * P^T A P (once per projection): coarse face coupling = sum of the four fine
+// couplings crossing the coarse face, coarse dd = sum of the children's dd. Flags the coarse tile of every
+// coarse cell that carries an equation.
+__global__ void __launch_bounds__(256) k_coarsen_operator(Dims df, Dims dc, Tiles Tc, float scale, const float *__restrict__ wx, const float *__restrict__ wy,
                                                          const float *__restrict__ wz, const float *__restrict__ dd, float *__restrict__ cwx,
-                                                         float *__restrict__ cwy, float *__restrict__ cwz, float *__restrict__ cdd) {
+                                                         float *__restrict__ cwy, float *__restrict__ cwz, float *__restrict__ cdd,
+                                                         unsigned char *__restrict__ tile_flags) {
 	const int I = blockIdx.x * blockDim.x + threadIdx.x;
 	const int J = blockIdx.y * blockDim.y + threadIdx.y;
 	const int K = blockIdx.z;
 	if (I >= dc.nx || J >= dc.ny) return;
 	float sx = 0.f, sy = 0.f, sz = 0.f, sd = 0.f;
+	bool live = false;
 #pragma unroll
 	for (int dk = 0; dk < 2; ++dk)
 #pragma unroll
@@ -126,36 +347,48 @@ __global__ void __launch_bounds__(256) k_coarsen_operator(Dims df, Dims dc, floa
 				const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
 				if (i >= df.nx || j >= df.ny || k >= df.nzl) continue;
 				const long long c = i + (long long)df.nx * (j + (long long)df.ny * k);
-				sd += dd[c];
-				if (!di) sx += wx[c];
-				if (!dj) sy += wy[c];
-				if (!dk) sz += wz[c];
+				const float a = wx[c], bq = wy[c], cq = wz[c], e = dd[c];
+				sd += e;
+				if (!di) sx += a;
+				if (!dj) sy += bq;
+				if (!dk) sz += cq;
+				// a child with an equation has a positive diagonal: its own lower faces, its upper faces, or dd
+				live = live || a > 0.f || bq > 0.f || cq > 0.f || e > 0.f || wx[c + 1] > 0.f || wy[c + df.nx] > 0.f || wz[c + df.plane] > 0.f;
 			}
 	const long long C = I + (long long)dc.nx * (J + (long long)dc.ny * K);
 	cwx[C] = scale * sx;
 	cwy[C] = scale * sy;
 	cwz[C] = scale * sz;
 	cdd[C] = scale * sd;
+	if (live) tile_flags[tile_of(Tc, I, J, K)] = 1;
 }
 
-// Hand-off CG -> MG: b0 = float(r)
-template <class VecT>
-__global__ void __launch_bounds__(256) k_to_mg(long long n, const VecT *__restrict__ r, float *__restrict__ b, const CGState *__restrict__ st) {
-	if (st->done) return;
-	for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) b[c] = (float)r[c];
-}
-
-// Hand-off MG -> CG: z = x0, rr = z.r                                  (pcg_solver.h:286-287)
-template <class VecT>
-__global__ void __launch_bounds__(256) k_from_mg(long long n, const float *__restrict__ x0, const VecT *__restrict__ r, VecT *__restrict__ z, RedBuf rb, CGState *st) {
-	if (st->done) return;
-	double red[1] = {0.0};
-	for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
-		const VecT zv = (VecT)x0[c];
-		if ((const void *)x0 != (const void *)z) z[c] = zv;
-		red[0] += (double)zv * (double)r[c];
+// flags -> ascending id list + count (single CTA; tile grids are at most a few 10^4 entries)
+__global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned char *__restrict__ flags, int n, int *__restrict__ ids, int *__restrict__ count) {
+	__shared__ int warp_sums[32];
+	__shared__ int base;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) base = 0;
+	__syncthreads();
+	for (int start = 0; start < n; start += 1024) {
+		const int idx = start + tid;
+		const int f = (idx < n && flags[idx]) ? 1 : 0;
+		const unsigned ballot = __ballot_sync(0xffffffffu, f);
+		const int before = __popc(ballot & ((1u << lane) - 1u));
+		if (lane == 0) warp_sums[wid] = __popc(ballot);
+		__syncthreads();
+		int woff = 0;
+		for (int w = 0; w < wid; ++w) woff += warp_sums[w];
+		if (f) ids[base + woff + before] = idx;
+		__syncthreads();
+		if (tid == 0) {
+			int tot = 0;
+			for (int w = 0; w < 32; ++w) tot += warp_sums[w];
+			base += tot;
+		}
+		__syncthreads();
 	}
-	grid_reduce<1, 0u>(red, rb, [&](double (&t)[1]) { st->rr = t[0]; });
+	if (tid == 0) *count = base;
 }
 
 } // namespace shkz

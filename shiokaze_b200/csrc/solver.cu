@@ -14,6 +14,7 @@
 #include "kernels_assemble.cuh"
 #include "kernels_cg.cuh"
 #include "kernels_mg.cuh"
+#include "kernels_legacy.cuh"
 #include "slab_comm.h"
 
 using namespace shkz;
@@ -137,9 +138,12 @@ struct Profiler {
 
 struct HostLevel {
 	Dims d;
-	std::string tag_rbgs, tag_residual, tag_restrict, tag_prolong, tag_coarsen;
-	CellArray wx, wy, wz, dd, x, b, r;
-	bool own_coef = true, own_x = true, own_b = true; // level 0 may alias CG arrays
+	int bz = 4, tiles_total = 0;
+	std::string tag_sweep, tag_restrict, tag_prolong, tag_coarsen, tag_compact;
+	CellArray wx, wy, wz, dd, xa, xb, b;
+	CellArray legacy_r; // residual array of the unfused validation path (allocated on first use)
+	bool own_coef = true, own_b = true; // level 0 may alias CG arrays
+	PlainArray tile_flags, tile_ids, tile_count;
 	MGLevel view;
 };
 
@@ -150,6 +154,7 @@ struct shkz_b200_solver {
 	double dx = 0;
 	int real = SHKZ_B200_REAL_F32;
 	int device = 0;
+	int num_sms = 148;
 	size_t real_bytes = 4;
 	bool whole_grid = true;
 	// geometry / assembly products (RealT)
@@ -159,13 +164,18 @@ struct shkz_b200_solver {
 	// operator + CG vectors; element sizes depend on the precision mode they were allocated for
 	int alloc_precision = -1;
 	CellArray wx, wy, wz, dd; // CoefT
-	CellArray b, x, r, s, z;    // VecT
+	CellArray b, x, r, s, q;    // VecT
 	std::vector<HostLevel> levels;
 	int mg_min_size_built = -1;
+	int tail_first = -1;        // first level of the shared-memory tail of the V-cycle (-1: none)
+	size_t tail_smem = 0;
+	TailArgs tail_args{};
+	std::map<const void *, int> occupancy; // resident CTAs per SM of each persistent kernel
 	// reductions / control
 	PlainArray partials, counter, state;
 	CGState *h_state = nullptr; // pinned
 	size_t max_blocks = 0;
+	unsigned last_iterations = 0; // of the previous solve: sizes the first batch of iterations before the host looks
 	// host-call staging (device)
 	PlainArray st_vel[3], st_act[3], st_solid, st_fluid, st_pressure, st_pact;
 	// slab communicator
@@ -174,6 +184,8 @@ struct shkz_b200_solver {
 	uint64_t launches = 0;
 	Profiler prof;
 	bool have_system = false;
+	bool have_hierarchy = false;
+	const float *debug_vcycle_result = nullptr;
 	AsmParams last_asm{};
 	cudaEvent_t ev[8]{};
 	bool events = false;
@@ -185,16 +197,27 @@ struct shkz_b200_solver {
 namespace {
 
 void release_precision_arrays(shkz_b200_solver *S) {
-	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd, &S->b, &S->x, &S->r, &S->s, &S->z}) a->release();
+	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd, &S->b, &S->x, &S->r, &S->s, &S->q}) a->release();
 	for (HostLevel &L : S->levels) {
 		if (L.own_coef) { L.wx.release(); L.wy.release(); L.wz.release(); L.dd.release(); }
-		if (L.own_x) L.x.release();
 		if (L.own_b) L.b.release();
-		L.r.release();
+		L.xa.release(); L.xb.release(); L.legacy_r.release();
+		L.tile_flags.release(); L.tile_ids.release(); L.tile_count.release();
 	}
 	S->levels.clear();
 	S->alloc_precision = -1;
 	S->have_system = false;
+	S->have_hierarchy = false;
+	S->tail_first = -1;
+}
+
+// planes per tile: as deep as possible (each tile relaxes two extra halo planes) while the level still
+// yields about one full wave of tiles
+int pick_bz(const Dims &d) {
+	const long long xy = (long long)((d.nx + TX - 1) / TX) * ((d.ny + TY - 1) / TY);
+	int bz = 32;
+	while (bz > 4 && xy * ((d.nzl + bz - 1) / bz) < 592) bz >>= 1;
+	return bz;
 }
 
 template <class VecT, class CoefT>
@@ -204,11 +227,13 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 	release_precision_arrays(S);
 	const Dims &d = S->d;
 	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd}) CKR(a->alloc(d, sizeof(CoefT)));
-	for (CellArray *a : {&S->b, &S->x, &S->r, &S->s, &S->z}) CKR(a->alloc(d, sizeof(VecT)));
-	// multigrid hierarchy (always allocated: switching the preconditioner must not reallocate)
+	for (CellArray *a : {&S->b, &S->x, &S->r, &S->s, &S->q}) CKR(a->alloc(d, sizeof(VecT)));
+	// multigrid hierarchy (always allocated: switching the preconditioner must not reallocate; level 0 also
+	// carries the tile list every CG kernel runs over)
 	Dims cur = d;
 	for (int l = 0;; ++l) {
-		HostLevel L;
+		S->levels.emplace_back();
+		HostLevel &L = S->levels.back();
 		L.d = cur;
 		if (l == 0 && sizeof(CoefT) == sizeof(float)) {
 			L.own_coef = false;
@@ -217,25 +242,64 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 			for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.dd}) CKR(a->alloc(cur, sizeof(float)));
 		}
 		if (l == 0 && sizeof(VecT) == sizeof(float)) {
-			L.own_x = L.own_b = false;
-			L.x = S->z; // the V-cycle writes z directly
-			L.b = S->r; // and smooths against r directly
+			L.own_b = false;
+			L.b = S->r; // an all-float CG smooths against r directly
 		} else {
-			CKR(L.x.alloc(cur, sizeof(float)));
 			CKR(L.b.alloc(cur, sizeof(float)));
 		}
-		CKR(L.r.alloc(cur, sizeof(float)));
-		L.tag_rbgs = "rbgs@" + std::to_string(l); L.tag_residual = "residual@" + std::to_string(l); L.tag_restrict = "restrict@" + std::to_string(l);
-		L.tag_prolong = "prolong_add@" + std::to_string(l); L.tag_coarsen = "coarsen_operator@" + std::to_string(l);
+		CKR(L.xa.alloc(cur, sizeof(float)));
+		CKR(L.xb.alloc(cur, sizeof(float)));
+		L.bz = pick_bz(cur);
+		const int ntx = (cur.nx + TX - 1) / TX, nty = (cur.ny + TY - 1) / TY, ntz = (cur.nzl + L.bz - 1) / L.bz;
+		L.tiles_total = ntx * nty * ntz;
+		CKR(L.tile_flags.alloc((size_t)L.tiles_total));
+		CKR(L.tile_ids.alloc((size_t)L.tiles_total * sizeof(int)));
+		CKR(L.tile_count.alloc(sizeof(int)));
+		const std::string n = std::to_string(l);
+		L.tag_sweep = "sweep@" + n; L.tag_restrict = "residual_restrict@" + n; L.tag_prolong = "prolong_add@" + n;
+		L.tag_coarsen = "coarsen_operator@" + n; L.tag_compact = "compact_tiles@" + n;
 		L.view.d = cur;
+		L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz};
 		L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.dd = L.dd.ptr<float>(cur);
-		L.view.x = L.x.ptr<float>(cur); L.view.b = L.b.ptr<float>(cur); L.view.r = L.r.ptr<float>(cur);
-		S->levels.push_back(L);
+		L.view.b = L.b.ptr<float>(cur); L.view.xa = L.xa.ptr<float>(cur); L.view.xb = L.xb.ptr<float>(cur);
 		const int big = cur.nx > cur.ny ? (cur.nx > cur.nzg ? cur.nx : cur.nzg) : (cur.ny > cur.nzg ? cur.ny : cur.nzg);
 		if (big <= min_size) break;
 		// slabs: keep aggregates inside one rank (even local extent and even first plane)
 		if (!S->whole_grid && ((cur.nzl & 1) || (cur.k0 & 1) || cur.nzl < 2)) break;
 		cur = make_dims((cur.nx + 1) / 2, (cur.ny + 1) / 2, (cur.nzl + 1) / 2, cur.k0 / 2, (cur.nzg + 1) / 2);
+	}
+	// the shared-memory tail: the longest run of coarsest levels that fits one CTA's shared memory
+	S->tail_first = -1;
+	if (S->whole_grid) {
+		const size_t limit = 200 * 1024;
+		size_t bytes = 0;
+		int first = (int)S->levels.size();
+		while (first > 0 && (int)S->levels.size() - (first - 1) <= TAIL_MAX_LEVELS) {
+			const Dims &dl = S->levels[first - 1].d;
+			const size_t add = (size_t)TAIL_ARRAYS * (size_t)(dl.ncell + 2 * dl.plane) * sizeof(float);
+			if (bytes + add > limit) break;
+			bytes += add;
+			--first;
+		}
+		if (first < (int)S->levels.size()) {
+			S->tail_first = first;
+			S->tail_smem = bytes;
+			TailArgs &A = S->tail_args;
+			A = TailArgs{};
+			A.nlev = (int)S->levels.size() - first;
+			int off = 0;
+			for (int m = 0; m < A.nlev; ++m) {
+				const HostLevel &L = S->levels[first + m];
+				A.L[m].d = L.d;
+				A.L[m].wx = L.view.wx; A.L[m].wy = L.view.wy; A.L[m].wz = L.view.wz; A.L[m].dd = L.view.dd;
+				A.L[m].stride = (int)(L.d.ncell + 2 * L.d.plane);
+				A.L[m].offset = off;
+				off += TAIL_ARRAYS * A.L[m].stride;
+			}
+			A.b_in = S->levels[first].view.b;
+			A.x_out = S->levels[first].view.xa;
+			CK(cudaFuncSetAttribute(k_vcycle_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->tail_smem));
+		}
 	}
 	S->alloc_precision = precision;
 	S->mg_min_size_built = min_size;
@@ -258,6 +322,27 @@ int flat_blocks(long long n) {
 		(S)->launches++;                                 \
 	} while (0)
 
+// persistent grid of a tile kernel: one resident wave, never more CTAs than the level has tiles
+template <class K>
+int tile_grid(shkz_b200_solver *S, K kernel, dim3 block, int tiles_total) {
+	const void *key = reinterpret_cast<const void *>(kernel);
+	auto it = S->occupancy.find(key);
+	int per_sm;
+	if (it == S->occupancy.end()) {
+		per_sm = 1;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(block.x * block.y * block.z), 0) != cudaSuccess || per_sm < 1) {
+			cudaGetLastError();
+			per_sm = 1;
+		}
+		S->occupancy[key] = per_sm;
+	} else per_sm = it->second;
+	const long long wave = (long long)per_sm * S->num_sms;
+	const long long g = tiles_total < wave ? tiles_total : wave;
+	return (int)(g < 1 ? 1 : g);
+}
+#define LAUNCH_TILES(S, tag, kernel, block, tiles_total, stream, ...) \
+	LAUNCH(S, tag, kernel, tile_grid(S, kernel, block, tiles_total), block, stream, __VA_ARGS__)
+
 // ---- halo exchange of one cell array (ghost planes), a no-op on a whole grid ----
 template <class T>
 int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
@@ -265,52 +350,126 @@ int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
 	return S->comm->exchange(p, d.plane, d.nzl, sizeof(T), st) ? fail(SHKZ_B200_ERR_COMM, "halo exchange failed: %s", S->comm->error()) : SHKZ_B200_OK;
 }
 
-// ---- multigrid ----
-void rbgs(shkz_b200_solver *S, const HostLevel &H, int color, bool zero_x, const CGState *st, cudaStream_t stream) {
-	const MGLevel &L = H.view;
-	const dim3 block(32, 8, 1);
-	const dim3 grid(((L.d.nx + 1) / 2 + 31) / 32, (L.d.ny + 7) / 8, L.d.nzl);
-	if (zero_x) LAUNCH(S, H.tag_rbgs.c_str(), k_rbgs<true>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, color, st);
-	else LAUNCH(S, H.tag_rbgs.c_str(), k_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, color, st);
+int compact_tiles(shkz_b200_solver *S, HostLevel &H, cudaStream_t stream) {
+	LAUNCH(S, H.tag_compact.c_str(), k_compact_tiles, 1, 1024, stream, static_cast<const unsigned char *>(H.tile_flags.base), H.tiles_total,
+	       static_cast<int *>(H.tile_ids.base), static_cast<int *>(H.tile_count.base));
+	return SHKZ_B200_OK;
 }
 
-int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, const CGState *st, cudaStream_t stream) {
-	const HostLevel &H = S->levels[l];
+// ---- multigrid ----
+template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
+void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, float *xn, const float *ec, const Dims &dc, CGState *st, cudaStream_t stream) {
 	const MGLevel &L = H.view;
-	const bool last = (l + 1 == S->levels.size());
-	const int pre = last ? (P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps) : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
-	const int post = last ? pre : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
-	for (int sw = 0; sw < pre; ++sw) {
-		rbgs(S, H, 0, sw == 0, st, stream);
-		CKR(halo(S, L.d, L.x, stream));
-		rbgs(S, H, 1, false, st, stream);
-		CKR(halo(S, L.d, L.x, stream));
+	LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep<FIRST, ZERO_X, PROLONG, DOT>), sweep_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
+	             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->redbuf(), st);
+}
+
+// One V-cycle on level l and below, right-hand side in the level's b. *result = buffer holding the solution.
+// dot: also reduce (solution . b) into the CG state (level 0 only).
+int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result) {
+	HostLevel &H = S->levels[l];
+	const MGLevel &L = H.view;
+	const int coarse = P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps;
+	if ((int)l == S->tail_first) {
+		TailArgs A = S->tail_args;
+		A.pre = P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps;
+		A.post = P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps;
+		A.coarse = coarse;
+		const int slot_ = S->prof.begin("vcycle_tail", stream);
+		k_vcycle_tail<<<1, TAIL_THREADS, S->tail_smem, stream>>>(A, st);
+		S->prof.end(slot_, stream);
+		S->launches++;
+		*result = L.xa;
+		if (dot) LAUNCH_TILES(S, "dot_zb", k_dot_zb, cg_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.xa, (const float *)L.b, S->redbuf(), st);
+		return SHKZ_B200_OK;
 	}
+	const bool last = (l + 1 == S->levels.size());
+	const int pre = last ? coarse : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
+	const int post = last ? coarse : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
+	float *bufs[2] = {L.xa, L.xb};
+	const float *cur = nullptr;
+	int w = 0;
+	const Dims none{};
+	for (int sw = 0; sw < pre; ++sw) {
+		if (sw == 0) launch_sweep<0, true, false, false>(S, H, nullptr, bufs[w], nullptr, none, st, stream);
+		else launch_sweep<0, false, false, false>(S, H, cur, bufs[w], nullptr, none, st, stream);
+		cur = bufs[w];
+		w ^= 1;
+	}
+	const float *ec = nullptr;
+	Dims dc = none;
 	if (!last) {
 		const MGLevel &C = S->levels[l + 1].view;
-		LAUNCH(S, H.tag_residual.c_str(), k_residual, stencil_grid(L.d), stencil_block(), stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, L.x, L.r, st);
-		LAUNCH(S, H.tag_restrict.c_str(), k_restrict, cell_grid(C.d, 0, 0, 0), cell_block(), stream, L.d, C.d, L.r, C.b, st);
-		CKR(vcycle(S, l + 1, P, st, stream));
-		LAUNCH(S, H.tag_prolong.c_str(), k_prolong_add, cell_grid(L.d, 0, 0, 0), cell_block(), stream, L.d, C.d, C.x, L.x, st);
-		CKR(halo(S, L.d, L.x, stream));
+		dc = C.d;
+		LAUNCH_TILES(S, H.tag_restrict.c_str(), k_residual_restrict, restrict_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx, (const float *)L.wy,
+		             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st);
+		CKR(vcycle(S, l + 1, P, st, stream, false, &ec));
+		if (post == 0) {
+			LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, dc, ec, cur, bufs[w], (const CGState *)st);
+			cur = bufs[w];
+			w ^= 1;
+		}
 	}
 	for (int sw = 0; sw < post; ++sw) {
-		rbgs(S, H, 1, false, st, stream);
-		CKR(halo(S, L.d, L.x, stream));
-		rbgs(S, H, 0, false, st, stream);
-		if (sw + 1 < post || l > 0) CKR(halo(S, L.d, L.x, stream));
+		const bool prolong = !last && sw == 0, dotnow = dot && sw + 1 == post;
+		if (prolong && dotnow) launch_sweep<1, false, true, true>(S, H, cur, bufs[w], ec, dc, st, stream);
+		else if (prolong) launch_sweep<1, false, true, false>(S, H, cur, bufs[w], ec, dc, st, stream);
+		else if (dotnow) launch_sweep<1, false, false, true>(S, H, cur, bufs[w], nullptr, none, st, stream);
+		else launch_sweep<1, false, false, false>(S, H, cur, bufs[w], nullptr, none, st, stream);
+		cur = bufs[w];
+		w ^= 1;
+	}
+	if (dot && post == 0) LAUNCH_TILES(S, "dot_zb", k_dot_zb, cg_block(), H.tiles_total, stream, L.d, L.tiles, cur, (const float *)L.b, S->redbuf(), st);
+	*result = cur;
+	return SHKZ_B200_OK;
+}
+
+// The same V-cycle with one launch per colour / transfer step on dense grids (validation only).
+int legacy_vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, cudaStream_t stream) {
+	HostLevel &H = S->levels[l];
+	const MGLevel &L = H.view;
+	const bool last = (l + 1 == S->levels.size());
+	const int coarse = P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps;
+	const int pre = last ? coarse : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
+	const int post = last ? coarse : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
+	const dim3 block(32, 8, 1), grid(((L.d.nx + 1) / 2 + 31) / 32, (L.d.ny + 7) / 8, L.d.nzl);
+	const CGState *st = nullptr;
+	float *x = L.xa;
+	for (int sw = 0; sw < pre; ++sw) {
+		if (sw == 0) LAUNCH(S, "legacy_rbgs", k_legacy_rbgs<true>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, x, 0, st);
+		else LAUNCH(S, "legacy_rbgs", k_legacy_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, x, 0, st);
+		LAUNCH(S, "legacy_rbgs", k_legacy_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, x, 1, st);
+	}
+	if (!last) {
+		HostLevel &HC = S->levels[l + 1];
+		const MGLevel &C = HC.view;
+		if (!H.legacy_r.base) CKR(H.legacy_r.alloc(L.d, sizeof(float)));
+		float *r = H.legacy_r.ptr<float>(L.d);
+		LAUNCH(S, "legacy_residual", k_legacy_residual, legacy_stencil_grid(L.d), legacy_stencil_block(), stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, x, r, st);
+		LAUNCH(S, "legacy_restrict", k_legacy_restrict, cell_grid(C.d, 0, 0, 0), cell_block(), stream, L.d, C.d, r, C.b, st);
+		CKR(legacy_vcycle(S, l + 1, P, stream));
+		LAUNCH(S, "legacy_prolong", k_legacy_prolong_add, cell_grid(L.d, 0, 0, 0), cell_block(), stream, L.d, C.d, C.xa, x, st);
+	}
+	for (int sw = 0; sw < post; ++sw) {
+		LAUNCH(S, "legacy_rbgs", k_legacy_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, x, 1, st);
+		LAUNCH(S, "legacy_rbgs", k_legacy_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, x, 0, st);
 	}
 	return SHKZ_B200_OK;
 }
 
 int build_hierarchy(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	for (size_t l = 0; l + 1 < S->levels.size(); ++l) {
-		const MGLevel &F = S->levels[l].view, &C = S->levels[l + 1].view;
-		LAUNCH(S, S->levels[l].tag_coarsen.c_str(), k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, (float)P.mg_coarse_scale, F.wx, F.wy, F.wz, F.dd, C.wx,
-		       C.wy, C.wz, C.dd);
+		const MGLevel &F = S->levels[l].view;
+		HostLevel &HC = S->levels[l + 1];
+		const MGLevel &C = HC.view;
+		CK(cudaMemsetAsync(HC.tile_flags.base, 0, (size_t)HC.tiles_total, stream));
+		LAUNCH(S, S->levels[l].tag_coarsen.c_str(), k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, C.tiles, (float)P.mg_coarse_scale,
+		       (const float *)F.wx, (const float *)F.wy, (const float *)F.wz, (const float *)F.dd, C.wx, C.wy, C.wz, C.dd, static_cast<unsigned char *>(HC.tile_flags.base));
 		CKR(halo(S, C.d, C.wz, stream));
+		CKR(compact_tiles(S, HC, stream));
 	}
 	CK(cudaGetLastError());
+	S->have_hierarchy = true;
 	return SHKZ_B200_OK;
 }
 
@@ -318,58 +477,54 @@ int build_hierarchy(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t
 template <class VecT, class CoefT>
 int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	const Dims &d = S->d;
-	const long long n = d.ncell;
 	const RedBuf rb = S->redbuf();
 	CGState *st = S->dstate();
-	VecT *b = S->b.ptr<VecT>(d), *x = S->x.ptr<VecT>(d), *r = S->r.ptr<VecT>(d), *s = S->s.ptr<VecT>(d), *z = S->z.ptr<VecT>(d);
+	HostLevel &H0 = S->levels[0];
+	const Tiles T = H0.view.tiles;
+	const int tt = H0.tiles_total;
+	VecT *b = S->b.ptr<VecT>(d), *x = S->x.ptr<VecT>(d), *r = S->r.ptr<VecT>(d), *s = S->s.ptr<VecT>(d), *q = S->q.ptr<VecT>(d);
 	const CoefT *wx = S->wx.ptr<CoefT>(d), *wy = S->wy.ptr<CoefT>(d), *wz = S->wz.ptr<CoefT>(d), *dd = S->dd.ptr<CoefT>(d);
 	const bool mg = P.precond == SHKZ_B200_PRECOND_MG;
-	const int fb = flat_blocks(n);
-	const bool alias = sizeof(VecT) == sizeof(float);
+	constexpr bool kFloatVec = sizeof(VecT) == sizeof(float);
+	float *b0 = kFloatVec ? nullptr : H0.view.b; // an all-float CG hands r itself to multigrid
 
 	if (S->comm && !S->whole_grid) CKR(S->comm->allreduce_begin_state(st, stream) ? fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error()) : SHKZ_B200_OK);
-	LAUNCH(S, "cg_begin", k_cg_begin<VecT>, 1, 32, stream, n, P.residual, (int)P.max_iterations, st);
-	CK(cudaMemsetAsync(x, 0, sizeof(VecT) * (size_t)n, stream));
-	CK(cudaMemcpyAsync(r, b, sizeof(VecT) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+	LAUNCH(S, "cg_begin", k_cg_begin, 1, 32, stream, P.residual, (int)P.max_iterations, st);
+	if (mg && !kFloatVec) LAUNCH_TILES(S, "cg_init", (k_cg_init<VecT, true>), cg_block(), tt, stream, d, T, (const VecT *)b, x, r, s, b0);
+	else LAUNCH_TILES(S, "cg_init", (k_cg_init<VecT, false>), cg_block(), tt, stream, d, T, (const VecT *)b, x, r, s, b0);
 
-	auto precondition = [&]() -> int {
-		const MGLevel &L0 = S->levels[0].view;
-		if (!alias) LAUNCH(S, "to_mg", k_to_mg<VecT>, fb, 256, stream, n, r, L0.b, st);
-		CKR(vcycle(S, 0, P, st, stream));
-		LAUNCH(S, "from_mg", k_from_mg<VecT>, fb, 256, stream, n, L0.x, r, z, rb, st);
-		return SHKZ_B200_OK;
-	};
+	const float *z = nullptr;
+	if (mg) CKR(vcycle(S, 0, P, st, stream, true, &z));
+	else LAUNCH_TILES(S, "dot_rr", k_dot_rr<VecT>, cg_block(), tt, stream, d, T, (const VecT *)r, rb, st);
 
-	if (mg) {
-		CKR(precondition());
-		LAUNCH(S, "copy_dot", k_copy_dot<VecT>, fb, 256, stream, n, z, r, s, rb, st);
-	} else {
-		LAUNCH(S, "copy_dot", k_copy_dot<VecT>, fb, 256, stream, n, r, r, s, rb, st);
-	}
-	const int check = P.check_every < 1 ? 1 : P.check_every;
+	const unsigned check = P.check_every < 1 ? 1 : (unsigned)P.check_every;
 	unsigned it = 0;
+	// the host looks at the device's convergence flag after a first batch sized by the previous solve, then every `check`
+	unsigned batch = S->last_iterations ? S->last_iterations : check;
 	while (it < P.max_iterations) {
-		for (int c = 0; c < check && it < P.max_iterations; ++c, ++it) {
+		for (unsigned c = 0; c < batch && it < P.max_iterations; ++c, ++it) {
+			if (mg) LAUNCH_TILES(S, "xpay", (k_xpay<VecT, float>), cg_block(), tt, stream, d, T, z, s, (const CGState *)st);
+			else LAUNCH_TILES(S, "xpay", (k_xpay<VecT, VecT>), cg_block(), tt, stream, d, T, (const VecT *)r, s, (const CGState *)st);
 			CKR(halo(S, d, s, stream));
-			LAUNCH(S, "spmv_dot", (k_spmv_dot<VecT, CoefT>), stencil_grid(d), stencil_block(), stream, d, wx, wy, wz, dd, s, z, rb, st);
+			LAUNCH_TILES(S, "spmv_dot", (k_spmv_dot<VecT, CoefT>), cg_block(), tt, stream, d, T, wx, wy, wz, dd, (const VecT *)s, q, rb, st);
 			if (mg) {
-				LAUNCH(S, "axpy2_norm", (k_axpy2_norm<VecT, false>), fb, 256, stream, n, s, z, x, r, rb, st);
-				CKR(precondition());
-				LAUNCH(S, "beta_from_zr", k_beta_from_zr, 1, 1, stream, st);
-				LAUNCH(S, "xpay", k_xpay<VecT>, fb, 256, stream, n, z, s, st);
+				if (kFloatVec) LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, false>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
+				else LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, true>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
+				CKR(vcycle(S, 0, P, st, stream, true, &z));
 			} else {
-				LAUNCH(S, "axpy2_norm", (k_axpy2_norm<VecT, true>), fb, 256, stream, n, s, z, x, r, rb, st);
-				LAUNCH(S, "xpay", k_xpay<VecT>, fb, 256, stream, n, r, s, st);
+				LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, true, false>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
 			}
 		}
 		CK(cudaMemcpyAsync(S->h_state, st, sizeof(CGState), cudaMemcpyDeviceToHost, stream));
 		CK(cudaStreamSynchronize(stream));
 		S->prof.collect();
 		if (S->h_state->done) break;
+		batch = check;
 	}
 	CK(cudaMemcpyAsync(S->h_state, st, sizeof(CGState), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
+	S->last_iterations = S->h_state->converged ? (unsigned)S->h_state->iter : 0u;
 	return SHKZ_B200_OK;
 }
 
@@ -432,18 +587,23 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	CKR(halo(S, d, in_rows, stream));
 	{
 		const bool share = sizeof(CoefT) == sizeof(float);
-		const MGLevel &L0 = S->levels[0].view;
+		HostLevel &H0 = S->levels[0];
+		const MGLevel &L0 = H0.view;
+		CK(cudaMemsetAsync(H0.tile_flags.base, 0, (size_t)H0.tiles_total, stream));
 		LAUNCH(S, "build_system", (k_build_system<RealT, CoefT, VecT>), cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, (const uint8_t *)in_rows, careas,
 		       crhos, cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->dd.ptr<CoefT>(d), share ? nullptr : L0.wx,
-		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.dd, S->b.ptr<VecT>(d), rb, st);
+		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.dd, S->b.ptr<VecT>(d), L0.tiles, static_cast<unsigned char *>(H0.tile_flags.base), rb, st);
+		CKR(compact_tiles(S, H0, stream));
 		CKR(halo(S, d, S->wz.ptr<CoefT>(d), stream));
 		if (!share) CKR(halo(S, d, L0.wz, stream));
 	}
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(S->ev[1], stream));
+	S->have_hierarchy = false;
 	if (P.precond == SHKZ_B200_PRECOND_MG) CKR(build_hierarchy(S, P, stream));
 	CK(cudaEventRecord(S->ev[2], stream));
 	S->have_system = true;
+	S->have_hierarchy = S->have_hierarchy && P.precond == SHKZ_B200_PRECOND_MG;
 	CKR((solve<VecT, CoefT>(S, P, stream)));
 	CK(cudaEventRecord(S->ev[3], stream));
 	// pressure scatter + velocity update
@@ -559,7 +719,10 @@ int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int
 	if ((long long)nz + 2 > 65535) return fail(SHKZ_B200_ERR_ARG, "nz too large for the launch geometry");
 	CKR(device_ready(device));
 	CK(cudaSetDevice(device));
+	int num_sms = 0;
+	CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
 	shkz_b200_solver *S = new shkz_b200_solver();
+	S->num_sms = num_sms > 0 ? num_sms : 148;
 	S->d = make_dims(nx, ny, k1 - k0, k0, nz);
 	S->dx = dx;
 	S->real = real;
@@ -578,9 +741,8 @@ int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int
 	}
 	// reduction scratch: the largest grid any reducing kernel uses
 	{
-		const dim3 g1 = stencil_grid(d), g2 = cell_grid(d, 1, 1, 1);
-		size_t m = (size_t)g1.x * g1.y * g1.z, m2 = (size_t)g2.x * g2.y * g2.z;
-		S->max_blocks = (m > m2 ? m : m2) + 148 * 16;
+		const dim3 g2 = cell_grid(d, 1, 1, 1);
+		S->max_blocks = (size_t)g2.x * g2.y * g2.z + 148 * 16;
 		tryalloc(S->partials.alloc(S->max_blocks * 4 * sizeof(double)));
 		tryalloc(S->counter.alloc(64));
 		tryalloc(S->state.alloc(sizeof(CGState)));
@@ -755,6 +917,8 @@ int shkz_b200_debug_fetch(shkz_b200_solver *S, const char *name, void *dst, size
 	else if (n == "wz") cell(S->wz, coef);
 	else if (n == "rhs") cell(S->b, vec);
 	else if (n == "x") cell(S->x, vec);
+	else if (n == "vcycle" && S->debug_vcycle_result) { src = S->debug_vcycle_result; bytes = (size_t)d.ncell * 4; }
+	else if (n == "tile_count" && !S->levels.empty()) { src = S->levels[0].tile_count.base; bytes = sizeof(int); }
 	else if (n == "in_rows") cell(S->in_rows, 1);
 	else if (n == "phi") cell(S->phi, S->real_bytes);
 	else if (n.size() == 6 && n.compare(0, 5, "areas") == 0 && n[5] >= '0' && n[5] <= '2') { src = S->areas[n[5] - '0'].base; bytes = face_count(d, n[5] - '0') * S->real_bytes; }
@@ -774,6 +938,35 @@ int shkz_b200_debug_fetch(shkz_b200_solver *S, const char *name, void *dst, size
 	if (!dst) return SHKZ_B200_OK;
 	if (dst_bytes < bytes) return fail(SHKZ_B200_ERR_ARG, "buffer too small for '%s': %zu < %zu", name, dst_bytes, bytes);
 	CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_debug_vcycle(shkz_b200_solver *S, const shkz_b200_params *params, int legacy) {
+	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	if (!S->have_system || !S->have_hierarchy) return fail(SHKZ_B200_ERR_STATE, "debug_vcycle() needs a prior project() with the multigrid preconditioner");
+	shkz_b200_params P;
+	CKR(check_params(params, P));
+	if (P.precision != S->alloc_precision) return fail(SHKZ_B200_ERR_STATE, "debug_vcycle() precision differs from the assembled system");
+	CK(cudaSetDevice(S->device));
+	cudaStream_t stream = nullptr;
+	const Dims &d = S->d;
+	HostLevel &H0 = S->levels[0];
+	const Tiles T = H0.view.tiles;
+	// level-0 right-hand side := float(rhs of the last project())
+	if (P.precision == SHKZ_B200_PREC_FP32)
+		LAUNCH_TILES(S, "cg_init", (k_cg_init<float, false>), cg_block(), H0.tiles_total, stream, d, T, (const float *)S->b.ptr<float>(d), S->x.ptr<float>(d), S->r.ptr<float>(d), S->s.ptr<float>(d), (float *)nullptr);
+	else
+		LAUNCH_TILES(S, "cg_init", (k_cg_init<double, true>), cg_block(), H0.tiles_total, stream, d, T, (const double *)S->b.ptr<double>(d), S->x.ptr<double>(d), S->r.ptr<double>(d), S->s.ptr<double>(d), H0.view.b);
+	const float *z = nullptr;
+	if (legacy) {
+		CKR(legacy_vcycle(S, 0, P, stream));
+		z = H0.view.xa;
+	} else {
+		CKR(vcycle(S, 0, P, nullptr, stream, false, &z));
+	}
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaGetLastError());
+	S->debug_vcycle_result = z;
 	return SHKZ_B200_OK;
 }
 

@@ -183,6 +183,11 @@ class MacPressureSolver3:
         capi.check(capi.lib().shkz_b200_debug_fetch(self._h, name.encode(), buf.ctypes.data, buf.nbytes, None))
         return buf
 
+    def debug_vcycle(self, legacy: bool = False) -> np.ndarray:
+        """One V-cycle applied to the last right-hand side (fused tile kernels, or the unfused validation kernels)."""
+        capi.check(capi.lib().shkz_b200_debug_vcycle(self._h, C.byref(self.params), int(bool(legacy))))
+        return self.debug_fetch("vcycle").view(np.float32).reshape(self.nzl, self.ny, self.nx).copy()
+
     def close(self):
         if getattr(self, "_h", None):
             capi.lib().shkz_b200_destroy(self._h)
