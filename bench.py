@@ -305,8 +305,8 @@ def run_ours(args):
             hv[d].numpy()[...] = hv0[d]; ha[d].numpy()[...] = ha0[d]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        S.project(sc.dt, [t.numpy() for t in hv], [t.numpy() for t in ha], hsolid.numpy() if hsolid is not None else None,
-                  hfluid.numpy(), sc.fluid_levelset)
+        _, _, e2e_res = S.project(sc.dt, [t.numpy() for t in hv], [t.numpy() for t in ha], hsolid.numpy() if hsolid is not None else None,
+                                  hfluid.numpy(), sc.fluid_levelset)
         t1 = time.perf_counter()
         if it >= min(2, args.warmup):
             e2e_s += t1 - t0
@@ -358,7 +358,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"mixed": "f64", "fp64": "f64", "fp32": "f32"}[args.precision], "data": "synthetic", "config": config_dict(args, "gpu"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": (e2e_s / e2e_steps * 1e3) if e2e_steps else None},
+                    "ms_per_step": (e2e_s / e2e_steps * 1e3) if e2e_steps else None,
+                    "ms_h2d": e2e_res.stats["ms_h2d"] if e2e_steps else None, "ms_d2h": e2e_res.stats["ms_d2h"] if e2e_steps else None},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "solve": {"iterations": iters[-1], "reresid": res.reresid, "converged": res.converged, "n_rows": int(n_rows),
                       "cell_iters_per_s": n_rows * iters[-1] / (phase["ms_solve"] * 1e-3), **phase},

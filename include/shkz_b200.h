@@ -172,8 +172,9 @@ int shkz_b200_debug_fetch(shkz_b200_solver *solver, const char *name, void *dst,
 
 
 /* ---- test hook: apply ONE multigrid V-cycle to the right-hand side of the last project() and keep the result for
- * debug_fetch("vcycle"). legacy != 0 runs the unfused one-launch-per-colour kernels on dense grids instead of the
- * fused tile kernels; the two must agree bit for bit (tests/test_gpu_parity.py). */
+ * debug_fetch("vcycle"). legacy: 0 = the product kernels; 1 = the unfused one-launch-per-colour kernels on dense
+ * grids; 2 = the product path with the scalar sweep kernel forced; 3 = with the quad kernel (no TMA) forced. All must agree bit for bit
+ * (tests/test_gpu_parity.py). */
 int shkz_b200_debug_vcycle(shkz_b200_solver *solver, const shkz_b200_params *params, int legacy);
 
 #ifdef __cplusplus

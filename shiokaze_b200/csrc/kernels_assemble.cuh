@@ -231,9 +231,10 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
                                                      VecT *__restrict__ rhs, Tiles T, unsigned char *__restrict__ tile_flags, RedBuf rb, CGState *st) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	const int j = blockIdx.y * blockDim.y + threadIdx.y;
-	const int k = blockIdx.z;
 	double red[3] = {0.0, 0.0, 0.0}; // |b|_inf, row count, dirichlet flag
-	if (i < d.nx && j < d.ny) {
+	// a block walks planes blockIdx.z, blockIdx.z + gridDim.z, ...: a few thousand blocks in all, so the grid-wide
+	// reduction at the end stays cheap (one counter atomic per block)
+	if (i < d.nx && j < d.ny) for (int k = blockIdx.z; k < d.nzl; k += gridDim.z) {
 		const int kg = k + d.k0;
 		const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
 		double dirichlet = 0.0, b = 0.0, lower[3] = {0.0, 0.0, 0.0};
@@ -265,8 +266,8 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
 				}
 			}
 			if (P.apply_rhs_correct) b = __dadd_rn(b, P.rhs_correct);
-			red[0] = fabs(b);
-			red[1] = 1.0;
+			red[0] = fmax(red[0], fabs(b));
+			red[1] += 1.0;
 			tile_flags[tile_of(T, i, j, k)] = 1; // the solve only visits tiles that hold an unknown
 		}
 		wx[c] = (CoefT)lower[0]; wy[c] = (CoefT)lower[1]; wz[c] = (CoefT)lower[2]; dd[c] = (CoefT)dirichlet;

@@ -168,6 +168,188 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(Dims d, Tiles T, con
 	}
 }
 
+// ---- the same sweep, vectorised: requires nx % 4 == 0 (every level of a power-of-two grid down to 4) -----------
+// A thread owns FOUR x-adjacent cells (one aligned float4 per array and plane) of one tile row; the block holds
+// TY+2 row slots (the two extra ones relax the halo rows in phase 1 only) plus one warp for the two halo
+// columns. All global loads of a plane happen once, at the top of the step; the coefficients of the plane are
+// carried in registers to the next step where the second colour needs them, so phase 2 touches shared memory only.
+// Rows r and r+2 share a warp, hence which cells of the quad carry the first colour is warp-uniform.
+constexpr int S4_ROWS = TY + 2;
+constexpr int S4_ROW_WARPS = S4_ROWS / 2;          // 9
+constexpr int S4_THREADS = 32 * (S4_ROW_WARPS + 1); // + the halo-column warp
+constexpr int S4_PITCH = TX + 8;                    // own quads start at column 4 (16-byte aligned), halo columns at 3 and TX+4
+static_assert(TY == 16 && TX == 64, "k_sweep4 thread mapping assumes 64 x 16 tiles");
+
+struct Quad { // operator data of four x-adjacent cells in one plane
+	float4 wx;  // lower x faces of the four cells
+	float wx4;  // ... and of the cell after them
+	float4 wy, wyu, wz, dd, b; // lower y faces, upper y faces (next row's wy), lower z faces, Dirichlet diagonal, rhs
+};
+
+template <int M> __device__ __forceinline__ float q_get(const float4 &v) { return M == 0 ? v.x : (M == 1 ? v.y : (M == 2 ? v.z : v.w)); }
+template <int M> __device__ __forceinline__ void q_set(float4 &v, float f) { if (M == 0) v.x = f; else if (M == 1) v.y = f; else if (M == 2) v.z = f; else v.w = f; }
+
+// relax cell M of the quad: x = values of the quad itself, xl / xr = the cells left and right of it, xd / xu = the rows below and
+// above, zm / zp = the planes below and above, wzu = upper z faces
+template <int M, bool ZERO>
+__device__ __forceinline__ float relax_cell(const Quad &Q, const float4 &wzu, const float4 &x, float xl, float xr, const float4 &xd, const float4 &xu,
+                                            const float4 &zm, const float4 &zp) {
+	const float w0 = q_get<M>(Q.wx), w1 = M == 3 ? Q.wx4 : q_get<(M + 1) & 3>(Q.wx);
+	const float w2 = q_get<M>(Q.wy), w3 = q_get<M>(Q.wyu), w4 = q_get<M>(Q.wz), w5 = q_get<M>(wzu);
+	if (ZERO) return gs_relax0(w0, w1, w2, w3, w4, w5, q_get<M>(Q.dd), q_get<M>(Q.b));
+	const float x0 = M == 0 ? xl : q_get<(M + 3) & 3>(x), x1 = M == 3 ? xr : q_get<(M + 1) & 3>(x);
+	return gs_relax(w0, w1, w2, w3, w4, w5, q_get<M>(Q.dd), q_get<M>(Q.b), x0, x1, q_get<M>(xd), q_get<M>(xu), q_get<M>(zm), q_get<M>(zp));
+}
+// relax cells A and A+2 of the quad, keep the other two
+template <int A, bool ZERO>
+__device__ __forceinline__ float4 relax_quad(const Quad &Q, const float4 &wzu, const float4 &x, float xl, float xr, const float4 &xd, const float4 &xu,
+                                             const float4 &zm, const float4 &zp) {
+	float4 out = x;
+	q_set<A>(out, relax_cell<A, ZERO>(Q, wzu, x, xl, xr, xd, xu, zm, zp));
+	q_set<A + 2>(out, relax_cell<A + 2, ZERO>(Q, wzu, x, xl, xr, xd, xu, zm, zp));
+	return out;
+}
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
+__global__ void __launch_bounds__(S4_THREADS, 2) k_sweep4(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
+                                                         const float *__restrict__ dd, const float *__restrict__ b, const float *__restrict__ xo,
+                                                         float *__restrict__ xn, const float *__restrict__ ec, Dims dc, RedBuf rb, CGState *st) {
+	if (st && st->done) return;
+	__shared__ __align__(16) float H[3][S4_ROWS][S4_PITCH];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const bool colwarp = warp == S4_ROW_WARPS;
+	const int tx = lane & 15, half = lane >> 4;
+	const int r = warp < S4_ROW_WARPS - 1 ? ((warp >> 1) * 4 + (warp & 1) + 2 * half) : TY + half; // row slot of a row-warp thread
+	const int ntiles = *T.count;
+	const long long nx = d.nx, ny = d.ny, plane = d.plane;
+	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+	double red[1] = {0.0};
+
+	auto EC = [&](int i, int j, int k) -> long long { return (i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1)); };
+	auto XO = [&](long long c, int i, int j, int k) -> float { // one cell of x_old (see k_sweep)
+		if (ZERO_X) return 0.f;
+		float v = xo[c];
+		if (PROLONG) v += ec[EC(i, j, k)];
+		return v;
+	};
+	auto XO4 = [&](long long c0, int i, int j, int k) -> float4 { // an aligned quad of x_old
+		if (ZERO_X) return zero4;
+		float4 v = ld4(xo + c0);
+		if (PROLONG) {
+			const float2 e = *reinterpret_cast<const float2 *>(ec + EC(i, j, k));
+			v.x += e.x; v.y += e.x; v.z += e.y; v.w += e.y;
+		}
+		return v;
+	};
+	auto scalar_half_update = [&](int i, int j, int p, bool in_slab) -> float { // halo columns
+		const long long c = i + nx * (j + ny * p);
+		if (in_slab && ((i + j + p + d.k0) & 1) == FIRST) {
+			const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
+			if (ZERO_X) return gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c]);
+			return gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], XO(c - 1, i - 1, j, p), XO(c + 1, i + 1, j, p), XO(c - nx, i, j - 1, p),
+			                XO(c + nx, i, j + 1, p), XO(c - plane, i, j, p - 1), XO(c + plane, i, j, p + 1));
+		}
+		return XO(c, i, j, p);
+	};
+
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int ke = min(kb + T.bz, d.nzl);
+		if (colwarp) {
+			// ---- halo columns i0-1 and i0+TX of the TY tile rows: one cell per lane and plane
+			const int side = lane >> 4, ci = side ? i0 + TX : i0 - 1, cj = j0 + (lane & 15);
+			const bool cv = ci >= 0 && ci < d.nx && cj < d.ny;
+			for (int p = kb - 1; p <= ke; ++p) {
+				H[(p + 3) % 3][(lane & 15) + 1][side ? TX + 4 : 3] = cv ? scalar_half_update(ci, cj, p, p >= 0 && p < d.nzl) : 0.f;
+				__syncthreads();
+			}
+			__syncthreads();
+			continue;
+		}
+		const int i = i0 + 4 * tx, j = j0 - 1 + r;
+		const bool valid = i < d.nx && j >= 0 && j < d.ny;
+		const bool finish = valid && r >= 1 && r <= TY;
+		const long long row = i + nx * j; // flat index of the quad in plane 0
+		// x_old of the own quad in planes p-1, p (p+1 is loaded in the step), lower z faces of plane p
+		float4 xm = zero4, xc = zero4, wz_cur = zero4;
+		if (valid) {
+			if (kb - 2 >= -1) xm = XO4(row + plane * (kb - 2), i, j, kb - 2);
+			xc = XO4(row + plane * (kb - 1), i, j, kb - 1);
+			wz_cur = ld4(wz + row + plane * (kb - 1));
+		}
+		float4 hm = zero4, hc = zero4;
+		Quad prv; // operator data of plane p-1
+		prv.wx = prv.wy = prv.wyu = prv.wz = prv.dd = prv.b = zero4;
+		prv.wx4 = 0.f;
+		for (int p = kb - 1; p <= ke; ++p) {
+			const int slot = (p + 3) % 3;
+			const bool in_slab = p >= 0 && p < d.nzl;
+			const long long c0 = row + plane * p;
+			// ---- loads of the step
+			Quad cur;
+			cur.wz = wz_cur;
+			float4 wz_next = zero4, xp = zero4, xd = zero4, xu = zero4;
+			float xl = 0.f, xr = 0.f;
+			const bool relaxing = valid && in_slab;
+			if (valid && p + 1 <= d.nzl) {
+				wz_next = ld4(wz + c0 + plane);
+				xp = XO4(c0 + plane, i, j, p + 1);
+			}
+			if (relaxing) {
+				cur.wx = ld4(wx + c0); cur.wx4 = wx[c0 + 4];
+				cur.wy = ld4(wy + c0); cur.wyu = ld4(wy + c0 + nx);
+				cur.dd = ld4(dd + c0); cur.b = ld4(b + c0);
+				if (!ZERO_X) {
+					xl = XO(c0 - 1, i - 1, j, p); xr = XO(c0 + 4, i + 4, j, p);
+					xd = XO4(c0 - nx, i, j - 1, p); xu = XO4(c0 + nx, i, j + 1, p);
+				}
+			} else {
+				cur.wx = cur.wy = cur.wyu = cur.dd = cur.b = zero4;
+				cur.wx4 = 0.f;
+			}
+			// ---- phase 1: half-updated plane p
+			float4 hp = xc;
+			const int a1 = (FIRST + j + p + d.k0) & 1; // first relaxed cell of the quad in this row and plane (i is a multiple of 4)
+			if (relaxing) {
+				if (a1 == 0) hp = relax_quad<0, ZERO_X>(cur, wz_next, xc, xl, xr, xd, xu, xm, xp);
+				else hp = relax_quad<1, ZERO_X>(cur, wz_next, xc, xl, xr, xd, xu, xm, xp);
+			}
+			*reinterpret_cast<float4 *>(&H[slot][r][4 + 4 * tx]) = valid ? hp : zero4;
+			__syncthreads();
+			// ---- phase 2: finish plane k = p - 1 (second colour) from half-updated planes k-1 (hm), k (hc + shared memory), k+1 (hp)
+			const int k = p - 1;
+			if (finish && k >= kb) {
+				const int ks = (k + 3) % 3;
+				const float hl = H[ks][r][3 + 4 * tx], hr = H[ks][r][8 + 4 * tx];
+				const float4 hd = *reinterpret_cast<const float4 *>(&H[ks][r - 1][4 + 4 * tx]);
+				const float4 hu = *reinterpret_cast<const float4 *>(&H[ks][r + 1][4 + 4 * tx]);
+				const int a2 = (FIRST + 1 + j + k + d.k0) & 1; // first cell of the other colour
+				float4 xnew;
+				if (a2 == 0) xnew = relax_quad<0, false>(prv, cur.wz, hc, hl, hr, hd, hu, hm, hp);
+				else xnew = relax_quad<1, false>(prv, cur.wz, hc, hl, hr, hd, hu, hm, hp);
+				*reinterpret_cast<float4 *>(xn + c0 - plane) = xnew;
+				if (DOT) red[0] += (double)xnew.x * (double)prv.b.x + (double)xnew.y * (double)prv.b.y + (double)xnew.z * (double)prv.b.z + (double)xnew.w * (double)prv.b.w;
+			}
+			hm = hc; hc = hp;
+			xm = xc; xc = xp;
+			wz_cur = wz_next;
+			prv = cur;
+		}
+		__syncthreads(); // the next tile's first slot may be one this tile's last phase 2 still reads
+	}
+	if (DOT) {
+		grid_reduce<1, 0u>(red, rb, [&](double (&tot)[1]) {
+			const double zr = tot[0];
+			st->beta = st->iter == 0 ? 0.0 : zr / st->rho; // pcg_solver.h:286-288
+			st->rho = zr;
+			if (zr == 0.0 || zr != zr) st->done = 1;        // pcg_solver.h:263-271
+		});
+	}
+}
+
 // coarse b = P^T (b - A x): block (TX/2, TY/2), one coarse column per thread, aggregates never straddle tiles
 inline dim3 restrict_block() { return dim3(TX / 2, TY / 2, 1); }
 __global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_residual_restrict(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy,

@@ -1,0 +1,271 @@
+// The red-black sweep of kernels_mg.cuh with its operands staged through shared memory by the Tensor Memory
+// Accelerator (sm_100a): a three-deep ring of plane stages, each filled by six 3-D tiled bulk-tensor loads
+// (cp.async.bulk.tensor -> UTMALDG) that one elected thread issues two planes ahead and that complete on an mbarrier.
+// The compute threads never wait on a global load: all their operands come from shared memory, the only global
+// traffic they issue themselves is the float4 store of x_new (and the coarse correction of the PROLONG variant).
+// Out-of-range box parts (tile halo beyond the grid, planes beyond the ghost planes) are zero-filled by the TMA
+// unit, which is exactly what a wall needs (zero coefficient).
+//
+// Arithmetic, thread mapping and the half-updated-plane ring H are those of k_sweep4: results are bit-identical.
+#pragma once
+#include <cuda.h>
+#include "kernels_mg.cuh"
+
+namespace shkz {
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+	unsigned ok;
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+	    "selp.u32 %0, 1, 0, p;\n"
+	    "}\n"
+	    : "=r"(ok)
+	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+	while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int x, int y, int z) {
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+	             "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+	             : "memory");
+}
+
+// ---- stage layout (floats); every array starts on a 128-byte boundary ------------------------------------------------
+constexpr int ST_W = S4_PITCH;                 // 72 columns: grid columns i0-4 .. i0+67
+constexpr int ST_XO_ROWS = TY + 4;             // rows j0-2 .. j0+17
+constexpr int ST_WY_ROWS = TY + 3;             // rows j0-1 .. j0+17
+constexpr int ST_ROWS = TY + 2;                // rows j0-1 .. j0+16
+constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
+constexpr int ST_XO = 0;
+constexpr int ST_WY = ST_XO + pad32(ST_XO_ROWS * ST_W);
+constexpr int ST_WX = ST_WY + pad32(ST_WY_ROWS * ST_W);
+constexpr int ST_WZ = ST_WX + pad32(ST_ROWS * ST_W);
+constexpr int ST_DD = ST_WZ + pad32(ST_ROWS * ST_W);
+constexpr int ST_B = ST_DD + pad32(ST_ROWS * ST_W);
+constexpr int ST_FLOATS = ST_B + pad32(ST_ROWS * ST_W);
+constexpr int ST_STAGES = 3;
+constexpr unsigned ST_TX_BYTES = (unsigned)((ST_XO_ROWS + ST_WY_ROWS + 4 * ST_ROWS) * ST_W * sizeof(float)); // bytes one stage's six boxes deliver
+constexpr unsigned ST_TX_BYTES_NOX = (unsigned)((ST_WY_ROWS + 4 * ST_ROWS) * ST_W * sizeof(float));          // ... without x_old (ZERO_X)
+constexpr int H_FLOATS = 3 * S4_ROWS * S4_PITCH;
+constexpr size_t SWEEP_TMA_SMEM = (size_t)(ST_STAGES * ST_FLOATS + H_FLOATS) * sizeof(float) + 128;
+
+struct SweepMaps { // tensor maps of one level's arrays, box widths as documented above
+	CUtensorMap wx, wy, wz, dd, b, xo;
+};
+
+template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
+__global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, const __grid_constant__ SweepMaps M, const float *__restrict__ xo, float *__restrict__ xn,
+                                                            const float *__restrict__ ec, Dims dc, RedBuf rb, CGState *st) {
+	if (st && st->done) return;
+	extern __shared__ __align__(128) float smem[];
+	float *stage_base = smem;
+	float(*H)[S4_ROWS][S4_PITCH] = reinterpret_cast<float(*)[S4_ROWS][S4_PITCH]>(smem + ST_STAGES * ST_FLOATS);
+	unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + ST_STAGES * ST_FLOATS + H_FLOATS);
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const bool colwarp = warp == S4_ROW_WARPS;
+	const bool producer = tid == S4_THREADS - 1; // last lane of the halo-column warp
+	const int tx = lane & 15, half = lane >> 4;
+	const int r = warp < S4_ROW_WARPS - 1 ? ((warp >> 1) * 4 + (warp & 1) + 2 * half) : TY + half;
+	const int ntiles = *T.count;
+	const long long nx = d.nx, ny = d.ny, plane = d.plane;
+	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+	double red[1] = {0.0};
+
+	if (tid == 0) {
+		for (int sidx = 0; sidx < ST_STAGES; ++sidx) mbar_init(&full[sidx], 1);
+		fence_barrier_init();
+	}
+	__syncthreads();
+
+	auto EC = [&](int i, int j, int k) -> long long { return (i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1)); };
+	unsigned loads_done = 0; // stage loads this CTA has consumed so far (same value in every thread)
+
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int i0, j0, kb;
+		tile_origin(T, T.ids[t], i0, j0, kb);
+		const int ke = min(kb + T.bz, d.nzl);
+		const unsigned base = loads_done;           // load index of plane kb-1
+		auto issue = [&](int p) {                   // producer: fill the stage of plane p
+			const unsigned n = base + (unsigned)(p - (kb - 1));
+			float *sp = stage_base + (n % ST_STAGES) * ST_FLOATS;
+			unsigned long long *bar = &full[n % ST_STAGES];
+			fence_proxy_async(); // the stage's previous contents were read through the generic proxy
+			mbar_expect_tx(bar, ZERO_X ? ST_TX_BYTES_NOX : ST_TX_BYTES);
+			if (!ZERO_X) tma_load_3d(sp + ST_XO, &M.xo, bar, i0 - 4, j0 - 2, p + 1);
+			tma_load_3d(sp + ST_WY, &M.wy, bar, i0 - 4, j0 - 1, p + 1);
+			tma_load_3d(sp + ST_WX, &M.wx, bar, i0 - 4, j0 - 1, p + 1);
+			tma_load_3d(sp + ST_WZ, &M.wz, bar, i0 - 4, j0 - 1, p + 1);
+			tma_load_3d(sp + ST_DD, &M.dd, bar, i0 - 4, j0 - 1, p + 1);
+			tma_load_3d(sp + ST_B, &M.b, bar, i0 - 4, j0 - 1, p + 1);
+		};
+		auto stage_of = [&](int p) -> const float * { return stage_base + ((base + (unsigned)(p - (kb - 1))) % ST_STAGES) * ST_FLOATS; };
+		auto wait_plane = [&](int p) {
+			const unsigned n = base + (unsigned)(p - (kb - 1));
+			mbar_wait(&full[n % ST_STAGES], (n / ST_STAGES) & 1u);
+		};
+		if (producer) {
+			issue(kb - 1);
+			issue(kb);
+			issue(kb + 1);
+		}
+
+		if (colwarp) {
+			// ---- halo columns (stage columns 3 and TX+4) of the TY tile rows: one cell per lane and plane
+			const int side = lane >> 4, cc = side ? TX + 4 : 3, rr = (lane & 15) + 1; // stage column, row slot
+			const int ci = i0 - 4 + cc, cj = j0 - 1 + rr;
+			const bool cv = ci >= 0 && ci < d.nx && cj < d.ny;
+			float xm = 0.f, xc = 0.f;
+			if (!ZERO_X && cv && kb - 2 >= -1) {
+				xm = xo[ci + nx * (cj + ny * (kb - 2))];
+				if (PROLONG) xm += ec[EC(ci, cj, kb - 2)];
+			}
+			wait_plane(kb - 1);
+			if (!ZERO_X) {
+				xc = stage_of(kb - 1)[ST_XO + (rr + 1) * ST_W + cc];
+				if (PROLONG && cv) xc += ec[EC(ci, cj, kb - 1)];
+			}
+			for (int p = kb - 1; p <= ke; ++p) {
+				wait_plane(p + 1);
+				const float *P = stage_of(p), *N = stage_of(p + 1);
+				const bool in_slab = p >= 0 && p < d.nzl;
+				float xp = 0.f;
+				if (!ZERO_X) {
+					xp = N[ST_XO + (rr + 1) * ST_W + cc];
+					if (PROLONG && cv && p + 1 <= d.nzl) xp += ec[EC(ci, cj, p + 1)];
+				}
+				float h = xc;
+				if (in_slab && ((ci + cj + p + d.k0) & 1) == FIRST) {
+					const float w0 = P[ST_WX + rr * ST_W + cc], w1 = P[ST_WX + rr * ST_W + cc + 1], w2 = P[ST_WY + rr * ST_W + cc], w3 = P[ST_WY + (rr + 1) * ST_W + cc];
+					const float w4 = P[ST_WZ + rr * ST_W + cc], w5 = N[ST_WZ + rr * ST_W + cc], dg = P[ST_DD + rr * ST_W + cc], bb = P[ST_B + rr * ST_W + cc];
+					if (ZERO_X) h = gs_relax0(w0, w1, w2, w3, w4, w5, dg, bb);
+					else {
+						float x0 = P[ST_XO + (rr + 1) * ST_W + cc - 1], x1 = P[ST_XO + (rr + 1) * ST_W + cc + 1], x2 = P[ST_XO + rr * ST_W + cc], x3 = P[ST_XO + (rr + 2) * ST_W + cc];
+						if (PROLONG && cv) {
+							x0 += ec[EC(ci - 1, cj, p)]; x1 += ec[EC(ci + 1, cj, p)]; x2 += ec[EC(ci, cj - 1, p)]; x3 += ec[EC(ci, cj + 1, p)];
+						}
+						h = gs_relax(w0, w1, w2, w3, w4, w5, dg, bb, x0, x1, x2, x3, xm, xp);
+					}
+				}
+				H[(p + 3) % 3][rr][cc] = cv ? h : 0.f;
+				__syncthreads();
+				if (producer && p + 3 <= ke + 1) issue(p + 3); // the stage of plane p is free: every phase-1 read of it is behind the barrier
+				xm = xc; xc = xp;
+			}
+			loads_done = base + (unsigned)(ke - kb + 3);
+			__syncthreads();
+			continue;
+		}
+
+		const int i = i0 + 4 * tx, j = j0 - 1 + r;
+		const bool valid = i < d.nx && j >= 0 && j < d.ny;
+		const bool finish = valid && r >= 1 && r <= TY;
+		const long long row = i + nx * j;
+		const int q = 4 + 4 * tx; // stage / H column of the own quad
+		auto LDQ = [&](const float *sp, int arr, int rowi) -> float4 { return *reinterpret_cast<const float4 *>(sp + arr + rowi * ST_W + q); };
+		auto ECQ = [&](float4 v, int ii, int jj, int kk) -> float4 { // + coarse correction of an aligned quad
+			const float2 e = *reinterpret_cast<const float2 *>(ec + EC(ii, jj, kk));
+			v.x += e.x; v.y += e.x; v.z += e.y; v.w += e.y;
+			return v;
+		};
+		float4 xm = zero4, xc = zero4, wz_cur = zero4;
+		if (!ZERO_X && valid && kb - 2 >= -1) {
+			xm = ld4(xo + row + plane * (kb - 2));
+			if (PROLONG) xm = ECQ(xm, i, j, kb - 2);
+		}
+		wait_plane(kb - 1);
+		{
+			const float *P = stage_of(kb - 1);
+			if (!ZERO_X) {
+				xc = LDQ(P, ST_XO, r + 1);
+				if (PROLONG && valid) xc = ECQ(xc, i, j, kb - 1);
+			}
+			wz_cur = LDQ(P, ST_WZ, r);
+		}
+		float4 hm = zero4, hc = zero4;
+		Quad prv;
+		prv.wx = prv.wy = prv.wyu = prv.wz = prv.dd = prv.b = zero4;
+		prv.wx4 = 0.f;
+		for (int p = kb - 1; p <= ke; ++p) {
+			const int slot = (p + 3) % 3;
+			const bool in_slab = p >= 0 && p < d.nzl;
+			wait_plane(p + 1);
+			const float *P = stage_of(p), *N = stage_of(p + 1);
+			Quad cur;
+			cur.wz = wz_cur;
+			cur.wx = LDQ(P, ST_WX, r); cur.wx4 = P[ST_WX + r * ST_W + q + 4];
+			cur.wy = LDQ(P, ST_WY, r); cur.wyu = LDQ(P, ST_WY, r + 1);
+			cur.dd = LDQ(P, ST_DD, r); cur.b = LDQ(P, ST_B, r);
+			const float4 wz_next = LDQ(N, ST_WZ, r);
+			float4 xp = zero4, xd = zero4, xu = zero4;
+			float xl = 0.f, xr = 0.f;
+			if (!ZERO_X) {
+				xp = LDQ(N, ST_XO, r + 1);
+				xl = P[ST_XO + (r + 1) * ST_W + q - 1]; xr = P[ST_XO + (r + 1) * ST_W + q + 4];
+				xd = LDQ(P, ST_XO, r); xu = LDQ(P, ST_XO, r + 2);
+				if (PROLONG && valid) {
+					if (p + 1 <= d.nzl) xp = ECQ(xp, i, j, p + 1);
+					if (in_slab) {
+						xl += ec[EC(i - 1, j, p)]; xr += ec[EC(i + 4, j, p)];
+						xd = ECQ(xd, i, j - 1, p); xu = ECQ(xu, i, j + 1, p);
+					}
+				}
+			}
+			// ---- phase 1: half-updated plane p
+			float4 hp = xc;
+			if (in_slab) {
+				const int a1 = (FIRST + j + p + d.k0) & 1;
+				if (a1 == 0) hp = relax_quad<0, ZERO_X>(cur, wz_next, xc, xl, xr, xd, xu, xm, xp);
+				else hp = relax_quad<1, ZERO_X>(cur, wz_next, xc, xl, xr, xd, xu, xm, xp);
+			}
+			if (!valid) hp = zero4;
+			*reinterpret_cast<float4 *>(&H[slot][r][q]) = hp;
+			__syncthreads();
+			// ---- phase 2: finish plane k = p - 1
+			const int k = p - 1;
+			if (finish && k >= kb) {
+				const int ks = (k + 3) % 3;
+				const float hl = H[ks][r][q - 1], hr = H[ks][r][q + 4];
+				const float4 hd = *reinterpret_cast<const float4 *>(&H[ks][r - 1][q]);
+				const float4 hu = *reinterpret_cast<const float4 *>(&H[ks][r + 1][q]);
+				const int a2 = (FIRST + 1 + j + k + d.k0) & 1;
+				float4 xnew;
+				if (a2 == 0) xnew = relax_quad<0, false>(prv, cur.wz, hc, hl, hr, hd, hu, hm, hp);
+				else xnew = relax_quad<1, false>(prv, cur.wz, hc, hl, hr, hd, hu, hm, hp);
+				*reinterpret_cast<float4 *>(xn + row + plane * k) = xnew;
+				if (DOT) red[0] += (double)xnew.x * (double)prv.b.x + (double)xnew.y * (double)prv.b.y + (double)xnew.z * (double)prv.b.z + (double)xnew.w * (double)prv.b.w;
+			}
+			hm = hc; hc = hp;
+			xm = xc; xc = xp;
+			wz_cur = wz_next;
+			prv = cur;
+		}
+		loads_done = base + (unsigned)(ke - kb + 3);
+		__syncthreads();
+	}
+	if (DOT) {
+		grid_reduce<1, 0u>(red, rb, [&](double (&tot)[1]) {
+			const double zr = tot[0];
+			st->beta = st->iter == 0 ? 0.0 : zr / st->rho; // pcg_solver.h:286-288
+			st->rho = zr;
+			if (zr == 0.0 || zr != zr) st->done = 1;        // pcg_solver.h:263-271
+		});
+	}
+}
+
+} // namespace shkz

@@ -15,6 +15,7 @@
 #include "kernels_cg.cuh"
 #include "kernels_mg.cuh"
 #include "kernels_legacy.cuh"
+#include "kernels_mg_tma.cuh"
 #include "slab_comm.h"
 
 using namespace shkz;
@@ -145,7 +146,37 @@ struct HostLevel {
 	bool own_coef = true, own_b = true; // level 0 may alias CG arrays
 	PlainArray tile_flags, tile_ids, tile_count;
 	MGLevel view;
+	bool tma = false; // tensor maps built: the level's sweeps run the TMA-staged kernel
+	CUtensorMap map_wx, map_wy, map_wz, map_dd, map_b, map_xa, map_xb;
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+	static EncodeTiledFn fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+		else cudaGetLastError();
+	}
+	return fn;
+}
+
+// 3-D map of a cell array WITH its ghost planes (z coordinate = plane + 1), box = ST_W columns x rows x 1 plane, zero fill outside
+bool make_plane_map(CUtensorMap *map, void *base, const Dims &d, int rows) {
+	EncodeTiledFn enc = encode_tiled();
+	if (!enc || !base) return false;
+	const cuuint64_t dims[3] = {(cuuint64_t)d.nx, (cuuint64_t)d.ny, (cuuint64_t)d.nzl + 2};
+	const cuuint64_t strides[2] = {(cuuint64_t)d.nx * sizeof(float), (cuuint64_t)d.plane * sizeof(float)};
+	const cuuint32_t box[3] = {(cuuint32_t)ST_W, (cuuint32_t)rows, 1u};
+	const cuuint32_t estr[3] = {1u, 1u, 1u};
+	return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+	           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 } // namespace
 
@@ -186,6 +217,7 @@ struct shkz_b200_solver {
 	bool have_system = false;
 	bool have_hierarchy = false;
 	const float *debug_vcycle_result = nullptr;
+	int sweep_mode = 0; // 0: best kernel per level (TMA-staged > quad > scalar); 1: no TMA; 2: scalar only (debug / A-B timing)
 	AsmParams last_asm{};
 	cudaEvent_t ev[8]{};
 	bool events = false;
@@ -262,6 +294,10 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 		L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz};
 		L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.dd = L.dd.ptr<float>(cur);
 		L.view.b = L.b.ptr<float>(cur); L.view.xa = L.xa.ptr<float>(cur); L.view.xb = L.xb.ptr<float>(cur);
+		L.tma = (cur.nx & 3) == 0 && make_plane_map(&L.map_wx, L.wx.base, cur, ST_ROWS) && make_plane_map(&L.map_wy, L.wy.base, cur, ST_WY_ROWS) &&
+		        make_plane_map(&L.map_wz, L.wz.base, cur, ST_ROWS) && make_plane_map(&L.map_dd, L.dd.base, cur, ST_ROWS) &&
+		        make_plane_map(&L.map_b, L.b.base, cur, ST_ROWS) && make_plane_map(&L.map_xa, L.xa.base, cur, ST_XO_ROWS) &&
+		        make_plane_map(&L.map_xb, L.xb.base, cur, ST_XO_ROWS);
 		const int big = cur.nx > cur.ny ? (cur.nx > cur.nzg ? cur.nx : cur.nzg) : (cur.ny > cur.nzg ? cur.ny : cur.nzg);
 		if (big <= min_size) break;
 		// slabs: keep aggregates inside one rank (even local extent and even first plane)
@@ -324,13 +360,14 @@ int flat_blocks(long long n) {
 
 // persistent grid of a tile kernel: one resident wave, never more CTAs than the level has tiles
 template <class K>
-int tile_grid(shkz_b200_solver *S, K kernel, dim3 block, int tiles_total) {
+int tile_grid(shkz_b200_solver *S, K kernel, dim3 block, int tiles_total, size_t smem = 0) {
 	const void *key = reinterpret_cast<const void *>(kernel);
 	auto it = S->occupancy.find(key);
 	int per_sm;
 	if (it == S->occupancy.end()) {
 		per_sm = 1;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(block.x * block.y * block.z), 0) != cudaSuccess || per_sm < 1) {
+		if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)(block.x * block.y * block.z), smem) != cudaSuccess || per_sm < 1) {
 			cudaGetLastError();
 			per_sm = 1;
 		}
@@ -342,6 +379,14 @@ int tile_grid(shkz_b200_solver *S, K kernel, dim3 block, int tiles_total) {
 }
 #define LAUNCH_TILES(S, tag, kernel, block, tiles_total, stream, ...) \
 	LAUNCH(S, tag, kernel, tile_grid(S, kernel, block, tiles_total), block, stream, __VA_ARGS__)
+#define LAUNCH_TILES_SMEM(S, tag, kernel, block, tiles_total, smem, stream, ...)                            \
+	do {                                                                                                    \
+		const int grid_ = tile_grid(S, kernel, block, tiles_total, smem);                                   \
+		const int slot_ = (S)->prof.begin(tag, stream);                                                     \
+		kernel<<<grid_, block, smem, stream>>>(__VA_ARGS__);                                                \
+		(S)->prof.end(slot_, stream);                                                                       \
+		(S)->launches++;                                                                                    \
+	} while (0)
 
 // ---- halo exchange of one cell array (ghost planes), a no-op on a whole grid ----
 template <class T>
@@ -360,8 +405,18 @@ int compact_tiles(shkz_b200_solver *S, HostLevel &H, cudaStream_t stream) {
 template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
 void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, float *xn, const float *ec, const Dims &dc, CGState *st, cudaStream_t stream) {
 	const MGLevel &L = H.view;
-	LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep<FIRST, ZERO_X, PROLONG, DOT>), sweep_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
-	             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->redbuf(), st);
+	if (H.tma && S->sweep_mode == 0) { // operands staged through shared memory by TMA
+		SweepMaps maps;
+		maps.wx = H.map_wx; maps.wy = H.map_wy; maps.wz = H.map_wz; maps.dd = H.map_dd; maps.b = H.map_b;
+		maps.xo = xo == L.xb ? H.map_xb : H.map_xa;
+		LAUNCH_TILES_SMEM(S, H.tag_sweep.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
+		                  L.tiles, maps, xo, xn, ec, dc, S->redbuf(), st);
+	} else if ((L.d.nx & 3) == 0 && S->sweep_mode <= 1) // aligned quads, direct global loads
+		LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep4<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
+		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->redbuf(), st);
+	else
+		LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep<FIRST, ZERO_X, PROLONG, DOT>), sweep_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
+		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->redbuf(), st);
 }
 
 // One V-cycle on level l and below, right-hand side in the level's b. *result = buffer holding the solution.
@@ -506,7 +561,8 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 			if (mg) LAUNCH_TILES(S, "xpay", (k_xpay<VecT, float>), cg_block(), tt, stream, d, T, z, s, (const CGState *)st);
 			else LAUNCH_TILES(S, "xpay", (k_xpay<VecT, VecT>), cg_block(), tt, stream, d, T, (const VecT *)r, s, (const CGState *)st);
 			CKR(halo(S, d, s, stream));
-			LAUNCH_TILES(S, "spmv_dot", (k_spmv_dot<VecT, CoefT>), cg_block(), tt, stream, d, T, wx, wy, wz, dd, (const VecT *)s, q, rb, st);
+			if ((d.nx & 3) == 0) LAUNCH_TILES(S, "spmv_dot", (k_spmv_dot4<VecT, CoefT>), cg_block4(), tt, stream, d, T, wx, wy, wz, dd, (const VecT *)s, q, rb, st);
+			else LAUNCH_TILES(S, "spmv_dot", (k_spmv_dot<VecT, CoefT>), cg_block(), tt, stream, d, T, wx, wy, wz, dd, (const VecT *)s, q, rb, st);
 			if (mg) {
 				if (kFloatVec) LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, false>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
 				else LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, true>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
@@ -590,7 +646,13 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		HostLevel &H0 = S->levels[0];
 		const MGLevel &L0 = H0.view;
 		CK(cudaMemsetAsync(H0.tile_flags.base, 0, (size_t)H0.tiles_total, stream));
-		LAUNCH(S, "build_system", (k_build_system<RealT, CoefT, VecT>), cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, (const uint8_t *)in_rows, careas,
+		dim3 bgrid = cell_grid(d, 0, 0, 0); // z extent folded into a loop: ~one wave of blocks
+		{
+			const long long xy = (long long)bgrid.x * bgrid.y, want = (long long)S->num_sms * 32;
+			long long gz = (want + xy - 1) / xy;
+			bgrid.z = (unsigned)(gz < 1 ? 1 : (gz > d.nzl ? d.nzl : gz));
+		}
+		LAUNCH(S, "build_system", (k_build_system<RealT, CoefT, VecT>), bgrid, cell_block(), stream, d, A, (const RealT *)phi, (const uint8_t *)in_rows, careas,
 		       crhos, cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->dd.ptr<CoefT>(d), share ? nullptr : L0.wx,
 		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.dd, S->b.ptr<VecT>(d), L0.tiles, static_cast<unsigned char *>(H0.tile_flags.base), rb, st);
 		CKR(compact_tiles(S, H0, stream));
@@ -723,6 +785,7 @@ int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int
 	CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
 	shkz_b200_solver *S = new shkz_b200_solver();
 	S->num_sms = num_sms > 0 ? num_sms : 148;
+	if (const char *e = getenv("SHKZ_B200_SWEEP_MODE")) S->sweep_mode = atoi(e); // A-B timing of the sweep kernels
 	S->d = make_dims(nx, ny, k1 - k0, k0, nz);
 	S->dx = dx;
 	S->real = real;
@@ -958,11 +1021,15 @@ int shkz_b200_debug_vcycle(shkz_b200_solver *S, const shkz_b200_params *params, 
 	else
 		LAUNCH_TILES(S, "cg_init", (k_cg_init<double, true>), cg_block(), H0.tiles_total, stream, d, T, (const double *)S->b.ptr<double>(d), S->x.ptr<double>(d), S->r.ptr<double>(d), S->s.ptr<double>(d), H0.view.b);
 	const float *z = nullptr;
-	if (legacy) {
+	if (legacy == 1) {
 		CKR(legacy_vcycle(S, 0, P, stream));
 		z = H0.view.xa;
 	} else {
-		CKR(vcycle(S, 0, P, nullptr, stream, false, &z));
+		const int keep = S->sweep_mode;
+		S->sweep_mode = legacy == 2 ? 2 : (legacy == 3 ? 1 : 0);
+		const int rc = vcycle(S, 0, P, nullptr, stream, false, &z);
+		S->sweep_mode = keep;
+		CKR(rc);
 	}
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());

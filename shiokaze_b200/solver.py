@@ -183,9 +183,10 @@ class MacPressureSolver3:
         capi.check(capi.lib().shkz_b200_debug_fetch(self._h, name.encode(), buf.ctypes.data, buf.nbytes, None))
         return buf
 
-    def debug_vcycle(self, legacy: bool = False) -> np.ndarray:
-        """One V-cycle applied to the last right-hand side (fused tile kernels, or the unfused validation kernels)."""
-        capi.check(capi.lib().shkz_b200_debug_vcycle(self._h, C.byref(self.params), int(bool(legacy))))
+    def debug_vcycle(self, legacy=0) -> np.ndarray:
+        """One V-cycle applied to the last right-hand side: 0 product kernels, 1 unfused validation kernels,
+        2 product path with the scalar sweep kernel forced."""
+        capi.check(capi.lib().shkz_b200_debug_vcycle(self._h, C.byref(self.params), int(legacy)))
         return self.debug_fetch("vcycle").view(np.float32).reshape(self.nzl, self.ny, self.nx).copy()
 
     def close(self):

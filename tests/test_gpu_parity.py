@@ -311,7 +311,8 @@ def test_device_entry_point_matches_host_entry_point(cuda_device):
 
 
 @pytest.mark.parametrize("case", [("dambreak_solid", 40, 2, 2), ("smoke", 40, 1, 1), ("flip", 48, 2, 1), ("blobs", (33, 21, 19), 2, 2),
-                                  ("dambreak_solid", 96, 2, 2), ("smoke", 130, 2, 2), ("blobs", (70, 18, 37), 3, 0)])
+                                  ("dambreak_solid", 96, 2, 2), ("smoke", 130, 2, 2), ("blobs", (70, 18, 37), 3, 0), ("blobs", (72, 40, 21), 2, 2),
+                                  ("smoke", 256, 2, 2)])
 @pytest.mark.parametrize("precision", ["mixed", "fp32"])
 def test_fused_vcycle_equals_unfused_vcycle_bit_for_bit(cuda_device, case, precision):
     """The fused sweep / residual+restrict / shared-memory-tail kernels against one-launch-per-colour kernels."""
@@ -320,9 +321,13 @@ def test_fused_vcycle_equals_unfused_vcycle_bit_for_bit(cuda_device, case, preci
           "blobs": lambda: scenes.random_blobs(*n, seed=11)}[kind]()
     S = solver_for(sc, Precision=precision, Precond="mg", MGPreSweeps=pre, MGPostSweeps=post, MaxIterations=1)
     out = S.project_scene(sc)
-    fused = S.debug_vcycle(legacy=False)
-    legacy = S.debug_vcycle(legacy=True)
+    fused = S.debug_vcycle(legacy=0)
+    scalar = S.debug_vcycle(legacy=2)
+    quad = S.debug_vcycle(legacy=3)
+    legacy = S.debug_vcycle(legacy=1)
     assert np.isfinite(fused).all()
+    assert np.array_equal(fused, scalar)      # TMA-staged sweep kernel == scalar sweep kernel
+    assert np.array_equal(quad, scalar)       # quad (direct-load) sweep kernel == scalar sweep kernel
     assert float(np.abs(legacy).max()) > 0
     # cells without an equation are only defined after a post-sweep (the dense kernels also prolong into them)
     rows = out["pressure_active"].astype(bool)
