@@ -16,8 +16,12 @@ struct AsmParams {
 	int second_order_fluid, second_order_solid;
 	int have_solid, fluid_levelset;
 	int apply_rhs_correct;
-	int pad;
+	int dx_pow2;   // dx is an exact power of two: x / dx == x * inv_dx bit for bit
+	double inv_dx;
 };
+
+// x / dx with the reference's rounding; a multiplication when that is exact
+__device__ __forceinline__ double div_dx(const AsmParams &P, double x) { return P.dx_pow2 ? __dmul_rn(x, P.inv_dx) : __ddiv_rn(x, P.dx); }
 
 template <class RealT>
 struct FaceGrids { // face-shaped, no ghost planes: x (nx+1,ny,nzl)  y (nx,ny+1,nzl)  z (nx,ny,nzl+1)
@@ -110,7 +114,10 @@ __global__ void __launch_bounds__(256) k_face_fractions(Dims d, AsmParams P, con
 				else if (dim == 1) { q00 = SOLID(i, j, k); q10 = SOLID(i + 1, j, k); q11 = SOLID(i + 1, j, k + 1); q01 = SOLID(i, j, k + 1); }
 				else { q00 = SOLID(i, j, k); q10 = SOLID(i + 1, j, k); q11 = SOLID(i + 1, j + 1, k); q01 = SOLID(i, j + 1, k); }
 #undef SOLID
-				area = __dsub_rn(1.0, get_area(q00, q10, q11, q01));
+				// all four corners open / solid: the polygon is empty / the unit square, exactly (no arithmetic needed)
+				if (q00 >= 0.0 && q10 >= 0.0 && q11 >= 0.0 && q01 >= 0.0) area = 1.0;
+				else if (q00 < 0.0 && q10 < 0.0 && q11 < 0.0 && q01 < 0.0) area = 0.0;
+				else area = __dsub_rn(1.0, get_area(q00, q10, q11, q01));
 			}
 			if (area != 0.0 && area < P.eps_solid) area = P.eps_solid; // :141
 		}
@@ -197,18 +204,24 @@ __global__ void __launch_bounds__(256) k_label_rows(Dims d, const RealT *__restr
 	bool inside = false;
 	if (phi[c] < (RealT)0) {
 		const int qo[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+		// all loads first (independent, in flight together), then the reference's test
+		RealT pq[6], ar[6], rh[6];
+		bool in_grid[6];
 #pragma unroll
 		for (int nq = 0; nq < 6; ++nq) {
 			const int dim = nq >> 1;
 			const int qi = i + qo[nq][0], qj = j + qo[nq][1], qkg = kg + qo[nq][2];
-			if (qi < 0 || qj < 0 || qkg < 0 || qi >= d.nx || qj >= d.ny || qkg >= d.nzg) continue;
+			in_grid[nq] = !(qi < 0 || qj < 0 || qkg < 0 || qi >= d.nx || qj >= d.ny || qkg >= d.nzg);
+			const int up = (nq & 1) ? 0 : 1;
+			const long long f = face_index(d, dim, i + (dim == 0) * up, j + (dim == 1) * up, k + (dim == 2) * up);
 			const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
-			if (phi[q] < (RealT)0) {
-				const int up = (nq & 1) ? 0 : 1;
-				const long long f = face_index(d, dim, i + (dim == 0) * up, j + (dim == 1) * up, k + (dim == 2) * up);
-				if (areas.p[dim][f] != (RealT)0 && rhos.p[dim][f] != (RealT)0) inside = true;
-			}
+			pq[nq] = in_grid[nq] ? phi[q] : (RealT)1;
+			ar[nq] = areas.p[dim][f];
+			rh[nq] = rhos.p[dim][f];
 		}
+#pragma unroll
+		for (int nq = 0; nq < 6; ++nq)
+			if (in_grid[nq] && pq[nq] < (RealT)0 && ar[nq] != (RealT)0 && rh[nq] != (RealT)0) inside = true;
 	}
 	in_rows[c] = inside ? 1 : 0;
 }
@@ -241,20 +254,34 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
 		if (in_rows[c]) {
 			const int qo[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 			const double dx2 = __dmul_rn(P.dx, P.dx);
+			const double w_unit = __ddiv_rn(P.dt, dx2); // value of a fully open, fully wet face: (dt*1)/(dx2*1)
+			// all loads first (independent, in flight together), then the reference's arithmetic in its order
+			RealT ar[6], rh[6], uf[6], pq[6];
+			bool in_grid[6];
 #pragma unroll
 			for (int nq = 0; nq < 6; ++nq) {
 				const int dim = nq >> 1;
 				const int qi = i + qo[nq][0], qj = j + qo[nq][1], qkg = kg + qo[nq][2];
-				if (qi < 0 || qj < 0 || qkg < 0 || qi >= d.nx || qj >= d.ny || qkg >= d.nzg) continue;
+				in_grid[nq] = !(qi < 0 || qj < 0 || qkg < 0 || qi >= d.nx || qj >= d.ny || qkg >= d.nzg);
 				const int up = (nq & 1) ? 0 : 1;
 				const long long f = face_index(d, dim, i + (dim == 0) * up, j + (dim == 1) * up, k + (dim == 2) * up);
-				const double area = (double)areas.p[dim][f];
+				const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
+				ar[nq] = areas.p[dim][f];
+				rh[nq] = rhos.p[dim][f];
+				uf[nq] = vel.p[dim][f];
+				pq[nq] = in_grid[nq] ? phi[q] : (RealT)1;
+			}
+#pragma unroll
+			for (int nq = 0; nq < 6; ++nq) {
+				const int dim = nq >> 1;
+				if (!in_grid[nq]) continue;
+				const int up = (nq & 1) ? 0 : 1;
+				const double area = (double)ar[nq];
 				if (area != 0.0) {
-					const double rho = (double)rhos.p[dim][f];
+					const double rho = (double)rh[nq];
 					if (rho != 0.0) {
-						const double value = __ddiv_rn(__dmul_rn(P.dt, area), __dmul_rn(dx2, rho));
-						const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
-						if (phi[q] < (RealT)0) {
+						const double value = (area == 1.0 && rho == 1.0) ? w_unit : __ddiv_rn(__dmul_rn(P.dt, area), __dmul_rn(dx2, rho));
+						if (pq[nq] < (RealT)0) {
 							if (!up) lower[dim] = value;
 						} else {
 							dirichlet = __dadd_rn(dirichlet, value);
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
 						}
 					}
 					const double sgn = up ? -1.0 : 1.0; // -sgn[nq]
-					b = __dadd_rn(b, __ddiv_rn(__dmul_rn(__dmul_rn(sgn, area), (double)vel.p[dim][f]), P.dx));
+					b = __dadd_rn(b, div_dx(P, __dmul_rn(__dmul_rn(sgn, area), (double)uf[nq])));
 				}
 			}
 			if (P.apply_rhs_correct) b = __dadd_rn(b, P.rhs_correct);
@@ -309,26 +336,44 @@ __global__ void __launch_bounds__(256) k_update_velocity(Dims d, AsmParams P, co
 	const int k = blockIdx.z;
 	if (i > d.nx || j > d.ny) return;
 	const int kg = k + d.k0;
+	const long long c = i + (long long)d.nx * (j + (long long)d.ny * k); // may be a ghost / out-of-row slot for the far faces
+	// first the three activity bytes, then every other operand of the active faces at once (independent loads)
+	bool act[3];
+	long long fi[3];
 #pragma unroll
 	for (int dim = 0; dim < 3; ++dim) {
-		if (i >= d.nx + (dim == 0) || j >= d.ny + (dim == 1) || k >= d.nzl + (dim == 2)) continue;
-		const long long f = face_index(d, dim, i, j, k);
-		if (!active.p[dim][f]) continue;
+		const bool exists = !(i >= d.nx + (dim == 0) || j >= d.ny + (dim == 1) || k >= d.nzl + (dim == 2));
+		fi[dim] = face_index(d, dim, i, j, k);
+		act[dim] = exists && active.p[dim][fi[dim]] != 0;
+	}
+	RealT ar[3], rh[3], uf[3], pc = (RealT)0, pm[3], phc = (RealT)0, phm[3];
+	if (act[0] || act[1] || act[2]) { pc = pressure[c]; phc = phi[c]; }
+#pragma unroll
+	for (int dim = 0; dim < 3; ++dim) {
+		ar[dim] = rh[dim] = uf[dim] = pm[dim] = phm[dim] = (RealT)0;
+		if (!act[dim]) continue;
+		const long long cm = c - (dim == 0 ? 1 : (dim == 1 ? d.nx : d.plane));
+		ar[dim] = areas.p[dim][fi[dim]]; rh[dim] = rhos.p[dim][fi[dim]]; uf[dim] = vel.p[dim][fi[dim]];
+		pm[dim] = pressure[cm]; phm[dim] = phi[cm];
+	}
+#pragma unroll
+	for (int dim = 0; dim < 3; ++dim) {
+		if (!act[dim]) continue;
+		const long long f = fi[dim];
 		const int pd = dim == 0 ? i : (dim == 1 ? j : kg);
 		const int n_dim = dim == 0 ? d.nx : (dim == 1 ? d.ny : d.nzg);
-		const RealT rho = rhos.p[dim][f];
-		const long long c = i + (long long)d.nx * (j + (long long)d.ny * k); // may be a ghost / out-of-row slot for the far faces
-		const long long cm = c - (dim == 0 ? 1 : (dim == 1 ? d.nx : d.plane));
-		if (areas.p[dim][f] != (RealT)0 && rho != (RealT)0) {
+		const RealT rho = rh[dim];
+		if (ar[dim] != (RealT)0 && rho != (RealT)0) {
 			if (pd == 0 || pd == n_dim) vel.p[dim][f] = (RealT)0;
 			else {
-				const RealT diff = pressure[c] - pressure[cm]; // Real arithmetic, as the reference's expression
-				const RealT delta = (RealT)__ddiv_rn(__dmul_rn(P.dt, (double)diff), __dmul_rn((double)rho, P.dx));
-				vel.p[dim][f] = vel.p[dim][f] - delta; // array3::subtract (array3.h:663-671)
+				const RealT diff = pc - pm[dim]; // Real arithmetic, as the reference's expression
+				const double num = __dmul_rn(P.dt, (double)diff);
+				const RealT delta = (RealT)(rho == (RealT)1 ? div_dx(P, num) : __ddiv_rn(num, __dmul_rn((double)rho, P.dx)));
+				vel.p[dim][f] = uf[dim] - delta; // array3::subtract (array3.h:663-671)
 			}
 		} else {
-			if (pd == 0 && phi[c] < (RealT)0) vel.p[dim][f] = (RealT)0;
-			else if (pd == n_dim && phi[cm] < (RealT)0) vel.p[dim][f] = (RealT)0;
+			if (pd == 0 && phc < (RealT)0) vel.p[dim][f] = (RealT)0;
+			else if (pd == n_dim && phm[dim] < (RealT)0) vel.p[dim][f] = (RealT)0;
 			else { active.p[dim][f] = 0; vel.p[dim][f] = (RealT)0; } // set_off(): reads back as the background 0
 		}
 	}

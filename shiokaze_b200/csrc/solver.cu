@@ -1,6 +1,7 @@
 // Host side of libshkz_b200: device memory, launch sequences, and the C-ABI of include/shkz_b200.h.
 // No CPU compute path exists in this file: every entry point that computes needs a CUDA device.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -623,6 +624,11 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	A.second_order_fluid = P.second_order_fluid; A.second_order_solid = P.second_order_solid;
 	A.have_solid = solid != nullptr; A.fluid_levelset = fluid_levelset;
 	A.apply_rhs_correct = P.apply_rhs_correct;
+	{
+		int e = 0;
+		A.dx_pow2 = frexp(S->dx, &e) == 0.5 ? 1 : 0;
+		A.inv_dx = 1.0 / S->dx;
+	}
 	S->last_asm = A;
 	const RedBuf rb = S->redbuf();
 	CGState *st = S->dstate();

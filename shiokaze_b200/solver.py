@@ -106,9 +106,11 @@ class MacPressureSolver3:
         return ProjectionResult(int(st.iterations), float(st.reresid), bool(st.converged), int(st.n_rows), st.asdict())
 
     # -- host buffers (numpy): the call the Shiokaze plugin makes ------------------------------------
-    def project(self, dt, velocity, velocity_active, solid, fluid, fluid_levelset: bool, surface_tension: float = 0.0):
+    def project(self, dt, velocity, velocity_active, solid, fluid, fluid_levelset: bool, surface_tension: float = 0.0,
+                pressure_out=None, pressure_active_out=None):
         """In place on numpy arrays (velocity: 3 face arrays, velocity_active: 3 uint8). Returns
-        (pressure, pressure_active, ProjectionResult)."""
+        (pressure, pressure_active, ProjectionResult). pressure_out / pressure_active_out: optional caller-owned
+        result buffers (page-locked ones make the device-to-host copy run at PCIe speed)."""
         rt = self.np_real
         for v, a, shp in zip(velocity, velocity_active, self.face_shapes()):
             assert v.dtype == rt and v.flags.c_contiguous and v.shape == shp, (v.dtype, v.shape, shp)
@@ -118,8 +120,11 @@ class MacPressureSolver3:
             assert solid.dtype == rt and solid.flags.c_contiguous and solid.shape == (self.nzl + 1, self.ny + 1, self.nx + 1)
         self._volume_correction(dt)
         self.params.surface_tension = float(surface_tension)
-        pressure = np.zeros((self.nzl, self.ny, self.nx), dtype=rt)
-        pact = np.zeros((self.nzl, self.ny, self.nx), dtype=np.uint8)
+        shp = (self.nzl, self.ny, self.nx)
+        pressure = np.zeros(shp, dtype=rt) if pressure_out is None else pressure_out
+        pact = np.zeros(shp, dtype=np.uint8) if pressure_active_out is None else pressure_active_out
+        assert pressure.dtype == rt and pressure.flags.c_contiguous and pressure.shape == shp
+        assert pact.dtype == np.uint8 and pact.flags.c_contiguous and pact.shape == shp
         vp = (C.c_void_p * 3)(*[v.ctypes.data for v in velocity])
         ap = (C.c_void_p * 3)(*[a.ctypes.data for a in velocity_active])
         st = capi.Stats()
