@@ -39,7 +39,7 @@ enum shkz_b200_status {
 	SHKZ_B200_ERR_ARG = 1,       /* bad argument / unsupported combination */
 	SHKZ_B200_ERR_NO_DEVICE = 2, /* no CUDA device: the library never falls back to the CPU */
 	SHKZ_B200_ERR_CUDA = 3,      /* a CUDA runtime call failed */
-	SHKZ_B200_ERR_COMM = 4,      /* slab communicator (NCCL / IPC) failure */
+	SHKZ_B200_ERR_COMM = 4,      /* slab communicator (CUDA IPC / peer access) failure */
 	SHKZ_B200_ERR_STATE = 5      /* call sequence error */
 };
 
@@ -150,16 +150,16 @@ int shkz_b200_project_device(shkz_b200_solver *solver, double dt, void *const ve
  */
 int shkz_b200_resolve(shkz_b200_solver *solver, const shkz_b200_params *params, shkz_b200_stats *stats, void *cuda_stream);
 
-/* ---- z-slab communicator (one process per GPU; NVLink peer access through CUDA IPC + NCCL scalars) ---- */
-#define SHKZ_B200_NCCL_ID_BYTES 128
+/* ---- z-slab communicator: one solver per GPU of an NVLink domain. Halo planes and the CG scalars travel by direct
+ * peer-memory stores / loads inside the library's own kernels; no collective library is involved. Slabs must be equal
+ * (nz divisible by the number of ranks, rank r owns planes [r*nz/world, (r+1)*nz/world)).
+ * One process per GPU: every rank calls slab_export, the host exchanges the blobs by any means it has (the Python
+ * mirror uses torch.distributed), then every rank calls slab_connect with all blobs in rank order.
+ * One process driving several GPUs (what a Shiokaze host would do): create the solvers, then slab_connect_local. ---- */
 #define SHKZ_B200_IPC_BYTES 128
-/* rank 0 fills a fresh NCCL unique id that the host broadcasts to every rank */
-int shkz_b200_comm_unique_id(uint8_t id[SHKZ_B200_NCCL_ID_BYTES]);
-/* this rank's exported halo window + interprocess event (opaque bytes to hand to the z-neighbours) */
 int shkz_b200_slab_export(shkz_b200_solver *solver, uint8_t ipc[SHKZ_B200_IPC_BYTES]);
-/* connect: NCCL communicator over `world` ranks + the neighbours' exports (NULL at the domain ends) */
-int shkz_b200_slab_connect(shkz_b200_solver *solver, int rank, int world, const uint8_t id[SHKZ_B200_NCCL_ID_BYTES],
-                           const uint8_t *lower_ipc, const uint8_t *upper_ipc);
+int shkz_b200_slab_connect(shkz_b200_solver *solver, int rank, int world, const uint8_t *all_ipc /* world * SHKZ_B200_IPC_BYTES */);
+int shkz_b200_slab_connect_local(shkz_b200_solver *const *solvers, int world);
 
 /* ---- per-kernel timing (CUDA events around every launch; slows the call down, never on by default) ----
  * enable(1) resets the accumulators; entries are "<kernel>" or "<kernel>@<multigrid level>". */

@@ -6,5 +6,5 @@ Shiokaze module in plugin/. This Python package is the thin host mirror used by 
 interface, `scenes` generates the synthetic inputs, `dist` wires z-slabs over torch.distributed.
 There is no CPU fallback anywhere in this package.
 """
-from . import capi, scenes  # noqa: F401
+from . import capi, dist, scenes  # noqa: F401
 from .solver import MacPressureSolver3, ProjectionResult  # noqa: F401

@@ -12,14 +12,13 @@ OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_COMM, ERR_STATE = range(6)
 PRECOND_NONE, PRECOND_MG = 0, 1
 PREC_FP64, PREC_MIXED, PREC_FP32 = 0, 1, 2
 REAL_F32, REAL_F64 = 0, 1
-NCCL_ID_BYTES = 128
 IPC_BYTES = 128
 
 EXPORTS = [
     "shkz_b200_abi_version", "shkz_b200_last_error", "shkz_b200_default_params", "shkz_b200_device_count",
     "shkz_b200_create", "shkz_b200_create_slab", "shkz_b200_destroy", "shkz_b200_project_host",
-    "shkz_b200_project_device", "shkz_b200_resolve", "shkz_b200_comm_unique_id", "shkz_b200_slab_export",
-    "shkz_b200_slab_connect", "shkz_b200_debug_fetch", "shkz_b200_profile_enable", "shkz_b200_profile_count",
+    "shkz_b200_project_device", "shkz_b200_resolve", "shkz_b200_slab_export",
+    "shkz_b200_slab_connect", "shkz_b200_slab_connect_local", "shkz_b200_debug_fetch", "shkz_b200_profile_enable", "shkz_b200_profile_count",
     "shkz_b200_profile_get", "shkz_b200_debug_vcycle",
 ]
 
@@ -74,9 +73,9 @@ def lib():
     L.shkz_b200_project_host.argtypes = proj
     L.shkz_b200_project_device.argtypes = proj + [vp]
     L.shkz_b200_resolve.argtypes = [vp, C.POINTER(Params), C.POINTER(Stats), vp]
-    L.shkz_b200_comm_unique_id.argtypes = [u8p]
     L.shkz_b200_slab_export.argtypes = [vp, u8p]
-    L.shkz_b200_slab_connect.argtypes = [vp, C.c_int, C.c_int, u8p, u8p, u8p]
+    L.shkz_b200_slab_connect.argtypes = [vp, C.c_int, C.c_int, u8p]
+    L.shkz_b200_slab_connect_local.argtypes = [C.POINTER(vp), C.c_int]
     L.shkz_b200_debug_fetch.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.shkz_b200_profile_enable.argtypes = [vp, C.c_int]
     L.shkz_b200_profile_count.argtypes = [vp]

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "slab_comm.cuh"
+
 namespace shkz {
 
 // Local z-slab of a global nx*ny*nzg cell grid: planes [k0, k0+nzl). Every internal cell array is
@@ -61,6 +63,7 @@ __device__ __forceinline__ int tile_of(const Tiles &T, int i, int j, int k) { re
 struct RedBuf {
 	double *partials;      // [blocks][N]
 	unsigned int *counter; // zero between kernels
+	const CommDev *comm;   // z-slab solvers: the result is folded over all ranks (nullptr on a whole grid)
 };
 
 __device__ __forceinline__ unsigned linear_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
@@ -97,7 +100,9 @@ __device__ __forceinline__ void block_combine(double (&v)[N], double (*sm)[32]) 
 }
 
 // Grid-wide reduction with a deterministic combine order: every block stores its partial, the block
-// that arrives last folds all partials in a fixed order and runs `fin(total)` on one thread.
+// that arrives last folds all partials in a fixed order and runs `fin(total)` on one thread. On a z-slab
+// solver that thread first exchanges the rank totals with the other GPUs through peer memory
+// (slab_comm.cuh), so the reduction kernel IS the all-reduce: no separate collective is launched.
 // All values reduced here are sums, or maxima of non-negative numbers (identity 0 for both).
 template <int N, unsigned MAXMASK, class Fin>
 __device__ __forceinline__ void grid_reduce(double (&v)[N], RedBuf rb, Fin fin) {
@@ -130,6 +135,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[N], RedBuf rb, Fin fin) 
 	}
 	block_combine<N, MAXMASK>(acc, sm);
 	if (tid == 0) {
+		if (rb.comm) cross_rank_combine<N, MAXMASK>(acc, rb.comm); // peer-memory all-reduce, same bits on every rank
 		fin(acc);
 		*rb.counter = 0u;
 	}

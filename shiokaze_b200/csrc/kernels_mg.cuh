@@ -79,7 +79,7 @@ inline dim3 sweep_block() { return dim3(TX / 2, TY, 1); }
 template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
                                                         const float *__restrict__ dd, const float *__restrict__ b, const float *__restrict__ xo,
-                                                        float *__restrict__ xn, const float *__restrict__ ec, Dims dc, RedBuf rb, CGState *st) {
+                                                        float *__restrict__ xn, const float *__restrict__ ec, Dims dc, int slab_ghosts, RedBuf rb, CGState *st) {
 	if (st && st->done) return;
 	__shared__ float H[3][TY + 2][TX + 2];
 	const int px = threadIdx.x, ty = threadIdx.y;
@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(Dims d, Tiles T, con
 
 	// x_old at (i,j,k) / flat index c (k may be a ghost plane; i, j may be one step outside the grid: such reads
 	// wrap to another finite slot of the allocation and only ever meet a zero coefficient)
+	// (z-slab solvers: with ZERO_X the ghost planes still hold what the neighbours stored there, slab_ghosts)
 	auto XO = [&](long long c, int i, int j, int k) -> float {
-		if (ZERO_X) return 0.f;
+		if (ZERO_X && !(slab_ghosts && (k < 0 || k >= d.nzl))) return 0.f;
 		float v = xo[c];
 		if (PROLONG) v += ec[(i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1))];
 		return v;
@@ -215,7 +216,7 @@ __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast
 template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
 __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep4(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
                                                          const float *__restrict__ dd, const float *__restrict__ b, const float *__restrict__ xo,
-                                                         float *__restrict__ xn, const float *__restrict__ ec, Dims dc, RedBuf rb, CGState *st) {
+                                                         float *__restrict__ xn, const float *__restrict__ ec, Dims dc, int slab_ghosts, RedBuf rb, CGState *st) {
 	if (st && st->done) return;
 	__shared__ __align__(16) float H[3][S4_ROWS][S4_PITCH];
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -229,13 +230,13 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep4(Dims d, Tiles T, const
 
 	auto EC = [&](int i, int j, int k) -> long long { return (i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1)); };
 	auto XO = [&](long long c, int i, int j, int k) -> float { // one cell of x_old (see k_sweep)
-		if (ZERO_X) return 0.f;
+		if (ZERO_X && !(slab_ghosts && (k < 0 || k >= d.nzl))) return 0.f;
 		float v = xo[c];
 		if (PROLONG) v += ec[EC(i, j, k)];
 		return v;
 	};
 	auto XO4 = [&](long long c0, int i, int j, int k) -> float4 { // an aligned quad of x_old
-		if (ZERO_X) return zero4;
+		if (ZERO_X && !(slab_ghosts && (k < 0 || k >= d.nzl))) return zero4;
 		float4 v = ld4(xo + c0);
 		if (PROLONG) {
 			const float2 e = *reinterpret_cast<const float2 *>(ec + EC(i, j, k));
@@ -348,6 +349,36 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep4(Dims d, Tiles T, const
 			if (zr == 0.0 || zr != zr) st->done = 1;        // pcg_solver.h:263-271
 		});
 	}
+}
+
+// z-slab solvers: the half-updated version (first colour relaxed) of the own boundary planes, stored straight into the
+// neighbours' ghost planes of the same buffer. A neighbour's sweep kernel then finds in its ghost plane exactly what
+// both of its phases need (second-colour cells still old for phase 1, first-colour cells new for phase 2), which is
+// why the sweep kernels need no slab logic beyond reading their ghost planes. blockIdx.y: 0 = plane 0 to the lower
+// neighbour, 1 = plane nzl-1 to the upper one.
+template <int FIRST, bool ZERO_X>
+__global__ void __launch_bounds__(256) k_boundary_half_push(Dims d, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
+                                                           const float *__restrict__ dd, const float *__restrict__ b, const float *__restrict__ xo,
+                                                           const CommDev *cm, size_t off, unsigned long long seq) {
+	const int p = blockIdx.y ? d.nzl - 1 : 0;
+	char *peer = blockIdx.y ? cm->hi : cm->lo;
+	if (peer) {
+		float *dst = reinterpret_cast<float *>(peer + off) + (blockIdx.y ? 0 : (long long)(d.nzl + 1) * d.plane);
+		const long long nx = d.nx, plane = d.plane;
+		for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < plane; e += (long long)gridDim.x * blockDim.x) {
+			const int j = (int)(e / nx), i = (int)(e - (long long)j * nx);
+			const long long c = e + plane * p;
+			float v;
+			if (((i + j + p + d.k0) & 1) == FIRST) {
+				const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
+				// with ZERO_X the in-slab x_old is zero but the ghost planes already hold the neighbours' values: none yet, x_old = 0 everywhere
+				v = ZERO_X ? gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c])
+				           : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], xo[c - 1], xo[c + 1], xo[c - nx], xo[c + nx], xo[c - plane], xo[c + plane]);
+			} else v = ZERO_X ? 0.f : xo[c];
+			dst[e] = v;
+		}
+	}
+	signal_neighbours(cm, seq);
 }
 
 // coarse b = P^T (b - A x): block (TX/2, TY/2), one coarse column per thread, aggregates never straddle tiles

@@ -70,7 +70,7 @@ struct SweepMaps { // tensor maps of one level's arrays, box widths as documente
 
 template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
 __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, const __grid_constant__ SweepMaps M, const float *__restrict__ xo, float *__restrict__ xn,
-                                                            const float *__restrict__ ec, Dims dc, RedBuf rb, CGState *st) {
+                                                            const float *__restrict__ ec, Dims dc, int slab_ghosts, RedBuf rb, CGState *st) {
 	if (st && st->done) return;
 	extern __shared__ __align__(128) float smem[];
 	float *stage_base = smem;
@@ -131,15 +131,18 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 			const int ci = i0 - 4 + cc, cj = j0 - 1 + rr;
 			const bool cv = ci >= 0 && ci < d.nx && cj < d.ny;
 			float xm = 0.f, xc = 0.f;
+			// ZERO_X on a z-slab: x_old is zero inside the slab, the ghost planes hold the neighbours' half-updated planes
+			auto ghost1 = [&](int k) -> float { return (ZERO_X && slab_ghosts && cv && (k < 0 || k >= d.nzl) && k >= -1 && k <= d.nzl) ? xo[ci + nx * (cj + ny * k)] : 0.f; };
 			if (!ZERO_X && cv && kb - 2 >= -1) {
 				xm = xo[ci + nx * (cj + ny * (kb - 2))];
 				if (PROLONG) xm += ec[EC(ci, cj, kb - 2)];
 			}
+			if (ZERO_X) xm = ghost1(kb - 2);
 			wait_plane(kb - 1);
 			if (!ZERO_X) {
 				xc = stage_of(kb - 1)[ST_XO + (rr + 1) * ST_W + cc];
 				if (PROLONG && cv) xc += ec[EC(ci, cj, kb - 1)];
-			}
+			} else xc = ghost1(kb - 1);
 			for (int p = kb - 1; p <= ke; ++p) {
 				wait_plane(p + 1);
 				const float *P = stage_of(p), *N = stage_of(p + 1);
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 				if (!ZERO_X) {
 					xp = N[ST_XO + (rr + 1) * ST_W + cc];
 					if (PROLONG && cv && p + 1 <= d.nzl) xp += ec[EC(ci, cj, p + 1)];
-				}
+				} else xp = ghost1(p + 1);
 				float h = xc;
 				if (in_slab && ((ci + cj + p + d.k0) & 1) == FIRST) {
 					const float w0 = P[ST_WX + rr * ST_W + cc], w1 = P[ST_WX + rr * ST_W + cc + 1], w2 = P[ST_WY + rr * ST_W + cc], w3 = P[ST_WY + (rr + 1) * ST_W + cc];
@@ -184,17 +187,21 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 			return v;
 		};
 		float4 xm = zero4, xc = zero4, wz_cur = zero4;
+		auto ghost4 = [&](int k) -> float4 { // ZERO_X on a z-slab: the ghost planes are the only non-zero part of x_old
+			return (ZERO_X && slab_ghosts && valid && (k < 0 || k >= d.nzl) && k >= -1 && k <= d.nzl) ? ld4(xo + row + plane * k) : zero4;
+		};
 		if (!ZERO_X && valid && kb - 2 >= -1) {
 			xm = ld4(xo + row + plane * (kb - 2));
 			if (PROLONG) xm = ECQ(xm, i, j, kb - 2);
 		}
+		if (ZERO_X) xm = ghost4(kb - 2);
 		wait_plane(kb - 1);
 		{
 			const float *P = stage_of(kb - 1);
 			if (!ZERO_X) {
 				xc = LDQ(P, ST_XO, r + 1);
 				if (PROLONG && valid) xc = ECQ(xc, i, j, kb - 1);
-			}
+			} else xc = ghost4(kb - 1);
 			wz_cur = LDQ(P, ST_WZ, r);
 		}
 		float4 hm = zero4, hc = zero4;
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 						xd = ECQ(xd, i, j - 1, p); xu = ECQ(xu, i, j + 1, p);
 					}
 				}
-			}
+			} else xp = ghost4(p + 1);
 			// ---- phase 1: half-updated plane p
 			float4 hp = xc;
 			if (in_slab) {

@@ -1,0 +1,112 @@
+// Device side of the z-slab communicator: halo planes and CG scalars move between the GPUs of one NVLink domain
+// by plain loads / stores on peer-mapped memory inside our own kernels (no NCCL call anywhere in the solve).
+//
+// Every slab solver carves all of its ghosted cell arrays from ONE device allocation (the "arena"), exported
+// once through CUDA IPC (or used directly when the slabs live in one process). All ranks run the same allocation
+// sequence on slabs of equal size, so an array sits at the same offset in every arena and a neighbour's ghost plane
+// is just (mapped arena base + offset). The first ARENA_HEADER bytes hold the synchronisation words:
+//   flag_from_lo / flag_from_hi   number of the last halo exchange whose planes the lower / upper neighbour has
+//                                 stored here (written remotely, release order: planes, system fence, flag)
+//   red_seq                       count of cross-rank reductions this rank has taken part in
+//   mail[4 slots][8 ranks][8]     all-to-all mailbox of the reductions: every rank stores its partial sums into
+//                                 the slot of every rank (itself included), then each rank folds the world's
+//                                 partials in rank order, so all ranks obtain bit-identical results
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "slab_comm.h"
+
+namespace shkz {
+
+// Fold the world's partial results (sums, or maxima where MAXMASK has the bit set) — called by ONE thread per rank.
+template <int N, unsigned MAXMASK>
+__device__ __forceinline__ void cross_rank_combine(double (&v)[N], const CommDev *cm) {
+	static_assert(N <= 7, "mailbox entries hold seven values and a sequence word");
+	unsigned long long *seqp = reinterpret_cast<unsigned long long *>(cm->self + HDR_RED_SEQ);
+	const unsigned long long seq = *seqp + 1ull;
+	*seqp = seq;
+	const size_t entry = ((size_t)(seq & 3ull) * COMM_MAX_WORLD + (size_t)cm->rank) * 8;
+	for (int p = 0; p < cm->world; ++p) {
+		volatile double *m = reinterpret_cast<volatile double *>(cm->peer[p] + HDR_MAIL) + entry;
+#pragma unroll
+		for (int n = 0; n < N; ++n) m[n] = v[n];
+	}
+	__threadfence_system();
+	for (int p = 0; p < cm->world; ++p)
+		*(reinterpret_cast<volatile unsigned long long *>(cm->peer[p] + HDR_MAIL) + entry + 7) = seq;
+	double tot[N];
+#pragma unroll
+	for (int n = 0; n < N; ++n) tot[n] = 0.0;
+	for (int q = 0; q < cm->world; ++q) {
+		const size_t e = ((size_t)(seq & 3ull) * COMM_MAX_WORLD + (size_t)q) * 8;
+		volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_MAIL) + e + 7;
+		while (*f < seq) {}
+		__threadfence_system();
+		const volatile double *m = reinterpret_cast<const volatile double *>(cm->self + HDR_MAIL) + e;
+#pragma unroll
+		for (int n = 0; n < N; ++n) {
+			const double p = m[n];
+			tot[n] = ((MAXMASK >> n) & 1u) ? fmax(tot[n], p) : tot[n] + p;
+		}
+	}
+#pragma unroll
+	for (int n = 0; n < N; ++n) v[n] = tot[n];
+}
+
+// Called by every thread of every block of a kernel that has stored planes into the neighbours' arenas: the block that
+// finishes last publishes exchange number `seq` in the neighbours' flag words (release order: data, system fence, flag).
+__device__ __forceinline__ void signal_neighbours(const CommDev *cm, unsigned long long seq) {
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+		unsigned int *ticket = reinterpret_cast<unsigned int *>(cm->self + HDR_PUSH_TICKET);
+		const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+		if (atomicAdd(ticket, 1u) == nblocks - 1) {
+			*ticket = 0u;
+			__threadfence_system();
+			if (cm->lo) *reinterpret_cast<volatile unsigned long long *>(cm->lo + HDR_FLAG_FROM_HI) = seq;
+			if (cm->hi) *reinterpret_cast<volatile unsigned long long *>(cm->hi + HDR_FLAG_FROM_LO) = seq;
+		}
+	}
+}
+
+// Halo exchange number `seq` of the cell array at arena offset `off` (offset of its lower ghost plane): store the own
+// boundary planes into the neighbours' ghost planes, then publish `seq` in their flag words.
+__global__ void __launch_bounds__(256) k_halo_push(const CommDev *cm, size_t off, size_t plane_bytes, int nzl, unsigned long long seq) {
+	const char *src_lo = cm->self + off + plane_bytes;                 // own plane 0
+	const char *src_hi = cm->self + off + plane_bytes * (size_t)nzl;   // own plane nzl-1
+	char *dst_lo = cm->lo ? cm->lo + off + plane_bytes * (size_t)(nzl + 1) : nullptr; // lower neighbour's upper ghost plane
+	char *dst_hi = cm->hi ? cm->hi + off : nullptr;                                    // upper neighbour's lower ghost plane
+	const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	if ((plane_bytes & 15) == 0) {
+		const size_t n16 = plane_bytes >> 4;
+		for (size_t e = tid; e < n16; e += nth) {
+			if (dst_lo) reinterpret_cast<uint4 *>(dst_lo)[e] = reinterpret_cast<const uint4 *>(src_lo)[e];
+			if (dst_hi) reinterpret_cast<uint4 *>(dst_hi)[e] = reinterpret_cast<const uint4 *>(src_hi)[e];
+		}
+	} else {
+		for (size_t e = tid; e < plane_bytes; e += nth) {
+			if (dst_lo) dst_lo[e] = src_lo[e];
+			if (dst_hi) dst_hi[e] = src_hi[e];
+		}
+	}
+	signal_neighbours(cm, seq);
+}
+
+// ... and wait until both neighbours have delivered theirs.
+__global__ void k_halo_wait(const CommDev *cm, unsigned long long seq) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		if (cm->lo) {
+			volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_LO);
+			while (*f < seq) {}
+		}
+		if (cm->hi) {
+			volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_HI);
+			while (*f < seq) {}
+		}
+		__threadfence_system();
+	}
+}
+
+} // namespace shkz

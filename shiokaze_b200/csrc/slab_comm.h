@@ -1,29 +1,59 @@
-// z-slab communicator: halo planes between neighbouring ranks and the CG scalar all-reduce.
+// Host side of the z-slab communicator (device side: slab_comm.cuh): the arena every ghosted array of a slab solver
+// is carved from, its export / import through CUDA IPC (one process per GPU) or direct peer access (one process,
+// several GPUs), and the numbering of halo exchanges.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 namespace shkz {
 
-struct CGState;
+constexpr int COMM_MAX_WORLD = 8;
+constexpr size_t HDR_FLAG_FROM_LO = 0, HDR_FLAG_FROM_HI = 128, HDR_RED_SEQ = 256, HDR_PUSH_TICKET = 384, HDR_MAIL = 1024;
+constexpr size_t ARENA_HEADER = 65536;
+
+struct CommDev {
+	int rank, world;
+	char *self;                 // own arena
+	char *lo, *hi;              // arenas of the z-neighbours as mapped into this process (nullptr at the domain ends)
+	char *peer[COMM_MAX_WORLD]; // every rank's arena (peer[rank] == self)
+};
+
 
 class SlabComm {
 public:
-	SlabComm(long long plane_cells, int device);
+	SlabComm(int device) : m_device(device) {}
 	~SlabComm();
-	static int unique_id(uint8_t *id, std::string &err);
-	int export_window(uint8_t *ipc);
-	int connect(int rank, int world, const uint8_t *id, const uint8_t *lower_ipc, const uint8_t *upper_ipc);
-	// fill the ghost planes of a cell array (pointer at plane 0) from the neighbouring slabs
-	int exchange(void *p, long long plane_cells, int nzl, size_t elem, cudaStream_t stream);
-	int allreduce_begin_state(CGState *st, cudaStream_t stream);
-	int allreduce_sum_x(CGState *st, cudaStream_t stream);
+	// arena
+	int create_arena(size_t bytes);
+	void *carve(size_t bytes); // 256-byte aligned, zero-filled; nullptr when the arena is exhausted
+	bool owns(const void *p) const { return m_base && p >= (const void *)m_base && p < (const void *)(m_base + m_size); }
+	size_t offset_of(const void *p) const { return (size_t)((const char *)p - m_base); }
+	size_t mark() const { return m_used; }
+	void rewind(size_t mark) { m_used = mark; } // drop everything carved after mark()
+	// wiring
+	int export_handle(uint8_t *blob, size_t blob_bytes);                             // this rank's arena, for the other processes
+	int connect_ipc(int rank, int world, const uint8_t *blobs, size_t blob_bytes);   // blobs: world entries, rank-major
+	int connect_local(int rank, int world, SlabComm *const *all);                    // same process: peer access
+	bool connected() const { return m_connected; }
+	int rank() const { return m_rank; }
+	int world() const { return m_world; }
+	const CommDev *device_view() const { return m_dev; }
+	unsigned long long next_exchange() { return ++m_exchange; }
 	const char *error() const { return m_error.c_str(); }
+
 private:
+	int finish_connect();
 	std::string m_error;
-	long long m_plane;
 	int m_device;
+	char *m_base = nullptr;
+	size_t m_size = 0, m_used = 0;
+	bool m_connected = false, m_ipc = false;
+	int m_rank = 0, m_world = 1;
+	char *m_peer[COMM_MAX_WORLD] = {};
+	CommDev *m_dev = nullptr;
+	unsigned long long m_exchange = 0;
 };
 
 } // namespace shkz

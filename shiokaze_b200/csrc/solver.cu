@@ -46,20 +46,29 @@ int fail(int code, const char *fmt, ...) {
 		if (r_ != SHKZ_B200_OK) return r_; \
 	} while (0)
 
-// A cell-shaped device array with one ghost plane on each side; `p` points at plane 0.
+// A cell-shaped device array with one ghost plane on each side; `p` points at plane 0. Slab solvers carve these
+// from their communicator's arena (slab_comm.h) so that neighbours can address the ghost planes.
 struct CellArray {
 	void *base = nullptr;
 	size_t bytes = 0;
-	int alloc(const Dims &d, size_t elem) {
+	bool in_arena = false;
+	int alloc(const Dims &d, size_t elem, SlabComm *arena = nullptr) {
 		bytes = (size_t)(d.nzl + 2) * (size_t)d.plane * elem;
+		if (arena) {
+			base = arena->carve(bytes);
+			in_arena = true;
+			if (!base) return fail(SHKZ_B200_ERR_CUDA, "slab arena exhausted (%zu more bytes needed)", bytes);
+			return SHKZ_B200_OK;
+		}
 		CK(cudaMalloc(&base, bytes));
 		CK(cudaMemset(base, 0, bytes));
 		return SHKZ_B200_OK;
 	}
 	void release() {
-		if (base) cudaFree(base);
+		if (base && !in_arena) cudaFree(base);
 		base = nullptr;
 		bytes = 0;
+		in_arena = false;
 	}
 	template <class T> T *ptr(const Dims &d) const { return base ? static_cast<T *>(base) + d.plane : nullptr; }
 };
@@ -210,8 +219,9 @@ struct shkz_b200_solver {
 	unsigned last_iterations = 0; // of the previous solve: sizes the first batch of iterations before the host looks
 	// host-call staging (device)
 	PlainArray st_vel[3], st_act[3], st_solid, st_fluid, st_pressure, st_pact;
-	// slab communicator
+	// slab communicator (nullptr on a whole grid)
 	SlabComm *comm = nullptr;
+	size_t arena_mark = 0; // arena fill level after the creation-time arrays
 	// bookkeeping
 	uint64_t launches = 0;
 	Profiler prof;
@@ -223,7 +233,10 @@ struct shkz_b200_solver {
 	cudaEvent_t ev[8]{};
 	bool events = false;
 
-	RedBuf redbuf() const { return RedBuf{static_cast<double *>(partials.base), static_cast<unsigned int *>(counter.base)}; }
+	SlabComm *arena() const { return whole_grid ? nullptr : comm; }
+	RedBuf redbuf() const {
+		return RedBuf{static_cast<double *>(partials.base), static_cast<unsigned int *>(counter.base), (comm && comm->connected()) ? comm->device_view() : nullptr};
+	}
 	CGState *dstate() const { return static_cast<CGState *>(state.base); }
 };
 
@@ -242,6 +255,7 @@ void release_precision_arrays(shkz_b200_solver *S) {
 	S->have_system = false;
 	S->have_hierarchy = false;
 	S->tail_first = -1;
+	if (S->arena()) S->arena()->rewind(S->arena_mark); // every rank re-carves the same sequence, offsets stay in step
 }
 
 // planes per tile: as deep as possible (each tile relaxes two extra halo planes) while the level still
@@ -259,8 +273,9 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 	if (S->alloc_precision == precision && S->mg_min_size_built == min_size) return SHKZ_B200_OK;
 	release_precision_arrays(S);
 	const Dims &d = S->d;
-	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd}) CKR(a->alloc(d, sizeof(CoefT)));
-	for (CellArray *a : {&S->b, &S->x, &S->r, &S->s, &S->q}) CKR(a->alloc(d, sizeof(VecT)));
+	SlabComm *arena = S->arena();
+	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd}) CKR(a->alloc(d, sizeof(CoefT), arena));
+	for (CellArray *a : {&S->b, &S->x, &S->r, &S->s, &S->q}) CKR(a->alloc(d, sizeof(VecT), arena));
 	// multigrid hierarchy (always allocated: switching the preconditioner must not reallocate; level 0 also
 	// carries the tile list every CG kernel runs over)
 	Dims cur = d;
@@ -272,16 +287,16 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 			L.own_coef = false;
 			L.wx = S->wx; L.wy = S->wy; L.wz = S->wz; L.dd = S->dd;
 		} else {
-			for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.dd}) CKR(a->alloc(cur, sizeof(float)));
+			for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.dd}) CKR(a->alloc(cur, sizeof(float), arena));
 		}
 		if (l == 0 && sizeof(VecT) == sizeof(float)) {
 			L.own_b = false;
 			L.b = S->r; // an all-float CG smooths against r directly
 		} else {
-			CKR(L.b.alloc(cur, sizeof(float)));
+			CKR(L.b.alloc(cur, sizeof(float), arena));
 		}
-		CKR(L.xa.alloc(cur, sizeof(float)));
-		CKR(L.xb.alloc(cur, sizeof(float)));
+		CKR(L.xa.alloc(cur, sizeof(float), arena));
+		CKR(L.xb.alloc(cur, sizeof(float), arena));
 		L.bz = pick_bz(cur);
 		const int ntx = (cur.nx + TX - 1) / TX, nty = (cur.ny + TY - 1) / TY, ntz = (cur.nzl + L.bz - 1) / L.bz;
 		L.tiles_total = ntx * nty * ntz;
@@ -389,11 +404,24 @@ int tile_grid(shkz_b200_solver *S, K kernel, dim3 block, int tiles_total, size_t
 		(S)->launches++;                                                                                    \
 	} while (0)
 
-// ---- halo exchange of one cell array (ghost planes), a no-op on a whole grid ----
+// ---- halo exchange of one cell array (ghost planes), a no-op on a whole grid: the own boundary planes are stored
+// ---- into the neighbours' ghost planes over NVLink by our own kernel, then the stream waits for theirs
+int halo_wait(shkz_b200_solver *S, unsigned long long seq, cudaStream_t st) {
+	LAUNCH(S, "halo_wait", k_halo_wait, 1, 32, st, S->comm->device_view(), seq);
+	return SHKZ_B200_OK;
+}
 template <class T>
 int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
-	if (S->whole_grid || !S->comm) return SHKZ_B200_OK;
-	return S->comm->exchange(p, d.plane, d.nzl, sizeof(T), st) ? fail(SHKZ_B200_ERR_COMM, "halo exchange failed: %s", S->comm->error()) : SHKZ_B200_OK;
+	if (S->whole_grid) return SHKZ_B200_OK;
+	if (!S->comm || !S->comm->connected()) return fail(SHKZ_B200_ERR_STATE, "slab solver is not connected");
+	const void *base = reinterpret_cast<const char *>(p) - (size_t)d.plane * sizeof(T);
+	if (!S->comm->owns(base)) return fail(SHKZ_B200_ERR_STATE, "halo exchange of an array outside the slab arena");
+	const size_t plane_bytes = (size_t)d.plane * sizeof(T);
+	const unsigned long long seq = S->comm->next_exchange();
+	const size_t chunks = (plane_bytes + 15) / 16;
+	const int blocks = (int)((chunks + 255) / 256 > 296 ? 296 : ((chunks + 255) / 256 < 1 ? 1 : (chunks + 255) / 256));
+	LAUNCH(S, "halo_push", k_halo_push, blocks, 256, st, S->comm->device_view(), S->comm->offset_of(base), plane_bytes, d.nzl, seq);
+	return halo_wait(S, seq, st);
 }
 
 int compact_tiles(shkz_b200_solver *S, HostLevel &H, cudaStream_t stream) {
@@ -411,18 +439,21 @@ void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, floa
 		maps.wx = H.map_wx; maps.wy = H.map_wy; maps.wz = H.map_wz; maps.dd = H.map_dd; maps.b = H.map_b;
 		maps.xo = xo == L.xb ? H.map_xb : H.map_xa;
 		LAUNCH_TILES_SMEM(S, H.tag_sweep.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
-		                  L.tiles, maps, xo, xn, ec, dc, S->redbuf(), st);
+		                  L.tiles, maps, xo, xn, ec, dc, S->whole_grid ? 0 : 1, S->redbuf(), st);
 	} else if ((L.d.nx & 3) == 0 && S->sweep_mode <= 1) // aligned quads, direct global loads
 		LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep4<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
-		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->redbuf(), st);
+		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->whole_grid ? 0 : 1, S->redbuf(), st);
 	else
 		LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep<FIRST, ZERO_X, PROLONG, DOT>), sweep_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
-		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->redbuf(), st);
+		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->whole_grid ? 0 : 1, S->redbuf(), st);
 }
 
 // One V-cycle on level l and below, right-hand side in the level's b. *result = buffer holding the solution.
 // dot: also reduce (solution . b) into the CG state (level 0 only).
+int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result);
+
 int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result) {
+	if (!S->whole_grid) return vcycle_slab(S, l, P, st, stream, dot, result);
 	HostLevel &H = S->levels[l];
 	const MGLevel &L = H.view;
 	const int coarse = P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps;
@@ -472,6 +503,66 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st
 		else if (prolong) launch_sweep<1, false, true, false>(S, H, cur, bufs[w], ec, dc, st, stream);
 		else if (dotnow) launch_sweep<1, false, false, true>(S, H, cur, bufs[w], nullptr, none, st, stream);
 		else launch_sweep<1, false, false, false>(S, H, cur, bufs[w], nullptr, none, st, stream);
+		cur = bufs[w];
+		w ^= 1;
+	}
+	if (dot && post == 0) LAUNCH_TILES(S, "dot_zb", k_dot_zb, cg_block(), H.tiles_total, stream, L.d, L.tiles, cur, (const float *)L.b, S->redbuf(), st);
+	*result = cur;
+	return SHKZ_B200_OK;
+}
+
+// The V-cycle on a z-slab: same kernels, same arithmetic, same result bits as on the whole grid. Before every sweep
+// each rank relaxes the first colour of its two boundary planes and stores them into the neighbours' ghost planes
+// (k_boundary_half_push); after it, the finished boundary planes follow (halo). The shared-memory tail and the folded
+// prolongation are whole-grid features: here every level is swept in place and the correction is added by its own kernel.
+template <int FIRST>
+int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, float *xn, bool dot, CGState *st, cudaStream_t stream) {
+	const MGLevel &L = H.view;
+	const Dims none{};
+	const unsigned long long seq = S->comm->next_exchange();
+	const size_t off = S->comm->offset_of(reinterpret_cast<const char *>(xo) - (size_t)L.d.plane * sizeof(float));
+	const long long pb = (L.d.plane + 255) / 256;
+	const dim3 grid((unsigned)(pb > 148 ? 148 : (pb < 1 ? 1 : pb)), 2, 1);
+	if (zero_x) LAUNCH(S, "boundary_half", (k_boundary_half_push<FIRST, true>), grid, 256, stream, L.d, (const float *)L.wx, (const float *)L.wy, (const float *)L.wz,
+	                   (const float *)L.dd, (const float *)L.b, xo, S->comm->device_view(), off, seq);
+	else LAUNCH(S, "boundary_half", (k_boundary_half_push<FIRST, false>), grid, 256, stream, L.d, (const float *)L.wx, (const float *)L.wy, (const float *)L.wz,
+	            (const float *)L.dd, (const float *)L.b, xo, S->comm->device_view(), off, seq);
+	CKR(halo_wait(S, seq, stream));
+	if (zero_x) launch_sweep<FIRST, true, false, false>(S, H, xo, xn, nullptr, none, st, stream);
+	else if (dot) launch_sweep<FIRST, false, false, true>(S, H, xo, xn, nullptr, none, st, stream);
+	else launch_sweep<FIRST, false, false, false>(S, H, xo, xn, nullptr, none, st, stream);
+	return halo(S, L.d, xn, stream);
+}
+
+int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result) {
+	HostLevel &H = S->levels[l];
+	const MGLevel &L = H.view;
+	const bool last = (l + 1 == S->levels.size());
+	const int coarse = P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps;
+	const int pre = last ? coarse : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
+	const int post = last ? coarse : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
+	float *bufs[2] = {L.xa, L.xb};
+	const float *cur = nullptr;
+	int w = 0;
+	for (int sw = 0; sw < pre; ++sw) {
+		// the very first sweep starts from x = 0: the "old" buffer is only a landing place for the neighbours' boundary planes
+		CKR(slab_sweep<0>(S, H, sw == 0, sw == 0 ? bufs[w ^ 1] : cur, bufs[w], false, st, stream));
+		cur = bufs[w];
+		w ^= 1;
+	}
+	if (!last) {
+		const MGLevel &C = S->levels[l + 1].view;
+		LAUNCH_TILES(S, H.tag_restrict.c_str(), k_residual_restrict, restrict_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx, (const float *)L.wy,
+		             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st);
+		const float *ec = nullptr;
+		CKR(vcycle_slab(S, l + 1, P, st, stream, false, &ec));
+		LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, C.d, ec, cur, bufs[w], (const CGState *)st);
+		CKR(halo(S, L.d, bufs[w], stream));
+		cur = bufs[w];
+		w ^= 1;
+	}
+	for (int sw = 0; sw < post; ++sw) {
+		CKR(slab_sweep<1>(S, H, false, cur, bufs[w], dot && sw + 1 == post, st, stream));
 		cur = bufs[w];
 		w ^= 1;
 	}
@@ -544,7 +635,6 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	constexpr bool kFloatVec = sizeof(VecT) == sizeof(float);
 	float *b0 = kFloatVec ? nullptr : H0.view.b; // an all-float CG hands r itself to multigrid
 
-	if (S->comm && !S->whole_grid) CKR(S->comm->allreduce_begin_state(st, stream) ? fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error()) : SHKZ_B200_OK);
 	LAUNCH(S, "cg_begin", k_cg_begin, 1, 32, stream, P.residual, (int)P.max_iterations, st);
 	if (mg && !kFloatVec) LAUNCH_TILES(S, "cg_init", (k_cg_init<VecT, true>), cg_block(), tt, stream, d, T, (const VecT *)b, x, r, s, b0);
 	else LAUNCH_TILES(S, "cg_init", (k_cg_init<VecT, false>), cg_block(), tt, stream, d, T, (const VecT *)b, x, r, s, b0);
@@ -588,7 +678,7 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 void fill_stats(const shkz_b200_solver *S, shkz_b200_stats *out) {
 	if (!out) return;
 	const CGState &h = *S->h_state;
-	out->n_rows = h.n_rows;
+	out->n_rows = h.n_rows; // (z-slab solvers: the count is reduced over all ranks, like every CG scalar)
 	out->n_rows_global = h.n_rows;
 	out->iterations = (uint32_t)h.iter;
 	out->converged = h.converged;
@@ -677,7 +767,6 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	// pressure scatter + velocity update
 	if (!S->h_state->has_dirichlet && S->h_state->n_rows) {
 		LAUNCH(S, "sum_rows", k_sum_rows<VecT>, flat_blocks(d.ncell), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows, rb, st);
-		if (S->comm && !S->whole_grid) CKR(S->comm->allreduce_sum_x(st, stream) ? fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error()) : SHKZ_B200_OK);
 	}
 	LAUNCH(S, "store_pressure", (k_store_pressure<RealT, VecT>), (unsigned)((d.ncell + 255) / 256), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows,
 	       (const CGState *)st, pres);
@@ -801,9 +890,20 @@ int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int
 	const Dims &d = S->d;
 	int rc = SHKZ_B200_OK;
 	auto tryalloc = [&](int r) { if (rc == SHKZ_B200_OK) rc = r; };
-	tryalloc(S->phi.alloc(d, S->real_bytes));
-	tryalloc(S->pressure.alloc(d, S->real_bytes));
-	tryalloc(S->in_rows.alloc(d, 1));
+	if (!S->whole_grid) {
+		// one arena for every ghosted array (see slab_comm.h); generous bound on what any precision mode carves
+		if (nz % (k1 - k0) != 0 || k0 % (k1 - k0) != 0) rc = fail(SHKZ_B200_ERR_ARG, "z-slabs must be equal: nz %d, slab [%d,%d)", nz, k0, k1);
+		S->comm = new SlabComm(device);
+		const size_t cells = (size_t)(d.nzl + 2) * (size_t)d.plane;
+		if (rc == SHKZ_B200_OK && S->comm->create_arena(ARENA_HEADER + cells * 136 + (size_t)64 * 1024 * 1024)) rc = fail(SHKZ_B200_ERR_CUDA, "%s", S->comm->error());
+	}
+	tryalloc(S->phi.alloc(d, S->real_bytes, S->arena()));
+	tryalloc(S->pressure.alloc(d, S->real_bytes, S->arena()));
+	tryalloc(S->in_rows.alloc(d, 1, S->arena()));
+	if (!S->whole_grid) {
+		tryalloc(S->curv.alloc(d, S->real_bytes, S->arena())); // (a whole grid allocates it on first use)
+		S->arena_mark = S->comm->mark();
+	}
 	for (int dim = 0; dim < 3; ++dim) {
 		tryalloc(S->areas[dim].alloc(face_count(d, dim) * S->real_bytes));
 		tryalloc(S->rhos[dim].alloc(face_count(d, dim) * S->real_bytes));
@@ -860,7 +960,7 @@ int shkz_b200_project_device(shkz_b200_solver *S, double dt, void *const vel[3],
 	if (!vel || !vel_active || !fluid) return fail(SHKZ_B200_ERR_ARG, "vel / vel_active / fluid must not be NULL");
 	for (int dim = 0; dim < 3; ++dim)
 		if (!vel[dim] || !vel_active[dim]) return fail(SHKZ_B200_ERR_ARG, "vel[%d] / vel_active[%d] is NULL", dim, dim);
-	if (!S->whole_grid && !S->comm) return fail(SHKZ_B200_ERR_STATE, "slab solver is not connected (call shkz_b200_slab_connect)");
+	if (!S->whole_grid && !(S->comm && S->comm->connected())) return fail(SHKZ_B200_ERR_STATE, "slab solver is not connected (call shkz_b200_slab_connect)");
 	shkz_b200_params P;
 	CKR(check_params(params, P));
 	CKR(device_ready(S->device));
@@ -1043,27 +1143,37 @@ int shkz_b200_debug_vcycle(shkz_b200_solver *S, const shkz_b200_params *params, 
 	return SHKZ_B200_OK;
 }
 
-int shkz_b200_comm_unique_id(uint8_t id[SHKZ_B200_NCCL_ID_BYTES]) {
-	if (!id) return fail(SHKZ_B200_ERR_ARG, "id is NULL");
-	std::string err;
-	if (SlabComm::unique_id(id, err)) return fail(SHKZ_B200_ERR_COMM, "%s", err.c_str());
-	return SHKZ_B200_OK;
-}
-
 int shkz_b200_slab_export(shkz_b200_solver *S, uint8_t ipc[SHKZ_B200_IPC_BYTES]) {
 	if (!S || !ipc) return fail(SHKZ_B200_ERR_ARG, "solver / ipc is NULL");
+	if (S->whole_grid || !S->comm) return fail(SHKZ_B200_ERR_STATE, "not a z-slab solver");
 	CK(cudaSetDevice(S->device));
-	if (!S->comm) S->comm = new SlabComm(S->d.plane, S->device);
-	if (S->comm->export_window(ipc)) return fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error());
+	if (S->comm->export_handle(ipc, SHKZ_B200_IPC_BYTES)) return fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error());
 	return SHKZ_B200_OK;
 }
 
-int shkz_b200_slab_connect(shkz_b200_solver *S, int rank, int world, const uint8_t id[SHKZ_B200_NCCL_ID_BYTES], const uint8_t *lower_ipc,
-                           const uint8_t *upper_ipc) {
-	if (!S || !id) return fail(SHKZ_B200_ERR_ARG, "solver / id is NULL");
+int shkz_b200_slab_connect(shkz_b200_solver *S, int rank, int world, const uint8_t *all_ipc) {
+	if (!S || !all_ipc) return fail(SHKZ_B200_ERR_ARG, "solver / all_ipc is NULL");
+	if (S->whole_grid || !S->comm) return fail(SHKZ_B200_ERR_STATE, "not a z-slab solver");
+	if (world < 1 || world > COMM_MAX_WORLD) return fail(SHKZ_B200_ERR_ARG, "world must be 1..%d", COMM_MAX_WORLD);
+	if (S->d.nzl * world != S->d.nzg || S->d.k0 != rank * S->d.nzl) return fail(SHKZ_B200_ERR_ARG, "rank %d of %d does not own slab [%d,%d) of %d planes", rank, world, S->d.k0, S->d.k0 + S->d.nzl, S->d.nzg);
 	CK(cudaSetDevice(S->device));
-	if (!S->comm) return fail(SHKZ_B200_ERR_STATE, "call shkz_b200_slab_export first");
-	if (S->comm->connect(rank, world, id, lower_ipc, upper_ipc)) return fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error());
+	if (S->comm->connect_ipc(rank, world, all_ipc, SHKZ_B200_IPC_BYTES)) return fail(SHKZ_B200_ERR_COMM, "%s", S->comm->error());
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_slab_connect_local(shkz_b200_solver *const *solvers, int world) {
+	if (!solvers || world < 1 || world > COMM_MAX_WORLD) return fail(SHKZ_B200_ERR_ARG, "solvers is NULL or world not in 1..%d", COMM_MAX_WORLD);
+	SlabComm *all[COMM_MAX_WORLD] = {};
+	for (int r = 0; r < world; ++r) {
+		shkz_b200_solver *S = solvers[r];
+		if (!S || S->whole_grid || !S->comm) return fail(SHKZ_B200_ERR_STATE, "solver %d is not a z-slab solver", r);
+		if (S->d.nzl * world != S->d.nzg || S->d.k0 != r * S->d.nzl) return fail(SHKZ_B200_ERR_ARG, "solver %d does not own slab %d of %d", r, r, world);
+		all[r] = S->comm;
+	}
+	for (int r = 0; r < world; ++r) {
+		CK(cudaSetDevice(solvers[r]->device));
+		if (solvers[r]->comm->connect_local(r, world, all)) return fail(SHKZ_B200_ERR_COMM, "%s", solvers[r]->comm->error());
+	}
 	return SHKZ_B200_OK;
 }
 

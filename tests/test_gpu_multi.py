@@ -1,0 +1,86 @@
+"""z-slab solvers on several GPUs of one box (run with `gpurun --gpus 2|4 -- python -m pytest tests -m gpu`): the slabs
+are driven from this one process, one host thread per GPU, and talk through peer memory (csrc/slab_comm.cuh).
+Skipped where fewer than two CUDA devices are visible."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import dense_oracle
+from shiokaze_b200 import MacPressureSolver3, capi, dist, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def world_sizes():
+    n = capi.lib().shkz_b200_device_count()
+    return [w for w in (2, 4, 8) if w <= n]
+
+
+def make_slab_solvers(sc, world, **flags):
+    solvers = [MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, device=r, zrange=dist.slab_range(sc.nz, r, world), **flags) for r in range(world)]
+    dist.connect_local(solvers)
+    return solvers
+
+
+@pytest.fixture(scope="module")
+def worlds(cuda_device):
+    w = world_sizes()
+    if not w:
+        pytest.skip("needs at least two CUDA devices")
+    return w
+
+
+@pytest.mark.parametrize("kind,n", [("dambreak_solid", 32), ("smoke", 32), ("flip", 64), ("box", 32)])
+def test_slab_projection_matches_whole_grid_and_oracle(worlds, kind, n):
+    sc = {"dambreak_solid": lambda: scenes.dambreak(n, True), "smoke": lambda: scenes.smoke_plume(n), "flip": lambda: scenes.flip_splash(n),
+          "box": lambda: scenes.liquid_box(n)}[kind]()
+    flags = dict(Precision="fp64", Precond="mg", Residual=1e-10)
+    W = MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, **flags)
+    whole = W.project_scene(sc)
+    W.close()
+    ref = dense_oracle.project(sc, residual=1e-10) if n <= 32 else None
+    for world in worlds:
+        solvers = make_slab_solvers(sc, world, **flags)
+        parts = dist.project_local(solvers, dist.split_dense(sc, world))
+        out = dist.join_dense(parts, world)
+        for p in parts:   # every rank reports the same (globally reduced) solve
+            assert p["result"].iterations == parts[0]["result"].iterations and p["result"].reresid == parts[0]["result"].reresid
+            assert p["result"].n_rows == whole["result"].n_rows
+        assert out["result"].converged
+        assert abs(out["result"].iterations - whole["result"].iterations) <= 1
+        assert np.array_equal(out["pressure_active"], whole["pressure_active"])
+        for d in range(3):
+            assert np.array_equal(out["vel_active"][d], whole["vel_active"][d])
+        assert rel_l2(out["vel"], whole["vel"]) < 1e-6
+        if ref is not None:
+            assert np.array_equal(out["pressure_active"], ref.in_rows)
+            assert rel_l2(out["vel"], ref.vel) < 1e-5
+        for s in solvers:
+            s.close()
+
+
+@pytest.mark.parametrize("precision", ["mixed", "fp32"])
+def test_slab_vcycle_equals_whole_grid_vcycle_bit_for_bit(worlds, precision):
+    """Halo planes, half-updated boundary planes and the level structure reproduce the whole-grid V-cycle exactly."""
+    sc = scenes.dambreak(64, True)
+    flags = dict(Precision=precision, Precond="mg", MaxIterations=1)
+    W = MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, **flags)
+    W.project_scene(sc)
+    whole = W.debug_vcycle(0)
+    W.close()
+    for world in worlds:
+        solvers = make_slab_solvers(sc, world, **flags)
+        dist.project_local(solvers, dist.split_dense(sc, world))
+        parts = dist.run_per_slab([(lambda s=s: s.debug_vcycle(0)) for s in solvers])
+        assert np.array_equal(np.concatenate(parts, axis=0), whole)
+        for s in solvers:
+            s.close()
+
+
+def test_unconnected_slab_refuses_to_project(cuda_device):
+    sc = scenes.smoke_plume(16)
+    S = MacPressureSolver3((16, 16, 16), sc.dx, zrange=(0, 8))
+    with pytest.raises(capi.ShkzError) as e:
+        S.project_scene(dist.split_dense(sc, 2)[0])
+    assert e.value.code == capi.ERR_STATE
+    S.close()
