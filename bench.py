@@ -104,6 +104,8 @@ def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, level
     mg = precond == "mg"
     b0 = 4 if (mg and V == 8) else 0          # float copy of r handed to multigrid
     name, _, lvl = kernel.partition("@")
+    if lvl and not lvl.isdigit():
+        return None                           # gathered coarse levels of a z-slab run ("@g0", ...): tiny, not modelled
     n = levels_rows[int(lvl)] if lvl else n_rows
     pre, post = max(1, sweeps[0]), max(0, sweeps[1])
     # one launch = one FULL red-black sweep: 4 coefficient arrays + b + x_old read, x_new written (fp32);
@@ -327,7 +329,8 @@ def run_ours(args):
     if rank == 0 and table:
         peak, how = measured_peak()
         levels_rows = [n_rows / (8 ** l) for l in range(16)]
-        ab = lambda k: algorithmic_bytes_per_launch(k, res.n_rows, args.precision, [res.n_rows / (8 ** l) for l in range(16)], args.precond, (args.pre, args.post))
+        rank_rows = res.n_rows / world        # a slab solver reports the global row count; kernels are timed on rank 0's slab
+        ab = lambda k: algorithmic_bytes_per_launch(k, rank_rows, args.precision, [rank_rows / (8 ** l) for l in range(16)], args.precond, (args.pre, args.post))
         solve_kernels = {k: v for k, v in table.items() if ab(k)}
         dom = max(solve_kernels, key=lambda k: solve_kernels[k][1])
         cnt, tot = solve_kernels[dom]

@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(256) k_boundary_half_push(Dims d, const float 
 		}
 	}
 	signal_neighbours(cm, seq);
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) wait_neighbours(cm, seq);
 }
 
 // coarse b = P^T (b - A x): block (TX/2, TY/2), one coarse column per thread, aggregates never straddle tiles
@@ -574,6 +575,17 @@ __global__ void __launch_bounds__(256) k_coarsen_operator(Dims df, Dims dc, Tile
 	cwz[C] = scale * sz;
 	cdd[C] = scale * sd;
 	if (live) tile_flags[tile_of(Tc, I, J, K)] = 1;
+}
+
+// flag the tiles of a level that hold at least one cell with an equation (positive diagonal)
+__global__ void __launch_bounds__(256) k_flag_live_tiles(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
+                                                        const float *__restrict__ dd, unsigned char *__restrict__ tile_flags) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int j = blockIdx.y * blockDim.y + threadIdx.y;
+	const int k = blockIdx.z;
+	if (i >= d.nx || j >= d.ny) return;
+	const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+	if (gs_diag(wx[c], wx[c + 1], wy[c], wy[c + d.nx], wz[c], wz[c + d.plane], dd[c]) > 0.f) tile_flags[tile_of(T, i, j, k)] = 1;
 }
 
 // flags -> ascending id list + count (single CTA; tile grids are at most a few 10^4 entries)

@@ -71,8 +71,22 @@ __device__ __forceinline__ void signal_neighbours(const CommDev *cm, unsigned lo
 	}
 }
 
+// Block until both neighbours have published exchange number `seq` here (ONE thread of a kernel calls this last; the
+// kernel then cannot complete, and the stream cannot move on, before the ghost planes are in place).
+__device__ __forceinline__ void wait_neighbours(const CommDev *cm, unsigned long long seq) {
+	if (cm->lo) {
+		volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_LO);
+		while (*f < seq) {}
+	}
+	if (cm->hi) {
+		volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_HI);
+		while (*f < seq) {}
+	}
+	__threadfence_system();
+}
+
 // Halo exchange number `seq` of the cell array at arena offset `off` (offset of its lower ghost plane): store the own
-// boundary planes into the neighbours' ghost planes, then publish `seq` in their flag words.
+// boundary planes into the neighbours' ghost planes, publish `seq` in their flag words, wait for their planes.
 __global__ void __launch_bounds__(256) k_halo_push(const CommDev *cm, size_t off, size_t plane_bytes, int nzl, unsigned long long seq) {
 	const char *src_lo = cm->self + off + plane_bytes;                 // own plane 0
 	const char *src_hi = cm->self + off + plane_bytes * (size_t)nzl;   // own plane nzl-1
@@ -92,20 +106,35 @@ __global__ void __launch_bounds__(256) k_halo_push(const CommDev *cm, size_t off
 		}
 	}
 	signal_neighbours(cm, seq);
+	if (blockIdx.x == 0 && threadIdx.x == 0) wait_neighbours(cm, seq); // ... and the kernel ends when theirs have arrived
 }
 
-// ... and wait until both neighbours have delivered theirs.
-__global__ void k_halo_wait(const CommDev *cm, unsigned long long seq) {
-	if (threadIdx.x == 0 && blockIdx.x == 0) {
-		if (cm->lo) {
-			volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_LO);
-			while (*f < seq) {}
+// All-gather by stores: `bytes` at arena offset src_off of this rank go to arena offset dst_off of EVERY rank (the offsets
+// already include this rank's position in the gathered array). The last block to finish runs a barrier over all ranks
+// (a mailbox reduction of nothing), so when the kernel ends on a rank, every rank's part has landed there.
+__global__ void __launch_bounds__(256) k_gather_push(const CommDev *cm, size_t src_off, size_t dst_off, size_t bytes) {
+	const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	const char *src = cm->self + src_off;
+	if ((bytes & 15) == 0) {
+		const size_t n16 = bytes >> 4;
+		for (size_t e = tid; e < n16; e += nth) {
+			const uint4 v = reinterpret_cast<const uint4 *>(src)[e];
+			for (int p = 0; p < cm->world; ++p) reinterpret_cast<uint4 *>(cm->peer[p] + dst_off)[e] = v;
 		}
-		if (cm->hi) {
-			volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_HI);
-			while (*f < seq) {}
+	} else {
+		for (size_t e = tid; e < bytes; e += nth)
+			for (int p = 0; p < cm->world; ++p) cm->peer[p][dst_off + e] = src[e];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned int *ticket = reinterpret_cast<unsigned int *>(cm->self + HDR_PUSH_TICKET);
+		if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+			*ticket = 0u;
+			__threadfence_system();
+			double nothing[1] = {0.0};
+			cross_rank_combine<1, 0u>(nothing, cm);
 		}
-		__threadfence_system();
 	}
 }
 

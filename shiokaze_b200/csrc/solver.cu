@@ -211,6 +211,13 @@ struct shkz_b200_solver {
 	int tail_first = -1;        // first level of the shared-memory tail of the V-cycle (-1: none)
 	size_t tail_smem = 0;
 	TailArgs tail_args{};
+	// z-slab solvers: from level `agg_level` down the hierarchy is GLOBAL — every rank gathers the whole coarse
+	// problem over NVLink and solves it redundantly with the whole-grid kernels (glevels[0] is level agg_level)
+	std::vector<HostLevel> glevels;
+	int agg_level = -1;
+	int gtail_first = -1;
+	size_t gtail_smem = 0;
+	TailArgs gtail_args{};
 	std::map<const void *, int> occupancy; // resident CTAs per SM of each persistent kernel
 	// reductions / control
 	PlainArray partials, counter, state;
@@ -250,6 +257,14 @@ void release_precision_arrays(shkz_b200_solver *S) {
 		L.xa.release(); L.xb.release(); L.legacy_r.release();
 		L.tile_flags.release(); L.tile_ids.release(); L.tile_count.release();
 	}
+	for (HostLevel &L : S->glevels) {
+		L.wx.release(); L.wy.release(); L.wz.release(); L.dd.release(); L.b.release();
+		L.xa.release(); L.xb.release(); L.legacy_r.release();
+		L.tile_flags.release(); L.tile_ids.release(); L.tile_count.release();
+	}
+	S->glevels.clear();
+	S->agg_level = -1;
+	S->gtail_first = -1;
 	S->levels.clear();
 	S->alloc_precision = -1;
 	S->have_system = false;
@@ -267,6 +282,68 @@ int pick_bz(const Dims &d) {
 	return bz;
 }
 
+// arrays, tile list and tensor maps of one multigrid level (coefficient / rhs arrays may have been aliased by the caller)
+int finish_level(HostLevel &L, const Dims &cur, const std::string &n, SlabComm *arena) {
+	L.d = cur;
+	if (!L.wx.base) for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.dd}) CKR(a->alloc(cur, sizeof(float), arena));
+	if (!L.b.base) CKR(L.b.alloc(cur, sizeof(float), arena));
+	CKR(L.xa.alloc(cur, sizeof(float), arena));
+	CKR(L.xb.alloc(cur, sizeof(float), arena));
+	L.bz = pick_bz(cur);
+	const int ntx = (cur.nx + TX - 1) / TX, nty = (cur.ny + TY - 1) / TY, ntz = (cur.nzl + L.bz - 1) / L.bz;
+	L.tiles_total = ntx * nty * ntz;
+	CKR(L.tile_flags.alloc((size_t)L.tiles_total));
+	CKR(L.tile_ids.alloc((size_t)L.tiles_total * sizeof(int)));
+	CKR(L.tile_count.alloc(sizeof(int)));
+	L.tag_sweep = "sweep@" + n; L.tag_restrict = "residual_restrict@" + n; L.tag_prolong = "prolong_add@" + n;
+	L.tag_coarsen = "coarsen_operator@" + n; L.tag_compact = "compact_tiles@" + n;
+	L.view.d = cur;
+	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz};
+	L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.dd = L.dd.ptr<float>(cur);
+	L.view.b = L.b.ptr<float>(cur); L.view.xa = L.xa.ptr<float>(cur); L.view.xb = L.xb.ptr<float>(cur);
+	L.tma = (cur.nx & 3) == 0 && make_plane_map(&L.map_wx, L.wx.base, cur, ST_ROWS) && make_plane_map(&L.map_wy, L.wy.base, cur, ST_WY_ROWS) &&
+	        make_plane_map(&L.map_wz, L.wz.base, cur, ST_ROWS) && make_plane_map(&L.map_dd, L.dd.base, cur, ST_ROWS) &&
+	        make_plane_map(&L.map_b, L.b.base, cur, ST_ROWS) && make_plane_map(&L.map_xa, L.xa.base, cur, ST_XO_ROWS) &&
+	        make_plane_map(&L.map_xb, L.xb.base, cur, ST_XO_ROWS);
+	return SHKZ_B200_OK;
+}
+
+int big_extent(const Dims &d) { return d.nx > d.ny ? (d.nx > d.nzg ? d.nx : d.nzg) : (d.ny > d.nzg ? d.ny : d.nzg); }
+
+// the shared-memory tail of a whole-grid hierarchy: the longest run of coarsest levels that fits one CTA's shared memory
+int setup_tail(const std::vector<HostLevel> &lv, int &tail_first, size_t &tail_smem, TailArgs &A) {
+	tail_first = -1;
+	const size_t limit = 200 * 1024;
+	size_t bytes = 0;
+	int first = (int)lv.size();
+	while (first > 0 && (int)lv.size() - (first - 1) <= TAIL_MAX_LEVELS) {
+		const Dims &dl = lv[first - 1].d;
+		const size_t add = (size_t)TAIL_ARRAYS * (size_t)(dl.ncell + 2 * dl.plane) * sizeof(float);
+		if (bytes + add > limit) break;
+		bytes += add;
+		--first;
+	}
+	if (first >= (int)lv.size()) return SHKZ_B200_OK;
+	tail_first = first;
+	tail_smem = bytes;
+	A = TailArgs{};
+	A.nlev = (int)lv.size() - first;
+	int off = 0;
+	for (int m = 0; m < A.nlev; ++m) {
+		const HostLevel &L = lv[first + m];
+		A.L[m].d = L.d;
+		A.L[m].wx = L.view.wx; A.L[m].wy = L.view.wy; A.L[m].wz = L.view.wz; A.L[m].dd = L.view.dd;
+		A.L[m].stride = (int)(L.d.ncell + 2 * L.d.plane);
+		A.L[m].offset = off;
+		off += TAIL_ARRAYS * A.L[m].stride;
+	}
+	A.b_in = lv[first].view.b;
+	A.x_out = lv[first].view.xa;
+	return SHKZ_B200_OK;
+}
+
+constexpr int AGG_MAX_EXTENT = 64; // z-slab solvers: levels this small (largest global extent) are gathered and solved on every rank
+
 template <class VecT, class CoefT>
 int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_params &P) {
 	const int min_size = P.mg_min_size < 2 ? 2 : P.mg_min_size;
@@ -282,76 +359,42 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 	for (int l = 0;; ++l) {
 		S->levels.emplace_back();
 		HostLevel &L = S->levels.back();
-		L.d = cur;
 		if (l == 0 && sizeof(CoefT) == sizeof(float)) {
 			L.own_coef = false;
 			L.wx = S->wx; L.wy = S->wy; L.wz = S->wz; L.dd = S->dd;
-		} else {
-			for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.dd}) CKR(a->alloc(cur, sizeof(float), arena));
 		}
 		if (l == 0 && sizeof(VecT) == sizeof(float)) {
 			L.own_b = false;
 			L.b = S->r; // an all-float CG smooths against r directly
-		} else {
-			CKR(L.b.alloc(cur, sizeof(float), arena));
 		}
-		CKR(L.xa.alloc(cur, sizeof(float), arena));
-		CKR(L.xb.alloc(cur, sizeof(float), arena));
-		L.bz = pick_bz(cur);
-		const int ntx = (cur.nx + TX - 1) / TX, nty = (cur.ny + TY - 1) / TY, ntz = (cur.nzl + L.bz - 1) / L.bz;
-		L.tiles_total = ntx * nty * ntz;
-		CKR(L.tile_flags.alloc((size_t)L.tiles_total));
-		CKR(L.tile_ids.alloc((size_t)L.tiles_total * sizeof(int)));
-		CKR(L.tile_count.alloc(sizeof(int)));
-		const std::string n = std::to_string(l);
-		L.tag_sweep = "sweep@" + n; L.tag_restrict = "residual_restrict@" + n; L.tag_prolong = "prolong_add@" + n;
-		L.tag_coarsen = "coarsen_operator@" + n; L.tag_compact = "compact_tiles@" + n;
-		L.view.d = cur;
-		L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz};
-		L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.dd = L.dd.ptr<float>(cur);
-		L.view.b = L.b.ptr<float>(cur); L.view.xa = L.xa.ptr<float>(cur); L.view.xb = L.xb.ptr<float>(cur);
-		L.tma = (cur.nx & 3) == 0 && make_plane_map(&L.map_wx, L.wx.base, cur, ST_ROWS) && make_plane_map(&L.map_wy, L.wy.base, cur, ST_WY_ROWS) &&
-		        make_plane_map(&L.map_wz, L.wz.base, cur, ST_ROWS) && make_plane_map(&L.map_dd, L.dd.base, cur, ST_ROWS) &&
-		        make_plane_map(&L.map_b, L.b.base, cur, ST_ROWS) && make_plane_map(&L.map_xa, L.xa.base, cur, ST_XO_ROWS) &&
-		        make_plane_map(&L.map_xb, L.xb.base, cur, ST_XO_ROWS);
-		const int big = cur.nx > cur.ny ? (cur.nx > cur.nzg ? cur.nx : cur.nzg) : (cur.ny > cur.nzg ? cur.ny : cur.nzg);
-		if (big <= min_size) break;
-		// slabs: keep aggregates inside one rank (even local extent and even first plane)
-		if (!S->whole_grid && ((cur.nzl & 1) || (cur.k0 & 1) || cur.nzl < 2)) break;
+		CKR(finish_level(L, cur, std::to_string(l), arena));
+		if (big_extent(cur) <= min_size) break;
+		if (!S->whole_grid) {
+			// slabs: aggregates stay inside one rank (even local extent and even first plane); small levels go global
+			if (l >= 1 && big_extent(cur) <= AGG_MAX_EXTENT) { S->agg_level = l; break; }
+			if ((cur.nzl & 1) || (cur.k0 & 1) || cur.nzl < 2) { if (l >= 1) S->agg_level = l; break; }
+		}
 		cur = make_dims((cur.nx + 1) / 2, (cur.ny + 1) / 2, (cur.nzl + 1) / 2, cur.k0 / 2, (cur.nzg + 1) / 2);
 	}
-	// the shared-memory tail: the longest run of coarsest levels that fits one CTA's shared memory
 	S->tail_first = -1;
 	if (S->whole_grid) {
-		const size_t limit = 200 * 1024;
-		size_t bytes = 0;
-		int first = (int)S->levels.size();
-		while (first > 0 && (int)S->levels.size() - (first - 1) <= TAIL_MAX_LEVELS) {
-			const Dims &dl = S->levels[first - 1].d;
-			const size_t add = (size_t)TAIL_ARRAYS * (size_t)(dl.ncell + 2 * dl.plane) * sizeof(float);
-			if (bytes + add > limit) break;
-			bytes += add;
-			--first;
+		CKR(setup_tail(S->levels, S->tail_first, S->tail_smem, S->tail_args));
+	} else if (S->agg_level >= 0) {
+		// the global continuation of the hierarchy: whole-grid levels, in the arena because every rank stores its part of
+		// the operator and of each right-hand side straight into every other rank's copy
+		const Dims &ds = S->levels[S->agg_level].d;
+		Dims g = make_dims(ds.nx, ds.ny, ds.nzg, 0, ds.nzg);
+		for (int l = 0;; ++l) {
+			S->glevels.emplace_back();
+			CKR(finish_level(S->glevels.back(), g, "g" + std::to_string(l), arena));
+			if (big_extent(g) <= min_size) break;
+			g = make_dims((g.nx + 1) / 2, (g.ny + 1) / 2, (g.nzl + 1) / 2, 0, (g.nzg + 1) / 2);
 		}
-		if (first < (int)S->levels.size()) {
-			S->tail_first = first;
-			S->tail_smem = bytes;
-			TailArgs &A = S->tail_args;
-			A = TailArgs{};
-			A.nlev = (int)S->levels.size() - first;
-			int off = 0;
-			for (int m = 0; m < A.nlev; ++m) {
-				const HostLevel &L = S->levels[first + m];
-				A.L[m].d = L.d;
-				A.L[m].wx = L.view.wx; A.L[m].wy = L.view.wy; A.L[m].wz = L.view.wz; A.L[m].dd = L.view.dd;
-				A.L[m].stride = (int)(L.d.ncell + 2 * L.d.plane);
-				A.L[m].offset = off;
-				off += TAIL_ARRAYS * A.L[m].stride;
-			}
-			A.b_in = S->levels[first].view.b;
-			A.x_out = S->levels[first].view.xa;
-			CK(cudaFuncSetAttribute(k_vcycle_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->tail_smem));
-		}
+		CKR(setup_tail(S->glevels, S->gtail_first, S->gtail_smem, S->gtail_args));
+	}
+	{
+		const size_t smem = S->tail_smem > S->gtail_smem ? S->tail_smem : S->gtail_smem;
+		if (smem) CK(cudaFuncSetAttribute(k_vcycle_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	}
 	S->alloc_precision = precision;
 	S->mg_min_size_built = min_size;
@@ -406,10 +449,6 @@ int tile_grid(shkz_b200_solver *S, K kernel, dim3 block, int tiles_total, size_t
 
 // ---- halo exchange of one cell array (ghost planes), a no-op on a whole grid: the own boundary planes are stored
 // ---- into the neighbours' ghost planes over NVLink by our own kernel, then the stream waits for theirs
-int halo_wait(shkz_b200_solver *S, unsigned long long seq, cudaStream_t st) {
-	LAUNCH(S, "halo_wait", k_halo_wait, 1, 32, st, S->comm->device_view(), seq);
-	return SHKZ_B200_OK;
-}
 template <class T>
 int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
 	if (S->whole_grid) return SHKZ_B200_OK;
@@ -420,8 +459,8 @@ int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
 	const unsigned long long seq = S->comm->next_exchange();
 	const size_t chunks = (plane_bytes + 15) / 16;
 	const int blocks = (int)((chunks + 255) / 256 > 296 ? 296 : ((chunks + 255) / 256 < 1 ? 1 : (chunks + 255) / 256));
-	LAUNCH(S, "halo_push", k_halo_push, blocks, 256, st, S->comm->device_view(), S->comm->offset_of(base), plane_bytes, d.nzl, seq);
-	return halo_wait(S, seq, st);
+	LAUNCH(S, "halo", k_halo_push, blocks, 256, st, S->comm->device_view(), S->comm->offset_of(base), plane_bytes, d.nzl, seq);
+	return SHKZ_B200_OK;
 }
 
 int compact_tiles(shkz_b200_solver *S, HostLevel &H, cudaStream_t stream) {
@@ -432,45 +471,49 @@ int compact_tiles(shkz_b200_solver *S, HostLevel &H, cudaStream_t stream) {
 
 // ---- multigrid ----
 template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
-void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, float *xn, const float *ec, const Dims &dc, CGState *st, cudaStream_t stream) {
+void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, float *xn, const float *ec, const Dims &dc, CGState *st, cudaStream_t stream,
+                  int slab_ghosts = 0) {
 	const MGLevel &L = H.view;
 	if (H.tma && S->sweep_mode == 0) { // operands staged through shared memory by TMA
 		SweepMaps maps;
 		maps.wx = H.map_wx; maps.wy = H.map_wy; maps.wz = H.map_wz; maps.dd = H.map_dd; maps.b = H.map_b;
 		maps.xo = xo == L.xb ? H.map_xb : H.map_xa;
 		LAUNCH_TILES_SMEM(S, H.tag_sweep.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
-		                  L.tiles, maps, xo, xn, ec, dc, S->whole_grid ? 0 : 1, S->redbuf(), st);
+		                  L.tiles, maps, xo, xn, ec, dc, slab_ghosts, S->redbuf(), st);
 	} else if ((L.d.nx & 3) == 0 && S->sweep_mode <= 1) // aligned quads, direct global loads
 		LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep4<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
-		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->whole_grid ? 0 : 1, S->redbuf(), st);
+		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, slab_ghosts, S->redbuf(), st);
 	else
 		LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep<FIRST, ZERO_X, PROLONG, DOT>), sweep_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
-		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, S->whole_grid ? 0 : 1, S->redbuf(), st);
+		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, slab_ghosts, S->redbuf(), st);
 }
 
 // One V-cycle on level l and below, right-hand side in the level's b. *result = buffer holding the solution.
 // dot: also reduce (solution . b) into the CG state (level 0 only).
 int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result);
 
-int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result) {
-	if (!S->whole_grid) return vcycle_slab(S, l, P, st, stream, dot, result);
-	HostLevel &H = S->levels[l];
+// global = true: the gathered coarse hierarchy of a z-slab solver (whole-grid semantics on every rank)
+int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result, bool global = false) {
+	if (!S->whole_grid && !global) return vcycle_slab(S, l, P, st, stream, dot, result);
+	std::vector<HostLevel> &lv = global ? S->glevels : S->levels;
+	const int tail_first = global ? S->gtail_first : S->tail_first;
+	HostLevel &H = lv[l];
 	const MGLevel &L = H.view;
 	const int coarse = P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps;
-	if ((int)l == S->tail_first) {
-		TailArgs A = S->tail_args;
+	if ((int)l == tail_first) {
+		TailArgs A = global ? S->gtail_args : S->tail_args;
 		A.pre = P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps;
 		A.post = P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps;
 		A.coarse = coarse;
 		const int slot_ = S->prof.begin("vcycle_tail", stream);
-		k_vcycle_tail<<<1, TAIL_THREADS, S->tail_smem, stream>>>(A, st);
+		k_vcycle_tail<<<1, TAIL_THREADS, global ? S->gtail_smem : S->tail_smem, stream>>>(A, st);
 		S->prof.end(slot_, stream);
 		S->launches++;
 		*result = L.xa;
 		if (dot) LAUNCH_TILES(S, "dot_zb", k_dot_zb, cg_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.xa, (const float *)L.b, S->redbuf(), st);
 		return SHKZ_B200_OK;
 	}
-	const bool last = (l + 1 == S->levels.size());
+	const bool last = (l + 1 == lv.size());
 	const int pre = last ? coarse : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
 	const int post = last ? coarse : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
 	float *bufs[2] = {L.xa, L.xb};
@@ -486,11 +529,11 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st
 	const float *ec = nullptr;
 	Dims dc = none;
 	if (!last) {
-		const MGLevel &C = S->levels[l + 1].view;
+		const MGLevel &C = lv[l + 1].view;
 		dc = C.d;
 		LAUNCH_TILES(S, H.tag_restrict.c_str(), k_residual_restrict, restrict_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx, (const float *)L.wy,
 		             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st);
-		CKR(vcycle(S, l + 1, P, st, stream, false, &ec));
+		CKR(vcycle(S, l + 1, P, st, stream, false, &ec, global));
 		if (post == 0) {
 			LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, dc, ec, cur, bufs[w], (const CGState *)st);
 			cur = bufs[w];
@@ -515,6 +558,17 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st
 // each rank relaxes the first colour of its two boundary planes and stores them into the neighbours' ghost planes
 // (k_boundary_half_push); after it, the finished boundary planes follow (halo). The shared-memory tail and the folded
 // prolongation are whole-grid features: here every level is swept in place and the correction is added by its own kernel.
+// z-slab solvers: the own nzl planes of a slab array -> planes [k0, k0+nzl) of the same-shaped GLOBAL array in every rank's arena;
+// the kernel ends with a barrier over all ranks, so afterwards every copy is complete
+int gather_planes(shkz_b200_solver *S, const Dims &d, const float *src_plane0, float *dst_plane0, cudaStream_t stream) {
+	const size_t plane_bytes = (size_t)d.plane * sizeof(float);
+	const size_t src_off = S->comm->offset_of(src_plane0), dst_off = S->comm->offset_of(dst_plane0) + (size_t)d.k0 * plane_bytes;
+	const size_t chunks = (plane_bytes * (size_t)d.nzl + 15) / 16;
+	const int blocks = (int)((chunks + 255) / 256 > 296 ? 296 : ((chunks + 255) / 256 < 1 ? 1 : (chunks + 255) / 256));
+	LAUNCH(S, "gather_planes", k_gather_push, blocks, 256, stream, S->comm->device_view(), src_off, dst_off, plane_bytes * (size_t)d.nzl);
+	return SHKZ_B200_OK;
+}
+
 template <int FIRST>
 int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, float *xn, bool dot, CGState *st, cudaStream_t stream) {
 	const MGLevel &L = H.view;
@@ -527,16 +581,25 @@ int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, 
 	                   (const float *)L.dd, (const float *)L.b, xo, S->comm->device_view(), off, seq);
 	else LAUNCH(S, "boundary_half", (k_boundary_half_push<FIRST, false>), grid, 256, stream, L.d, (const float *)L.wx, (const float *)L.wy, (const float *)L.wz,
 	            (const float *)L.dd, (const float *)L.b, xo, S->comm->device_view(), off, seq);
-	CKR(halo_wait(S, seq, stream));
-	if (zero_x) launch_sweep<FIRST, true, false, false>(S, H, xo, xn, nullptr, none, st, stream);
-	else if (dot) launch_sweep<FIRST, false, false, true>(S, H, xo, xn, nullptr, none, st, stream);
-	else launch_sweep<FIRST, false, false, false>(S, H, xo, xn, nullptr, none, st, stream);
+	if (zero_x) launch_sweep<FIRST, true, false, false>(S, H, xo, xn, nullptr, none, st, stream, 1);
+	else if (dot) launch_sweep<FIRST, false, false, true>(S, H, xo, xn, nullptr, none, st, stream, 1);
+	else launch_sweep<FIRST, false, false, false>(S, H, xo, xn, nullptr, none, st, stream, 1);
 	return halo(S, L.d, xn, stream);
 }
 
 int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result) {
 	HostLevel &H = S->levels[l];
 	const MGLevel &L = H.view;
+	if ((int)l == S->agg_level) {
+		// every rank stores its planes of this level's right-hand side into every rank's copy of the global level, then all
+		// of them run the same whole-grid V-cycle on it; the slab's view of the result starts k0 planes into the global array
+		HostLevel &G = S->glevels[0];
+		CKR(gather_planes(S, L.d, L.b, G.view.b, stream));
+		const float *xg = nullptr;
+		CKR(vcycle(S, 0, P, st, stream, false, &xg, true));
+		*result = xg + (long long)L.d.k0 * L.d.plane;
+		return SHKZ_B200_OK;
+	}
 	const bool last = (l + 1 == S->levels.size());
 	const int coarse = P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps;
 	const int pre = last ? coarse : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
@@ -604,16 +667,36 @@ int legacy_vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, cuda
 	return SHKZ_B200_OK;
 }
 
-int build_hierarchy(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
-	for (size_t l = 0; l + 1 < S->levels.size(); ++l) {
-		const MGLevel &F = S->levels[l].view;
-		HostLevel &HC = S->levels[l + 1];
+int coarsen_levels(shkz_b200_solver *S, std::vector<HostLevel> &lv, bool slab, const shkz_b200_params &P, cudaStream_t stream) {
+	for (size_t l = 0; l + 1 < lv.size(); ++l) {
+		const MGLevel &F = lv[l].view;
+		HostLevel &HC = lv[l + 1];
 		const MGLevel &C = HC.view;
 		CK(cudaMemsetAsync(HC.tile_flags.base, 0, (size_t)HC.tiles_total, stream));
-		LAUNCH(S, S->levels[l].tag_coarsen.c_str(), k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, C.tiles, (float)P.mg_coarse_scale,
+		LAUNCH(S, lv[l].tag_coarsen.c_str(), k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, C.tiles, (float)P.mg_coarse_scale,
 		       (const float *)F.wx, (const float *)F.wy, (const float *)F.wz, (const float *)F.dd, C.wx, C.wy, C.wz, C.dd, static_cast<unsigned char *>(HC.tile_flags.base));
-		CKR(halo(S, C.d, C.wz, stream));
+		if (slab) CKR(halo(S, C.d, C.wz, stream));
 		CKR(compact_tiles(S, HC, stream));
+	}
+	return SHKZ_B200_OK;
+}
+
+int build_hierarchy(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
+	CKR(coarsen_levels(S, S->levels, !S->whole_grid, P, stream));
+	if (S->agg_level >= 0) {
+		// gather the operator of the first global level from the slabs, then coarsen it on every rank
+		const MGLevel &L = S->levels[S->agg_level].view;
+		HostLevel &HG = S->glevels[0];
+		const MGLevel &G = HG.view;
+		CKR(gather_planes(S, L.d, L.wx, G.wx, stream));
+		CKR(gather_planes(S, L.d, L.wy, G.wy, stream));
+		CKR(gather_planes(S, L.d, L.wz, G.wz, stream));
+		CKR(gather_planes(S, L.d, L.dd, G.dd, stream));
+		CK(cudaMemsetAsync(HG.tile_flags.base, 0, (size_t)HG.tiles_total, stream));
+		LAUNCH(S, "flag_live_tiles", k_flag_live_tiles, cell_grid(G.d, 0, 0, 0), cell_block(), stream, G.d, G.tiles, (const float *)G.wx, (const float *)G.wy,
+		       (const float *)G.wz, (const float *)G.dd, static_cast<unsigned char *>(HG.tile_flags.base));
+		CKR(compact_tiles(S, HG, stream));
+		CKR(coarsen_levels(S, S->glevels, false, P, stream));
 	}
 	CK(cudaGetLastError());
 	S->have_hierarchy = true;
@@ -685,7 +768,7 @@ void fill_stats(const shkz_b200_solver *S, shkz_b200_stats *out) {
 	out->rhs_absmax = h.bnorm;
 	out->reresid = h.bnorm > 0 ? h.rnorm / h.bnorm : 0.0;
 	out->has_dirichlet = h.has_dirichlet;
-	out->mg_levels = (int)S->levels.size();
+	out->mg_levels = (int)(S->levels.size() + (S->glevels.empty() ? 0 : S->glevels.size() - 1));
 	out->kernel_launches = S->launches;
 }
 
