@@ -104,13 +104,15 @@ def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, level
     mg = precond == "mg"
     b0 = 4 if (mg and V == 8) else 0          # float copy of r handed to multigrid
     name, _, lvl = kernel.partition("@")
+    variant = lvl.lstrip("0123456789g")       # sweep variants: z (x_old = 0, not read), p (+ coarse correction read), d (+ z.r reduced)
+    lvl = lvl[:len(lvl) - len(variant)] if variant else lvl
     if lvl and not lvl.isdigit():
         return None                           # gathered coarse levels of a z-slab run ("@g0", ...): tiny, not modelled
     n = levels_rows[int(lvl)] if lvl else n_rows
     pre, post = max(1, sweeps[0]), max(0, sweeps[1])
     # one launch = one FULL red-black sweep: 4 coefficient arrays + b + x_old read, x_new written (fp32);
     # the first pre-sweep does not read x_old, the first post-sweep also reads the coarse correction (1/8 value per cell)
-    sweep_avg = ((24.0 + 28.0 * (pre - 1)) + ((28.5 + 28.0 * (post - 1)) if post else 0.0)) / (pre + post)
+    sweep_bytes = 24.0 if "z" in variant else (28.5 if "p" in variant else 28.0)
     per_row = {
         "cg_init": 4 * V + b0,                # read b ; write x r s (+ b0)
         "spmv_dot": 2 * V + 4 * Cc,           # read s, wx wy wz dd ; write q (s.q fused)
@@ -118,7 +120,7 @@ def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, level
         "xpay": (2 * V + 4) if mg else 3 * V, # read z s ; write s
         "dot_rr": V,
         "dot_zb": 8,
-        "sweep": sweep_avg,
+        "sweep": sweep_bytes,
         "residual_restrict": 4 * 4 + 4 + 4 + 0.5,   # coefficients, b, x ; coarse b written
         "prolong_add": 8 + 0.5,
     }.get(name)
@@ -339,7 +341,10 @@ def run_ours(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(dom.split("@")[0] + ("@" + dom.split("@")[1] if "@" in dom else ""), None)
+                tj = json.load(f)
+            ent = tj.get(dom) or tj.get(dom.rstrip("zpd"))      # a variant without its own capture: the plain sweep of that level
+            if ent:
+                traffic = ent["bytes_per_row"] * rank_rows / (8 ** int(dom.split("@")[1].rstrip("zpd")) if "@" in dom else 1)
         except Exception:
             pass
         total_profiled = sum(v[1] for v in table.values())

@@ -81,6 +81,8 @@ typedef struct shkz_b200_params {
 	int32_t mg_min_size;          /* stop coarsening when the largest extent is <= this (default 4) */
 	int32_t check_every;          /* host reads the convergence flag every this many iterations (default 4) */
 	double mg_coarse_scale;       /* coarse operator = scale * (P^T A P), piecewise-constant P (default 0.5) */
+	int32_t mg_gamma;             /* coarse-grid visits per level below level 0: 1 = V-cycle (default), 2 = W-cycle */
+	int32_t reserved;
 } shkz_b200_params;
 
 typedef struct shkz_b200_stats {

@@ -29,7 +29,8 @@ class Params(C.Structure):
                 ("surface_tension", C.c_double), ("rhs_correct", C.c_double), ("residual", C.c_double),
                 ("max_iterations", C.c_uint32), ("precond", C.c_int32), ("precision", C.c_int32),
                 ("mg_pre_sweeps", C.c_int32), ("mg_post_sweeps", C.c_int32), ("mg_coarse_sweeps", C.c_int32),
-                ("mg_min_size", C.c_int32), ("check_every", C.c_int32), ("mg_coarse_scale", C.c_double)]
+                ("mg_min_size", C.c_int32), ("check_every", C.c_int32), ("mg_coarse_scale", C.c_double),
+                ("mg_gamma", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):

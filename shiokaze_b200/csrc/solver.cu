@@ -474,17 +474,19 @@ template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
 void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, float *xn, const float *ec, const Dims &dc, CGState *st, cudaStream_t stream,
                   int slab_ghosts = 0) {
 	const MGLevel &L = H.view;
+	// profiler entry per variant: "sweep@<level>" + z (first pre-sweep, x_old = 0) / p (prolongation folded in) / d (z.r reduction folded in)
+	const std::string tag = H.tag_sweep + (ZERO_X ? "z" : "") + (PROLONG ? "p" : "") + (DOT ? "d" : "");
 	if (H.tma && S->sweep_mode == 0) { // operands staged through shared memory by TMA
 		SweepMaps maps;
 		maps.wx = H.map_wx; maps.wy = H.map_wy; maps.wz = H.map_wz; maps.dd = H.map_dd; maps.b = H.map_b;
 		maps.xo = xo == L.xb ? H.map_xb : H.map_xa;
-		LAUNCH_TILES_SMEM(S, H.tag_sweep.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
+		LAUNCH_TILES_SMEM(S, tag.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
 		                  L.tiles, maps, xo, xn, ec, dc, slab_ghosts, S->redbuf(), st);
 	} else if ((L.d.nx & 3) == 0 && S->sweep_mode <= 1) // aligned quads, direct global loads
-		LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep4<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
+		LAUNCH_TILES(S, tag.c_str(), (k_sweep4<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
 		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, slab_ghosts, S->redbuf(), st);
 	else
-		LAUNCH_TILES(S, H.tag_sweep.c_str(), (k_sweep<FIRST, ZERO_X, PROLONG, DOT>), sweep_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
+		LAUNCH_TILES(S, tag.c_str(), (k_sweep<FIRST, ZERO_X, PROLONG, DOT>), sweep_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
 		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, slab_ghosts, S->redbuf(), st);
 }
 
@@ -531,13 +533,17 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st
 	if (!last) {
 		const MGLevel &C = lv[l + 1].view;
 		dc = C.d;
-		LAUNCH_TILES(S, H.tag_restrict.c_str(), k_residual_restrict, restrict_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx, (const float *)L.wy,
-		             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st);
-		CKR(vcycle(S, l + 1, P, st, stream, false, &ec, global));
-		if (post == 0) {
-			LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, dc, ec, cur, bufs[w], (const CGState *)st);
-			cur = bufs[w];
-			w ^= 1;
+		// gamma coarse-grid visits (W-cycle: 2) on every level but the finest; the last correction is folded into the first post-sweep
+		const int gamma = (l >= 1 && P.mg_gamma > 1) ? P.mg_gamma : 1;
+		for (int g = 0; g < gamma; ++g) {
+			LAUNCH_TILES(S, H.tag_restrict.c_str(), k_residual_restrict, restrict_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx, (const float *)L.wy,
+			             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st);
+			CKR(vcycle(S, l + 1, P, st, stream, false, &ec, global));
+			if (g + 1 < gamma || post == 0) {
+				LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, dc, ec, cur, bufs[w], (const CGState *)st);
+				cur = bufs[w];
+				w ^= 1;
+			}
 		}
 	}
 	for (int sw = 0; sw < post; ++sw) {
@@ -939,6 +945,7 @@ void shkz_b200_default_params(shkz_b200_params *p) {
 	p->mg_min_size = 4;
 	p->check_every = 4;
 	p->mg_coarse_scale = 0.5;
+	p->mg_gamma = 1;
 }
 
 int shkz_b200_device_count(void) {

@@ -76,6 +76,7 @@ class MacPressureSolver3:
             elif key == "MGMinSize": p.mg_min_size = int(value)
             elif key == "MGCoarseScale": p.mg_coarse_scale = float(value)
             elif key == "CheckEvery": p.check_every = int(value)
+            elif key == "MGGamma": p.mg_gamma = int(value)
             else:
                 raise KeyError(f"unknown flag {key}")
 
