@@ -10,7 +10,9 @@ on the workload BASELINE.json quotes the metric on: configs[1], the macsmoke3 bu
 all-fluid Neumann box (16.8 M unknowns). `value` is grid cells projected per second with the inputs
 resident in HBM (restored from pristine device copies inside the timed region), `e2e` is the same through
 the host-buffer C-ABI call a Shiokaze plugin makes (pinned host buffers, H2D and D2H inside the timed region).
-For N > 1 every rank owns a 256x256x256 z-slab of a 256x256x(256 N) box (weak scaling).
+For N > 1 every rank owns a 256x256x256 z-slab of a 256x256x(256 N) box (weak scaling, the default); with
+`--scaling strong` the n^3 grid itself is cut into N z-slabs (configs[3] flip_splash 512^3 over 1/2/4 GPUs and
+configs[4] liquid_box 1024^3 over 2/4/8 GPUs are quoted that way).
 """
 from __future__ import annotations
 
@@ -184,11 +186,12 @@ def run_reference_arm(args):
         reference_sample(args.workload, args.n, budget, threads)
     samples = [reference_sample(args.workload, args.n, budget, threads) for _ in range(args.steps)]
     ms = float(np.mean([s["ms_per_solve"] for s in samples]))
-    cells = float(args.n) ** 3 * args.gpus
-    value = cells / (ms * args.gpus * 1e-3) / 1e6  # the reference has no multi-GPU path: N slabs take N times as long
+    copies = 1 if args.scaling == "strong" else args.gpus
+    cells = float(args.n) ** 3 * copies
+    value = cells / (ms * copies * 1e-3) / 1e6  # the reference has no multi-GPU path: N slabs take N times as long
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms * args.gpus, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": ms * copies, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, "cpu"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": samples[0]["cores"], "kind": samples[0]["kind"], "sample": samples[0]["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,9 +202,11 @@ def run_reference_arm(args):
 
 
 def config_dict(args, where):
-    return {"workload": f"{args.workload} {args.n}^3 per GPU ({'macsmoke3 buoyant plume, all-fluid Neumann box' if args.workload == 'smoke_plume' else args.workload}), "
+    strong = args.scaling == "strong"
+    nzg = args.n if strong else args.n * args.gpus
+    return {"workload": f"{args.workload} {args.n}^3 {'cut into z-slabs' if strong else 'per GPU'} ({'macsmoke3 buoyant plume, all-fluid Neumann box' if args.workload == 'smoke_plume' else args.workload}), "
                         f"one project() call: assembly + MG-PCG solve to Residual={args.residual:g} + velocity update",
-            "grid": [args.n, args.n, args.n * args.gpus], "slab_per_gpu": [args.n, args.n, args.n], "parallelism": f"z-slab x{args.gpus}",
+            "grid": [args.n, args.n, nzg], "slab_per_gpu": [args.n, args.n, nzg // args.gpus], "parallelism": f"z-slab x{args.gpus}",
             "precision": args.precision, "precond": args.precond, "mg_sweeps": [args.pre, args.post], "residual": args.residual,
             "l2_policy": "inputs (318 MB per step) and solver working set (>1 GB) exceed the 126 MB L2; no explicit flush",
             "where": where}
@@ -227,8 +232,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
-    nzg = n * world
-    zr = (rank * n, (rank + 1) * n)
+    strong = args.scaling == "strong"
+    if strong and n % world:
+        raise SystemExit(f"--scaling strong: n={n} is not divisible by {world} slabs")
+    nzg = n if strong else n * world
+    nzl = nzg // world
+    zr = (rank * nzl, (rank + 1) * nzl)
     if world > 1:
         from shiokaze_b200 import dist as sdist
         sc = sdist.slab_scene(args.workload, n, nzg, zr)
@@ -294,28 +303,30 @@ def run_ours(args):
         t = torch.empty(a.shape, dtype=torch.from_numpy(np.zeros(1, a.dtype)).dtype, pin_memory=True)
         t.numpy()[...] = a
         return t
-    hv0 = [np.ascontiguousarray(v) for v in sc.vel]
-    ha0 = [np.ascontiguousarray(a) for a in sc.vel_active]
-    hv = [pinned(v) for v in hv0]
-    ha = [pinned(a) for a in ha0]
-    hfluid = pinned(sc.fluid)
-    hsolid = pinned(sc.solid) if sc.solid is not None else None
-    hpres = pinned(np.zeros(sc.fluid.shape, dtype=np.float32))
-    hpact = pinned(np.zeros(sc.fluid.shape, dtype=np.uint8))
-    h2d = sum(v.nbytes for v in hv0) + sum(a.nbytes for a in ha0) + sc.fluid.nbytes + (sc.solid.nbytes if sc.solid is not None else 0)
-    d2h = sum(v.nbytes for v in hv0) + sum(a.nbytes for a in ha0) + sc.fluid.nbytes + sc.fluid.size
+    h2d = sum(v.nbytes for v in sc.vel) + sum(a.nbytes for a in sc.vel_active) + sc.fluid.nbytes + (sc.solid.nbytes if sc.solid is not None else 0)
+    d2h = sum(v.nbytes for v in sc.vel) + sum(a.nbytes for a in sc.vel_active) + sc.fluid.nbytes + sc.fluid.size
     e2e_s = 0.0
     e2e_steps = args.steps if world == 1 else 0   # slab e2e goes through the same call; measured on one GPU
-    for it in range(min(2, args.warmup) + e2e_steps):
-        for d in range(3):
-            hv[d].numpy()[...] = hv0[d]; ha[d].numpy()[...] = ha0[d]
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        _, _, e2e_res = S.project(sc.dt, [t.numpy() for t in hv], [t.numpy() for t in ha], hsolid.numpy() if hsolid is not None else None,
-                                  hfluid.numpy(), sc.fluid_levelset, pressure_out=hpres.numpy(), pressure_active_out=hpact.numpy())
-        t1 = time.perf_counter()
-        if it >= min(2, args.warmup):
-            e2e_s += t1 - t0
+    if e2e_steps:
+        hv0 = [np.ascontiguousarray(v) for v in sc.vel]
+        ha0 = [np.ascontiguousarray(a) for a in sc.vel_active]
+        hv = [pinned(v) for v in hv0]
+        ha = [pinned(a) for a in ha0]
+        hfluid = pinned(sc.fluid)
+        hsolid = pinned(sc.solid) if sc.solid is not None else None
+        hpres = pinned(np.zeros(sc.fluid.shape, dtype=np.float32))
+        hpact = pinned(np.zeros(sc.fluid.shape, dtype=np.uint8))
+        for it in range(min(2, args.warmup) + e2e_steps):
+            for d in range(3):
+                hv[d].numpy()[...] = hv0[d]; ha[d].numpy()[...] = ha0[d]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, _, e2e_res = S.project(sc.dt, [t.numpy() for t in hv], [t.numpy() for t in ha], hsolid.numpy() if hsolid is not None else None,
+                                      hfluid.numpy(), sc.fluid_levelset, pressure_out=hpres.numpy(), pressure_active_out=hpact.numpy())
+            t1 = time.perf_counter()
+            if it >= min(2, args.warmup):
+                e2e_s += t1 - t0
+        del hv, ha, hfluid, hsolid, hpres, hpact
     e2e_value = (cells_global * e2e_steps / e2e_s / 1e6) if e2e_s > 0 else None
 
     # ---- roofline of the dominant kernel: CUDA events around every launch of one extra solve ----
@@ -365,7 +376,7 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": {"mixed": "f64", "fp64": "f64", "fp32": "f32"}[args.precision], "data": "synthetic", "config": config_dict(args, "gpu"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": (e2e_s / e2e_steps * 1e3) if e2e_steps else None,
@@ -395,6 +406,7 @@ def main():
     ap.add_argument("--post", type=int, default=2)
     ap.add_argument("--residual", type=float, default=1e-4)
     ap.add_argument("--check-every", type=int, default=4)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: n^3 per GPU (weak) or the n^3 grid cut into N slabs (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -24,6 +24,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Optional, Tuple
 
+import os
+
 import numpy as np
 
 SQRT3 = float(np.sqrt(3.0))
@@ -105,10 +107,22 @@ def hash_noise(seed: int, dim: int, shape_zyx, k0: int) -> np.ndarray:
     nzl, nyl, nxl = shape_zyx
     i = np.arange(nxl, dtype=np.uint64)[None, None, :]
     j = np.arange(nyl, dtype=np.uint64)[None, :, None]
-    k = (np.arange(nzl, dtype=np.uint64) + np.uint64(k0))[:, None, None]
-    key = (np.uint64(dim) << np.uint64(60)) | (k << np.uint64(40)) | (j << np.uint64(20)) | i
-    h = splitmix64(np.uint64(seed) ^ key)
-    return (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    out = np.empty((nzl, nyl, nxl), dtype=np.float64)
+
+    def planes(a, b):
+        k = (np.arange(a, b, dtype=np.uint64) + np.uint64(k0))[:, None, None]
+        key = (np.uint64(dim) << np.uint64(60)) | (k << np.uint64(40)) | (j << np.uint64(20)) | i
+        h = splitmix64(np.uint64(seed) ^ key)
+        out[a:b] = (h >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+    step = 8
+    if nzl * nyl * nxl < (1 << 22):
+        planes(0, nzl)
+    else:  # counter-based, so z-chunks are independent: numpy releases the GIL inside its loops
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda a: planes(a, min(a + step, nzl)), range(0, nzl, step)))
+    return out
 
 
 def _face_shapes(nx, ny, nzl):
