@@ -399,7 +399,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="smoke_plume")
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=256, help="grid size n (n^3 cells per GPU, or in total with --scaling strong); --grid is the spelling to use under torchrun, whose own parser finds --n ambiguous")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "fp64", "fp32"])
     ap.add_argument("--precond", default="mg", choices=["mg", "none"])
     ap.add_argument("--pre", type=int, default=2)

@@ -212,6 +212,58 @@ __device__ __forceinline__ float4 relax_quad(const Quad &Q, const float4 &wzu, c
 }
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 ld4cg(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); } // L2: data a peer GPU may have just stored
+
+// z-slab solvers: the halo traffic of ONE red-black sweep, carried by the sweep kernel itself (cm == nullptr on a whole grid).
+//   start    wait for exchange `wait_in` (the ghost planes of x_old, pushed by the previous sweep of the neighbours);
+//            relax the first colour of the own boundary planes and store those half-updated planes into the neighbours'
+//            ghost planes of x_old; the block that finishes last publishes exchange `seq_half`
+//   tiles    first every tile that touches no ghost plane, then — once the neighbours' `seq_half` is here — the rest;
+//            the boundary planes of x_new go to the neighbours' ghost planes of x_new as they are computed
+//   end      the block that finishes last publishes exchange `seq_out` (0: nothing reads those ghost planes)
+// so one launch replaces three (half-plane push + wait, sweep, halo push + wait) and the NVLink round trip is hidden
+// behind the interior tiles. The ghost plane then holds exactly what both phases of the neighbour's sweep need (second-colour
+// cells still old for phase 1, first-colour cells new for phase 2), which is why the slab V-cycle equals the whole-grid one.
+struct SlabSweep {
+	const CommDev *cm;
+	size_t off_xo, off_xn;                 // arena offsets of the lower ghost planes of x_old / x_new
+	unsigned long long wait_in, seq_half, seq_out;
+	const float *wx, *wy, *wz, *dd, *b;    // the level's arrays (the TMA kernel otherwise only holds tensor maps)
+};
+
+// start of a fused slab sweep: every thread of the grid takes quads of the two boundary planes (nx % 4 == 0, 1-D blocks)
+template <int FIRST, bool ZERO_X>
+__device__ __forceinline__ void slab_push_half_planes(const Dims &d, const SlabSweep &sl, const float *__restrict__ xo) {
+	const CommDev *cm = sl.cm;
+	const long long nx = d.nx, plane = d.plane, quads = plane >> 2, nth = (long long)gridDim.x * blockDim.x;
+	const int qx = d.nx >> 2;
+	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+	for (int side = 0; side < 2; ++side) {
+		char *peer = side ? cm->hi : cm->lo;
+		if (!peer) continue;
+		const int p = side ? d.nzl - 1 : 0;
+		float *dst = reinterpret_cast<float *>(peer + sl.off_xo) + (side ? 0 : (long long)(d.nzl + 1) * plane);
+		for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < quads; e += nth) {
+			const int j = (int)(e / qx), i = 4 * (int)(e - (long long)j * qx);
+			const long long c = i + nx * j + plane * p;
+			Quad Q;
+			Q.wx = ld4(sl.wx + c); Q.wx4 = sl.wx[c + 4];
+			Q.wy = ld4(sl.wy + c); Q.wyu = ld4(sl.wy + c + nx);
+			Q.wz = ld4(sl.wz + c); Q.dd = ld4(sl.dd + c); Q.b = ld4(sl.b + c);
+			const float4 wzu = ld4(sl.wz + c + plane);
+			float4 x = zero4, xd = zero4, xu = zero4, zm = zero4, zp = zero4;
+			float xl = 0.f, xr = 0.f;
+			if (!ZERO_X) { // (the plane beyond the boundary is a ghost plane: read it where the neighbour's stores land, in L2)
+				x = ld4cg(xo + c); xl = __ldcg(xo + c - 1); xr = __ldcg(xo + c + 4);
+				xd = ld4cg(xo + c - nx); xu = ld4cg(xo + c + nx); zm = ld4cg(xo + c - plane); zp = ld4cg(xo + c + plane);
+			}
+			const int a1 = (FIRST + j + p + d.k0) & 1;
+			const float4 h = a1 == 0 ? relax_quad<0, ZERO_X>(Q, wzu, x, xl, xr, xd, xu, zm, zp) : relax_quad<1, ZERO_X>(Q, wzu, x, xl, xr, xd, xu, zm, zp);
+			*reinterpret_cast<float4 *>(dst + (c - plane * p)) = h;
+		}
+	}
+	signal_neighbours(cm, sl.seq_half);
+}
 
 template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
 __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep4(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy, const float *__restrict__ wz,
@@ -387,8 +439,9 @@ inline dim3 restrict_block() { return dim3(TX / 2, TY / 2, 1); }
 __global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_residual_restrict(Dims d, Tiles T, const float *__restrict__ wx, const float *__restrict__ wy,
                                                                           const float *__restrict__ wz, const float *__restrict__ dd, const float *__restrict__ b,
                                                                           const float *__restrict__ x, Dims dc, float *__restrict__ bc,
-                                                                          const CGState *__restrict__ st) {
+                                                                          const CGState *__restrict__ st, const CommDev *cm, unsigned long long wait_in) {
 	if (st && st->done) return;
+	if (cm && wait_in) block_wait_neighbours(cm, wait_in); // z-slabs: the ghost planes of x come from the neighbours' last fused sweep
 	const int ntiles = *T.count;
 	const long long nx = d.nx, ny = d.ny, plane = d.plane;
 	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {

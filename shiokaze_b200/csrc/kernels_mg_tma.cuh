@@ -68,10 +68,11 @@ struct SweepMaps { // tensor maps of one level's arrays, box widths as documente
 	CUtensorMap wx, wy, wz, dd, b, xo;
 };
 
-template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
+template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT, bool SLAB>
 __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, const __grid_constant__ SweepMaps M, const float *__restrict__ xo, float *__restrict__ xn,
-                                                            const float *__restrict__ ec, Dims dc, int slab_ghosts, RedBuf rb, CGState *st) {
+                                                            const float *__restrict__ ec, Dims dc, const SlabSweep sl, RedBuf rb, CGState *st) {
 	if (st && st->done) return;
+	constexpr bool slab_ghosts = SLAB; // z-slab solver: this launch also carries the sweep's halo traffic (SlabSweep, kernels_mg.cuh)
 	extern __shared__ __align__(128) float smem[];
 	float *stage_base = smem;
 	float(*H)[S4_ROWS][S4_PITCH] = reinterpret_cast<float(*)[S4_ROWS][S4_PITCH]>(smem + ST_STAGES * ST_FLOATS);
@@ -96,10 +97,23 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 	auto EC = [&](int i, int j, int k) -> long long { return (i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1)); };
 	unsigned loads_done = 0; // stage loads this CTA has consumed so far (same value in every thread)
 
+	float *push_lo = nullptr, *push_hi = nullptr; // neighbours' ghost planes of x_new that take the own boundary planes
+	if constexpr (SLAB) {
+		if (sl.wait_in) block_wait_neighbours(sl.cm, sl.wait_in);
+		slab_push_half_planes<FIRST, ZERO_X>(d, sl, xo);
+		if (sl.seq_out) {
+			if (sl.cm->lo) push_lo = reinterpret_cast<float *>(sl.cm->lo + sl.off_xn) + (long long)(d.nzl + 1) * plane;
+			if (sl.cm->hi) push_hi = reinterpret_cast<float *>(sl.cm->hi + sl.off_xn);
+		}
+	}
+
+	for (int pass = 0; pass < (slab_ghosts ? 2 : 1); ++pass) {
+	if (SLAB && pass == 1) block_wait_neighbours(sl.cm, sl.seq_half); // the neighbours' half-updated planes are in the ghost planes of x_old
 	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
 		int i0, j0, kb;
 		tile_origin(T, T.ids[t], i0, j0, kb);
 		const int ke = min(kb + T.bz, d.nzl);
+		if (slab_ghosts && (kb < 2 || ke + 1 >= d.nzl) != (pass == 1)) continue; // pass 0: tiles that read no ghost plane; pass 1: the others
 		const unsigned base = loads_done;           // load index of plane kb-1
 		auto issue = [&](int p) {                   // producer: fill the stage of plane p
 			const unsigned n = base + (unsigned)(p - (kb - 1));
@@ -132,7 +146,7 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 			const bool cv = ci >= 0 && ci < d.nx && cj < d.ny;
 			float xm = 0.f, xc = 0.f;
 			// ZERO_X on a z-slab: x_old is zero inside the slab, the ghost planes hold the neighbours' half-updated planes
-			auto ghost1 = [&](int k) -> float { return (ZERO_X && slab_ghosts && cv && (k < 0 || k >= d.nzl) && k >= -1 && k <= d.nzl) ? xo[ci + nx * (cj + ny * k)] : 0.f; };
+			auto ghost1 = [&](int k) -> float { return (ZERO_X && slab_ghosts && cv && (k < 0 || k >= d.nzl) && k >= -1 && k <= d.nzl) ? __ldcg(xo + ci + nx * (cj + ny * k)) : 0.f; };
 			if (!ZERO_X && cv && kb - 2 >= -1) {
 				xm = xo[ci + nx * (cj + ny * (kb - 2))];
 				if (PROLONG) xm += ec[EC(ci, cj, kb - 2)];
@@ -188,7 +202,7 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 		};
 		float4 xm = zero4, xc = zero4, wz_cur = zero4;
 		auto ghost4 = [&](int k) -> float4 { // ZERO_X on a z-slab: the ghost planes are the only non-zero part of x_old
-			return (ZERO_X && slab_ghosts && valid && (k < 0 || k >= d.nzl) && k >= -1 && k <= d.nzl) ? ld4(xo + row + plane * k) : zero4;
+			return (ZERO_X && slab_ghosts && valid && (k < 0 || k >= d.nzl) && k >= -1 && k <= d.nzl) ? ld4cg(xo + row + plane * k) : zero4;
 		};
 		if (!ZERO_X && valid && kb - 2 >= -1) {
 			xm = ld4(xo + row + plane * (kb - 2));
@@ -255,6 +269,8 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 				if (a2 == 0) xnew = relax_quad<0, false>(prv, cur.wz, hc, hl, hr, hd, hu, hm, hp);
 				else xnew = relax_quad<1, false>(prv, cur.wz, hc, hl, hr, hd, hu, hm, hp);
 				*reinterpret_cast<float4 *>(xn + row + plane * k) = xnew;
+				if (SLAB && k == 0 && push_lo) *reinterpret_cast<float4 *>(push_lo + row) = xnew;
+				if (SLAB && k == d.nzl - 1 && push_hi) *reinterpret_cast<float4 *>(push_hi + row) = xnew;
 				if (DOT) red[0] += (double)xnew.x * (double)prv.b.x + (double)xnew.y * (double)prv.b.y + (double)xnew.z * (double)prv.b.z + (double)xnew.w * (double)prv.b.w;
 			}
 			hm = hc; hc = hp;
@@ -265,6 +281,8 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 		loads_done = base + (unsigned)(ke - kb + 3);
 		__syncthreads();
 	}
+	}
+	if (slab_ghosts && sl.seq_out) signal_neighbours(sl.cm, sl.seq_out, HDR_PUSH_TICKET2);
 	if (DOT) {
 		grid_reduce<1, 0u>(red, rb, [&](double (&tot)[1]) {
 			const double zr = tot[0];

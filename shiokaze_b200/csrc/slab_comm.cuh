@@ -56,11 +56,12 @@ __device__ __forceinline__ void cross_rank_combine(double (&v)[N], const CommDev
 
 // Called by every thread of every block of a kernel that has stored planes into the neighbours' arenas: the block that
 // finishes last publishes exchange number `seq` in the neighbours' flag words (release order: data, system fence, flag).
-__device__ __forceinline__ void signal_neighbours(const CommDev *cm, unsigned long long seq) {
+// A kernel that publishes two exchanges (the fused slab sweep) counts the second one on its own ticket word.
+__device__ __forceinline__ void signal_neighbours(const CommDev *cm, unsigned long long seq, size_t ticket_word = HDR_PUSH_TICKET) {
 	__threadfence_system();
 	__syncthreads();
 	if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
-		unsigned int *ticket = reinterpret_cast<unsigned int *>(cm->self + HDR_PUSH_TICKET);
+		unsigned int *ticket = reinterpret_cast<unsigned int *>(cm->self + ticket_word);
 		const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
 		if (atomicAdd(ticket, 1u) == nblocks - 1) {
 			*ticket = 0u;
@@ -83,6 +84,18 @@ __device__ __forceinline__ void wait_neighbours(const CommDev *cm, unsigned long
 		while (*f < seq) {}
 	}
 	__threadfence_system();
+}
+
+// A block of a kernel that reads ghost planes whose exchange `seq` was published by a kernel that did not wait for it
+// (the fused slab sweep): one thread acquires the neighbours' flags, the barrier hands the ordering to the block.
+__device__ __forceinline__ void block_wait_neighbours(const CommDev *cm, unsigned long long seq) {
+	if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) wait_neighbours(cm, seq);
+	__syncthreads();
+}
+
+// ... and the stand-alone form for consumers that have no such prologue
+__global__ void k_comm_wait(const CommDev *cm, unsigned long long seq) {
+	if (threadIdx.x == 0) wait_neighbours(cm, seq);
 }
 
 // Halo exchange number `seq` of the cell array at arena offset `off` (offset of its lower ghost plane): store the own

@@ -10,7 +10,7 @@
 namespace shkz {
 
 constexpr int COMM_MAX_WORLD = 8;
-constexpr size_t HDR_FLAG_FROM_LO = 0, HDR_FLAG_FROM_HI = 128, HDR_RED_SEQ = 256, HDR_PUSH_TICKET = 384, HDR_MAIL = 1024;
+constexpr size_t HDR_FLAG_FROM_LO = 0, HDR_FLAG_FROM_HI = 128, HDR_RED_SEQ = 256, HDR_PUSH_TICKET = 384, HDR_PUSH_TICKET2 = 512, HDR_MAIL = 1024;
 constexpr size_t ARENA_HEADER = 65536;
 
 struct CommDev {

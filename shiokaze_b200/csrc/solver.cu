@@ -229,6 +229,7 @@ struct shkz_b200_solver {
 	// slab communicator (nullptr on a whole grid)
 	SlabComm *comm = nullptr;
 	size_t arena_mark = 0; // arena fill level after the creation-time arrays
+	unsigned long long pending_wait = 0; // exchange published by the last fused slab sweep that no kernel has waited for yet
 	// bookkeeping
 	uint64_t launches = 0;
 	Profiler prof;
@@ -472,7 +473,8 @@ int compact_tiles(shkz_b200_solver *S, HostLevel &H, cudaStream_t stream) {
 // ---- multigrid ----
 template <int FIRST, bool ZERO_X, bool PROLONG, bool DOT>
 void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, float *xn, const float *ec, const Dims &dc, CGState *st, cudaStream_t stream,
-                  int slab_ghosts = 0) {
+                  const SlabSweep sl = SlabSweep{}) {
+	const int slab_ghosts = sl.cm != nullptr;
 	const MGLevel &L = H.view;
 	// profiler entry per variant: "sweep@<level>" + z (first pre-sweep, x_old = 0) / p (prolongation folded in) / d (z.r reduction folded in)
 	const std::string tag = H.tag_sweep + (ZERO_X ? "z" : "") + (PROLONG ? "p" : "") + (DOT ? "d" : "");
@@ -480,8 +482,15 @@ void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, floa
 		SweepMaps maps;
 		maps.wx = H.map_wx; maps.wy = H.map_wy; maps.wz = H.map_wz; maps.dd = H.map_dd; maps.b = H.map_b;
 		maps.xo = xo == L.xb ? H.map_xb : H.map_xa;
-		LAUNCH_TILES_SMEM(S, tag.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
-		                  L.tiles, maps, xo, xn, ec, dc, slab_ghosts, S->redbuf(), st);
+		if constexpr (!PROLONG) {
+			if (slab_ghosts) { // z-slab: the same kernel also moves the sweep's halo planes
+				LAUNCH_TILES_SMEM(S, tag.c_str(), (k_sweep_tma<FIRST, ZERO_X, false, DOT, true>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
+				                  L.tiles, maps, xo, xn, ec, dc, sl, S->redbuf(), st);
+				return;
+			}
+		}
+		LAUNCH_TILES_SMEM(S, tag.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT, false>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
+		                  L.tiles, maps, xo, xn, ec, dc, sl, S->redbuf(), st);
 	} else if ((L.d.nx & 3) == 0 && S->sweep_mode <= 1) // aligned quads, direct global loads
 		LAUNCH_TILES(S, tag.c_str(), (k_sweep4<FIRST, ZERO_X, PROLONG, DOT>), dim3(S4_THREADS, 1, 1), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx,
 		             (const float *)L.wy, (const float *)L.wz, (const float *)L.dd, (const float *)L.b, xo, xn, ec, dc, slab_ghosts, S->redbuf(), st);
@@ -537,7 +546,7 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st
 		const int gamma = (l >= 1 && P.mg_gamma > 1) ? P.mg_gamma : 1;
 		for (int g = 0; g < gamma; ++g) {
 			LAUNCH_TILES(S, H.tag_restrict.c_str(), k_residual_restrict, restrict_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx, (const float *)L.wy,
-			             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st);
+			             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st, (const CommDev *)nullptr, 0ull);
 			CKR(vcycle(S, l + 1, P, st, stream, false, &ec, global));
 			if (g + 1 < gamma || post == 0) {
 				LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, dc, ec, cur, bufs[w], (const CGState *)st);
@@ -575,22 +584,50 @@ int gather_planes(shkz_b200_solver *S, const Dims &d, const float *src_plane0, f
 	return SHKZ_B200_OK;
 }
 
+// a consumer of ghost planes without a wait of its own: settle what the last fused sweep left pending
+void settle_pending(shkz_b200_solver *S, cudaStream_t stream) {
+	if (!S->pending_wait) return;
+	LAUNCH(S, "comm_wait", k_comm_wait, 1, 32, stream, S->comm->device_view(), S->pending_wait);
+	S->pending_wait = 0;
+}
+
+// One red-black sweep of a slab level. push_out: a later kernel reads the ghost planes of x_new (another sweep or the
+// residual), so the boundary planes of x_new travel too. Levels swept by the TMA kernel do all of it in ONE launch
+// (SlabSweep, kernels_mg.cuh); the others keep the three-launch form (half-plane push + wait, sweep, halo push + wait).
 template <int FIRST>
-int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, float *xn, bool dot, CGState *st, cudaStream_t stream) {
+int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, float *xn, bool dot, CGState *st, cudaStream_t stream, bool push_out) {
 	const MGLevel &L = H.view;
 	const Dims none{};
-	const unsigned long long seq = S->comm->next_exchange();
 	const size_t off = S->comm->offset_of(reinterpret_cast<const char *>(xo) - (size_t)L.d.plane * sizeof(float));
+	if (H.tma && S->sweep_mode == 0) {
+		SlabSweep sl{};
+		sl.cm = S->comm->device_view();
+		sl.off_xo = off;
+		sl.off_xn = S->comm->offset_of(reinterpret_cast<const char *>(xn) - (size_t)L.d.plane * sizeof(float));
+		sl.wait_in = zero_x ? 0ull : S->pending_wait; // (x_old = 0: nothing of the ghost planes is read before the half planes arrive)
+		sl.seq_half = S->comm->next_exchange();
+		sl.seq_out = push_out ? S->comm->next_exchange() : 0ull;
+		sl.wx = L.wx; sl.wy = L.wy; sl.wz = L.wz; sl.dd = L.dd; sl.b = L.b;
+		if (zero_x) launch_sweep<FIRST, true, false, false>(S, H, xo, xn, nullptr, none, st, stream, sl);
+		else if (dot) launch_sweep<FIRST, false, false, true>(S, H, xo, xn, nullptr, none, st, stream, sl);
+		else launch_sweep<FIRST, false, false, false>(S, H, xo, xn, nullptr, none, st, stream, sl);
+		S->pending_wait = sl.seq_out;
+		return SHKZ_B200_OK;
+	}
+	settle_pending(S, stream);
+	const unsigned long long seq = S->comm->next_exchange();
 	const long long pb = (L.d.plane + 255) / 256;
 	const dim3 grid((unsigned)(pb > 148 ? 148 : (pb < 1 ? 1 : pb)), 2, 1);
 	if (zero_x) LAUNCH(S, "boundary_half", (k_boundary_half_push<FIRST, true>), grid, 256, stream, L.d, (const float *)L.wx, (const float *)L.wy, (const float *)L.wz,
 	                   (const float *)L.dd, (const float *)L.b, xo, S->comm->device_view(), off, seq);
 	else LAUNCH(S, "boundary_half", (k_boundary_half_push<FIRST, false>), grid, 256, stream, L.d, (const float *)L.wx, (const float *)L.wy, (const float *)L.wz,
 	            (const float *)L.dd, (const float *)L.b, xo, S->comm->device_view(), off, seq);
-	if (zero_x) launch_sweep<FIRST, true, false, false>(S, H, xo, xn, nullptr, none, st, stream, 1);
-	else if (dot) launch_sweep<FIRST, false, false, true>(S, H, xo, xn, nullptr, none, st, stream, 1);
-	else launch_sweep<FIRST, false, false, false>(S, H, xo, xn, nullptr, none, st, stream, 1);
-	return halo(S, L.d, xn, stream);
+	SlabSweep ghosts{};
+	ghosts.cm = S->comm->device_view(); // (k_sweep4 / k_sweep only look at cm != nullptr: the ghost planes of x_old are live)
+	if (zero_x) launch_sweep<FIRST, true, false, false>(S, H, xo, xn, nullptr, none, st, stream, ghosts);
+	else if (dot) launch_sweep<FIRST, false, false, true>(S, H, xo, xn, nullptr, none, st, stream, ghosts);
+	else launch_sweep<FIRST, false, false, false>(S, H, xo, xn, nullptr, none, st, stream, ghosts);
+	return push_out ? halo(S, L.d, xn, stream) : SHKZ_B200_OK;
 }
 
 int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result) {
@@ -615,14 +652,15 @@ int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGStat
 	int w = 0;
 	for (int sw = 0; sw < pre; ++sw) {
 		// the very first sweep starts from x = 0: the "old" buffer is only a landing place for the neighbours' boundary planes
-		CKR(slab_sweep<0>(S, H, sw == 0, sw == 0 ? bufs[w ^ 1] : cur, bufs[w], false, st, stream));
+		CKR(slab_sweep<0>(S, H, sw == 0, sw == 0 ? bufs[w ^ 1] : cur, bufs[w], false, st, stream, true));
 		cur = bufs[w];
 		w ^= 1;
 	}
 	if (!last) {
 		const MGLevel &C = S->levels[l + 1].view;
 		LAUNCH_TILES(S, H.tag_restrict.c_str(), k_residual_restrict, restrict_block(), H.tiles_total, stream, L.d, L.tiles, (const float *)L.wx, (const float *)L.wy,
-		             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st);
+		             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st, S->comm->device_view(), S->pending_wait);
+		S->pending_wait = 0;
 		const float *ec = nullptr;
 		CKR(vcycle_slab(S, l + 1, P, st, stream, false, &ec));
 		LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, C.d, ec, cur, bufs[w], (const CGState *)st);
@@ -631,7 +669,7 @@ int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGStat
 		w ^= 1;
 	}
 	for (int sw = 0; sw < post; ++sw) {
-		CKR(slab_sweep<1>(S, H, false, cur, bufs[w], dot && sw + 1 == post, st, stream));
+		CKR(slab_sweep<1>(S, H, false, cur, bufs[w], dot && sw + 1 == post, st, stream, sw + 1 < post));
 		cur = bufs[w];
 		w ^= 1;
 	}

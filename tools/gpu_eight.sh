@@ -9,5 +9,5 @@ run() { # name nproc args...
   echo "$name rc=$?"; tail -2 gpurun_out/$name.err | cut -c1-300; tail -c 1500 gpurun_out/$name.json
 }
 run scale8_smoke256 8 --steps 5 --warmup 3
-run strong8_box1024 8 --workload liquid_box --n 1024 --scaling strong --steps 2 --warmup 3
-run strong4_flip512 4 --workload flip_splash --n 512 --scaling strong --steps 3 --warmup 3
+run strong8_box1024 8 --workload liquid_box --grid 1024 --scaling strong --steps 2 --warmup 3
+run strong4_flip512 4 --workload flip_splash --grid 512 --scaling strong --steps 3 --warmup 3
