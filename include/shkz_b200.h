@@ -83,6 +83,7 @@ typedef struct shkz_b200_params {
 	double mg_coarse_scale;       /* coarse operator = scale * (P^T A P), piecewise-constant P (default 0.5) */
 	int32_t mg_gamma;             /* coarse-grid visits per level below level 0: 1 = V-cycle (default), 2 = W-cycle */
 	int32_t reserved;
+	double mg_omega;              /* relaxation factor of the red-black sweeps, 0 < omega < 2 (1 = Gauss-Seidel; default 1.15) */
 } shkz_b200_params;
 
 typedef struct shkz_b200_stats {

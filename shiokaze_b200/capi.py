@@ -30,7 +30,7 @@ class Params(C.Structure):
                 ("max_iterations", C.c_uint32), ("precond", C.c_int32), ("precision", C.c_int32),
                 ("mg_pre_sweeps", C.c_int32), ("mg_post_sweeps", C.c_int32), ("mg_coarse_sweeps", C.c_int32),
                 ("mg_min_size", C.c_int32), ("check_every", C.c_int32), ("mg_coarse_scale", C.c_double),
-                ("mg_gamma", C.c_int32), ("reserved", C.c_int32)]
+                ("mg_gamma", C.c_int32), ("reserved", C.c_int32), ("mg_omega", C.c_double)]
 
 
 class Stats(C.Structure):

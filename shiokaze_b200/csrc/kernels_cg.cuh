@@ -106,8 +106,10 @@ __global__ void __launch_bounds__(TX *CG_BY) k_dot_zb(Dims d, Tiles T, const flo
 
 // s = z + beta s   (pcg_solver.h:289; plain CG passes z = r; the first iteration has beta = 0, s = 0)
 template <class VecT, class ZT>
-__global__ void __launch_bounds__(TX *CG_BY) k_xpay(Dims d, Tiles T, const ZT *__restrict__ z, VecT *__restrict__ s, const CGState *__restrict__ st) {
+// (z-slabs: the boundary planes of s go straight into the neighbours' ghost planes, SlabPush; the product kernel waits for them)
+__global__ void __launch_bounds__(TX *CG_BY) k_xpay(Dims d, Tiles T, const ZT *__restrict__ z, VecT *__restrict__ s, const CGState *__restrict__ st, const SlabPush sp) {
 	if (st->done) return;
+	VecT *const plo = push_target_lo<VecT>(sp, d.plane, d.nzl), *const phi = push_target_hi<VecT>(sp);
 	const VecT beta = (VecT)st->beta;
 	const int ntiles = *T.count;
 	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -118,17 +120,23 @@ __global__ void __launch_bounds__(TX *CG_BY) k_xpay(Dims d, Tiles T, const ZT *_
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
 				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-				s[c] = (VecT)z[c] + beta * s[c];
+				const VecT v = (VecT)z[c] + beta * s[c];
+				s[c] = v;
+				if (k == 0 && plo) plo[c] = v;
+				if (k == d.nzl - 1 && phi) phi[c - (long long)k * d.plane] = v;
 			}
 	}
+	if (sp.cm) signal_neighbours(sp.cm, sp.seq);
 }
 
 // q = A s,  sq = s.q ; last block: alpha = rho / sq            (pcg_solver.h:276-277)
 // A thread marches its cell column through the tile's planes keeping the z neighbours in registers.
 template <class VecT, class CoefT>
 __global__ void __launch_bounds__(TX *CG_BY) k_spmv_dot(Dims d, Tiles T, const CoefT *__restrict__ wx, const CoefT *__restrict__ wy, const CoefT *__restrict__ wz,
-                                                       const CoefT *__restrict__ dd, const VecT *__restrict__ s, VecT *__restrict__ q, RedBuf rb, CGState *st) {
+                                                       const CoefT *__restrict__ dd, const VecT *__restrict__ s, VecT *__restrict__ q, RedBuf rb, CGState *st,
+                                                       unsigned long long wait_in) {
 	if (st->done) return;
+	if (wait_in) block_wait_neighbours(rb.comm, wait_in); // z-slabs: the ghost planes of s, pushed by the neighbours' k_xpay
 	double red[1] = {0.0};
 	const int ntiles = *T.count;
 	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -195,8 +203,10 @@ __device__ __forceinline__ VecT spmv_cell(CoefT dd, CoefT w0, CoefT w1, CoefT w2
 
 template <class VecT, class CoefT>
 __global__ void __launch_bounds__((TX / 4) * TY, 3) k_spmv_dot4(Dims d, Tiles T, const CoefT *__restrict__ wx, const CoefT *__restrict__ wy, const CoefT *__restrict__ wz,
-                                                               const CoefT *__restrict__ dd, const VecT *__restrict__ s, VecT *__restrict__ q, RedBuf rb, CGState *st) {
+                                                               const CoefT *__restrict__ dd, const VecT *__restrict__ s, VecT *__restrict__ q, RedBuf rb, CGState *st,
+                                                               unsigned long long wait_in) {
 	if (st->done) return;
+	if (wait_in) block_wait_neighbours(rb.comm, wait_in); // z-slabs: the ghost planes of s, pushed by the neighbours' k_xpay
 	double red[1] = {0.0};
 	const int ntiles = *T.count;
 	const long long nx = d.nx;

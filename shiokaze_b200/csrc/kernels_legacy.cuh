@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) k_legacy_rbgs(Dims d, const float *__rest
 	const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
 	const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + d.nx], w4 = wz[c], w5 = wz[c + d.plane];
 	const float v = ZERO_X ? gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c])
-	                       : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], x[c - 1], x[c + 1], x[c - d.nx], x[c + d.nx], x[c - d.plane], x[c + d.plane]);
+	                       : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], x[c - 1], x[c + 1], x[c - d.nx], x[c + d.nx], x[c - d.plane], x[c + d.plane], x[c]);
 	x[c] = v;
 }
 

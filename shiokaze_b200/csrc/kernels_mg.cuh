@@ -33,8 +33,11 @@ namespace shkz {
 __device__ __forceinline__ float gs_diag(float w0, float w1, float w2, float w3, float w4, float w5, float dd) {
 	return dd + ((w0 + w1) + (w2 + w3) + (w4 + w5));
 }
+// relaxation factor of the red-black sweeps (MGOmega; 1 = Gauss-Seidel, > 1 = SOR); set per device before every solve
+__constant__ float c_mg_omega = 1.f;
+// xc = current value of the cell (only used when omega != 1)
 __device__ __forceinline__ float gs_relax(float w0, float w1, float w2, float w3, float w4, float w5, float dd, float b, float x0, float x1, float x2,
-                                          float x3, float x4, float x5) {
+                                          float x3, float x4, float x5, float xc) {
 	const float dg = gs_diag(w0, w1, w2, w3, w4, w5, dd);
 	float acc = b;
 	acc = __fmaf_rn(w0, x0, acc);
@@ -43,11 +46,15 @@ __device__ __forceinline__ float gs_relax(float w0, float w1, float w2, float w3
 	acc = __fmaf_rn(w3, x3, acc);
 	acc = __fmaf_rn(w4, x4, acc);
 	acc = __fmaf_rn(w5, x5, acc);
-	return dg > 0.f ? __fdividef(acc, dg) : 0.f;
+	if (!(dg > 0.f)) return 0.f;
+	const float g = __fdividef(acc, dg);
+	return c_mg_omega == 1.f ? g : __fmaf_rn(c_mg_omega, __fsub_rn(g, xc), xc); // (intrinsics: the compiler must not contract the division's multiply into this)
 }
-__device__ __forceinline__ float gs_relax0(float w0, float w1, float w2, float w3, float w4, float w5, float dd, float b) {
+__device__ __forceinline__ float gs_relax0(float w0, float w1, float w2, float w3, float w4, float w5, float dd, float b) { // ... from x = 0
 	const float dg = gs_diag(w0, w1, w2, w3, w4, w5, dd);
-	return dg > 0.f ? __fdividef(b, dg) : 0.f;
+	if (!(dg > 0.f)) return 0.f;
+	const float g = __fdividef(b, dg);
+	return c_mg_omega == 1.f ? g : __fmul_rn(c_mg_omega, g);
 }
 // b - A x at one cell; 0 on cells without an equation (their b may be stale)
 __device__ __forceinline__ float residual7(float w0, float w1, float w2, float w3, float w4, float w5, float dd, float b, float xc, float x0, float x1,
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(Dims d, Tiles T, con
 			const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
 			if (ZERO_X) return gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c]);
 			return gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], XO(c - 1, i - 1, j, p), XO(c + 1, i + 1, j, p), XO(c - nx, i, j - 1, p),
-			                XO(c + nx, i, j + 1, p), XO(c - plane, i, j, p - 1), XO(c + plane, i, j, p + 1));
+			                XO(c + nx, i, j + 1, p), XO(c - plane, i, j, p - 1), XO(c + plane, i, j, p + 1), XO(c, i, j, p));
 		}
 		return XO(c, i, j, p);
 	};
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(Dims d, Tiles T, con
 					if (((par + e) & 1) != FIRST) {
 						const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
 						xnew = gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], H[ks][ly][lx - 1], H[ks][ly][lx + 1], H[ks][ly - 1][lx], H[ks][ly + 1][lx],
-						                e ? hm1 : hm0, e ? hp1 : hp0);
+						                e ? hm1 : hm0, e ? hp1 : hp0, xnew);
 					}
 					xn[c] = xnew;
 					if (DOT) red[0] += (double)xnew * (double)b[c];
@@ -199,7 +206,7 @@ __device__ __forceinline__ float relax_cell(const Quad &Q, const float4 &wzu, co
 	const float w2 = q_get<M>(Q.wy), w3 = q_get<M>(Q.wyu), w4 = q_get<M>(Q.wz), w5 = q_get<M>(wzu);
 	if (ZERO) return gs_relax0(w0, w1, w2, w3, w4, w5, q_get<M>(Q.dd), q_get<M>(Q.b));
 	const float x0 = M == 0 ? xl : q_get<(M + 3) & 3>(x), x1 = M == 3 ? xr : q_get<(M + 1) & 3>(x);
-	return gs_relax(w0, w1, w2, w3, w4, w5, q_get<M>(Q.dd), q_get<M>(Q.b), x0, x1, q_get<M>(xd), q_get<M>(xu), q_get<M>(zm), q_get<M>(zp));
+	return gs_relax(w0, w1, w2, w3, w4, w5, q_get<M>(Q.dd), q_get<M>(Q.b), x0, x1, q_get<M>(xd), q_get<M>(xu), q_get<M>(zm), q_get<M>(zp), q_get<M>(x));
 }
 // relax cells A and A+2 of the quad, keep the other two
 template <int A, bool ZERO>
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep4(Dims d, Tiles T, const
 			const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
 			if (ZERO_X) return gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c]);
 			return gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], XO(c - 1, i - 1, j, p), XO(c + 1, i + 1, j, p), XO(c - nx, i, j - 1, p),
-			                XO(c + nx, i, j + 1, p), XO(c - plane, i, j, p - 1), XO(c + plane, i, j, p + 1));
+			                XO(c + nx, i, j + 1, p), XO(c - plane, i, j, p - 1), XO(c + plane, i, j, p + 1), XO(c, i, j, p));
 		}
 		return XO(c, i, j, p);
 	};
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(256) k_boundary_half_push(Dims d, const float 
 				const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
 				// with ZERO_X the in-slab x_old is zero but the ghost planes already hold the neighbours' values: none yet, x_old = 0 everywhere
 				v = ZERO_X ? gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c])
-				           : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], xo[c - 1], xo[c + 1], xo[c - nx], xo[c + nx], xo[c - plane], xo[c + plane]);
+				           : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], xo[c - 1], xo[c + 1], xo[c - nx], xo[c + nx], xo[c - plane], xo[c + plane], xo[c]);
 			} else v = ZERO_X ? 0.f : xo[c];
 			dst[e] = v;
 		}
@@ -471,9 +478,11 @@ __global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_residual_restrict(Dims 
 }
 
 // x_new = x_old + P e (only used when MGPostSweeps = 0; otherwise the first post-sweep folds it in)
+// (z-slabs: the boundary planes of x_new go straight into the neighbours' ghost planes, SlabPush; the first post-sweep waits for them)
 __global__ void __launch_bounds__(TX *8) k_prolong_add(Dims d, Tiles T, Dims dc, const float *__restrict__ ec, const float *__restrict__ xo, float *__restrict__ xn,
-                                                      const CGState *__restrict__ st) {
+                                                      const CGState *__restrict__ st, const SlabPush sp) {
 	if (st && st->done) return;
+	float *const plo = push_target_lo<float>(sp, d.plane, d.nzl), *const phi = push_target_hi<float>(sp);
 	const int ntiles = *T.count;
 	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
 		int i0, j0, kb;
@@ -483,9 +492,13 @@ __global__ void __launch_bounds__(TX *8) k_prolong_add(Dims d, Tiles T, Dims dc,
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += 8) {
 				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-				xn[c] = xo[c] + ec[(i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1))];
+				const float v = xo[c] + ec[(i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1))];
+				xn[c] = v;
+				if (k == 0 && plo) plo[c] = v;
+				if (k == d.nzl - 1 && phi) phi[c - (long long)k * d.plane] = v;
 			}
 	}
+	if (sp.cm) signal_neighbours(sp.cm, sp.seq);
 }
 
 // ---- the shared-memory tail of the V-cycle ----------------------------------------------------------------
@@ -534,7 +547,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vcycle_tail(TailArgs A, const 
 			if (((i + j + k + d.k0) & 1) != color) continue;
 			const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
 			x[c] = zero_x ? gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c])
-			              : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], x[c - 1], x[c + 1], x[c - nx], x[c + nx], x[c - plane], x[c + plane]);
+			              : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], x[c - 1], x[c + 1], x[c - nx], x[c + nx], x[c - plane], x[c + plane], x[c]);
 		}
 		__syncthreads();
 	};

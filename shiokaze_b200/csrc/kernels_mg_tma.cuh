@@ -138,6 +138,22 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 			issue(kb);
 			issue(kb + 1);
 		}
+		// PROLONG: x_old + P e_coarse is formed IN the stage. As soon as the box of plane p+2 has landed (one step before anybody
+		// needs it) every row-warp thread adds the coarse correction to its OWN quad of it — the only part of that plane it reads
+		// before the next block barrier — and the halo-column warp does the rim (rows 0 and 19, quads 0 and 17 of the other rows),
+		// which others read one barrier later. No extra barrier, no extra registers downstream: after this, the kernel reads
+		// corrected values from shared memory exactly like the plain sweep. The float2 of e is requested a whole step ahead.
+		// Cells outside the grid keep the TMA's zero fill (they only ever meet zero coefficients).
+		auto ec_quad = [&](int rowi, int c4, int pz) -> float2 { // correction of x_old box quad (rowi, c4) in plane pz, 0 where there is none
+			const int gi = i0 - 4 + 4 * c4, gj = j0 - 2 + rowi;
+			return (gi >= 0 && gi < d.nx && gj >= 0 && gj < d.ny && pz >= -1 && pz <= d.nzl) ? *reinterpret_cast<const float2 *>(ec + EC(gi, gj, pz)) : make_float2(0.f, 0.f);
+		};
+		auto add_quad = [&](int pz, int rowi, int c4, float2 e) {
+			float4 *cell = reinterpret_cast<float4 *>(stage_base + ((base + (unsigned)(pz - (kb - 1))) % ST_STAGES) * ST_FLOATS + ST_XO + rowi * ST_W + 4 * c4);
+			float4 v = *cell;
+			v.x += e.x; v.y += e.x; v.z += e.y; v.w += e.y;
+			*cell = v;
+		};
 
 		if (colwarp) {
 			// ---- halo columns (stage columns 3 and TX+4) of the TY tile rows: one cell per lane and plane
@@ -152,36 +168,54 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 				if (PROLONG) xm += ec[EC(ci, cj, kb - 2)];
 			}
 			if (ZERO_X) xm = ghost1(kb - 2);
-			wait_plane(kb - 1);
-			if (!ZERO_X) {
-				xc = stage_of(kb - 1)[ST_XO + (rr + 1) * ST_W + cc];
-				if (PROLONG && cv) xc += ec[EC(ci, cj, kb - 1)];
-			} else xc = ghost1(kb - 1);
+			// PROLONG: the rim of the x_old box, 72 quads over 32 lanes — rows 0 and 19 whole, quads 0 and 17 of rows 1..18
+			auto rim = [&](int u, int &rowi, int &c4) -> bool {
+				const int qn = lane + 32 * u;
+				if (qn < 36) { rowi = qn < 18 ? 0 : ST_XO_ROWS - 1; c4 = qn % 18; }
+				else { rowi = 1 + ((qn - 36) >> 1); c4 = (qn & 1) ? 17 : 0; }
+				return qn < 72;
+			};
+			auto rim_load = [&](int pz, float2 (&e)[3]) {
+#pragma unroll
+				for (int u = 0; u < 3; ++u) { int rowi, c4; e[u] = rim(u, rowi, c4) ? ec_quad(rowi, c4, pz) : make_float2(0.f, 0.f); }
+			};
+			auto rim_add = [&](int pz, const float2 (&e)[3]) {
+				wait_plane(pz);
+#pragma unroll
+				for (int u = 0; u < 3; ++u) { int rowi, c4; if (rim(u, rowi, c4)) add_quad(pz, rowi, c4, e[u]); }
+				__syncwarp();
+			};
+			float2 e_rim[3];
+			if (PROLONG) {
+				rim_load(kb - 1, e_rim); rim_add(kb - 1, e_rim);
+				__syncthreads(); // plane kb-1 is read by everybody right away
+				rim_load(kb, e_rim); rim_add(kb, e_rim);
+			} else wait_plane(kb - 1);
+			if (!ZERO_X) xc = stage_of(kb - 1)[ST_XO + (rr + 1) * ST_W + cc];
+			else xc = ghost1(kb - 1);
 			for (int p = kb - 1; p <= ke; ++p) {
-				wait_plane(p + 1);
+				const bool fix = PROLONG && p + 2 <= ke + 1;
+				if (fix) rim_load(p + 2, e_rim);
+				if (!PROLONG) wait_plane(p + 1);
 				const float *P = stage_of(p), *N = stage_of(p + 1);
 				const bool in_slab = p >= 0 && p < d.nzl;
 				float xp = 0.f;
-				if (!ZERO_X) {
-					xp = N[ST_XO + (rr + 1) * ST_W + cc];
-					if (PROLONG && cv && p + 1 <= d.nzl) xp += ec[EC(ci, cj, p + 1)];
-				} else xp = ghost1(p + 1);
+				if (!ZERO_X) xp = N[ST_XO + (rr + 1) * ST_W + cc];
+				else xp = ghost1(p + 1);
 				float h = xc;
 				if (in_slab && ((ci + cj + p + d.k0) & 1) == FIRST) {
 					const float w0 = P[ST_WX + rr * ST_W + cc], w1 = P[ST_WX + rr * ST_W + cc + 1], w2 = P[ST_WY + rr * ST_W + cc], w3 = P[ST_WY + (rr + 1) * ST_W + cc];
 					const float w4 = P[ST_WZ + rr * ST_W + cc], w5 = N[ST_WZ + rr * ST_W + cc], dg = P[ST_DD + rr * ST_W + cc], bb = P[ST_B + rr * ST_W + cc];
 					if (ZERO_X) h = gs_relax0(w0, w1, w2, w3, w4, w5, dg, bb);
 					else {
-						float x0 = P[ST_XO + (rr + 1) * ST_W + cc - 1], x1 = P[ST_XO + (rr + 1) * ST_W + cc + 1], x2 = P[ST_XO + rr * ST_W + cc], x3 = P[ST_XO + (rr + 2) * ST_W + cc];
-						if (PROLONG && cv) {
-							x0 += ec[EC(ci - 1, cj, p)]; x1 += ec[EC(ci + 1, cj, p)]; x2 += ec[EC(ci, cj - 1, p)]; x3 += ec[EC(ci, cj + 1, p)];
-						}
-						h = gs_relax(w0, w1, w2, w3, w4, w5, dg, bb, x0, x1, x2, x3, xm, xp);
+						const float x0 = P[ST_XO + (rr + 1) * ST_W + cc - 1], x1 = P[ST_XO + (rr + 1) * ST_W + cc + 1], x2 = P[ST_XO + rr * ST_W + cc], x3 = P[ST_XO + (rr + 2) * ST_W + cc];
+						h = gs_relax(w0, w1, w2, w3, w4, w5, dg, bb, x0, x1, x2, x3, xm, xp, xc);
 					}
 				}
 				H[(p + 3) % 3][rr][cc] = cv ? h : 0.f;
 				__syncthreads();
 				if (producer && p + 3 <= ke + 1) issue(p + 3); // the stage of plane p is free: every phase-1 read of it is behind the barrier
+				if (fix) rim_add(p + 2, e_rim);
 				xm = xc; xc = xp;
 			}
 			loads_done = base + (unsigned)(ke - kb + 3);
@@ -209,13 +243,20 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 			if (PROLONG) xm = ECQ(xm, i, j, kb - 2);
 		}
 		if (ZERO_X) xm = ghost4(kb - 2);
-		wait_plane(kb - 1);
+		float2 e_own = make_float2(0.f, 0.f); // PROLONG: correction of the own quad, box row r+1, quad tx+1
+		if (PROLONG) {
+			e_own = ec_quad(r + 1, tx + 1, kb - 1);
+			wait_plane(kb - 1);
+			add_quad(kb - 1, r + 1, tx + 1, e_own);
+			__syncthreads(); // plane kb-1 is read by everybody right away
+			e_own = ec_quad(r + 1, tx + 1, kb);
+			wait_plane(kb);
+			add_quad(kb, r + 1, tx + 1, e_own);
+		} else wait_plane(kb - 1);
 		{
 			const float *P = stage_of(kb - 1);
-			if (!ZERO_X) {
-				xc = LDQ(P, ST_XO, r + 1);
-				if (PROLONG && valid) xc = ECQ(xc, i, j, kb - 1);
-			} else xc = ghost4(kb - 1);
+			if (!ZERO_X) xc = LDQ(P, ST_XO, r + 1);
+			else xc = ghost4(kb - 1);
 			wz_cur = LDQ(P, ST_WZ, r);
 		}
 		float4 hm = zero4, hc = zero4;
@@ -225,7 +266,9 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 		for (int p = kb - 1; p <= ke; ++p) {
 			const int slot = (p + 3) % 3;
 			const bool in_slab = p >= 0 && p < d.nzl;
-			wait_plane(p + 1);
+			const bool fix = PROLONG && p + 2 <= ke + 1;
+			if (fix) e_own = ec_quad(r + 1, tx + 1, p + 2);
+			if (!PROLONG) wait_plane(p + 1);
 			const float *P = stage_of(p), *N = stage_of(p + 1);
 			Quad cur;
 			cur.wz = wz_cur;
@@ -239,13 +282,6 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 				xp = LDQ(N, ST_XO, r + 1);
 				xl = P[ST_XO + (r + 1) * ST_W + q - 1]; xr = P[ST_XO + (r + 1) * ST_W + q + 4];
 				xd = LDQ(P, ST_XO, r); xu = LDQ(P, ST_XO, r + 2);
-				if (PROLONG && valid) {
-					if (p + 1 <= d.nzl) xp = ECQ(xp, i, j, p + 1);
-					if (in_slab) {
-						xl += ec[EC(i - 1, j, p)]; xr += ec[EC(i + 4, j, p)];
-						xd = ECQ(xd, i, j - 1, p); xu = ECQ(xu, i, j + 1, p);
-					}
-				}
 			} else xp = ghost4(p + 1);
 			// ---- phase 1: half-updated plane p
 			float4 hp = xc;
@@ -272,6 +308,10 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 				if (SLAB && k == 0 && push_lo) *reinterpret_cast<float4 *>(push_lo + row) = xnew;
 				if (SLAB && k == d.nzl - 1 && push_hi) *reinterpret_cast<float4 *>(push_hi + row) = xnew;
 				if (DOT) red[0] += (double)xnew.x * (double)prv.b.x + (double)xnew.y * (double)prv.b.y + (double)xnew.z * (double)prv.b.z + (double)xnew.w * (double)prv.b.w;
+			}
+			if (fix) { // the box of plane p+2 has had a whole step to land
+				wait_plane(p + 2);
+				add_quad(p + 2, r + 1, tx + 1, e_own);
 			}
 			hm = hc; hc = hp;
 			xm = xc; xc = xp;

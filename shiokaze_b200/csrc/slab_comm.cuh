@@ -86,6 +86,20 @@ __device__ __forceinline__ void wait_neighbours(const CommDev *cm, unsigned long
 	__threadfence_system();
 }
 
+// A kernel that writes a cell array and sends its boundary planes along: `off` = arena offset of the array's lower ghost plane
+// (cm == nullptr: whole grid, or nobody reads the ghost planes); the block that finishes last publishes exchange `seq`.
+struct SlabPush {
+	const CommDev *cm;
+	size_t off;
+	unsigned long long seq;
+};
+template <class T> __device__ __forceinline__ T *push_target_lo(const SlabPush &sp, long long plane, int nzl) { // lower neighbour's upper ghost plane
+	return (sp.cm && sp.cm->lo) ? reinterpret_cast<T *>(sp.cm->lo + sp.off) + (long long)(nzl + 1) * plane : nullptr;
+}
+template <class T> __device__ __forceinline__ T *push_target_hi(const SlabPush &sp) { // upper neighbour's lower ghost plane
+	return (sp.cm && sp.cm->hi) ? reinterpret_cast<T *>(sp.cm->hi + sp.off) : nullptr;
+}
+
 // A block of a kernel that reads ghost planes whose exchange `seq` was published by a kernel that did not wait for it
 // (the fused slab sweep): one thread acquires the neighbours' flags, the barrier hands the ordering to the block.
 __device__ __forceinline__ void block_wait_neighbours(const CommDev *cm, unsigned long long seq) {

@@ -549,7 +549,7 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st
 			             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st, (const CommDev *)nullptr, 0ull);
 			CKR(vcycle(S, l + 1, P, st, stream, false, &ec, global));
 			if (g + 1 < gamma || post == 0) {
-				LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, dc, ec, cur, bufs[w], (const CGState *)st);
+				LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, dc, ec, cur, bufs[w], (const CGState *)st, SlabPush{});
 				cur = bufs[w];
 				w ^= 1;
 			}
@@ -582,6 +582,17 @@ int gather_planes(shkz_b200_solver *S, const Dims &d, const float *src_plane0, f
 	const int blocks = (int)((chunks + 255) / 256 > 296 ? 296 : ((chunks + 255) / 256 < 1 ? 1 : (chunks + 255) / 256));
 	LAUNCH(S, "gather_planes", k_gather_push, blocks, 256, stream, S->comm->device_view(), src_off, dst_off, plane_bytes * (size_t)d.nzl);
 	return SHKZ_B200_OK;
+}
+
+// the SlabPush of a kernel that writes cell array `p` of a slab solver (exchange number taken here)
+template <class T>
+SlabPush slab_push(shkz_b200_solver *S, const Dims &d, T *p) {
+	SlabPush sp{};
+	if (S->whole_grid) return sp;
+	sp.cm = S->comm->device_view();
+	sp.off = S->comm->offset_of(reinterpret_cast<const char *>(p) - (size_t)d.plane * sizeof(T));
+	sp.seq = S->comm->next_exchange();
+	return sp;
 }
 
 // a consumer of ghost planes without a wait of its own: settle what the last fused sweep left pending
@@ -663,8 +674,10 @@ int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGStat
 		S->pending_wait = 0;
 		const float *ec = nullptr;
 		CKR(vcycle_slab(S, l + 1, P, st, stream, false, &ec));
-		LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, C.d, ec, cur, bufs[w], (const CGState *)st);
-		CKR(halo(S, L.d, bufs[w], stream));
+		// (the correction's boundary planes travel with the kernel that writes them; whoever reads the ghost planes next waits)
+		const SlabPush sp = post > 0 ? slab_push(S, L.d, bufs[w]) : SlabPush{};
+		LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, C.d, ec, cur, bufs[w], (const CGState *)st, sp);
+		if (sp.cm) S->pending_wait = sp.seq;
 		cur = bufs[w];
 		w ^= 1;
 	}
@@ -689,6 +702,7 @@ int legacy_vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, cuda
 	const dim3 block(32, 8, 1), grid(((L.d.nx + 1) / 2 + 31) / 32, (L.d.ny + 7) / 8, L.d.nzl);
 	const CGState *st = nullptr;
 	float *x = L.xa;
+	CK(cudaMemsetAsync(H.xa.base, 0, H.xa.bytes, stream)); // x = 0: with omega != 1 the second colour of the first sweep reads its own old value
 	for (int sw = 0; sw < pre; ++sw) {
 		if (sw == 0) LAUNCH(S, "legacy_rbgs", k_legacy_rbgs<true>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, x, 0, st);
 		else LAUNCH(S, "legacy_rbgs", k_legacy_rbgs<false>, grid, block, stream, L.d, L.wx, L.wy, L.wz, L.dd, L.b, x, 0, st);
@@ -747,6 +761,13 @@ int build_hierarchy(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t
 	return SHKZ_B200_OK;
 }
 
+// relaxation factor of the sweeps: a per-device constant, set before anything that smooths
+int set_omega(const shkz_b200_params &P, cudaStream_t stream) {
+	const float w = (float)P.mg_omega;
+	CK(cudaMemcpyToSymbolAsync(c_mg_omega, &w, sizeof w, 0, cudaMemcpyHostToDevice, stream));
+	return SHKZ_B200_OK;
+}
+
 // ---- the CG driver (pcg_solver.h:246-295 with the loop control on the device) ----
 template <class VecT, class CoefT>
 int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
@@ -776,11 +797,12 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	unsigned batch = S->last_iterations ? S->last_iterations : check;
 	while (it < P.max_iterations) {
 		for (unsigned c = 0; c < batch && it < P.max_iterations; ++c, ++it) {
-			if (mg) LAUNCH_TILES(S, "xpay", (k_xpay<VecT, float>), cg_block(), tt, stream, d, T, z, s, (const CGState *)st);
-			else LAUNCH_TILES(S, "xpay", (k_xpay<VecT, VecT>), cg_block(), tt, stream, d, T, (const VecT *)r, s, (const CGState *)st);
-			CKR(halo(S, d, s, stream));
-			if ((d.nx & 3) == 0) LAUNCH_TILES(S, "spmv_dot", (k_spmv_dot4<VecT, CoefT>), cg_block4(), tt, stream, d, T, wx, wy, wz, dd, (const VecT *)s, q, rb, st);
-			else LAUNCH_TILES(S, "spmv_dot", (k_spmv_dot<VecT, CoefT>), cg_block(), tt, stream, d, T, wx, wy, wz, dd, (const VecT *)s, q, rb, st);
+			// z-slabs: k_xpay stores the boundary planes of s into the neighbours' ghost planes, the product waits for theirs
+			const SlabPush sp = S->whole_grid ? SlabPush{} : slab_push(S, d, s);
+			if (mg) LAUNCH_TILES(S, "xpay", (k_xpay<VecT, float>), cg_block(), tt, stream, d, T, z, s, (const CGState *)st, sp);
+			else LAUNCH_TILES(S, "xpay", (k_xpay<VecT, VecT>), cg_block(), tt, stream, d, T, (const VecT *)r, s, (const CGState *)st, sp);
+			if ((d.nx & 3) == 0) LAUNCH_TILES(S, "spmv_dot", (k_spmv_dot4<VecT, CoefT>), cg_block4(), tt, stream, d, T, wx, wy, wz, dd, (const VecT *)s, q, rb, st, sp.seq);
+			else LAUNCH_TILES(S, "spmv_dot", (k_spmv_dot<VecT, CoefT>), cg_block(), tt, stream, d, T, wx, wy, wz, dd, (const VecT *)s, q, rb, st, sp.seq);
 			if (mg) {
 				if (kFloatVec) LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, false>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
 				else LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, true>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
@@ -889,6 +911,7 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	CK(cudaEventRecord(S->ev[2], stream));
 	S->have_system = true;
 	S->have_hierarchy = S->have_hierarchy && P.precond == SHKZ_B200_PRECOND_MG;
+	CKR(set_omega(P, stream));
 	CKR((solve<VecT, CoefT>(S, P, stream)));
 	CK(cudaEventRecord(S->ev[3], stream));
 	// pressure scatter + velocity update
@@ -942,6 +965,7 @@ int check_params(const shkz_b200_params *p, shkz_b200_params &out) {
 	if (out.precond != SHKZ_B200_PRECOND_NONE && out.precond != SHKZ_B200_PRECOND_MG) return fail(SHKZ_B200_ERR_ARG, "unknown precond %d", out.precond);
 	if (out.precision < 0 || out.precision > 2) return fail(SHKZ_B200_ERR_ARG, "unknown precision %d", out.precision);
 	if (!(out.mg_coarse_scale > 0.0)) return fail(SHKZ_B200_ERR_ARG, "mg_coarse_scale must be > 0");
+	if (!(out.mg_omega > 0.0 && out.mg_omega < 2.0)) return fail(SHKZ_B200_ERR_ARG, "mg_omega must be in (0, 2)");
 	return SHKZ_B200_OK;
 }
 
@@ -984,6 +1008,7 @@ void shkz_b200_default_params(shkz_b200_params *p) {
 	p->check_every = 4;
 	p->mg_coarse_scale = 0.5;
 	p->mg_gamma = 1;
+	p->mg_omega = 1.15;
 }
 
 int shkz_b200_device_count(void) {
@@ -1164,6 +1189,7 @@ int shkz_b200_resolve(shkz_b200_solver *S, const shkz_b200_params *params, shkz_
 	CK(cudaEventRecord(S->ev[1], stream));
 	if (P.precond == SHKZ_B200_PRECOND_MG) CKR(build_hierarchy(S, P, stream));
 	CK(cudaEventRecord(S->ev[2], stream));
+	CKR(set_omega(P, stream));
 	int rc;
 	if (P.precision == SHKZ_B200_PREC_FP64) rc = solve<double, double>(S, P, stream);
 	else if (P.precision == SHKZ_B200_PREC_MIXED) rc = solve<double, float>(S, P, stream);
@@ -1249,6 +1275,7 @@ int shkz_b200_debug_vcycle(shkz_b200_solver *S, const shkz_b200_params *params, 
 	const Dims &d = S->d;
 	HostLevel &H0 = S->levels[0];
 	const Tiles T = H0.view.tiles;
+	CKR(set_omega(P, stream));
 	// level-0 right-hand side := float(rhs of the last project())
 	if (P.precision == SHKZ_B200_PREC_FP32)
 		LAUNCH_TILES(S, "cg_init", (k_cg_init<float, false>), cg_block(), H0.tiles_total, stream, d, T, (const float *)S->b.ptr<float>(d), S->x.ptr<float>(d), S->r.ptr<float>(d), S->s.ptr<float>(d), (float *)nullptr);

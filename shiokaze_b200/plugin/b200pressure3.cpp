@@ -166,6 +166,7 @@ protected:
 		config.get_string("Precond",precond,"Preconditioner: mg (multigrid V-cycle) or none (the reference's plain CG)");
 		config.get_integer("MGPreSweeps",m_cuda_param.mg_pre_sweeps,"Red-black sweeps before the coarse correction");
 		config.get_integer("MGPostSweeps",m_cuda_param.mg_post_sweeps,"Red-black sweeps after the coarse correction");
+		config.get_double("MGOmega",m_cuda_param.mg_omega,"Relaxation factor of the red-black sweeps (1 = Gauss-Seidel)");
 		config.get_integer("GPU",m_device,"CUDA device index");
 		m_cuda_param.precision = precision == "fp64" ? SHKZ_B200_PREC_FP64 : (precision == "fp32" ? SHKZ_B200_PREC_FP32 : SHKZ_B200_PREC_MIXED);
 		m_cuda_param.precond = precond == "none" ? SHKZ_B200_PRECOND_NONE : SHKZ_B200_PRECOND_MG;

@@ -77,6 +77,7 @@ class MacPressureSolver3:
             elif key == "MGCoarseScale": p.mg_coarse_scale = float(value)
             elif key == "CheckEvery": p.check_every = int(value)
             elif key == "MGGamma": p.mg_gamma = int(value)
+            elif key == "MGOmega": p.mg_omega = float(value)
             else:
                 raise KeyError(f"unknown flag {key}")
 
