@@ -343,7 +343,10 @@ int setup_tail(const std::vector<HostLevel> &lv, int &tail_first, size_t &tail_s
 	return SHKZ_B200_OK;
 }
 
-constexpr int AGG_MAX_EXTENT = 64; // z-slab solvers: levels this small (largest global extent) are gathered and solved on every rank
+// z-slab solvers: levels this small (largest global extent, or global cell count: a long thin stack of slabs) are gathered and solved
+// redundantly on every rank — a whole-grid kernel on 2 M cells takes ~10 us, a slab sweep never less than two NVLink round trips
+constexpr int AGG_MAX_EXTENT = 64;
+constexpr long long AGG_MAX_CELLS = 1ll << 21;
 
 template <class VecT, class CoefT>
 int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_params &P) {
@@ -372,7 +375,7 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 		if (big_extent(cur) <= min_size) break;
 		if (!S->whole_grid) {
 			// slabs: aggregates stay inside one rank (even local extent and even first plane); small levels go global
-			if (l >= 1 && big_extent(cur) <= AGG_MAX_EXTENT) { S->agg_level = l; break; }
+			if (l >= 1 && (big_extent(cur) <= AGG_MAX_EXTENT || (long long)cur.plane * cur.nzg <= AGG_MAX_CELLS)) { S->agg_level = l; break; }
 			if ((cur.nzl & 1) || (cur.k0 & 1) || cur.nzl < 2) { if (l >= 1) S->agg_level = l; break; }
 		}
 		cur = make_dims((cur.nx + 1) / 2, (cur.ny + 1) / 2, (cur.nzl + 1) / 2, cur.k0 / 2, (cur.nzg + 1) / 2);
@@ -1048,7 +1051,7 @@ int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int
 		if (nz % (k1 - k0) != 0 || k0 % (k1 - k0) != 0) rc = fail(SHKZ_B200_ERR_ARG, "z-slabs must be equal: nz %d, slab [%d,%d)", nz, k0, k1);
 		S->comm = new SlabComm(device);
 		const size_t cells = (size_t)(d.nzl + 2) * (size_t)d.plane;
-		if (rc == SHKZ_B200_OK && S->comm->create_arena(ARENA_HEADER + cells * 136 + (size_t)64 * 1024 * 1024)) rc = fail(SHKZ_B200_ERR_CUDA, "%s", S->comm->error());
+		if (rc == SHKZ_B200_OK && S->comm->create_arena(ARENA_HEADER + cells * 136 + (size_t)160 * 1024 * 1024)) rc = fail(SHKZ_B200_ERR_CUDA, "%s", S->comm->error());
 	}
 	tryalloc(S->phi.alloc(d, S->real_bytes, S->arena()));
 	tryalloc(S->pressure.alloc(d, S->real_bytes, S->arena()));

@@ -10,4 +10,3 @@ run() { # name nproc args...
 }
 run scale8_smoke256 8 --steps 5 --warmup 3
 run strong8_box1024 8 --workload liquid_box --grid 1024 --scaling strong --steps 2 --warmup 3
-run strong4_flip512 4 --workload flip_splash --grid 512 --scaling strong --steps 3 --warmup 3
