@@ -344,25 +344,39 @@ def run_ours(args):
         levels_rows = [n_rows / (8 ** l) for l in range(16)]
         rank_rows = res.n_rows / world        # a slab solver reports the global row count; kernels are timed on rank 0's slab
         ab = lambda k: algorithmic_bytes_per_launch(k, rank_rows, args.precision, [rank_rows / (8 ** l) for l in range(16)], args.precond, (args.pre, args.post))
-        solve_kernels = {k: v for k, v in table.items() if ab(k)}
-        dom = max(solve_kernels, key=lambda k: solve_kernels[k][1])
-        cnt, tot = solve_kernels[dom]
-        per_launch = ab(dom)
+        # the dominant kernel = the kernel FUNCTION with the largest summed time: the sweep variants of one level (z: x_old = 0,
+        # p: coarse correction folded in, d: z.r folded in) are template instances of the same k_sweep_tma and count together,
+        # each launch with the algorithmic bytes of its own variant
+        def base_tag(k):
+            name, _, lvl = k.partition("@")
+            return name + ("@" + lvl.rstrip("zpd") if lvl else "")
+        groups = {}
+        for k, (c, t) in table.items():
+            if ab(k):
+                g = groups.setdefault(base_tag(k), {"launches": 0, "ms": 0.0, "bytes": 0.0, "variants": {}})
+                g["launches"] += c; g["ms"] += t; g["bytes"] += ab(k) * c
+                g["variants"][k] = {"launches": c, "avg_launch_ms": t / c, "algorithmic_bytes_per_launch": ab(k), "achieved": ab(k) / (t / c * 1e-3) / 1e9}
+        dom = max(groups, key=lambda k: groups[k]["ms"])
+        cnt, tot = groups[dom]["launches"], groups[dom]["ms"]
+        per_launch = groups[dom]["bytes"] / cnt
         achieved = per_launch / (tot / cnt * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
-            ent = tj.get(dom) or tj.get(dom.rstrip("zpd"))      # a variant without its own capture: the plain sweep of that level
-            if ent:
-                traffic = ent["bytes_per_row"] * rank_rows / (8 ** int(dom.split("@")[1].rstrip("zpd")) if "@" in dom else 1)
+            acc = 0.0
+            for k, v in groups[dom]["variants"].items():
+                ent = tj.get(k) or tj.get(base_tag(k))        # a variant without its own capture: the plain kernel of that level
+                lvl = int(base_tag(k).split("@")[1]) if "@" in k else 0
+                acc += ent["bytes_per_row"] * rank_rows / (8 ** lvl) * v["launches"]
+            traffic = acc / cnt
         except Exception:
-            pass
+            traffic = None
         total_profiled = sum(v[1] for v in table.values())
         alg_total = sum((ab(k) or 0) * v[0] for k, v in table.items())
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": how, "launches": cnt, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_launch": per_launch,
-                    "share_of_step": tot / total_profiled if total_profiled else None,
+                    "share_of_step": tot / total_profiled if total_profiled else None, "variants": groups[dom]["variants"],
                     "solve_whole": {"algorithmic_GB": alg_total / 1e9, "ms": res.stats["ms_solve"], "achieved": alg_total / 1e9 / (res.stats["ms_solve"] * 1e-3),
                                     "frac": alg_total / 1e9 / (res.stats["ms_solve"] * 1e-3) / peak},
                     "by_kernel_ms": {k: round(v[1], 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])[:12]}}

@@ -164,6 +164,46 @@ int shkz_b200_slab_export(shkz_b200_solver *solver, uint8_t ipc[SHKZ_B200_IPC_BY
 int shkz_b200_slab_connect(shkz_b200_solver *solver, int rank, int world, const uint8_t *all_ipc /* world * SHKZ_B200_IPC_BYTES */);
 int shkz_b200_slab_connect_local(shkz_b200_solver *const *solvers, int world);
 
+/* ---- assembled systems: CG on a CSR matrix ------------------------------------------------------
+ * Replaces RCMatrix_solver_interface<size_t,double>::solve (include/shiokaze/linsolver/RCMatrix_solver.h:77) as implemented by
+ * the reference's `pcg` module (src/linsolver/pcg.cpp:45-73 -> local/include/pcgsolver/pcg_solver.h:246-295), for callers that
+ * assemble an RCMatrix themselves (the stock macpressuresolver3, macstreamfuncsolver3, the 2-D solvers). The Shiokaze module
+ * on top is shiokaze_b200/plugin/b200cg.cpp (`LinSolver=b200cg`).
+ * Algorithm: the reference's effective one — plain CG (its MIC(0) output is overwritten, pcg_solver.h:383), stop when
+ * |r|_inf <= residual * |b|_inf, iterations counted as it+1, reresid = |r|_inf / |b|_inf; |b|_inf == 0 => 0 iterations, x = 0.
+ * The matrix must be symmetric positive (semi-)definite; rows in CSR with 64-bit row pointers and 32-bit column indices. */
+enum shkz_b200_csr_precond { SHKZ_B200_CSR_PRECOND_NONE = 0, SHKZ_B200_CSR_PRECOND_JACOBI = 1 };
+
+typedef struct shkz_b200_csr_params {
+	uint32_t struct_size;      /* = sizeof(shkz_b200_csr_params) */
+	uint32_t max_iterations;   /* LinSolver.MaxIterations (30000, pcg.cpp:77) */
+	double residual;           /* LinSolver.Residual (1e-4, pcg.cpp:76) */
+	int32_t precond;           /* shkz_b200_csr_precond (default NONE = what the reference computes) */
+	int32_t check_every;       /* host reads the convergence flag every this many iterations (default 16) */
+} shkz_b200_csr_params;
+
+typedef struct shkz_b200_csr_stats {
+	uint32_t iterations;       /* as the reference counts them (pcg_solver.h:282) */
+	int32_t converged;
+	double reresid;            /* |r|_inf / |b|_inf at exit */
+	double rhs_absmax;
+	int32_t ell_width;         /* > 0: rows were laid out as ELL of this width; 0: CSR, one warp per row */
+	int32_t reserved;
+	uint64_t kernel_launches;
+	float ms_h2d, ms_solve, ms_d2h;
+	float reserved2;
+} shkz_b200_csr_stats;
+
+typedef struct shkz_b200_csr shkz_b200_csr; /* opaque: device buffers reused across solves */
+
+const char *shkz_b200_csr_last_error(void);
+void shkz_b200_csr_default_params(shkz_b200_csr_params *params);
+int shkz_b200_csr_create(int device, shkz_b200_csr **out);
+void shkz_b200_csr_destroy(shkz_b200_csr *solver);
+/* Solve A x = rhs (host pointers; x is overwritten, the start vector is 0 as in pcg_solver.h:249). */
+int shkz_b200_csr_solve_host(shkz_b200_csr *solver, uint64_t n, const int64_t *rowptr /* n+1 */, const int32_t *col, const double *val,
+                             const double *rhs, double *x, const shkz_b200_csr_params *params, shkz_b200_csr_stats *stats);
+
 /* ---- per-kernel timing (CUDA events around every launch; slows the call down, never on by default) ----
  * enable(1) resets the accumulators; entries are "<kernel>" or "<kernel>@<multigrid level>". */
 int shkz_b200_profile_enable(shkz_b200_solver *solver, int on);

@@ -20,7 +20,9 @@ EXPORTS = [
     "shkz_b200_project_device", "shkz_b200_resolve", "shkz_b200_slab_export",
     "shkz_b200_slab_connect", "shkz_b200_slab_connect_local", "shkz_b200_debug_fetch", "shkz_b200_profile_enable", "shkz_b200_profile_count",
     "shkz_b200_profile_get", "shkz_b200_debug_vcycle",
+    "shkz_b200_csr_last_error", "shkz_b200_csr_default_params", "shkz_b200_csr_create", "shkz_b200_csr_destroy", "shkz_b200_csr_solve_host",
 ]
+CSR_PRECOND_NONE, CSR_PRECOND_JACOBI = 0, 1
 
 
 class Params(C.Structure):
@@ -41,6 +43,20 @@ class Stats(C.Structure):
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class CsrParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("max_iterations", C.c_uint32), ("residual", C.c_double), ("precond", C.c_int32),
+                ("check_every", C.c_int32)]
+
+
+class CsrStats(C.Structure):
+    _fields_ = [("iterations", C.c_uint32), ("converged", C.c_int32), ("reresid", C.c_double), ("rhs_absmax", C.c_double),
+                ("ell_width", C.c_int32), ("reserved", C.c_int32), ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_float),
+                ("ms_solve", C.c_float), ("ms_d2h", C.c_float), ("reserved2", C.c_float)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
 class ShkzError(RuntimeError):
@@ -82,6 +98,13 @@ def lib():
     L.shkz_b200_profile_count.argtypes = [vp]
     L.shkz_b200_profile_get.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     L.shkz_b200_debug_vcycle.argtypes = [vp, C.POINTER(Params), C.c_int]
+    L.shkz_b200_csr_last_error.restype = C.c_char_p
+    L.shkz_b200_csr_default_params.argtypes = [C.POINTER(CsrParams)]
+    L.shkz_b200_csr_default_params.restype = None
+    L.shkz_b200_csr_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.shkz_b200_csr_destroy.argtypes = [vp]
+    L.shkz_b200_csr_destroy.restype = None
+    L.shkz_b200_csr_solve_host.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(CsrParams), C.POINTER(CsrStats)]
     _lib = L
     return L
 
@@ -89,6 +112,11 @@ def lib():
 def check(code):
     if code != OK:
         raise ShkzError(code, lib().shkz_b200_last_error().decode(errors="replace"))
+
+
+def check_csr(code):
+    if code != OK:
+        raise ShkzError(code, lib().shkz_b200_csr_last_error().decode(errors="replace"))
 
 
 def default_params() -> Params:

@@ -108,13 +108,13 @@ __device__ __forceinline__ void block_wait_neighbours(const CommDev *cm, unsigne
 }
 
 // ... and the stand-alone form for consumers that have no such prologue
-__global__ void k_comm_wait(const CommDev *cm, unsigned long long seq) {
+static __global__ void k_comm_wait(const CommDev *cm, unsigned long long seq) {
 	if (threadIdx.x == 0) wait_neighbours(cm, seq);
 }
 
 // Halo exchange number `seq` of the cell array at arena offset `off` (offset of its lower ghost plane): store the own
 // boundary planes into the neighbours' ghost planes, publish `seq` in their flag words, wait for their planes.
-__global__ void __launch_bounds__(256) k_halo_push(const CommDev *cm, size_t off, size_t plane_bytes, int nzl, unsigned long long seq) {
+static __global__ void __launch_bounds__(256) k_halo_push(const CommDev *cm, size_t off, size_t plane_bytes, int nzl, unsigned long long seq) {
 	const char *src_lo = cm->self + off + plane_bytes;                 // own plane 0
 	const char *src_hi = cm->self + off + plane_bytes * (size_t)nzl;   // own plane nzl-1
 	char *dst_lo = cm->lo ? cm->lo + off + plane_bytes * (size_t)(nzl + 1) : nullptr; // lower neighbour's upper ghost plane
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_halo_push(const CommDev *cm, size_t off
 // All-gather by stores: `bytes` at arena offset src_off of this rank go to arena offset dst_off of EVERY rank (the offsets
 // already include this rank's position in the gathered array). The last block to finish runs a barrier over all ranks
 // (a mailbox reduction of nothing), so when the kernel ends on a rank, every rank's part has landed there.
-__global__ void __launch_bounds__(256) k_gather_push(const CommDev *cm, size_t src_off, size_t dst_off, size_t bytes) {
+static __global__ void __launch_bounds__(256) k_gather_push(const CommDev *cm, size_t src_off, size_t dst_off, size_t bytes) {
 	const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
 	const char *src = cm->self + src_off;
 	if ((bytes & 15) == 0) {

@@ -67,3 +67,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(base, f), errors="replace").read()
                 assert "dense_oracle" not in src and "oracle." not in src.replace("oracle/", ""), os.path.join(base, f)
+
+
+def test_csr_entry_points_refuse_without_a_device_and_check_arguments():
+    L = capi.lib()
+    p = capi.CsrParams()
+    L.shkz_b200_csr_default_params(C.byref(p))
+    assert p.struct_size == C.sizeof(capi.CsrParams)
+    assert p.residual == 1e-4 and p.max_iterations == 30000 and p.precond == capi.CSR_PRECOND_NONE      # pcg.cpp:76-77
+    assert L.shkz_b200_csr_create(0, None) == capi.ERR_ARG
+    assert L.shkz_b200_csr_solve_host(None, 0, None, None, None, None, None, None, None) == capi.ERR_ARG
+    if L.shkz_b200_device_count() == 0:
+        h = C.c_void_p()
+        assert L.shkz_b200_csr_create(0, C.byref(h)) == capi.ERR_NO_DEVICE and not h.value
+        assert b"no CPU fallback" in L.shkz_b200_csr_last_error()
+        from shiokaze_b200 import B200CG
+        with pytest.raises(capi.ShkzError):
+            B200CG()

@@ -105,3 +105,25 @@ def test_oracle_against_live_reference_build():
         assert np.array_equal(r.areas[d][tuple(sl)], o.areas[d][tuple(sl)])
         assert np.array_equal(r.vel_active[d], o.vel_active[d])
     assert rel_l2(o.vel, r.vel) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["dambreak24", "dambreak_solid24", "smoke16", "flip32", "blobs"])
+def test_csr_cg_oracle_matches_the_reference_build(name):
+    """The numpy restatement of the reference's linear solver (oracle/csr_cg_oracle.py), run on the assembled system of a
+    golden scene, reproduces what the unmodified reference build solved: its pressure on the row set and its iteration count."""
+    import csr_util
+    from oracle import csr_cg_oracle
+    make, _ = golden_cases()[name]
+    sc = make()
+    A, b, _ = csr_util.pressure_system(sc, real_is_double=True)
+    assert abs(A - A.T).max() == 0.0
+    g = load_golden(name, "f64_tight")
+    x, iterations, reresid, converged = csr_cg_oracle.cg(A, b, residual=1e-10)
+    rows = g["pressure_active"].astype(bool)
+    assert converged and reresid <= 1e-10 and A.shape[0] == int(rows.sum())
+    assert np.linalg.norm(x - g["pressure"][rows]) <= 1e-8 * np.linalg.norm(g["pressure"][rows])
+    assert abs(iterations - g["iterations"]) <= max(3, 0.03 * g["iterations"])
+    # edge cases of pcg_solver.h:253-258: zero right-hand side, MaxIterations = 0
+    assert csr_cg_oracle.cg(A, np.zeros_like(b))[1:] == (0, 0.0, True)
+    x0, it0, rr0, conv0 = csr_cg_oracle.cg(A, b, max_iterations=0)
+    assert (it0, rr0, conv0) == (0, 1.0, False) and not x0.any()
