@@ -24,10 +24,9 @@ template <class VecT, bool WRITE_B0>
 __global__ void __launch_bounds__(TX *CG_BY) k_cg_init(Dims d, Tiles T, const VecT *__restrict__ b, VecT *__restrict__ x, VecT *__restrict__ r,
                                                       VecT *__restrict__ s, float *__restrict__ b0) {
 	const int ntiles = *T.count;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
 		if (i >= d.nx) continue;
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
@@ -61,10 +60,9 @@ __global__ void __launch_bounds__(TX *CG_BY) k_dot_rr(Dims d, Tiles T, const Vec
 	if (st->done) return;
 	double red[1] = {0.0};
 	const int ntiles = *T.count;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
 		if (i >= d.nx) continue;
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
@@ -90,10 +88,9 @@ __global__ void __launch_bounds__(TX *CG_BY) k_dot_zb(Dims d, Tiles T, const flo
 	if (st->done) return;
 	double red[1] = {0.0};
 	const int ntiles = *T.count;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
 		if (i >= d.nx) continue;
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
@@ -112,10 +109,9 @@ __global__ void __launch_bounds__(TX *CG_BY) k_xpay(Dims d, Tiles T, const ZT *_
 	VecT *const plo = push_target_lo<VecT>(sp, d.plane, d.nzl), *const phi = push_target_hi<VecT>(sp);
 	const VecT beta = (VecT)st->beta;
 	const int ntiles = *T.count;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
 		if (i >= d.nx) continue;
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
@@ -139,10 +135,9 @@ __global__ void __launch_bounds__(TX *CG_BY) k_spmv_dot(Dims d, Tiles T, const C
 	if (wait_in) block_wait_neighbours(rb.comm, wait_in); // z-slabs: the ghost planes of s, pushed by the neighbours' k_xpay
 	double red[1] = {0.0};
 	const int ntiles = *T.count;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
 		if (i >= d.nx) continue;
 		for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
 			long long c = i + (long long)d.nx * (j + (long long)d.ny * kb);
@@ -210,10 +205,9 @@ __global__ void __launch_bounds__((TX / 4) * TY, 3) k_spmv_dot4(Dims d, Tiles T,
 	double red[1] = {0.0};
 	const int ntiles = *T.count;
 	const long long nx = d.nx;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int i = i0 + 4 * threadIdx.x, j = j0 + threadIdx.y, ke = min(kb + T.bz, d.nzl);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + 4 * threadIdx.x, j = j0 + threadIdx.y;
 		if (i >= d.nx || j >= d.ny) continue;
 		long long c = i + nx * (j + (long long)d.ny * kb);
 		V4<VecT> sm = ldv4(s + c - d.plane), sc = ldv4(s + c);
@@ -248,10 +242,9 @@ __global__ void __launch_bounds__(TX *CG_BY) k_axpy2_norm(Dims d, Tiles T, const
 	const VecT alpha = (VecT)st->alpha;
 	double red[2] = {0.0, 0.0};
 	const int ntiles = *T.count;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
 		if (i >= d.nx) continue;
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {

@@ -116,10 +116,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(Dims d, Tiles T, con
 		return XO(c, i, j, p);
 	};
 
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int ke = min(kb + T.bz, d.nzl);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
 		const int i = i0 + 2 * px, j = j0 + ty;
 		const bool v0 = i < d.nx && j < d.ny, v1 = i + 1 < d.nx && j < d.ny;
 		// halo ring cell of this thread (first RING_CELLS threads = whole warps)
@@ -314,10 +312,8 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep4(Dims d, Tiles T, const
 		return XO(c, i, j, p);
 	};
 
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int ke = min(kb + T.bz, d.nzl);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
 		if (colwarp) {
 			// ---- halo columns i0-1 and i0+TX of the TY tile rows: one cell per lane and plane
 			const int side = lane >> 4, ci = side ? i0 + TX : i0 - 1, cj = j0 + (lane & 15);
@@ -451,10 +447,8 @@ __global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_residual_restrict(Dims 
 	if (cm && wait_in) block_wait_neighbours(cm, wait_in); // z-slabs: the ghost planes of x come from the neighbours' last fused sweep
 	const int ntiles = *T.count;
 	const long long nx = d.nx, ny = d.ny, plane = d.plane;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int ke = min(kb + T.bz, d.nzl);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
 		const int I = (i0 >> 1) + threadIdx.x, J = (j0 >> 1) + threadIdx.y;
 		if (I >= dc.nx || J >= dc.ny) continue;
 		for (int k = kb; k < ke; k += 2) {
@@ -484,10 +478,9 @@ __global__ void __launch_bounds__(TX *8) k_prolong_add(Dims d, Tiles T, Dims dc,
 	if (st && st->done) return;
 	float *const plo = push_target_lo<float>(sp, d.plane, d.nzl), *const phi = push_target_hi<float>(sp);
 	const int ntiles = *T.count;
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int i = i0 + threadIdx.x, ke = min(kb + T.bz, d.nzl), je = min(j0 + TY, d.ny);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
 		if (i >= d.nx) continue;
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += 8) {

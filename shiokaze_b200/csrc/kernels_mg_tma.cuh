@@ -109,10 +109,8 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 
 	for (int pass = 0; pass < (slab_ghosts ? 2 : 1); ++pass) {
 	if (SLAB && pass == 1) block_wait_neighbours(sl.cm, sl.seq_half); // the neighbours' half-updated planes are in the ghost planes of x_old
-	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-		int i0, j0, kb;
-		tile_origin(T, T.ids[t], i0, j0, kb);
-		const int ke = min(kb + T.bz, d.nzl);
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
 		if (slab_ghosts && (kb < 2 || ke + 1 >= d.nzl) != (pass == 1)) continue; // pass 0: tiles that read no ghost plane; pass 1: the others
 		const unsigned base = loads_done;           // load index of plane kb-1
 		auto issue = [&](int p) {                   // producer: fill the stage of plane p

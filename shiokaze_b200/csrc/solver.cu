@@ -284,7 +284,9 @@ int pick_bz(const Dims &d) {
 }
 
 // arrays, tile list and tensor maps of one multigrid level (coefficient / rhs arrays may have been aliased by the caller)
-int finish_level(HostLevel &L, const Dims &cur, const std::string &n, SlabComm *arena) {
+// balanced: the level's kernels divide the active tiles evenly over the persistent grid (TileWalk, common.cuh) — every whole-grid level; the levels of a
+// z-slab keep whole tiles per CTA, the fused slab sweep orders them by whether they touch a ghost plane
+int finish_level(HostLevel &L, const Dims &cur, const std::string &n, SlabComm *arena, bool balanced) {
 	L.d = cur;
 	if (!L.wx.base) for (CellArray *a : {&L.wx, &L.wy, &L.wz, &L.dd}) CKR(a->alloc(cur, sizeof(float), arena));
 	if (!L.b.base) CKR(L.b.alloc(cur, sizeof(float), arena));
@@ -299,7 +301,7 @@ int finish_level(HostLevel &L, const Dims &cur, const std::string &n, SlabComm *
 	L.tag_sweep = "sweep@" + n; L.tag_restrict = "residual_restrict@" + n; L.tag_prolong = "prolong_add@" + n;
 	L.tag_coarsen = "coarsen_operator@" + n; L.tag_compact = "compact_tiles@" + n;
 	L.view.d = cur;
-	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz};
+	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz, balanced ? 1 : 0};
 	L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.dd = L.dd.ptr<float>(cur);
 	L.view.b = L.b.ptr<float>(cur); L.view.xa = L.xa.ptr<float>(cur); L.view.xb = L.xb.ptr<float>(cur);
 	L.tma = (cur.nx & 3) == 0 && make_plane_map(&L.map_wx, L.wx.base, cur, ST_ROWS) && make_plane_map(&L.map_wy, L.wy.base, cur, ST_WY_ROWS) &&
@@ -371,7 +373,7 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 			L.own_b = false;
 			L.b = S->r; // an all-float CG smooths against r directly
 		}
-		CKR(finish_level(L, cur, std::to_string(l), arena));
+		CKR(finish_level(L, cur, std::to_string(l), arena, S->whole_grid));
 		if (big_extent(cur) <= min_size) break;
 		if (!S->whole_grid) {
 			// slabs: aggregates stay inside one rank (even local extent and even first plane); small levels go global
@@ -390,7 +392,7 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 		Dims g = make_dims(ds.nx, ds.ny, ds.nzg, 0, ds.nzg);
 		for (int l = 0;; ++l) {
 			S->glevels.emplace_back();
-			CKR(finish_level(S->glevels.back(), g, "g" + std::to_string(l), arena));
+			CKR(finish_level(S->glevels.back(), g, "g" + std::to_string(l), arena, true));
 			if (big_extent(g) <= min_size) break;
 			g = make_dims((g.nx + 1) / 2, (g.ny + 1) / 2, (g.nzl + 1) / 2, 0, (g.nzg + 1) / 2);
 		}
