@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(TX *CG_BY) k_xpay(Dims d, Tiles T, const ZT *_
 	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
 		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
 		if (i >= d.nx) continue;
+		// (batching four cells per thread with all loads up front was tried: 13 % slower at 512^3 — 2048 resident threads with one cell each already
+		// keep more bytes in flight than 1024 threads with four)
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
 				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
@@ -182,6 +184,7 @@ __device__ __forceinline__ void stv4(double *p, const V4<double> &v) {
 	*reinterpret_cast<double2 *>(p + 2) = make_double2(v.c, v.d);
 }
 inline dim3 cg_block4() { return dim3(TX / 4, TY, 1); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <class VecT, class CoefT>
 __device__ __forceinline__ VecT spmv_cell(CoefT dd, CoefT w0, CoefT w1, CoefT w2, CoefT w3, CoefT w4, CoefT w5, VecT sc, VecT x0, VecT x1, VecT x2, VecT x3, VecT x4,
@@ -213,6 +216,10 @@ __global__ void __launch_bounds__((TX / 4) * TY, 3) k_spmv_dot4(Dims d, Tiles T,
 		V4<VecT> sm = ldv4(s + c - d.plane), sc = ldv4(s + c);
 		V4<CoefT> wzc = ldv4(wz + c);
 		for (int k = kb; k < ke; ++k, c += d.plane) {
+			// the product waits on DRAM for the operands nobody fetched ahead (ncu: 85 % long-scoreboard stalls at 35 % occupancy, no registers left
+			// to load them early): ask L2 for the next plane's wx, wy, dd and for s, wz two planes up now, the loads below then find them there
+			if (k + 1 < ke) { prefetch_l2(wx + c + d.plane); prefetch_l2(wy + c + d.plane); prefetch_l2(dd + c + d.plane); }
+			if (k + 2 <= ke) { prefetch_l2(s + c + 2 * d.plane); prefetch_l2(wz + c + 2 * d.plane); }
 			const V4<VecT> sp = ldv4(s + c + d.plane), sd = ldv4(s + c - nx), su = ldv4(s + c + nx);
 			const V4<CoefT> wzp = ldv4(wz + c + d.plane), wxq = ldv4(wx + c), wyq = ldv4(wy + c), wyu = ldv4(wy + c + nx), ddq = ldv4(dd + c);
 			const CoefT wx4 = wx[c + 4];
