@@ -539,8 +539,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vcycle_tail(TailArgs A, const 
 			const int k = c / plane, rem = c - k * plane, j = rem / nx, i = rem - j * nx;
 			if (((i + j + k + d.k0) & 1) != color) continue;
 			const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
+			// (a neighbour across a zero coefficient — a wall, whose flat index wraps to a cell of the SAME colour — is not read: the product is an
+			// exact zero either way, and the in-place update then never reads a value another thread may be writing)
 			x[c] = zero_x ? gs_relax0(w0, w1, w2, w3, w4, w5, dd[c], b[c])
-			              : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], x[c - 1], x[c + 1], x[c - nx], x[c + nx], x[c - plane], x[c + plane], x[c]);
+			              : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], w0 != 0.f ? x[c - 1] : 0.f, w1 != 0.f ? x[c + 1] : 0.f, w2 != 0.f ? x[c - nx] : 0.f,
+			                         w3 != 0.f ? x[c + nx] : 0.f, w4 != 0.f ? x[c - plane] : 0.f, w5 != 0.f ? x[c + plane] : 0.f, x[c]);
 		}
 		__syncthreads();
 	};

@@ -1,0 +1,28 @@
+#!/bin/bash
+# compute-sanitizer on small cases: memcheck (all kernels incl. the CSR solver) and racecheck (shared-memory hazards of the TMA sweep:
+# stage ring, half-updated-plane ring, in-stage coarse correction)
+mkdir -p gpurun_out
+cat > /tmp/san_case.py <<'PY'
+import sys; sys.path.insert(0, ".")
+import numpy as np, scipy.sparse as sp
+from shiokaze_b200 import MacPressureSolver3, B200CG, scenes
+mode = sys.argv[1]
+cases = [(scenes.dambreak(40, True), "mixed"), (scenes.smoke_plume(32), "fp32"), (scenes.random_blobs(20, 14, 18, seed=3), "fp64"), (scenes.flip_splash(48), "mixed")]
+if mode == "race":
+    cases = cases[:2]
+for sc, prec in cases:
+    S = MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, Precision=prec, Residual=1e-5)
+    out = S.project_scene(sc, surface_tension=0.01)
+    print(prec, sc.name, out["result"].iterations, out["result"].converged, out["result"].reresid, flush=True)
+    if prec != "fp64":
+        a = S.debug_vcycle(0); b = S.debug_vcycle(2); print("   vcycle fused == scalar:", np.array_equal(a, b), flush=True)
+    S.close()
+if mode == "mem":
+    n = 24; I = sp.identity(n); T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n))
+    A = (sp.kron(sp.kron(T, I), I) + sp.kron(sp.kron(I, T), I) + sp.kron(sp.kron(I, I), T)).tocsr()
+    C = B200CG(Residual=1e-8); x, r = C.solve(A, None, None, np.ones(A.shape[0])); print("csr ell", r.count, r.converged)
+    B = sp.random(400, 400, density=0.2, random_state=1, format="csr"); W = (B @ B.T + sp.identity(400)).tocsr()
+    x, r = C.solve(W, None, None, np.ones(400)); print("csr wide", r.count, r.converged, r.stats["ell_width"]); C.close()
+PY
+timeout 600 true compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san_case.py mem > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|vcycle|csr|mixed|fp32|fp64" gpurun_out/sanitizer_memcheck.log | tail -14
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python /tmp/san_case.py race > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|hazard|vcycle|mixed|fp32" gpurun_out/sanitizer_racecheck.log | sort | uniq -c | sort -rn | head -12
