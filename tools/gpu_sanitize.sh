@@ -24,5 +24,5 @@ if mode == "mem":
     B = sp.random(400, 400, density=0.2, random_state=1, format="csr"); W = (B @ B.T + sp.identity(400)).tocsr()
     x, r = C.solve(W, None, None, np.ones(400)); print("csr wide", r.count, r.converged, r.stats["ell_width"]); C.close()
 PY
-timeout 600 true compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san_case.py mem > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|vcycle|csr|mixed|fp32|fp64" gpurun_out/sanitizer_memcheck.log | tail -14
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san_case.py mem > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|vcycle|csr|mixed|fp32|fp64" gpurun_out/sanitizer_memcheck.log | tail -14
 timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python /tmp/san_case.py race > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|hazard|vcycle|mixed|fp32" gpurun_out/sanitizer_racecheck.log | sort | uniq -c | sort -rn | head -12
