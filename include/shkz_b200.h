@@ -148,6 +148,13 @@ int shkz_b200_project_device(shkz_b200_solver *solver, double dt, void *const ve
                              void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats, void *cuda_stream);
 
 /*
+ * Page-locked host memory for the buffers handed to shkz_b200_project_host: the H2D / D2H copies then run at PCIe speed (pageable
+ * std::vector storage costs 3-4x the time: measured through the Shiokaze module). Free with shkz_b200_host_free.
+ */
+int shkz_b200_host_alloc(size_t bytes, void **out);
+void shkz_b200_host_free(void *ptr);
+
+/*
  * Re-run only the linear solve of the last project() (same matrix, same right-hand side, x = 0):
  * the timed unit of the solver benchmark. Velocity and pressure outputs are not touched.
  */

@@ -1180,6 +1180,22 @@ int shkz_b200_project_host(shkz_b200_solver *S, double dt, void *const vel[3], u
 	return SHKZ_B200_OK;
 }
 
+int shkz_b200_host_alloc(size_t bytes, void **out) {
+	if (!out) return fail(SHKZ_B200_ERR_ARG, "out is NULL");
+	*out = nullptr;
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+		cudaGetLastError();
+		return fail(SHKZ_B200_ERR_NO_DEVICE, "no CUDA device available; libshkz_b200 has no CPU fallback");
+	}
+	CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+	return SHKZ_B200_OK;
+}
+
+void shkz_b200_host_free(void *ptr) {
+	if (ptr) cudaFreeHost(ptr);
+}
+
 int shkz_b200_resolve(shkz_b200_solver *S, const shkz_b200_params *params, shkz_b200_stats *stats, void *cuda_stream) {
 	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
 	if (!S->have_system) return fail(SHKZ_B200_ERR_STATE, "resolve() needs a prior project()");

@@ -21,6 +21,7 @@
 #include <shiokaze/core/console.h>
 #include <shiokaze/core/timer.h>
 #include <shiokaze/projection/macproject3_interface.h>
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <string>
@@ -44,15 +45,42 @@ protected:
 		console::dump( "<Red>b200pressure3: %s failed: %s<Default>\n", what, shkz_b200_last_error());
 		exit(-1);
 	}
-	// array3::linearize() with the activity mask alongside
-	static void gather( const array3<Real> &a, std::vector<Real> &values, std::vector<uint8_t> *active ) {
+	// Page-locked staging buffers (shkz_b200_host_alloc): one per grid handed to the C-ABI, kept for the life of the module
+	// (pageable std::vector storage made the H2D / D2H copies the largest part of the GPU call)
+	template <class T> struct staging {
+		T *p {nullptr};
+		size_t n {0};
+		T * ensure( size_t count ) {
+			if( count > n ) {
+				release();
+				void *q (nullptr);
+				if( shkz_b200_host_alloc(count*sizeof(T),&q) != SHKZ_B200_OK ) fatal("shkz_b200_host_alloc");
+				p = static_cast<T *>(q); n = count;
+			}
+			return p;
+		}
+		void release() { if( p ) shkz_b200_host_free(p); p = nullptr; n = 0; }
+	};
+	// array3::linearize() semantics (array3.h:198-208) with the activity mask alongside. A grid that is mostly active (the velocity
+	// of a smoke solver) is read in ONE pass over all cells — the iterator hands out the active value, else the fill / background
+	// value, exactly what operator() returns (array3.h:796-801) —, a sparse one (a narrow-band level set) by its actives and its inside.
+	static void gather( const array3<Real> &a, Real *values, uint8_t *active ) {
 		const shape3 s = a.shape();
-		values.assign(s.count(),a.get_background_value());
-		if( active ) active->assign(s.count(),0);
+		const size_t total = s.count();
+		if( 2 * a.count() >= total ) {
+			a.const_parallel_all([&]( int i, int j, int k, const auto &it ) {
+				const size_t n = i + s.w * (j + s.h * (size_t)k);
+				values[n] = it();
+				if( active ) active[n] = it.active() ? 1 : 0;
+			});
+			return;
+		}
+		std::fill(values,values+total,a.get_background_value());
+		if( active ) std::fill(active,active+total,(uint8_t)0);
 		a.const_parallel_actives([&]( int i, int j, int k, const auto &it ) {
 			const size_t n = i + s.w * (j + s.h * (size_t)k);
 			values[n] = it();
-			if( active ) (*active)[n] = 1;
+			if( active ) active[n] = 1;
 		});
 		a.const_parallel_inside([&]( int i, int j, int k, const auto &it ) {
 			if( ! it.active()) values[i + s.w * (j + s.h * (size_t)k)] = it();
@@ -71,9 +99,15 @@ protected:
 		//
 		// Host -> dense buffers
 		timer.tick(); console::dump( "Gathering dense buffers..." );
-		std::vector<Real> vel[DIM3], solid_dense, fluid_dense;
-		std::vector<uint8_t> vel_active[DIM3];
-		for( int dim : DIMS3 ) gather(velocity[dim],vel[dim],&vel_active[dim]);
+		Real *vel[DIM3], *solid_dense (nullptr), *fluid_dense;
+		uint8_t *vel_active[DIM3];
+		for( int dim : DIMS3 ) {
+			const size_t nf = velocity[dim].shape().count();
+			vel[dim] = m_hvel[dim].ensure(nf);
+			vel_active[dim] = m_hact[dim].ensure(nf);
+			gather(velocity[dim],vel[dim],vel_active[dim]);
+		}
+		fluid_dense = m_hfluid.ensure(m_shape.count());
 		gather(fluid,fluid_dense,nullptr);
 		const bool fluid_levelset = array_utility3::levelset_exist(fluid);
 		bool have_solid = array_utility3::levelset_exist(solid);
@@ -81,7 +115,10 @@ protected:
 			console::dump( "<Red>b200pressure3: a solid level set must be nodal (shape+1).<Default>\n" );
 			exit(-1);
 		}
-		if( have_solid ) gather(solid,solid_dense,nullptr);
+		if( have_solid ) {
+			solid_dense = m_hsolid.ensure(solid.shape().count());
+			gather(solid,solid_dense,nullptr);
+		}
 		console::dump( "Done. Took %s\n", timer.stock("gather").c_str());
 		//
 		// Volume correction: the PI controller is host state, as in macpressuresolver3.cpp:204-217
@@ -101,13 +138,13 @@ protected:
 		//
 		// The CUDA path
 		timer.tick(); console::dump( "Solving on the GPU...");
-		std::vector<Real> pressure(m_shape.count());
-		std::vector<uint8_t> pressure_active(m_shape.count());
-		void *vel_ptr[3] = { vel[0].data(), vel[1].data(), vel[2].data() };
-		uint8_t *act_ptr[3] = { vel_active[0].data(), vel_active[1].data(), vel_active[2].data() };
+		Real *pressure = m_hpressure.ensure(m_shape.count());
+		uint8_t *pressure_active = m_hpact.ensure(m_shape.count());
+		void *vel_ptr[3] = { vel[0], vel[1], vel[2] };
+		uint8_t *act_ptr[3] = { vel_active[0], vel_active[1], vel_active[2] };
 		shkz_b200_stats stats;
-		if( shkz_b200_project_host(m_solver,dt,vel_ptr,act_ptr,have_solid ? solid_dense.data() : nullptr,fluid_dense.data(),
-				fluid_levelset,&params,pressure.data(),pressure_active.data(),&stats) != SHKZ_B200_OK ) fatal("shkz_b200_project_host");
+		if( shkz_b200_project_host(m_solver,dt,vel_ptr,act_ptr,have_solid ? solid_dense : nullptr,fluid_dense,
+				fluid_levelset,&params,pressure,pressure_active,&stats) != SHKZ_B200_OK ) fatal("shkz_b200_project_host");
 		console::write(get_argument_name()+"_number_projection_iteration", stats.iterations);
 		console::write(get_argument_name()+"_solid_fluid_fractions", stats.ms_assemble);
 		console::write(get_argument_name()+"_build_highres_linsystem", stats.ms_setup);
@@ -116,11 +153,13 @@ protected:
 		//
 		// Dense buffers -> host grids
 		timer.tick(); console::dump( "Scattering results...");
+		// (exactly the row set is activated, macpressuresolver3.cpp:245-248; parallel_all + it.set() is the reference's own way of
+		// filling a grid in parallel, e.g. macutility3.cpp:341-349)
 		m_pressure.clear();
-		for( int k=0; k<(int)m_shape.d; ++k ) for( int j=0; j<(int)m_shape.h; ++j ) for( int i=0; i<(int)m_shape.w; ++i ) {
+		m_pressure.parallel_all([&]( int i, int j, int k, auto &it ) {
 			const size_t n = i + m_shape.w * (j + m_shape.h * (size_t)k);
-			if( pressure_active[n] ) m_pressure.set(i,j,k,pressure[n]);
-		}
+			if( pressure_active[n] ) it.set(pressure[n]);
+		});
 		velocity.parallel_actives([&]( int dim, int i, int j, int k, auto &it, int tn ) {
 			const shape3 s = velocity[dim].shape();
 			const size_t n = i + s.w * (j + s.h * (size_t)k);
@@ -186,6 +225,8 @@ protected:
 		return &m_pressure;
 	}
 	virtual ~b200pressure3() {
+		for( int dim : DIMS3 ) { m_hvel[dim].release(); m_hact[dim].release(); }
+		m_hsolid.release(); m_hfluid.release(); m_hpressure.release(); m_hpact.release();
 		if( m_solver ) shkz_b200_destroy(m_solver);
 	}
 	//
@@ -196,6 +237,8 @@ protected:
 	shkz_b200_params m_cuda_param;
 	shkz_b200_solver *m_solver {nullptr};
 	int m_device {0};
+	staging<Real> m_hvel[DIM3], m_hsolid, m_hfluid, m_hpressure;
+	staging<uint8_t> m_hact[DIM3], m_hpact;
 	//
 	shape3 m_shape;
 	double m_dx {0.0};
