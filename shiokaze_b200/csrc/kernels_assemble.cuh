@@ -23,6 +23,14 @@ struct AsmParams {
 // x / dx with the reference's rounding; a multiplication when that is exact
 __device__ __forceinline__ double div_dx(const AsmParams &P, double x) { return P.dx_pow2 ? __dmul_rn(x, P.inv_dx) : __ddiv_rn(x, P.dx); }
 
+// Without a solid level set the area fractions are in closed form — 0 on the domain walls, 1 elsewhere (macutility3.cpp:149-164) —, without a
+// liquid level set (a smoke solver) rho = 1 (:191-193): exactly what k_face_fractions stores, so the kernels that consume the fractions
+// skip those face-array reads (12 B per cell and array triple in each of k_label_rows, k_build_system and k_update_velocity).
+__device__ __forceinline__ bool closed_form_area(const AsmParams &P) { return !P.have_solid; }
+__device__ __forceinline__ bool closed_form_rho(const AsmParams &P) { return !P.fluid_levelset; }
+template <class RealT>
+__device__ __forceinline__ RealT wall_area(int pd, int n_dim) { return (pd == 0 || pd == n_dim) ? (RealT)0 : (RealT)1; }
+
 template <class RealT>
 struct FaceGrids { // face-shaped, no ghost planes: x (nx+1,ny,nzl)  y (nx,ny+1,nzl)  z (nx,ny,nzl+1)
 	RealT *p[3];
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(256) k_surface_tension(Dims d, AsmParams P, co
 
 // K4: row labelling (macpressuresolver3.cpp:121-156) as a dense mask. in_rows has ghost planes.
 template <class RealT>
-__global__ void __launch_bounds__(256) k_label_rows(Dims d, const RealT *__restrict__ phi, ConstFaceGrids<RealT> areas,
+__global__ void __launch_bounds__(256) k_label_rows(Dims d, AsmParams P, const RealT *__restrict__ phi, ConstFaceGrids<RealT> areas,
                                                    ConstFaceGrids<RealT> rhos, uint8_t *__restrict__ in_rows) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	const int j = blockIdx.y * blockDim.y + threadIdx.y;
@@ -216,8 +224,8 @@ __global__ void __launch_bounds__(256) k_label_rows(Dims d, const RealT *__restr
 			const long long f = face_index(d, dim, i + (dim == 0) * up, j + (dim == 1) * up, k + (dim == 2) * up);
 			const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
 			pq[nq] = in_grid[nq] ? phi[q] : (RealT)1;
-			ar[nq] = areas.p[dim][f];
-			rh[nq] = rhos.p[dim][f];
+			ar[nq] = closed_form_area(P) ? (RealT)1 : areas.p[dim][f]; // (the face towards an in-grid neighbour is never a wall face)
+			rh[nq] = closed_form_rho(P) ? (RealT)1 : rhos.p[dim][f];
 		}
 #pragma unroll
 		for (int nq = 0; nq < 6; ++nq)
@@ -266,8 +274,8 @@ __global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const
 				const int up = (nq & 1) ? 0 : 1;
 				const long long f = face_index(d, dim, i + (dim == 0) * up, j + (dim == 1) * up, k + (dim == 2) * up);
 				const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
-				ar[nq] = areas.p[dim][f];
-				rh[nq] = rhos.p[dim][f];
+				ar[nq] = closed_form_area(P) ? (in_grid[nq] ? (RealT)1 : (RealT)0) : areas.p[dim][f]; // (0 exactly on the faces whose neighbour is outside the grid)
+				rh[nq] = closed_form_rho(P) ? (RealT)1 : rhos.p[dim][f];
 				uf[nq] = vel.p[dim][f];
 				pq[nq] = in_grid[nq] ? phi[q] : (RealT)1;
 			}
@@ -353,7 +361,9 @@ __global__ void __launch_bounds__(256) k_update_velocity(Dims d, AsmParams P, co
 		ar[dim] = rh[dim] = uf[dim] = pm[dim] = phm[dim] = (RealT)0;
 		if (!act[dim]) continue;
 		const long long cm = c - (dim == 0 ? 1 : (dim == 1 ? d.nx : d.plane));
-		ar[dim] = areas.p[dim][fi[dim]]; rh[dim] = rhos.p[dim][fi[dim]]; uf[dim] = vel.p[dim][fi[dim]];
+		ar[dim] = closed_form_area(P) ? wall_area<RealT>(dim == 0 ? i : (dim == 1 ? j : kg), dim == 0 ? d.nx : (dim == 1 ? d.ny : d.nzg)) : areas.p[dim][fi[dim]];
+		rh[dim] = closed_form_rho(P) ? (RealT)1 : rhos.p[dim][fi[dim]];
+		uf[dim] = vel.p[dim][fi[dim]];
 		pm[dim] = pressure[cm]; phm[dim] = phi[cm];
 	}
 #pragma unroll

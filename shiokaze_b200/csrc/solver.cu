@@ -889,7 +889,7 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		CKR(halo(S, d, curv, stream));
 		LAUNCH(S, "surface_tension", k_surface_tension<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)curv, crhos, vel, masks);
 	}
-	LAUNCH(S, "label_rows", k_label_rows<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, (const RealT *)phi, careas, crhos, in_rows);
+	LAUNCH(S, "label_rows", k_label_rows<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, careas, crhos, in_rows);
 	CKR(halo(S, d, in_rows, stream));
 	{
 		const bool share = sizeof(CoefT) == sizeof(float);
