@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) k_label_rows(Dims d, AsmParams P, const R
 // float and level 0 shares the operator arrays). tile_flags (zeroed by the caller) marks the level-0 tiles
 // that hold at least one unknown.
 template <class RealT, class CoefT, class VecT>
-__global__ void __launch_bounds__(256) k_build_system(Dims d, AsmParams P, const RealT *__restrict__ phi, const uint8_t *__restrict__ in_rows,
+__global__ void __launch_bounds__(256, 4) k_build_system(Dims d, AsmParams P, const RealT *__restrict__ phi, const uint8_t *__restrict__ in_rows,
                                                      ConstFaceGrids<RealT> areas, ConstFaceGrids<RealT> rhos, ConstFaceGrids<RealT> vel,
                                                      CoefT *__restrict__ wx, CoefT *__restrict__ wy, CoefT *__restrict__ wz, CoefT *__restrict__ dd,
                                                      float *__restrict__ mwx, float *__restrict__ mwy, float *__restrict__ mwz, float *__restrict__ mdd,
