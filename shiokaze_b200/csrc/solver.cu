@@ -235,6 +235,7 @@ struct shkz_b200_solver {
 	Profiler prof;
 	bool have_system = false;
 	bool have_hierarchy = false;
+	bool fractions_stale = false; // closed-form fractions (no solid, no liquid level set): the face arrays were not written by the last project()
 	const float *debug_vcycle_result = nullptr;
 	int sweep_mode = 0; // 0: best kernel per level (TMA-staged > quad > scalar); 1: no TMA; 2: scalar only (debug / A-B timing)
 	AsmParams last_asm{};
@@ -881,8 +882,11 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	// fluid -> internal array with ghost planes (neighbour slabs fill them)
 	CK(cudaMemcpyAsync(phi, fluid_v, sizeof(RealT) * (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
 	CKR(halo(S, d, phi, stream));
-	LAUNCH(S, "face_fractions", k_face_fractions<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, solid, (const RealT *)phi, areas, rhos);
-	if (P.surface_tension != 0.0) {
+	// without a solid and without a liquid level set every consumer uses the closed form (kernels_assemble.cuh: closed_form_area / _rho): the six face
+	// arrays are only materialised when somebody asks for them (shkz_b200_debug_fetch)
+	S->fractions_stale = !A.have_solid && !A.fluid_levelset;
+	if (!S->fractions_stale) LAUNCH(S, "face_fractions", k_face_fractions<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, solid, (const RealT *)phi, areas, rhos);
+	if (P.surface_tension != 0.0 && A.fluid_levelset) { // (without a level set every rho is 1: no face takes the increment, macpressuresolver3.cpp:104-113)
 		RealT *curv = S->curv.ptr<RealT>(d);
 		if (!curv) { CKR(S->curv.alloc(d, sizeof(RealT))); curv = S->curv.ptr<RealT>(d); }
 		LAUNCH(S, "curvature", k_curvature<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, curv);
@@ -1252,6 +1256,20 @@ int shkz_b200_debug_fetch(shkz_b200_solver *S, const char *name, void *dst, size
 	const std::string n(name);
 	const void *src = nullptr;
 	size_t bytes = 0;
+	if (S->fractions_stale && (n.compare(0, 5, "areas") == 0 || n.compare(0, 4, "rhos") == 0)) {
+		const dim3 grid((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, d.nzl + 1), block(32, 8, 1);
+		if (S->real == SHKZ_B200_REAL_F32) {
+			FaceGrids<float> a, r;
+			for (int dim = 0; dim < 3; ++dim) { a.p[dim] = static_cast<float *>(S->areas[dim].base); r.p[dim] = static_cast<float *>(S->rhos[dim].base); }
+			k_face_fractions<float><<<grid, block>>>(d, S->last_asm, nullptr, S->phi.ptr<float>(d), a, r);
+		} else {
+			FaceGrids<double> a, r;
+			for (int dim = 0; dim < 3; ++dim) { a.p[dim] = static_cast<double *>(S->areas[dim].base); r.p[dim] = static_cast<double *>(S->rhos[dim].base); }
+			k_face_fractions<double><<<grid, block>>>(d, S->last_asm, nullptr, S->phi.ptr<double>(d), a, r);
+		}
+		CK(cudaDeviceSynchronize());
+		S->fractions_stale = false;
+	}
 	const size_t vec = S->alloc_precision == SHKZ_B200_PREC_FP32 ? 4 : 8;
 	const size_t coef = S->alloc_precision == SHKZ_B200_PREC_FP64 ? 8 : 4;
 	auto cell = [&](const CellArray &a, size_t elem) { src = a.base ? static_cast<const char *>(a.base) + (size_t)d.plane * elem : nullptr; bytes = (size_t)d.ncell * elem; };
