@@ -199,41 +199,6 @@ __global__ void __launch_bounds__(256) k_surface_tension(Dims d, AsmParams P, co
 	}
 }
 
-// K4: row labelling (macpressuresolver3.cpp:121-156) as a dense mask. in_rows has ghost planes.
-template <class RealT>
-__global__ void __launch_bounds__(256) k_label_rows(Dims d, AsmParams P, const RealT *__restrict__ phi, ConstFaceGrids<RealT> areas,
-                                                   ConstFaceGrids<RealT> rhos, uint8_t *__restrict__ in_rows) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const int j = blockIdx.y * blockDim.y + threadIdx.y;
-	const int k = blockIdx.z;
-	if (i >= d.nx || j >= d.ny) return;
-	const int kg = k + d.k0;
-	const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-	bool inside = false;
-	if (phi[c] < (RealT)0) {
-		const int qo[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
-		// all loads first (independent, in flight together), then the reference's test
-		RealT pq[6], ar[6], rh[6];
-		bool in_grid[6];
-#pragma unroll
-		for (int nq = 0; nq < 6; ++nq) {
-			const int dim = nq >> 1;
-			const int qi = i + qo[nq][0], qj = j + qo[nq][1], qkg = kg + qo[nq][2];
-			in_grid[nq] = !(qi < 0 || qj < 0 || qkg < 0 || qi >= d.nx || qj >= d.ny || qkg >= d.nzg);
-			const int up = (nq & 1) ? 0 : 1;
-			const long long f = face_index(d, dim, i + (dim == 0) * up, j + (dim == 1) * up, k + (dim == 2) * up);
-			const long long q = c + qo[nq][0] + (long long)d.nx * qo[nq][1] + d.plane * qo[nq][2];
-			pq[nq] = in_grid[nq] ? phi[q] : (RealT)1;
-			ar[nq] = closed_form_area(P) ? (RealT)1 : areas.p[dim][f]; // (the face towards an in-grid neighbour is never a wall face)
-			rh[nq] = closed_form_rho(P) ? (RealT)1 : rhos.p[dim][f];
-		}
-#pragma unroll
-		for (int nq = 0; nq < 6; ++nq)
-			if (in_grid[nq] && pq[nq] < (RealT)0 && ar[nq] != (RealT)0 && rh[nq] != (RealT)0) inside = true;
-	}
-	in_rows[c] = inside ? 1 : 0;
-}
-
 // K5 + K6: matrix-free coefficients and right-hand side (macpressuresolver3.cpp:163-217).
 //   w{x,y,z}[c] = dt*A/(dx^2*theta) of the LOWER face of c when both cells are rows, else 0
 //   dd[c]       = the part of the reference's diagonal that comes from AIR neighbours (ghost-fluid
@@ -245,7 +210,7 @@ __global__ void __launch_bounds__(256) k_label_rows(Dims d, AsmParams P, const R
 // float and level 0 shares the operator arrays). tile_flags (zeroed by the caller) marks the level-0 tiles
 // that hold at least one unknown.
 template <class RealT, class CoefT, class VecT>
-__global__ void __launch_bounds__(256, 4) k_build_system(Dims d, AsmParams P, const RealT *__restrict__ phi, const uint8_t *__restrict__ in_rows,
+__global__ void __launch_bounds__(256, 4) k_build_system(Dims d, AsmParams P, const RealT *__restrict__ phi, uint8_t *__restrict__ in_rows,
                                                      ConstFaceGrids<RealT> areas, ConstFaceGrids<RealT> rhos, ConstFaceGrids<RealT> vel,
                                                      CoefT *__restrict__ wx, CoefT *__restrict__ wy, CoefT *__restrict__ wz, CoefT *__restrict__ dd,
                                                      float *__restrict__ mwx, float *__restrict__ mwy, float *__restrict__ mwz, float *__restrict__ mdd,
@@ -259,7 +224,10 @@ __global__ void __launch_bounds__(256, 4) k_build_system(Dims d, AsmParams P, co
 		const int kg = k + d.k0;
 		const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
 		double dirichlet = 0.0, b = 0.0, lower[3] = {0.0, 0.0, 0.0};
-		if (in_rows[c]) {
+		// K4, the row labelling (macpressuresolver3.cpp:121-156), happens here: a cell is a row iff phi(c) < 0 and some in-grid neighbour q has
+		// phi(q) < 0 across a face with area != 0 and rho != 0 — the very operands the assembly of that row loads anyway
+		bool is_row = false;
+		if (phi[c] < (RealT)0) {
 			const int qo[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 			const double dx2 = __dmul_rn(P.dx, P.dx);
 			const double w_unit = __ddiv_rn(P.dt, dx2); // value of a fully open, fully wet face: (dt*1)/(dx2*1)
@@ -280,9 +248,12 @@ __global__ void __launch_bounds__(256, 4) k_build_system(Dims d, AsmParams P, co
 				pq[nq] = in_grid[nq] ? phi[q] : (RealT)1;
 			}
 #pragma unroll
+			for (int nq = 0; nq < 6; ++nq)
+				if (in_grid[nq] && pq[nq] < (RealT)0 && ar[nq] != (RealT)0 && rh[nq] != (RealT)0) is_row = true;
+#pragma unroll
 			for (int nq = 0; nq < 6; ++nq) {
 				const int dim = nq >> 1;
-				if (!in_grid[nq]) continue;
+				if (!is_row || !in_grid[nq]) continue;
 				const int up = (nq & 1) ? 0 : 1;
 				const double area = (double)ar[nq];
 				if (area != 0.0) {
@@ -300,11 +271,14 @@ __global__ void __launch_bounds__(256, 4) k_build_system(Dims d, AsmParams P, co
 					b = __dadd_rn(b, div_dx(P, __dmul_rn(__dmul_rn(sgn, area), (double)uf[nq])));
 				}
 			}
-			if (P.apply_rhs_correct) b = __dadd_rn(b, P.rhs_correct);
-			red[0] = fmax(red[0], fabs(b));
-			red[1] += 1.0;
-			tile_flags[tile_of(T, i, j, k)] = 1; // the solve only visits tiles that hold an unknown
+			if (is_row) {
+				if (P.apply_rhs_correct) b = __dadd_rn(b, P.rhs_correct);
+				red[0] = fmax(red[0], fabs(b));
+				red[1] += 1.0;
+				tile_flags[tile_of(T, i, j, k)] = 1; // the solve only visits tiles that hold an unknown
+			}
 		}
+		in_rows[c] = is_row ? 1 : 0;
 		wx[c] = (CoefT)lower[0]; wy[c] = (CoefT)lower[1]; wz[c] = (CoefT)lower[2]; dd[c] = (CoefT)dirichlet;
 		if (mwx != nullptr) { mwx[c] = (float)lower[0]; mwy[c] = (float)lower[1]; mwz[c] = (float)lower[2]; mdd[c] = (float)dirichlet; }
 		rhs[c] = (VecT)b;

@@ -893,8 +893,6 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		CKR(halo(S, d, curv, stream));
 		LAUNCH(S, "surface_tension", k_surface_tension<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)curv, crhos, vel, masks);
 	}
-	LAUNCH(S, "label_rows", k_label_rows<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, careas, crhos, in_rows);
-	CKR(halo(S, d, in_rows, stream));
 	{
 		const bool share = sizeof(CoefT) == sizeof(float);
 		HostLevel &H0 = S->levels[0];
@@ -906,7 +904,7 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 			long long gz = (want + xy - 1) / xy;
 			bgrid.z = (unsigned)(gz < 1 ? 1 : (gz > d.nzl ? d.nzl : gz));
 		}
-		LAUNCH(S, "build_system", (k_build_system<RealT, CoefT, VecT>), bgrid, cell_block(), stream, d, A, (const RealT *)phi, (const uint8_t *)in_rows, careas,
+		LAUNCH(S, "build_system", (k_build_system<RealT, CoefT, VecT>), bgrid, cell_block(), stream, d, A, (const RealT *)phi, in_rows, careas,
 		       crhos, cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->dd.ptr<CoefT>(d), share ? nullptr : L0.wx,
 		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.dd, S->b.ptr<VecT>(d), L0.tiles, static_cast<unsigned char *>(H0.tile_flags.base), rb, st);
 		CKR(compact_tiles(S, H0, stream));
