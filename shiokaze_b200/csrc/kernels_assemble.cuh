@@ -291,16 +291,24 @@ __global__ void __launch_bounds__(256, 4) k_build_system(Dims d, AsmParams P, co
 }
 
 // K12: pressure scatter to the Real grid (macpressuresolver3.cpp:245-248); singular systems lose their mean.
+// (the caller's pressure / activity grids, when given, are written by the same pass)
 template <class RealT, class VecT>
 __global__ void __launch_bounds__(256) k_store_pressure(Dims d, const VecT *__restrict__ x, const uint8_t *__restrict__ in_rows,
-                                                       const CGState *__restrict__ st, RealT *__restrict__ pressure) {
+                                                       const CGState *__restrict__ st, RealT *__restrict__ pressure, RealT *__restrict__ pressure_out,
+                                                       uint8_t *__restrict__ active_out) {
 	const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
 	if (c >= d.ncell) return;
 	double shift = 0.0;
 	if (!st->has_dirichlet && st->n_rows) shift = st->sum_x / (double)st->n_rows;
-	pressure[c] = in_rows[c] ? (RealT)((double)x[c] - shift) : (RealT)0;
+	const uint8_t row = in_rows[c];
+	const RealT p = row ? (RealT)((double)x[c] - shift) : (RealT)0;
+	pressure[c] = p;
+	if (pressure_out) pressure_out[c] = p;
+	if (active_out) active_out[c] = row;
 }
 
+// sum of x over the row set by itself: only for MGPostSweeps = 0, where the prolongation leaves values on cells without an equation
+// (every other configuration gets the sum from k_axpy2_norm)
 template <class VecT>
 __global__ void __launch_bounds__(256) k_sum_rows(Dims d, const VecT *__restrict__ x, const uint8_t *__restrict__ in_rows, RedBuf rb, CGState *st) {
 	double red[1] = {0.0};

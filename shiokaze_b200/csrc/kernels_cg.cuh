@@ -50,6 +50,7 @@ __global__ void k_cg_begin(double residual, int max_iter, CGState *st) {
 		st->converged = st->bnorm == 0.0 ? 1 : 0;
 		st->done = (st->bnorm == 0.0 || max_iter <= 0) ? 1 : 0;
 		st->rnorm = st->bnorm;
+		st->sum_x = 0.0;
 		st->alpha = st->beta = st->sz = st->rho = 0.0;
 	}
 }
@@ -240,14 +241,15 @@ __global__ void __launch_bounds__((TX / 4) * TY, 3) k_spmv_dot4(Dims d, Tiles T,
 	});
 }
 
-// x += alpha s ; r -= alpha q ; |r|_inf ; (plain CG: r.r) ; float copy of r for multigrid      (pcg_solver.h:278-285)
+// x += alpha s ; r -= alpha q ; |r|_inf ; (plain CG: r.r) ; sum of x ; float copy of r for multigrid      (pcg_solver.h:278-285)
+// (sum of x: a pure-Neumann system loses its mean when the pressure is stored; x is zero off the row set, so the sum over the active tiles is the sum over rows)
 // last block: convergence test, iteration count; for plain CG also beta and the new rho.
 template <class VecT, bool PLAIN, bool WRITE_B0>
 __global__ void __launch_bounds__(TX *CG_BY) k_axpy2_norm(Dims d, Tiles T, const VecT *__restrict__ s, const VecT *__restrict__ q, VecT *__restrict__ x,
                                                          VecT *__restrict__ r, float *__restrict__ b0, RedBuf rb, CGState *st) {
 	if (st->done) return;
 	const VecT alpha = (VecT)st->alpha;
-	double red[2] = {0.0, 0.0};
+	double red[3] = {0.0, 0.0, 0.0};
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
@@ -256,7 +258,9 @@ __global__ void __launch_bounds__(TX *CG_BY) k_axpy2_norm(Dims d, Tiles T, const
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
 				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-				x[c] += alpha * s[c];
+				const VecT xv = x[c] + alpha * s[c];
+				x[c] = xv;
+				red[2] += (double)xv;
 				const VecT rv = r[c] - alpha * q[c];
 				r[c] = rv;
 				if (WRITE_B0) b0[c] = (float)rv;
@@ -264,8 +268,9 @@ __global__ void __launch_bounds__(TX *CG_BY) k_axpy2_norm(Dims d, Tiles T, const
 				if (PLAIN) red[1] += (double)rv * (double)rv;
 			}
 	}
-	grid_reduce<2, 0x1u>(red, rb, [&](double (&t)[2]) {
+	grid_reduce<3, 0x1u>(red, rb, [&](double (&t)[3]) {
 		st->rnorm = t[0];
+		st->sum_x = t[2];
 		st->iter += 1;
 		if (t[0] <= st->tol) { st->done = 1; st->converged = 1; }
 		else if (st->iter >= st->max_iter) st->done = 1;

@@ -922,15 +922,13 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	CKR((solve<VecT, CoefT>(S, P, stream)));
 	CK(cudaEventRecord(S->ev[3], stream));
 	// pressure scatter + velocity update
-	if (!S->h_state->has_dirichlet && S->h_state->n_rows) {
+	if (!S->h_state->has_dirichlet && S->h_state->n_rows && P.precond == SHKZ_B200_PRECOND_MG && P.mg_post_sweeps <= 0) {
 		LAUNCH(S, "sum_rows", k_sum_rows<VecT>, flat_blocks(d.ncell), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows, rb, st);
 	}
 	LAUNCH(S, "store_pressure", (k_store_pressure<RealT, VecT>), (unsigned)((d.ncell + 255) / 256), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows,
-	       (const CGState *)st, pres);
+	       (const CGState *)st, pres, static_cast<RealT *>(pressure_v), pressure_active);
 	CKR(halo(S, d, pres, stream));
 	LAUNCH(S, "update_velocity", k_update_velocity<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)pres, careas, crhos, vel, masks);
-	if (pressure_v) CK(cudaMemcpyAsync(pressure_v, pres, sizeof(RealT) * (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
-	if (pressure_active) CK(cudaMemcpyAsync(pressure_active, in_rows, (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
 	CK(cudaEventRecord(S->ev[4], stream));
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
