@@ -129,6 +129,25 @@ def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, level
     return None if per_row is None else per_row * n
 
 
+def base_tag(k):
+    """"sweep@0p" -> "sweep@0": the variant letters of a profiler tag (z: x_old = 0, p: coarse correction folded in, d: z.r folded in) dropped."""
+    name, _, lvl = k.partition("@")
+    return name + ("@" + lvl.rstrip("zpd") if lvl else "")
+
+
+def group_kernels(table, ab):
+    """Profiler table {tag: (launches, total ms)} -> {kernel function: launches, ms, algorithmic bytes, variants}. The dominant kernel is the
+    kernel FUNCTION with the largest summed time: the sweep variants of one level are template instances of the same k_sweep_tma and count
+    together, each launch with the algorithmic bytes of its own variant (ab(tag) = bytes per launch, None for kernels outside the byte model)."""
+    groups = {}
+    for k, (c, t) in table.items():
+        if ab(k):
+            g = groups.setdefault(base_tag(k), {"launches": 0, "ms": 0.0, "bytes": 0.0, "variants": {}})
+            g["launches"] += c; g["ms"] += t; g["bytes"] += ab(k) * c
+            g["variants"][k] = {"launches": c, "avg_launch_ms": t / c, "algorithmic_bytes_per_launch": ab(k), "achieved": ab(k) / (t / c * 1e-3) / 1e9}
+    return groups
+
+
 def build_scene(workload, n, zrange=None):
     from shiokaze_b200 import scenes
     return scenes.BENCH_SCENES[workload](n, zrange=zrange) if zrange else scenes.BENCH_SCENES[workload](n)
@@ -344,18 +363,7 @@ def run_ours(args):
         levels_rows = [n_rows / (8 ** l) for l in range(16)]
         rank_rows = res.n_rows / world        # a slab solver reports the global row count; kernels are timed on rank 0's slab
         ab = lambda k: algorithmic_bytes_per_launch(k, rank_rows, args.precision, [rank_rows / (8 ** l) for l in range(16)], args.precond, (args.pre, args.post))
-        # the dominant kernel = the kernel FUNCTION with the largest summed time: the sweep variants of one level (z: x_old = 0,
-        # p: coarse correction folded in, d: z.r folded in) are template instances of the same k_sweep_tma and count together,
-        # each launch with the algorithmic bytes of its own variant
-        def base_tag(k):
-            name, _, lvl = k.partition("@")
-            return name + ("@" + lvl.rstrip("zpd") if lvl else "")
-        groups = {}
-        for k, (c, t) in table.items():
-            if ab(k):
-                g = groups.setdefault(base_tag(k), {"launches": 0, "ms": 0.0, "bytes": 0.0, "variants": {}})
-                g["launches"] += c; g["ms"] += t; g["bytes"] += ab(k) * c
-                g["variants"][k] = {"launches": c, "avg_launch_ms": t / c, "algorithmic_bytes_per_launch": ab(k), "achieved": ab(k) / (t / c * 1e-3) / 1e9}
+        groups = group_kernels(table, ab)
         dom = max(groups, key=lambda k: groups[k]["ms"])
         cnt, tot = groups[dom]["launches"], groups[dom]["ms"]
         per_launch = groups[dom]["bytes"] / cnt
