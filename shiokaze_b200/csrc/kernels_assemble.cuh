@@ -296,10 +296,12 @@ template <class RealT, class VecT>
 __global__ void __launch_bounds__(256) k_store_pressure(Dims d, const VecT *__restrict__ x, const uint8_t *__restrict__ in_rows,
                                                        const CGState *__restrict__ st, RealT *__restrict__ pressure, RealT *__restrict__ pressure_out,
                                                        uint8_t *__restrict__ active_out) {
+	__shared__ double shift_sh; // one fp64 division per block, not per cell
+	if (threadIdx.x == 0) shift_sh = (!st->has_dirichlet && st->n_rows) ? st->sum_x / (double)st->n_rows : 0.0;
+	__syncthreads();
+	const double shift = shift_sh;
 	const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
 	if (c >= d.ncell) return;
-	double shift = 0.0;
-	if (!st->has_dirichlet && st->n_rows) shift = st->sum_x / (double)st->n_rows;
 	const uint8_t row = in_rows[c];
 	const RealT p = row ? (RealT)((double)x[c] - shift) : (RealT)0;
 	pressure[c] = p;
