@@ -84,3 +84,21 @@ def test_csr_entry_points_refuse_without_a_device_and_check_arguments():
         from shiokaze_b200 import B200CG
         with pytest.raises(capi.ShkzError):
             B200CG()
+
+
+@pytest.mark.parametrize("flags,module", [({"Projection": "b200pressure3"}, "b200pressure3.so"), ({"LinSolver": "b200cg"}, "b200cg.so")])
+def test_shiokaze_modules_load_under_the_reference_loader_and_refuse_without_a_device(flags, module):
+    """The drop-in boundary without a GPU: the reference's own host (oracle/ref_driver) dlopens our module by name, casts it to the
+    interface, configures it — and the module then stops the run with the library's no-device error instead of computing anything."""
+    from oracle import refio
+    from shiokaze_b200 import scenes
+    if capi.lib().shkz_b200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    if not (refio.ref_available("f32") and os.path.isfile(os.path.join(refio.ref_dir("f32"), "libshiokaze_" + module))):
+        pytest.skip("oracle/_ref (reference build + modules) is not built here")
+    projection = flags.pop("Projection", None)
+    with pytest.raises(RuntimeError) as e:
+        refio.run_reference(scenes.dambreak(12), "f32", flags=flags, projection=projection, timeout=120)
+    text = str(e.value)
+    assert f'Loaded "{module}"' in text
+    assert "no CUDA device available" in text and "no CPU fallback" in text
