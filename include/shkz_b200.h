@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SHKZ_B200_ABI_VERSION 1
+#define SHKZ_B200_ABI_VERSION 2
 
 enum shkz_b200_status {
 	SHKZ_B200_OK = 0,
@@ -82,7 +82,8 @@ typedef struct shkz_b200_params {
 	int32_t check_every;          /* host reads the convergence flag every this many iterations (default 4) */
 	double mg_coarse_scale;       /* coarse operator = scale * (P^T A P), piecewise-constant P (default 0.5) */
 	int32_t mg_gamma;             /* coarse-grid visits per level below level 0: 1 = V-cycle (default), 2 = W-cycle */
-	int32_t reserved;
+	int32_t warm_start;           /* WarmStart (No): solve for the correction to the previous call's pressure, macpressuresolver3.cpp:221-242
+	                                 (kept per CELL by the solver; the reference keeps it per row number) */
 	double mg_omega;              /* relaxation factor of the red-black sweeps, 0 < omega < 2 (1 = Gauss-Seidel; default 1.15) */
 } shkz_b200_params;
 
@@ -97,6 +98,9 @@ typedef struct shkz_b200_stats {
 	int32_t mg_levels;
 	uint64_t kernel_launches; /* kernels of this library launched by the call */
 	float ms_h2d, ms_assemble, ms_setup, ms_solve, ms_update, ms_d2h, ms_total; /* CUDA-event times */
+	float ms_surftension;   /* part of ms_assemble spent on the surface-tension force (macpressuresolver3.cpp:85-115); 0 without it */
+	uint32_t active_tiles;  /* level-0 tiles (64 x 16 x bz cells) that hold an unknown: what every solve kernel walks over */
+	uint32_t total_tiles;
 } shkz_b200_stats;
 
 typedef struct shkz_b200_solver shkz_b200_solver; /* opaque */
@@ -221,7 +225,8 @@ int shkz_b200_profile_get(shkz_b200_solver *solver, int index, char *name, size_
 int shkz_b200_debug_fetch(shkz_b200_solver *solver, const char *name, void *dst, size_t dst_bytes, size_t *needed_bytes);
 
 
-/* ---- test hook: apply ONE multigrid V-cycle to the right-hand side of the last project() and keep the result for
+/* ---- test hook, ONLY in the library built with -DSHKZ_B200_TEST_HOOKS (shiokaze_b200/_build/libshkz_b200_testhooks.so; the product library does
+ * not carry it, nor the one-launch-per-colour validation kernels behind it): apply ONE multigrid V-cycle to the right-hand side of the last project() and keep the result for
  * debug_fetch("vcycle"). legacy: 0 = the product kernels; 1 = the unfused one-launch-per-colour kernels on dense
  * grids; 2 = the product path with the scalar sweep kernel forced; 3 = with the quad kernel (no TMA) forced. All must agree bit for bit
  * (tests/test_gpu_parity.py). */

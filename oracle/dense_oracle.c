@@ -159,7 +159,11 @@ static void surface_tension_force(const oracle_params *P, const double *fluid, d
 	double *curv = (double *)malloc(sizeof(double) * (size_t)nx * ny * nz);
 	for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
 #define F(a, b, c) fluid[cell_index(P, clampi(a, nx), clampi(b, ny), clampi(c, nz))]
-		double value = (+F(i - 1, j, k) + F(i + 1, j, k) + F(i, j - 1, k) + F(i, j + 1, k) + F(i, j, k - 1) + F(i, j, k + 1) - 6.0 * F(i, j, k)) / (dx * dx);
+		/* :93-98 — the six neighbour reads are Real values and add up as Real (float on the shipping build); "- 6.0*fluid" promotes to double */
+		double six;
+		if (P->real_is_double) six = F(i - 1, j, k) + F(i + 1, j, k) + F(i, j - 1, k) + F(i, j + 1, k) + F(i, j, k - 1) + F(i, j, k + 1);
+		else six = (double)((float)F(i - 1, j, k) + (float)F(i + 1, j, k) + (float)F(i, j - 1, k) + (float)F(i, j + 1, k) + (float)F(i, j, k - 1) + (float)F(i, j, k + 1));
+		double value = (six - 6.0 * F(i, j, k)) / (dx * dx);
 		curv[cell_index(P, i, j, k)] = RR(P, value);
 	}
 	for (int dim = 0; dim < 3; ++dim) {
@@ -333,9 +337,24 @@ done:
  *   rhs_out, diag_out and dirichlet_out are cell-shaped (0 outside the row set); dirichlet_out is the
  *   part of the diagonal contributed by air neighbours (diag = sum of couplings + dirichlet).
  */
+int oracle_project_warm(const oracle_params *P, double *vel[3], uint8_t *vel_active[3], const double *solid, const double *fluid,
+                        double *pressure, uint8_t *in_rows, double *areas_out[3], double *rhos_out[3],
+                        double *rhs_out, double *diag_out, double *dirichlet_out, oracle_stats *st,
+                        double *prev_pressure, uint64_t *prev_rows);
+
 int oracle_project(const oracle_params *P, double *vel[3], uint8_t *vel_active[3], const double *solid, const double *fluid,
                    double *pressure, uint8_t *in_rows, double *areas_out[3], double *rhos_out[3],
                    double *rhs_out, double *diag_out, double *dirichlet_out, oracle_stats *st) {
+	return oracle_project_warm(P, vel, vel_active, solid, fluid, pressure, in_rows, areas_out, rhos_out, rhs_out, diag_out, dirichlet_out, st, NULL, NULL);
+}
+
+/* ... with WarmStart=Yes (macpressuresolver3.cpp:221-230, 239-242) when prev_pressure != NULL: the previous result, indexed by ROW NUMBER
+ * as the reference keeps it (capacity nx*ny*nz doubles; *prev_rows = its current length, "resize(index)" pads with zeros / truncates),
+ * is multiplied into the right-hand side before the solve, added back to the solution afterwards and replaced by the sum. */
+int oracle_project_warm(const oracle_params *P, double *vel[3], uint8_t *vel_active[3], const double *solid, const double *fluid,
+                        double *pressure, uint8_t *in_rows, double *areas_out[3], double *rhos_out[3],
+                        double *rhs_out, double *diag_out, double *dirichlet_out, oracle_stats *st,
+                        double *prev_pressure, uint64_t *prev_rows) {
 	const int nx = P->nx, ny = P->ny, nz = P->nz;
 	const size_t ncell = (size_t)nx * ny * nz;
 	double *areas[3], *rhos[3];
@@ -353,7 +372,17 @@ int oracle_project(const oracle_params *P, double *vel[3], uint8_t *vel_active[3
 	st->n_rows = A.n;
 	st->nnz = A.rowstart[A.n];
 	double *x = (double *)calloc(A.n ? A.n : 1, sizeof(double));
+	if (prev_pressure) { /* :221-230 */
+		for (size_t r = (size_t)*prev_rows; r < A.n; ++r) prev_pressure[r] = 0.0;
+		*prev_rows = A.n;
+		double *ap = (double *)malloc(sizeof(double) * (A.n ? A.n : 1));
+		spmv(&A, prev_pressure, ap);
+		for (size_t r = 0; r < A.n; ++r) A.rhs[r] -= ap[r];
+		free(ap);
+	}
 	cg_solve(P, &A, x, st);
+	if (prev_pressure) /* :239-242 */
+		for (size_t r = 0; r < A.n; ++r) { x[r] += prev_pressure[r]; prev_pressure[r] = x[r]; }
 	/* :245-248 scatter to the Real pressure grid; activity == row set */
 	for (size_t c = 0; c < ncell; ++c) {
 		int in = index_map[c] != SIZE_MAX;

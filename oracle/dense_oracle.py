@@ -77,8 +77,9 @@ def _bptr3(arrs):
 
 def project(scene, residual=1e-4, max_iterations=30000, eps_fluid=1e-2, eps_solid=1e-2,
             second_order_fluid=True, second_order_solid=True, real_is_double=False,
-            rhs_correct=0.0, surface_tension=None) -> OracleResult:
-    """Dense restatement of macpressuresolver3::project() on a shiokaze_b200.scenes.Scene (whole grid)."""
+            rhs_correct=0.0, surface_tension=None, warm_state=None) -> OracleResult:
+    """Dense restatement of macpressuresolver3::project() on a shiokaze_b200.scenes.Scene (whole grid).
+    warm_state: WarmStart=Yes — a dict kept by the caller between calls (the module's m_prev_pressure, by row number)."""
     nx, ny, nz = scene.nx, scene.ny, scene.nz
     assert scene.zrange == (0, nz)
     P = Params(nx, ny, nz, int(second_order_fluid), int(second_order_solid), int(real_is_double),
@@ -97,13 +98,21 @@ def project(scene, residual=1e-4, max_iterations=30000, eps_fluid=1e-2, eps_soli
     diag = np.zeros((nz, ny, nx), dtype=np.float64)
     dirichlet = np.zeros((nz, ny, nx), dtype=np.float64)
     st = Stats()
-    rc = lib().oracle_project(C.byref(P), _dptr3(vel), _bptr3(act),
+    extra = []
+    fn = lib().oracle_project
+    if warm_state is not None:
+        if "prev" not in warm_state:
+            warm_state["prev"] = np.zeros(nx * ny * nz, dtype=np.float64)
+            warm_state["rows"] = C.c_uint64(0)
+        fn = lib().oracle_project_warm
+        extra = [warm_state["prev"].ctypes.data_as(C.POINTER(C.c_double)), C.byref(warm_state["rows"])]
+    rc = fn(C.byref(P), _dptr3(vel), _bptr3(act),
                               solid.ctypes.data_as(C.POINTER(C.c_double)) if solid is not None else None,
                               fluid.ctypes.data_as(C.POINTER(C.c_double)),
                               pressure.ctypes.data_as(C.POINTER(C.c_double)), in_rows.ctypes.data_as(C.POINTER(C.c_uint8)),
                               _dptr3(areas), _dptr3(rhos), rhs.ctypes.data_as(C.POINTER(C.c_double)),
                               diag.ctypes.data_as(C.POINTER(C.c_double)),
-                              dirichlet.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st))
+                              dirichlet.ctypes.data_as(C.POINTER(C.c_double)), C.byref(st), *extra)
     assert rc == 0
     return OracleResult(vel, act, pressure, in_rows, areas, rhos, rhs, diag, dirichlet, int(st.iterations), float(st.reresid),
                         int(st.n_rows), int(st.nnz), bool(st.converged), float(st.rhs_absmax))

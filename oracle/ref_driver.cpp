@@ -104,9 +104,11 @@ int main( int argc, const char *argv[] ) {
 		if( ! std::strncmp(argv[i],"in=",3)) in_path = argv[i]+3;
 		if( ! std::strncmp(argv[i],"out=",4)) out_path = argv[i]+4;
 		if( ! std::strcmp(argv[i],"DumpFractions=1")) dump_fractions = true;
+		// RecordDir=<existing directory>: console::write records (src/core/console.cpp:259-281) land in <dir>/record/<name>.out, as under ./run with Log=
+		if( ! std::strncmp(argv[i],"RecordDir=",10)) console::set_root_path(argv[i]+10);
 	}
 	if( in_path.empty() || out_path.empty()) {
-		std::fprintf(stderr,"usage: ref_driver in=<scene> out=<result> [DumpFractions=1] [Projection=<module>] [flag=value ...]\n");
+		std::fprintf(stderr,"usage: ref_driver in=<scene> out=<result> [DumpFractions=1] [RecordDir=<dir>] [Projection=<module>] [flag=value ...]\n");
 		return 2;
 	}
 	FILE *fp = std::fopen(in_path.c_str(),"rb");

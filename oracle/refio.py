@@ -71,6 +71,7 @@ class RefResult:
     sizeof_real: int
     phase_ms: dict
     stdout: str
+    records: Optional[dict] = None   # records=True: console::write record name -> list of values (one per call)
 
 
 def _read_block(f):
@@ -124,7 +125,7 @@ def _phase_times(text: str) -> dict:
 def run_reference(scene, real: str = "f32", flags: Optional[dict] = None, dump_fractions: bool = False,
                   repeat: int = 1, threads: Optional[int] = None, projection: Optional[str] = None,
                   current_volume: float = 0.0, target_volume: float = 0.0, extra_lib_dirs=(),
-                  timeout: Optional[float] = None) -> RefResult:
+                  timeout: Optional[float] = None, records: bool = False) -> RefResult:
     """One project() call of the reference (or of any drop-in module named by `projection`)."""
     d = ref_dir(real)
     if not ref_available(real):
@@ -139,6 +140,8 @@ def run_reference(scene, real: str = "f32", flags: Optional[dict] = None, dump_f
             argv.append(f"Projection={projection}")
         if threads:
             argv.append(f"Threads={threads}")
+        if records:
+            argv.append(f"RecordDir={tmp}")
         for k, v in (flags or {}).items():
             argv.append(f"{k}={v}")
         env = dict(os.environ)
@@ -148,9 +151,17 @@ def run_reference(scene, real: str = "f32", flags: Optional[dict] = None, dump_f
         if proc.returncode != 0 or not os.path.isfile(fout):
             raise RuntimeError(f"ref_driver failed ({proc.returncode}):\n{text[-4000:]}\n{proc.stderr[-4000:]}")
         res = read_result(fout)
+        rec = None
+        if records:
+            rec = {}
+            rdir = os.path.join(tmp, "record")
+            for fn in sorted(os.listdir(rdir)) if os.path.isdir(rdir) else []:
+                if fn.endswith(".out"):
+                    with open(os.path.join(rdir, fn)) as fh:
+                        rec[fn[:-4]] = [float(line.split()[1]) for line in fh if len(line.split()) >= 2]
     m = None
     for m in re.finditer(r"Took (\d+) iterations, Reresid=([-+0-9.]+(?:[eE][-+]?\d+)?|nan|inf|-nan)", text):
         pass
     iterations = int(m.group(1)) if m else -1
     reresid = float(m.group(2)) if m else float("nan")
-    return RefResult(iterations=iterations, reresid=reresid, phase_ms=_phase_times(text), stdout=text, **res)
+    return RefResult(iterations=iterations, reresid=reresid, phase_ms=_phase_times(text), stdout=text, records=rec, **res)

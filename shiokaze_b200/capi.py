@@ -7,6 +7,8 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libshkz_b200.so")
+HOOKS_LIB_PATH = os.path.join(HERE, "_build", "libshkz_b200_testhooks.so")  # same sources + -DSHKZ_B200_TEST_HOOKS (tests only)
+ABI_VERSION = 2
 
 OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_COMM, ERR_STATE = range(6)
 PRECOND_NONE, PRECOND_MG = 0, 1
@@ -32,14 +34,15 @@ class Params(C.Structure):
                 ("max_iterations", C.c_uint32), ("precond", C.c_int32), ("precision", C.c_int32),
                 ("mg_pre_sweeps", C.c_int32), ("mg_post_sweeps", C.c_int32), ("mg_coarse_sweeps", C.c_int32),
                 ("mg_min_size", C.c_int32), ("check_every", C.c_int32), ("mg_coarse_scale", C.c_double),
-                ("mg_gamma", C.c_int32), ("reserved", C.c_int32), ("mg_omega", C.c_double)]
+                ("mg_gamma", C.c_int32), ("warm_start", C.c_int32), ("mg_omega", C.c_double)]
 
 
 class Stats(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("n_rows_global", C.c_uint64), ("iterations", C.c_uint32), ("converged", C.c_int32),
                 ("reresid", C.c_double), ("rhs_absmax", C.c_double), ("has_dirichlet", C.c_int32), ("mg_levels", C.c_int32),
                 ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_float), ("ms_assemble", C.c_float), ("ms_setup", C.c_float),
-                ("ms_solve", C.c_float), ("ms_update", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float)]
+                ("ms_solve", C.c_float), ("ms_update", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+                ("ms_surftension", C.c_float), ("active_tiles", C.c_uint32), ("total_tiles", C.c_uint32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -65,17 +68,18 @@ class ShkzError(RuntimeError):
         self.code = code
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    """Load libshkz_b200.so (built in-tree by `make -C shiokaze_b200/csrc` / __graft_entry__.build())."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.isfile(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C shiokaze_b200/csrc` (there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+def lib(test_hooks: bool = False):
+    """Load libshkz_b200.so (built in-tree by `make -C shiokaze_b200/csrc` / __graft_entry__.build()).
+    test_hooks=True: the -DSHKZ_B200_TEST_HOOKS build of the same sources (adds shkz_b200_debug_vcycle + the validation kernels); tests only."""
+    if test_hooks in _libs:
+        return _libs[test_hooks]
+    path = HOOKS_LIB_PATH if test_hooks else LIB_PATH
+    if not os.path.isfile(path):
+        raise ImportError(f"{path} is missing: build it with `make -C shiokaze_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(path)
     vp, u8p = C.c_void_p, C.POINTER(C.c_uint8)
     L.shkz_b200_abi_version.restype = C.c_int
     L.shkz_b200_last_error.restype = C.c_char_p
@@ -108,13 +112,14 @@ def lib():
     L.shkz_b200_csr_destroy.argtypes = [vp]
     L.shkz_b200_csr_destroy.restype = None
     L.shkz_b200_csr_solve_host.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(CsrParams), C.POINTER(CsrStats)]
-    _lib = L
+    _libs[test_hooks] = L
     return L
 
 
-def check(code):
+def check(code, L=None):
+    """Raise on a non-zero status; L: the library the failing call went through (default: the product library)."""
     if code != OK:
-        raise ShkzError(code, lib().shkz_b200_last_error().decode(errors="replace"))
+        raise ShkzError(code, (L or lib()).shkz_b200_last_error().decode(errors="replace"))
 
 
 def check_csr(code):

@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(256) k_face_fractions(Dims d, AsmParams P, con
 	}
 }
 
+__device__ __forceinline__ float real_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double real_add(double a, double b) { return __dadd_rn(a, b); }
+
 // K3a: curvature = 7-point Laplacian of phi with clamped neighbours / dx^2 (macpressuresolver3.cpp:92-102)
 template <class RealT>
 __global__ void __launch_bounds__(256) k_curvature(Dims d, AsmParams P, const RealT *__restrict__ phi, RealT *__restrict__ curv) {
@@ -158,14 +161,16 @@ __global__ void __launch_bounds__(256) k_curvature(Dims d, AsmParams P, const Re
 	const int k = blockIdx.z;
 	if (i >= d.nx || j >= d.ny) return;
 	const int kg = k + d.k0;
-#define PHI(a, b, c) (double)phi[clampi(a, d.nx) + (long long)d.nx * (clampi(b, d.ny) + (long long)d.ny * (clampi(c, d.nzg) - d.k0))]
-	double s = PHI(i - 1, j, kg);
-	s = __dadd_rn(s, PHI(i + 1, j, kg));
-	s = __dadd_rn(s, PHI(i, j - 1, kg));
-	s = __dadd_rn(s, PHI(i, j + 1, kg));
-	s = __dadd_rn(s, PHI(i, j, kg - 1));
-	s = __dadd_rn(s, PHI(i, j, kg + 1));
-	s = __dsub_rn(s, __dmul_rn(6.0, PHI(i, j, kg)));
+	// the reference's expression (macpressuresolver3.cpp:93-98) adds the six neighbour values as Real — float on the shipping build —, left to right,
+	// and only the "- 6.0*fluid" term promotes to double
+#define PHI(a, b, c) phi[clampi(a, d.nx) + (long long)d.nx * (clampi(b, d.ny) + (long long)d.ny * (clampi(c, d.nzg) - d.k0))]
+	RealT sr = PHI(i - 1, j, kg);
+	sr = real_add(sr, PHI(i + 1, j, kg));
+	sr = real_add(sr, PHI(i, j - 1, kg));
+	sr = real_add(sr, PHI(i, j + 1, kg));
+	sr = real_add(sr, PHI(i, j, kg - 1));
+	sr = real_add(sr, PHI(i, j, kg + 1));
+	const double s = __dsub_rn((double)sr, __dmul_rn(6.0, (double)PHI(i, j, kg)));
 #undef PHI
 	curv[i + (long long)d.nx * (j + (long long)d.ny * k)] = (RealT)__ddiv_rn(s, __dmul_rn(P.dx, P.dx));
 }
@@ -292,10 +297,12 @@ __global__ void __launch_bounds__(256, 4) k_build_system(Dims d, AsmParams P, co
 
 // K12: pressure scatter to the Real grid (macpressuresolver3.cpp:245-248); singular systems lose their mean.
 // (the caller's pressure / activity grids, when given, are written by the same pass)
+// warm start (macpressuresolver3.cpp:239-242): the solve ran on b - A p_prev, so the pressure is x + p_prev, which also becomes the next p_prev
+// (zero off the row set: a cell that joins the row set later starts from nothing, like a new row of the reference's resized vector).
 template <class RealT, class VecT>
 __global__ void __launch_bounds__(256) k_store_pressure(Dims d, const VecT *__restrict__ x, const uint8_t *__restrict__ in_rows,
                                                        const CGState *__restrict__ st, RealT *__restrict__ pressure, RealT *__restrict__ pressure_out,
-                                                       uint8_t *__restrict__ active_out) {
+                                                       uint8_t *__restrict__ active_out, VecT *__restrict__ p_prev) {
 	__shared__ double shift_sh; // one fp64 division per block, not per cell
 	if (threadIdx.x == 0) shift_sh = (!st->has_dirichlet && st->n_rows) ? st->sum_x / (double)st->n_rows : 0.0;
 	__syncthreads();
@@ -303,7 +310,12 @@ __global__ void __launch_bounds__(256) k_store_pressure(Dims d, const VecT *__re
 	const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
 	if (c >= d.ncell) return;
 	const uint8_t row = in_rows[c];
-	const RealT p = row ? (RealT)((double)x[c] - shift) : (RealT)0;
+	double pv = row ? (double)x[c] - shift : 0.0;
+	if (p_prev) {
+		if (row) pv += (double)p_prev[c];
+		p_prev[c] = (VecT)pv;
+	}
+	const RealT p = (RealT)pv;
 	pressure[c] = p;
 	if (pressure_out) pressure_out[c] = p;
 	if (active_out) active_out[c] = row;

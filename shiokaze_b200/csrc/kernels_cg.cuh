@@ -168,6 +168,38 @@ __global__ void __launch_bounds__(TX *CG_BY) k_spmv_dot(Dims d, Tiles T, const C
 	});
 }
 
+// a10 warm start (macpressuresolver3.cpp:221-230): b -= A p_prev on the active tiles before the solve, |b|_inf of the new right-hand side
+// (p_prev is a DENSE per-cell field here; the reference keeps it by row number, which is the same thing as long as the row set does not move and
+// an artefact of its iteration order when it does). Cells off the row set have zero coefficients: their p_prev never enters.
+template <class VecT, class CoefT>
+__global__ void __launch_bounds__(TX *CG_BY) k_warm_rhs(Dims d, Tiles T, const CoefT *__restrict__ wx, const CoefT *__restrict__ wy, const CoefT *__restrict__ wz,
+                                                       const CoefT *__restrict__ dd, const VecT *__restrict__ p, VecT *__restrict__ b, RedBuf rb, CGState *st) {
+	double red[1] = {0.0};
+	const int ntiles = *T.count;
+	int i0, j0, kb, ke;
+	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
+		const int i = i0 + threadIdx.x, je = min(j0 + TY, d.ny);
+		if (i >= d.nx) continue;
+		for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
+			long long c = i + (long long)d.nx * (j + (long long)d.ny * kb);
+			for (int k = kb; k < ke; ++k, c += d.plane) {
+				const VecT pc = p[c];
+				VecT v = (VecT)dd[c] * pc;
+				v += (VecT)wx[c] * (pc - p[c - 1]);
+				v += (VecT)wx[c + 1] * (pc - p[c + 1]);
+				v += (VecT)wy[c] * (pc - p[c - d.nx]);
+				v += (VecT)wy[c + d.nx] * (pc - p[c + d.nx]);
+				v += (VecT)wz[c] * (pc - p[c - d.plane]);
+				v += (VecT)wz[c + d.plane] * (pc - p[c + d.plane]);
+				const VecT bv = b[c] - v;
+				b[c] = bv;
+				red[0] = fmax(red[0], fabs((double)bv));
+			}
+		}
+	}
+	grid_reduce<1, 0x1u>(red, rb, [&](double (&t)[1]) { st->bnorm = t[0]; });
+}
+
 // ---- the same product with FOUR x-adjacent cells per thread (nx % 4 == 0): aligned 16/32-byte loads, a quarter of the
 // ---- load instructions, four times the bytes in flight per thread. Block (TX/4, TY): one quad column per thread.
 template <class T> struct V4 { T a, b, c, d; };

@@ -1,6 +1,7 @@
 #include "slab_comm.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace shkz {
@@ -94,8 +95,45 @@ int SlabComm::connect_local(int rank, int world, SlabComm *const *all) {
 	return finish_connect();
 }
 
+unsigned long long SlabComm::read_abort() {
+	unsigned long long w = 0;
+	if (!m_base) return 0;
+	cudaSetDevice(m_device);
+	if (cudaMemcpy(&w, m_base + HDR_ABORT, sizeof w, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return w;
+}
+
+void SlabComm::raise_abort() {
+	if (!m_connected) return;
+	cudaSetDevice(m_device);
+	const unsigned long long w = (unsigned long long)(m_rank + 1) | ((unsigned long long)ABORT_HOST << 8);
+	cudaStream_t st = nullptr;
+	if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return; } // (the solver's own stream may be the one that is stuck)
+	for (int r = 0; r < m_world; ++r)
+		if (m_peer[r]) cudaMemcpyAsync(m_peer[r] + HDR_ABORT, &w, sizeof w, cudaMemcpyHostToDevice, st);
+	cudaStreamSynchronize(st);
+	cudaStreamDestroy(st);
+	cudaGetLastError();
+}
+
+std::string SlabComm::describe_abort(unsigned long long w) {
+	const int who = (int)(w & 0xff) - 1, what = (int)((w >> 8) & 0xff);
+	const unsigned long long seq = w >> 16;
+	const char *names[] = {"?", "the halo planes of its lower neighbour", "the halo planes of its upper neighbour", "the reduction mailbox", "its host gave up before launching"};
+	char buf[256];
+	if (what == ABORT_HOST) snprintf(buf, sizeof buf, "slab communicator aborted: rank %d failed on the host before it could take part", who);
+	else snprintf(buf, sizeof buf, "slab communicator aborted: rank %d timed out waiting for %s (exchange %llu)", who, names[what >= 0 && what <= 3 ? what : 0], seq);
+	return buf;
+}
+
 int SlabComm::finish_connect() {
 	CommDev h{};
+	{
+		// device-side waits give up after this long (default 20 s; a projection takes milliseconds): SHKZ_B200_COMM_TIMEOUT_MS
+		double ms = 20000.0;
+		if (const char *e = getenv("SHKZ_B200_COMM_TIMEOUT_MS")) { const double v = atof(e); if (v > 0.0) ms = v; }
+		h.timeout_ns = (unsigned long long)(ms * 1e6);
+	}
 	h.rank = m_rank; h.world = m_world; h.self = m_base;
 	h.lo = m_rank > 0 ? m_peer[m_rank - 1] : nullptr;
 	h.hi = m_rank + 1 < m_world ? m_peer[m_rank + 1] : nullptr;

@@ -19,6 +19,34 @@
 
 namespace shkz {
 
+// ---- bounded spin: every device-side wait of the communicator goes through here --------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+// Spin until *f >= seq. Returns false — after storing the abort word into EVERY rank's arena — when that takes longer than cm->timeout_ns, or at once
+// when another rank (or a host) has already aborted. A failed rank therefore costs the others one timeout, not a hung GPU: the kernels run to completion
+// on whatever data is there, the host finds the abort word after its stream synchronise and the call ends with SHKZ_B200_ERR_COMM.
+static __device__ __noinline__ bool spin_until(volatile unsigned long long *f, unsigned long long seq, const CommDev *cm, int what) {
+	volatile unsigned long long *abort_word = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_ABORT);
+	unsigned long long t0 = 0;
+	unsigned polls = 0;
+	while (*f < seq) {
+		if ((++polls & 255u) != 0) continue;
+		if (*abort_word) return false;
+		const unsigned long long now = global_ns();
+		if (!t0) t0 = now;
+		else if (now - t0 > cm->timeout_ns) {
+			const unsigned long long w = (unsigned long long)(cm->rank + 1) | ((unsigned long long)what << 8) | (seq << 16);
+			for (int p = 0; p < cm->world; ++p) *reinterpret_cast<volatile unsigned long long *>(cm->peer[p] + HDR_ABORT) = w;
+			__threadfence_system();
+			return false;
+		}
+	}
+	return true;
+}
+
 // Fold the world's partial results (sums, or maxima where MAXMASK has the bit set) — called by ONE thread per rank.
 template <int N, unsigned MAXMASK>
 __device__ __forceinline__ void cross_rank_combine(double (&v)[N], const CommDev *cm) {
@@ -41,7 +69,7 @@ __device__ __forceinline__ void cross_rank_combine(double (&v)[N], const CommDev
 	for (int q = 0; q < cm->world; ++q) {
 		const size_t e = ((size_t)(seq & 3ull) * COMM_MAX_WORLD + (size_t)q) * 8;
 		volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_MAIL) + e + 7;
-		while (*f < seq) {}
+		if (!spin_until(f, seq, cm, ABORT_WAIT_MAIL)) break; // (aborted: the totals are garbage, the host call fails)
 		__threadfence_system();
 		const volatile double *m = reinterpret_cast<const volatile double *>(cm->self + HDR_MAIL) + e;
 #pragma unroll
@@ -75,14 +103,8 @@ __device__ __forceinline__ void signal_neighbours(const CommDev *cm, unsigned lo
 // Block until both neighbours have published exchange number `seq` here (ONE thread of a kernel calls this last; the
 // kernel then cannot complete, and the stream cannot move on, before the ghost planes are in place).
 __device__ __forceinline__ void wait_neighbours(const CommDev *cm, unsigned long long seq) {
-	if (cm->lo) {
-		volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_LO);
-		while (*f < seq) {}
-	}
-	if (cm->hi) {
-		volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_HI);
-		while (*f < seq) {}
-	}
+	if (cm->lo) spin_until(reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_LO), seq, cm, ABORT_WAIT_LO);
+	if (cm->hi) spin_until(reinterpret_cast<volatile unsigned long long *>(cm->self + HDR_FLAG_FROM_HI), seq, cm, ABORT_WAIT_HI);
 	__threadfence_system();
 }
 

@@ -10,7 +10,13 @@
 namespace shkz {
 
 constexpr int COMM_MAX_WORLD = 8;
-constexpr size_t HDR_FLAG_FROM_LO = 0, HDR_FLAG_FROM_HI = 128, HDR_RED_SEQ = 256, HDR_PUSH_TICKET = 384, HDR_PUSH_TICKET2 = 512, HDR_MAIL = 1024;
+constexpr size_t HDR_FLAG_FROM_LO = 0, HDR_FLAG_FROM_HI = 128, HDR_RED_SEQ = 256, HDR_PUSH_TICKET = 384, HDR_PUSH_TICKET2 = 512, HDR_ABORT = 640, HDR_MAIL = 1024;
+// HDR_ABORT: 0 while the communicator is healthy. A rank whose device-side wait ran out of time (CommDev::timeout_ns), or whose host gave up
+// before launching (SlabComm::raise_abort), stores a non-zero word here IN EVERY RANK'S ARENA: every wait of every rank then returns at once,
+// the streams drain, and the host call ends with SHKZ_B200_ERR_COMM instead of hanging the NVLink domain.
+//   bits 0..7  = 1 + rank that raised it    bits 8..15 = what it waited for (1 lower neighbour, 2 upper neighbour, 3 reduction mailbox, 4 host)
+//   bits 16..  = the exchange / reduction number it waited for
+constexpr int ABORT_WAIT_LO = 1, ABORT_WAIT_HI = 2, ABORT_WAIT_MAIL = 3, ABORT_HOST = 4;
 constexpr size_t ARENA_HEADER = 65536;
 
 struct CommDev {
@@ -18,6 +24,7 @@ struct CommDev {
 	char *self;                 // own arena
 	char *lo, *hi;              // arenas of the z-neighbours as mapped into this process (nullptr at the domain ends)
 	char *peer[COMM_MAX_WORLD]; // every rank's arena (peer[rank] == self)
+	unsigned long long timeout_ns; // longest a device-side wait may spin before it aborts the communicator
 };
 
 
@@ -41,6 +48,11 @@ public:
 	int world() const { return m_world; }
 	const CommDev *device_view() const { return m_dev; }
 	unsigned long long next_exchange() { return ++m_exchange; }
+	// health: the abort word of the own arena (0 = fine), read after a stream synchronise; raise_abort() releases every rank's device-side waits
+	// when this rank's host cannot take part in a call the others may already be running
+	unsigned long long read_abort();
+	void raise_abort();
+	static std::string describe_abort(unsigned long long word);
 	const char *error() const { return m_error.c_str(); }
 
 private:

@@ -15,7 +15,9 @@
 #include "kernels_assemble.cuh"
 #include "kernels_cg.cuh"
 #include "kernels_mg.cuh"
-#include "kernels_legacy.cuh"
+#ifdef SHKZ_B200_TEST_HOOKS
+#include "kernels_legacy.cuh" // one-launch-per-colour validation kernels: only in the test-hook build of the library
+#endif
 #include "kernels_mg_tma.cuh"
 #include "slab_comm.h"
 
@@ -206,6 +208,8 @@ struct shkz_b200_solver {
 	int alloc_precision = -1;
 	CellArray wx, wy, wz, dd; // CoefT
 	CellArray b, x, r, s, q;    // VecT
+	CellArray p_prev;           // VecT: WarmStart=Yes — the previous call's pressure per cell (allocated on first use)
+	bool poisoned = false;      // the last solve ended on a non-finite scalar: the solver's persistent vectors are re-zeroed before the next one
 	std::vector<HostLevel> levels;
 	int mg_min_size_built = -1;
 	int tail_first = -1;        // first level of the shared-memory tail of the V-cycle (-1: none)
@@ -239,7 +243,7 @@ struct shkz_b200_solver {
 	const float *debug_vcycle_result = nullptr;
 	int sweep_mode = 0; // 0: best kernel per level (TMA-staged > quad > scalar); 1: no TMA; 2: scalar only (debug / A-B timing)
 	AsmParams last_asm{};
-	cudaEvent_t ev[8]{};
+	cudaEvent_t ev[12]{};
 	bool events = false;
 
 	SlabComm *arena() const { return whole_grid ? nullptr : comm; }
@@ -252,7 +256,7 @@ struct shkz_b200_solver {
 namespace {
 
 void release_precision_arrays(shkz_b200_solver *S) {
-	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd, &S->b, &S->x, &S->r, &S->s, &S->q}) a->release();
+	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd, &S->b, &S->x, &S->r, &S->s, &S->q, &S->p_prev}) a->release();
 	for (HostLevel &L : S->levels) {
 		if (L.own_coef) { L.wx.release(); L.wy.release(); L.wz.release(); L.dd.release(); }
 		if (L.own_b) L.b.release();
@@ -697,6 +701,7 @@ int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGStat
 	return SHKZ_B200_OK;
 }
 
+#ifdef SHKZ_B200_TEST_HOOKS
 // The same V-cycle with one launch per colour / transfer step on dense grids (validation only).
 int legacy_vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, cudaStream_t stream) {
 	HostLevel &H = S->levels[l];
@@ -730,6 +735,8 @@ int legacy_vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, cuda
 	}
 	return SHKZ_B200_OK;
 }
+
+#endif // SHKZ_B200_TEST_HOOKS
 
 int coarsen_levels(shkz_b200_solver *S, std::vector<HostLevel> &lv, bool slab, const shkz_b200_params &P, cudaStream_t stream) {
 	for (size_t l = 0; l + 1 < lv.size(); ++l) {
@@ -774,6 +781,31 @@ int set_omega(const shkz_b200_params &P, cudaStream_t stream) {
 	return SHKZ_B200_OK;
 }
 
+// z-slab solvers, after a stream synchronise: a device-side wait that ran out of time (or a rank that gave up) leaves an abort word in the arena
+int comm_health(shkz_b200_solver *S) {
+	if (S->whole_grid || !S->comm) return SHKZ_B200_OK;
+	const unsigned long long w = S->comm->read_abort();
+	if (w) return fail(SHKZ_B200_ERR_COMM, "%s", SlabComm::describe_abort(w).c_str());
+	return SHKZ_B200_OK;
+}
+
+// The solve kernels only ever write the ACTIVE tiles of x, s, q and of the multigrid buffers and rely on what lies outside them being finite (it meets
+// zero coefficients). A solve that ended on NaN / Inf (a non-finite input velocity, say) would leave those values behind in tiles that are dry next time:
+// wipe everything such a solve may have touched before the next one.
+int scrub_after_nonfinite(shkz_b200_solver *S, cudaStream_t stream) {
+	if (!S->poisoned) return SHKZ_B200_OK;
+	for (CellArray *a : {&S->x, &S->r, &S->s, &S->q, &S->p_prev})
+		if (a->base) CK(cudaMemsetAsync(a->base, 0, a->bytes, stream));
+	for (std::vector<HostLevel> *lv : {&S->levels, &S->glevels})
+		for (HostLevel &L : *lv) {
+			if (L.xa.base) CK(cudaMemsetAsync(L.xa.base, 0, L.xa.bytes, stream));
+			if (L.xb.base) CK(cudaMemsetAsync(L.xb.base, 0, L.xb.bytes, stream));
+			if (L.own_b && L.b.base) CK(cudaMemsetAsync(L.b.base, 0, L.b.bytes, stream));
+		}
+	S->poisoned = false;
+	return SHKZ_B200_OK;
+}
+
 // ---- the CG driver (pcg_solver.h:246-295 with the loop control on the device) ----
 template <class VecT, class CoefT>
 int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
@@ -788,6 +820,7 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	const bool mg = P.precond == SHKZ_B200_PRECOND_MG;
 	constexpr bool kFloatVec = sizeof(VecT) == sizeof(float);
 	float *b0 = kFloatVec ? nullptr : H0.view.b; // an all-float CG hands r itself to multigrid
+	CKR(scrub_after_nonfinite(S, stream));
 
 	LAUNCH(S, "cg_begin", k_cg_begin, 1, 32, stream, P.residual, (int)P.max_iterations, st);
 	if (mg && !kFloatVec) LAUNCH_TILES(S, "cg_init", (k_cg_init<VecT, true>), cg_block(), tt, stream, d, T, (const VecT *)b, x, r, s, b0);
@@ -821,13 +854,18 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 		CK(cudaStreamSynchronize(stream));
 		S->prof.collect();
 		if (S->h_state->done) break;
+		CKR(comm_health(S)); // (a slab whose neighbour never arrived has given up: do not iterate on garbage)
 		batch = check;
 	}
 	CK(cudaMemcpyAsync(S->h_state, st, sizeof(CGState), cudaMemcpyDeviceToHost, stream));
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
 	S->last_iterations = S->h_state->converged ? (unsigned)S->h_state->iter : 0u;
-	return SHKZ_B200_OK;
+	{
+		const CGState &h = *S->h_state;
+		S->poisoned = !(std::isfinite(h.rnorm) && std::isfinite(h.rho) && std::isfinite(h.alpha) && std::isfinite(h.beta) && std::isfinite(h.bnorm));
+	}
+	return comm_health(S);
 }
 
 void fill_stats(const shkz_b200_solver *S, shkz_b200_stats *out) {
@@ -886,12 +924,15 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	// arrays are only materialised when somebody asks for them (shkz_b200_debug_fetch)
 	S->fractions_stale = !A.have_solid && !A.fluid_levelset;
 	if (!S->fractions_stale) LAUNCH(S, "face_fractions", k_face_fractions<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, solid, (const RealT *)phi, areas, rhos);
-	if (P.surface_tension != 0.0 && A.fluid_levelset) { // (without a level set every rho is 1: no face takes the increment, macpressuresolver3.cpp:104-113)
+	const bool tension = P.surface_tension != 0.0 && A.fluid_levelset; // (without a level set every rho is 1: no face takes the increment, macpressuresolver3.cpp:104-113)
+	if (tension) {
+		CK(cudaEventRecord(S->ev[8], stream));
 		RealT *curv = S->curv.ptr<RealT>(d);
 		if (!curv) { CKR(S->curv.alloc(d, sizeof(RealT))); curv = S->curv.ptr<RealT>(d); }
 		LAUNCH(S, "curvature", k_curvature<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, curv);
 		CKR(halo(S, d, curv, stream));
 		LAUNCH(S, "surface_tension", k_surface_tension<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)curv, crhos, vel, masks);
+		CK(cudaEventRecord(S->ev[9], stream));
 	}
 	{
 		const bool share = sizeof(CoefT) == sizeof(float);
@@ -910,6 +951,13 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		CKR(compact_tiles(S, H0, stream));
 		CKR(halo(S, d, S->wz.ptr<CoefT>(d), stream));
 		if (!share) CKR(halo(S, d, L0.wz, stream));
+		if (P.warm_start) { // a10: b -= A p_prev (macpressuresolver3.cpp:221-230); the first call finds p_prev = 0
+			if (!S->p_prev.base) CKR(S->p_prev.alloc(d, sizeof(VecT), S->arena()));
+			VecT *pp = S->p_prev.ptr<VecT>(d);
+			CKR(halo(S, d, pp, stream));
+			LAUNCH_TILES(S, "warm_rhs", (k_warm_rhs<VecT, CoefT>), cg_block(), H0.tiles_total, stream, d, L0.tiles, (const CoefT *)S->wx.ptr<CoefT>(d),
+			             (const CoefT *)S->wy.ptr<CoefT>(d), (const CoefT *)S->wz.ptr<CoefT>(d), (const CoefT *)S->dd.ptr<CoefT>(d), (const VecT *)pp, S->b.ptr<VecT>(d), rb, st);
+		}
 	}
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(S->ev[1], stream));
@@ -926,7 +974,7 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		LAUNCH(S, "sum_rows", k_sum_rows<VecT>, flat_blocks(d.ncell), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows, rb, st);
 	}
 	LAUNCH(S, "store_pressure", (k_store_pressure<RealT, VecT>), (unsigned)((d.ncell + 255) / 256), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows,
-	       (const CGState *)st, pres, static_cast<RealT *>(pressure_v), pressure_active);
+	       (const CGState *)st, pres, static_cast<RealT *>(pressure_v), pressure_active, P.warm_start ? S->p_prev.ptr<VecT>(d) : (VecT *)nullptr);
 	CKR(halo(S, d, pres, stream));
 	LAUNCH(S, "update_velocity", k_update_velocity<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)pres, careas, crhos, vel, masks);
 	CK(cudaEventRecord(S->ev[4], stream));
@@ -940,8 +988,12 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		cudaEventElapsedTime(&stats->ms_solve, S->ev[2], S->ev[3]);
 		cudaEventElapsedTime(&stats->ms_update, S->ev[3], S->ev[4]);
 		cudaEventElapsedTime(&stats->ms_total, S->ev[0], S->ev[4]);
+		if (tension) cudaEventElapsedTime(&stats->ms_surftension, S->ev[8], S->ev[9]);
+		int nt = 0;
+		if (cudaMemcpy(&nt, S->levels[0].tile_count.base, sizeof nt, cudaMemcpyDeviceToHost) == cudaSuccess) stats->active_tiles = (uint32_t)nt;
+		stats->total_tiles = (uint32_t)S->levels[0].tiles_total;
 	}
-	return SHKZ_B200_OK;
+	return comm_health(S);
 }
 
 typedef int (*project_fn)(shkz_b200_solver *, double, void *const[3], uint8_t *const[3], const void *, const void *, int, const shkz_b200_params &, void *,
@@ -1127,12 +1179,25 @@ int shkz_b200_project_device(shkz_b200_solver *S, double dt, void *const vel[3],
 	if (!fn) return fail(SHKZ_B200_ERR_ARG, "unsupported real/precision combination");
 	if (stats) memset(stats, 0, sizeof *stats);
 	S->launches = 0;
-	return fn(S, dt, vel, vel_active, solid, fluid, fluid_levelset, P, pressure, pressure_active, stats, static_cast<cudaStream_t>(cuda_stream));
+	const int rc = fn(S, dt, vel, vel_active, solid, fluid, fluid_levelset, P, pressure, pressure_active, stats, static_cast<cudaStream_t>(cuda_stream));
+	// a z-slab call that fails on this rank's host must not leave the other ranks' kernels spinning on planes that will never arrive
+	if (rc != SHKZ_B200_OK && rc != SHKZ_B200_ERR_COMM && !S->whole_grid && S->comm) S->comm->raise_abort();
+	return rc;
 }
+
+static int project_host_impl(shkz_b200_solver *S, double dt, void *const vel[3], uint8_t *const vel_active[3], const void *solid, const void *fluid,
+                             int fluid_levelset, const shkz_b200_params *params, void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats);
 
 int shkz_b200_project_host(shkz_b200_solver *S, double dt, void *const vel[3], uint8_t *const vel_active[3], const void *solid, const void *fluid,
                            int fluid_levelset, const shkz_b200_params *params, void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats) {
 	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	const int rc = project_host_impl(S, dt, vel, vel_active, solid, fluid, fluid_levelset, params, pressure, pressure_active, stats);
+	if (rc != SHKZ_B200_OK && rc != SHKZ_B200_ERR_COMM && !S->whole_grid && S->comm) S->comm->raise_abort(); // (see shkz_b200_project_device)
+	return rc;
+}
+
+static int project_host_impl(shkz_b200_solver *S, double dt, void *const vel[3], uint8_t *const vel_active[3], const void *solid, const void *fluid,
+                             int fluid_levelset, const shkz_b200_params *params, void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats) {
 	if (!vel || !vel_active || !fluid) return fail(SHKZ_B200_ERR_ARG, "vel / vel_active / fluid must not be NULL");
 	CKR(device_ready(S->device));
 	CK(cudaSetDevice(S->device));
@@ -1300,6 +1365,10 @@ int shkz_b200_debug_fetch(shkz_b200_solver *S, const char *name, void *dst, size
 }
 
 int shkz_b200_debug_vcycle(shkz_b200_solver *S, const shkz_b200_params *params, int legacy) {
+#ifndef SHKZ_B200_TEST_HOOKS
+	(void)params; (void)legacy;
+	return fail(SHKZ_B200_ERR_STATE, "shkz_b200_debug_vcycle is only built into libshkz_b200_testhooks.so (-DSHKZ_B200_TEST_HOOKS)%s", S ? "" : "");
+#else
 	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
 	if (!S->have_system || !S->have_hierarchy) return fail(SHKZ_B200_ERR_STATE, "debug_vcycle() needs a prior project() with the multigrid preconditioner");
 	shkz_b200_params P;
@@ -1331,6 +1400,7 @@ int shkz_b200_debug_vcycle(shkz_b200_solver *S, const shkz_b200_params *params, 
 	CK(cudaGetLastError());
 	S->debug_vcycle_result = z;
 	return SHKZ_B200_OK;
+#endif
 }
 
 int shkz_b200_slab_export(shkz_b200_solver *S, uint8_t ipc[SHKZ_B200_IPC_BYTES]) {

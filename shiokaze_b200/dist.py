@@ -86,7 +86,7 @@ def join_dense(parts: Sequence[dict], world: int) -> dict:
 # ---- one process per GPU ---------------------------------------------------------------------------------
 def export_blob(solver) -> bytes:
     buf = (C.c_uint8 * capi.IPC_BYTES)()
-    capi.check(capi.lib().shkz_b200_slab_export(solver._h, buf))
+    capi.check(solver._L.shkz_b200_slab_export(solver._h, buf), solver._L)
     return bytes(buf)
 
 
@@ -94,7 +94,7 @@ def connect_blobs(solver, rank: int, world: int, blobs: Sequence[bytes]):
     if len(blobs) != world or any(len(b) != capi.IPC_BYTES for b in blobs):
         raise ValueError("need one IPC blob of capi.IPC_BYTES bytes per rank")
     flat = (C.c_uint8 * (capi.IPC_BYTES * world)).from_buffer_copy(b"".join(blobs))
-    capi.check(capi.lib().shkz_b200_slab_connect(solver._h, int(rank), int(world), flat))
+    capi.check(solver._L.shkz_b200_slab_connect(solver._h, int(rank), int(world), flat), solver._L)
 
 
 def gather_blobs(blob: bytes, world: int) -> List[bytes]:
@@ -116,7 +116,7 @@ def connect(solver, rank: int, world: int):
 # ---- one process, several GPUs ---------------------------------------------------------------------------------
 def connect_local(solvers: Sequence):
     arr = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
-    capi.check(capi.lib().shkz_b200_slab_connect_local(arr, len(solvers)))
+    capi.check(solvers[0]._L.shkz_b200_slab_connect_local(arr, len(solvers)), solvers[0]._L)
 
 
 def run_per_slab(calls):

@@ -127,12 +127,14 @@ protected:
 		params.apply_rhs_correct = 0;
 		params.rhs_correct = 0.0;
 		if( m_param.gain && m_target_volume ) {
+			timer.tick(); console::dump( "Computing volume correction...");
 			double x = (m_current_volume-m_target_volume)/m_target_volume;
 			double y = m_y_prev + x*dt; m_y_prev = y;
 			double kp = m_param.gain * 2.3/(25.0*0.01);
 			double ki = kp*kp/16.0;
 			params.rhs_correct = -(kp*x+ki*y)/(x+1.0);
 			params.apply_rhs_correct = 1;
+			console::dump( "Done. Took %s\n", timer.stock("volume_correction").c_str()); // (the constant is added to the rows by the assembly kernel)
 			console::write(get_argument_name()+"_volume_correct_rhs", params.rhs_correct);
 		}
 		//
@@ -145,11 +147,19 @@ protected:
 		shkz_b200_stats stats;
 		if( shkz_b200_project_host(m_solver,dt,vel_ptr,act_ptr,have_solid ? solid_dense : nullptr,fluid_dense,
 				fluid_levelset,&params,pressure,pressure_active,&stats) != SHKZ_B200_OK ) fatal("shkz_b200_project_host");
-		console::write(get_argument_name()+"_number_projection_iteration", stats.iterations);
-		console::write(get_argument_name()+"_solid_fluid_fractions", stats.ms_assemble);
-		console::write(get_argument_name()+"_build_highres_linsystem", stats.ms_setup);
-		console::write(get_argument_name()+"_update_velocity", stats.ms_update);
-		console::dump( "Done. Took %d iterations, Reresid=%e. Took %s\n", stats.iterations, stats.reresid, timer.stock("linsolve").c_str());
+		// the reference's records (macpressuresolver3.cpp:82,114,201,215,236-237,269,271 through scoped_timer::stock -> "<Arg>_<name>", milliseconds), fed
+		// from the CUDA-event times of the phases that replace them: fractions + labelling + assembly are ONE fused phase here (ms_assemble; the surface-tension
+		// part of it is reported separately like the reference does), the multigrid hierarchy is this solver's "build" step, the MG-PCG loop its "linsolve"
+		const std::string arg = get_argument_name();
+		console::write(arg+"_number_projection_iteration", stats.iterations);
+		console::write(arg+"_solid_fluid_fractions", stats.ms_assemble-stats.ms_surftension);
+		if( surface_tension ) console::write(arg+"_surftension_force", stats.ms_surftension);
+		console::write(arg+"_build_highres_linsystem", stats.ms_setup);
+		console::write(arg+"_linsolve", stats.ms_solve);
+		console::write(arg+"_update_velocity", stats.ms_update);
+		console::write(arg+"_h2d", stats.ms_h2d);
+		console::write(arg+"_d2h", stats.ms_d2h);
+		console::dump( "Done. Took %d iterations, Reresid=%e. Took %s\n", stats.iterations, stats.reresid, timer.stock("gpu_call").c_str());
 		//
 		// Dense buffers -> host grids
 		timer.tick(); console::dump( "Scattering results...");
@@ -178,11 +188,8 @@ protected:
 		config.get_double("Gain",m_param.gain,"Rate for volume correction");
 		config.get_bool("WarmStart",warm_start,"Start from the solution of previous pressure");
 		config.set_default_bool("ReportProgress",false);
-		if( warm_start ) {
-			console::dump( "<Red>b200pressure3: WarmStart=Yes is not supported.<Default>\n" );
-			exit(-1);
-		}
 		shkz_b200_default_params(&m_cuda_param);
+		m_cuda_param.warm_start = warm_start; // the previous pressure lives on the device, per cell (shkz_b200.h)
 		m_cuda_param.second_order_fluid = second_order_fluid;
 		m_cuda_param.second_order_solid = second_order_solid;
 		// the children's flags, under the groups the reference uses (macutility3.cpp:408-409, pcg.cpp:39-44)

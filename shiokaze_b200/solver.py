@@ -31,12 +31,13 @@ class ProjectionResult:
 class MacPressureSolver3:
     """project(dt, velocity, solid, fluid, surface_tension) with the reference's configurable parameters.
 
-    Reference flags: SecondOrderAccurateFluid, SecondOrderAccurateSolid, Gain, WarmStart (not supported: see
-    DESIGN.md), EpsFluid, EpsSolid, Residual, MaxIterations. Additive flags: Precond ("mg"|"none"),
+    Reference flags: SecondOrderAccurateFluid, SecondOrderAccurateSolid, Gain, WarmStart, EpsFluid, EpsSolid,
+    Residual, MaxIterations. Additive flags: Precond ("mg"|"none"),
     Precision ("mixed"|"fp64"|"fp32"), MGPreSweeps, MGPostSweeps, MGCoarseSweeps, MGMinSize, CheckEvery.
     """
 
-    def __init__(self, shape: Sequence[int], dx: float, real: str = "f32", device: int = 0, zrange=None, **flags):
+    def __init__(self, shape: Sequence[int], dx: float, real: str = "f32", device: int = 0, zrange=None, test_hooks: bool = False, **flags):
+        self._L = capi.lib(test_hooks)   # test_hooks: the -DSHKZ_B200_TEST_HOOKS build (debug_vcycle); never used by the product path
         self.nx, self.ny, self.nz = (int(v) for v in shape)
         self.dx = float(dx)
         self.real = real
@@ -49,10 +50,13 @@ class MacPressureSolver3:
         self._target_volume = self._current_volume = self._y_prev = 0.0
         self.configure(**flags)
         h = C.c_void_p()
-        capi.check(capi.lib().shkz_b200_create_slab(self.nx, self.ny, self.nz, self.zrange[0], self.zrange[1], self.dx,
+        self._ck(self._L.shkz_b200_create_slab(self.nx, self.ny, self.nz, self.zrange[0], self.zrange[1], self.dx,
                                                      capi.REAL_F32 if real == "f32" else capi.REAL_F64, device, C.byref(h)))
         self._h = h
         self.last_rhs_correct = 0.0
+
+    def _ck(self, code):
+        capi.check(code, self._L)
 
     # -- reference interface ----------------------------------------------------------------------
     def configure(self, **flags):
@@ -61,9 +65,7 @@ class MacPressureSolver3:
             if key == "SecondOrderAccurateFluid": p.second_order_fluid = int(bool(value))
             elif key == "SecondOrderAccurateSolid": p.second_order_solid = int(bool(value))
             elif key == "Gain": self.gain = float(value)
-            elif key == "WarmStart":
-                if value:
-                    raise NotImplementedError("WarmStart=Yes is not supported (reference default is No)")
+            elif key == "WarmStart": p.warm_start = int(bool(value))
             elif key == "EpsFluid": p.eps_fluid = float(value)
             elif key == "EpsSolid": p.eps_solid = float(value)
             elif key == "Residual": p.residual = float(value)
@@ -130,7 +132,7 @@ class MacPressureSolver3:
         vp = (C.c_void_p * 3)(*[v.ctypes.data for v in velocity])
         ap = (C.c_void_p * 3)(*[a.ctypes.data for a in velocity_active])
         st = capi.Stats()
-        capi.check(capi.lib().shkz_b200_project_host(self._h, float(dt), vp, ap, solid.ctypes.data if solid is not None else None,
+        self._ck(self._L.shkz_b200_project_host(self._h, float(dt), vp, ap, solid.ctypes.data if solid is not None else None,
                                                      fluid.ctypes.data, int(bool(fluid_levelset)), C.byref(self.params),
                                                      pressure.ctypes.data, pact.ctypes.data, C.byref(st)))
         return pressure, pact, self._finish(st)
@@ -154,7 +156,7 @@ class MacPressureSolver3:
         vp = (C.c_void_p * 3)(*[v.data_ptr() for v in velocity])
         ap = (C.c_void_p * 3)(*[a.data_ptr() for a in velocity_active])
         st = capi.Stats()
-        capi.check(capi.lib().shkz_b200_project_device(self._h, float(dt), vp, ap, solid.data_ptr() if solid is not None else None,
+        self._ck(self._L.shkz_b200_project_device(self._h, float(dt), vp, ap, solid.data_ptr() if solid is not None else None,
                                                        fluid.data_ptr(), int(bool(fluid_levelset)), C.byref(self.params),
                                                        pressure.data_ptr() if pressure is not None else None,
                                                        pressure_active.data_ptr() if pressure_active is not None else None,
@@ -164,17 +166,17 @@ class MacPressureSolver3:
     def resolve(self, stream: int = 0) -> ProjectionResult:
         """Repeat only the linear solve of the last project() (same matrix and right-hand side)."""
         st = capi.Stats()
-        capi.check(capi.lib().shkz_b200_resolve(self._h, C.byref(self.params), C.byref(st), stream or None))
+        self._ck(self._L.shkz_b200_resolve(self._h, C.byref(self.params), C.byref(st), stream or None))
         return self._finish(st)
 
     # -- per-kernel timing ---------------------------------------------------------------------------
     def profile(self, on: bool = True):
-        capi.check(capi.lib().shkz_b200_profile_enable(self._h, int(on)))
+        self._ck(self._L.shkz_b200_profile_enable(self._h, int(on)))
 
     def profile_table(self) -> dict:
         """name -> (launches, total ms) accumulated since profile(True)."""
         out = {}
-        L = capi.lib()
+        L = self._L
         for i in range(L.shkz_b200_profile_count(self._h)):
             name = C.create_string_buffer(64)
             n, ms = C.c_uint64(), C.c_double()
@@ -185,20 +187,20 @@ class MacPressureSolver3:
     # -- test hook ----------------------------------------------------------------------------------
     def debug_fetch(self, name: str) -> np.ndarray:
         need = C.c_size_t()
-        capi.check(capi.lib().shkz_b200_debug_fetch(self._h, name.encode(), None, 0, C.byref(need)))
+        self._ck(self._L.shkz_b200_debug_fetch(self._h, name.encode(), None, 0, C.byref(need)))
         buf = np.empty(need.value, dtype=np.uint8)
-        capi.check(capi.lib().shkz_b200_debug_fetch(self._h, name.encode(), buf.ctypes.data, buf.nbytes, None))
+        self._ck(self._L.shkz_b200_debug_fetch(self._h, name.encode(), buf.ctypes.data, buf.nbytes, None))
         return buf
 
     def debug_vcycle(self, legacy=0) -> np.ndarray:
         """One V-cycle applied to the last right-hand side: 0 product kernels, 1 unfused validation kernels,
         2 product path with the scalar sweep kernel forced."""
-        capi.check(capi.lib().shkz_b200_debug_vcycle(self._h, C.byref(self.params), int(legacy)))
+        self._ck(self._L.shkz_b200_debug_vcycle(self._h, C.byref(self.params), int(legacy)))
         return self.debug_fetch("vcycle").view(np.float32).reshape(self.nzl, self.ny, self.nx).copy()
 
     def close(self):
         if getattr(self, "_h", None):
-            capi.lib().shkz_b200_destroy(self._h)
+            self._L.shkz_b200_destroy(self._h)
             self._h = None
 
     def __del__(self):

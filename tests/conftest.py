@@ -43,6 +43,72 @@ def load_golden(name, tag):
                 pressure_active=out["pressure_active"], iterations=int(out["iterations"]), reresid=float(out["reresid"]))
 
 
+# ---- fixtures at BASELINE sizes, generated from the unmodified reference build by make_golden.py --big ----------------
+def _big_cases():
+    from shiokaze_b200 import scenes
+    return {
+        "dambreak64": lambda: scenes.dambreak(64),               # configs[0]
+        "flip64": lambda: scenes.flip_splash(64),                # configs[3] geometry
+        "smoke64": lambda: scenes.smoke_plume(64),               # configs[1] geometry
+        "dambreak_solid128": lambda: scenes.dambreak(128, True), # configs[2] geometry
+        "smoke128": lambda: scenes.smoke_plume(128),
+    }
+
+
+class _Lazy(dict):
+    def __missing__(self, key):
+        self.update(_big_cases())
+        return dict.__getitem__(self, key)
+
+    def __iter__(self):
+        if not len(self):
+            self.update(_big_cases())
+        return dict.__iter__(self)
+
+
+BIG_CASES = _Lazy()
+BIG_NAMES = ["dambreak64", "flip64", "smoke64", "dambreak_solid128", "smoke128"]
+BIG_SAMPLE_CAP = 100_000
+
+
+def big_selection(mask):
+    """Flat indices of the sampled entries of a (nz, ny, nx) field: the entries where `mask` holds on every s-th z-plane,
+    s chosen so that about BIG_SAMPLE_CAP values remain (all of them when the mask is that small). Deterministic in the mask."""
+    m = np.asarray(mask).astype(bool)
+    total = int(m.sum())
+    s = max(1, -(-total // BIG_SAMPLE_CAP))
+    keep = np.zeros(m.shape[0], dtype=bool)
+    keep[s // 2::s] = True
+    return np.flatnonzero(m & keep[:, None, None])
+
+
+def load_big_golden(name, tag, scene):
+    """-> dict(act[3], pressure_active: complete bool arrays; vel[3], pressure: float32 samples at big_selection(...);
+    vel_sum[3], vel_sumsq[3], pressure_sumsq, n_rows, iterations, reresid)."""
+    z = np.load(os.path.join(GOLDEN, "big_" + name + ".npz"))
+    g = {k[len(tag) + 1:]: z[k] for k in z.files if k.startswith(tag + ".")}
+    shp = (scene.nz, scene.ny, scene.nx)
+    fshp = [a.shape for a in scene.vel_active]
+
+    def unpack(bits, shape):
+        return np.unpackbits(bits)[:int(np.prod(shape))].reshape(shape).astype(np.uint8)
+    return dict(act=[unpack(g[f"act{d}"], fshp[d]) for d in range(3)], pressure_active=unpack(g["pressure_active"], shp),
+                vel=[g[f"vel{d}"] for d in range(3)], pressure=g["pressure"],
+                vel_sum=[float(g[f"vel{d}_sum"]) for d in range(3)], vel_sumsq=[float(g[f"vel{d}_sumsq"]) for d in range(3)],
+                pressure_sumsq=float(g["pressure_sumsq"]), n_rows=int(g["n_rows"]), iterations=int(g["iterations"]), reresid=float(g["reresid"]))
+
+
+def big_compare(out_vel, out_act, out_pact, g, scene):
+    """(masks equal?, rel. L2 of the sampled velocities, rel. error of the whole-field sum of squares)."""
+    masks = all(np.array_equal(np.asarray(out_act[d]).astype(np.uint8), g["act"][d]) for d in range(3)) and \
+        np.array_equal(np.asarray(out_pact).astype(np.uint8), g["pressure_active"])
+    samples = [np.asarray(out_vel[d]).ravel()[big_selection(scene.vel_active[d])] for d in range(3)]
+    rel = rel_l2(samples, g["vel"])
+    ssq = sum(float((np.asarray(v, dtype=np.float64) ** 2).sum()) for v in out_vel)
+    gsq = sum(g["vel_sumsq"])
+    return masks, rel, abs(ssq - gsq) / gsq if gsq > 0 else abs(ssq)
+
+
 def load_accuracy_golden():
     with open(os.path.join(GOLDEN, "accuracytest3.json")) as f:
         return json.load(f)

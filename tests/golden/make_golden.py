@@ -1,7 +1,9 @@
 """Regenerates tests/golden/*.npz and accuracytest3.json from the UNMODIFIED reference build
 (oracle/_ref, made by `make -C oracle ref` from /root/reference). Run in the build container only:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                 the small scenes (complete dense outputs)
+    python tests/golden/make_golden.py --big [names]   BASELINE sizes: dam-break 64^3 (configs[0]), smoke 64^3 / 128^3,
+                                                       dam-break + solid 128^3, FLIP splash 64^3 (compact: big_*.npz)
 
 Every fixture is one project() call of the reference's macpressuresolver3 + pcg on a scene of
 shiokaze_b200.scenes (regenerated from the formula at test time, so only OUTPUTS are stored).
@@ -50,6 +52,55 @@ def run(name, real, residual):
     return out
 
 
+# ---- fixtures at BASELINE sizes (configs[0] and the 64^3 / 128^3 rungs of the others): compact storage ----------------
+# masks bit-packed (complete), velocity / pressure as float32 SAMPLES on whole z-planes of the input-active faces /
+# of the row set (conftest.big_selection: at most ~100 k values per array), plus float64 sum and sum of squares of every
+# complete field, so that a test sees both the local values and the whole field.
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import BIG_CASES, big_selection  # noqa: E402
+
+
+def run_big(name, real, residual, extra_flags=None, repeat=1):
+    sc = BIG_CASES[name]()
+    flags = {"Residual": residual}
+    flags.update(extra_flags or {})
+    r = refio.run_reference(sc, real, flags=flags, threads=os.cpu_count(), repeat=repeat)
+    out = {}
+    for d in range(3):
+        sel = big_selection(sc.vel_active[d])
+        v = r.vel[d]
+        out[f"vel{d}"] = v.ravel()[sel].astype(np.float32)
+        out[f"vel{d}_sum"] = np.float64(v.sum())
+        out[f"vel{d}_sumsq"] = np.float64((v * v).sum())
+        out[f"act{d}"] = np.packbits(r.vel_active[d].astype(bool))
+    rows = r.pressure_active.astype(bool)
+    out["pressure_active"] = np.packbits(rows)
+    out["pressure"] = r.pressure.ravel()[big_selection(rows)].astype(np.float32)
+    out["pressure_sumsq"] = np.float64((r.pressure * r.pressure).sum())
+    out["n_rows"] = np.int64(rows.sum())
+    out["iterations"] = np.int64(r.iterations)
+    out["reresid"] = np.float64(r.reresid)
+    return out
+
+
+def main_big(only=None):
+    assert refio.ref_available("f32") and refio.ref_available("f64")
+    for name in BIG_CASES:
+        if only and name not in only:
+            continue
+        blob = {}
+        for real, residual, tag in (("f32", 1e-4, "f32_default"), ("f32", 1e-10, "f32_tight"), ("f64", 1e-10, "f64_tight")):
+            for k, v in run_big(name, real, residual).items():
+                blob[f"{tag}.{k}"] = v
+        if name == "dambreak64":
+            # a10 warm start (macpressuresolver3.cpp:221-242): the SAME inputs projected twice with WarmStart=Yes, results of the second call
+            for k, v in run_big(name, "f32", 1e-4, {"WarmStart": "Yes"}, repeat=2).items():
+                blob[f"f32_warm2.{k}"] = v
+        np.savez_compressed(os.path.join(HERE, "big_" + name + ".npz"), **blob)
+        print(name, "iterations", {t: int(blob[t + ".iterations"]) for t in sorted({k.split(".")[0] for k in blob})},
+              "rows", int(blob["f32_tight.n_rows"]), flush=True)
+
+
 def main():
     assert refio.ref_available("f32") and refio.ref_available("f64")
     for name in CASES:
@@ -78,4 +129,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--big":
+        main_big(sys.argv[2:])
+    else:
+        main()

@@ -23,7 +23,20 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), name
     assert sorted(capi.EXPORTS) == names
-    assert L.shkz_b200_abi_version() == 1
+    assert L.shkz_b200_abi_version() == capi.ABI_VERSION
+
+
+def test_validation_kernels_ship_only_in_the_test_hook_library():
+    """kernels_legacy.cuh + shkz_b200_debug_vcycle are test code: the product library carries neither the kernels nor a working hook."""
+    prod = open(capi.LIB_PATH, "rb").read()
+    hooks = open(capi.HOOKS_LIB_PATH, "rb").read()
+    assert b"k_legacy_rbgs" not in prod and b"k_legacy_residual" not in prod
+    assert b"k_legacy_rbgs" in hooks
+    assert capi.lib().shkz_b200_debug_vcycle(None, None, 0) == capi.ERR_STATE          # compiled out
+    assert b"testhooks" in capi.lib().shkz_b200_last_error()
+    H = capi.lib(test_hooks=True)
+    assert H.shkz_b200_abi_version() == capi.ABI_VERSION
+    assert H.shkz_b200_debug_vcycle(None, None, 0) == capi.ERR_ARG                     # present: complains about the NULL solver
 
 
 def test_default_params_are_the_reference_defaults():
@@ -33,6 +46,7 @@ def test_default_params_are_the_reference_defaults():
     assert (p.eps_fluid, p.eps_solid) == (1e-2, 1e-2)                      # macutility3.cpp:419-420
     assert p.residual == 1e-4 and p.max_iterations == 30000                # pcg.cpp:76-77
     assert p.precond == capi.PRECOND_MG and p.precision == capi.PREC_MIXED
+    assert p.warm_start == 0                                               # macpressuresolver3.cpp:304
 
 
 def test_argument_errors_do_not_need_a_device():

@@ -63,7 +63,7 @@ def test_slab_projection_matches_whole_grid_and_oracle(worlds, kind, n):
 def test_slab_vcycle_equals_whole_grid_vcycle_bit_for_bit(worlds, precision):
     """Halo planes, half-updated boundary planes and the level structure reproduce the whole-grid V-cycle exactly."""
     sc = scenes.dambreak(64, True)
-    flags = dict(Precision=precision, Precond="mg", MaxIterations=1)
+    flags = dict(Precision=precision, Precond="mg", MaxIterations=1, test_hooks=True)   # debug_vcycle lives in the test-hook build of the library
     W = MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, **flags)
     W.project_scene(sc)
     whole = W.debug_vcycle(0)

@@ -19,8 +19,8 @@ F32_TOL = 1e-3   # north_star: fp32
 F64_TOL = 1e-5   # north_star: fp64
 
 
-def solver_for(sc, real="f32", **flags):
-    return MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, real=real, **flags)
+def solver_for(sc, real="f32", test_hooks=False, **flags):
+    return MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, real=real, test_hooks=test_hooks, **flags)
 
 
 def apply_case(S, kw):
@@ -319,7 +319,7 @@ def test_fused_vcycle_equals_unfused_vcycle_bit_for_bit(cuda_device, case, preci
     kind, n, pre, post = case
     sc = {"dambreak_solid": lambda: scenes.dambreak(n, True), "smoke": lambda: scenes.smoke_plume(n), "flip": lambda: scenes.flip_splash(n),
           "blobs": lambda: scenes.random_blobs(*n, seed=11)}[kind]()
-    S = solver_for(sc, Precision=precision, Precond="mg", MGPreSweeps=pre, MGPostSweeps=post, MaxIterations=1)
+    S = solver_for(sc, Precision=precision, Precond="mg", MGPreSweeps=pre, MGPostSweeps=post, MaxIterations=1, test_hooks=True)
     out = S.project_scene(sc)
     fused = S.debug_vcycle(legacy=0)
     scalar = S.debug_vcycle(legacy=2)

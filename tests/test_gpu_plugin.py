@@ -44,3 +44,36 @@ def test_module_reference_flags_and_volume_correction(cuda_device):
                                current_volume=1.05, target_volume=1.0)
     assert rel_l2(ours.vel, ref.vel) < 1e-5
     assert abs(ours.iterations - ref.iterations) <= max(3, 0.06 * ref.iterations)   # Precond=none is the reference's CG
+
+
+def test_module_warm_start_through_the_loader(cuda_device):
+    """WarmStart=Yes is a documented flag of the module this one replaces (macpressuresolver3.cpp:279, 221-242): the same host, the same
+    inputs projected twice (ref_driver repeat=2), reference module vs ours."""
+    if not have_plugin("f32"):
+        pytest.skip("oracle/_ref (reference build + module) was not shipped to this box")
+    sc = scenes.dambreak(32, True)
+    flags = {"WarmStart": "Yes"}
+    ref = refio.run_reference(sc, "f32", flags=flags, repeat=2)
+    ours = refio.run_reference(sc, "f32", flags={**flags, "Precond": "none", "Precision": "fp64"}, projection="b200pressure3", repeat=2)
+    assert np.array_equal(ours.pressure_active, ref.pressure_active)
+    for d in range(3):
+        assert np.array_equal(ours.vel_active[d], ref.vel_active[d])
+    assert rel_l2(ours.vel, ref.vel) < 1e-4
+    assert abs(ours.iterations - ref.iterations) <= max(3, 0.1 * ref.iterations)      # second call: the correction solve
+    cold = refio.run_reference(sc, "f32", projection="b200pressure3", flags={"Precond": "none", "Precision": "fp64"})
+    assert ours.iterations != cold.iterations or ref.iterations == cold.iterations
+
+
+def test_module_emits_the_reference_records(cuda_device):
+    """console::write names of macpressuresolver3.cpp (scoped_timer::stock -> "<Arg>_<name>"): the records a Shiokaze log analyser looks for."""
+    if not have_plugin("f32"):
+        pytest.skip("oracle/_ref (reference build + module) was not shipped to this box")
+    sc = scenes.dambreak(24)
+    sc.surface_tension = 0.05
+    ref = refio.run_reference(sc, "f32", current_volume=1.05, target_volume=1.0, records=True)
+    out = refio.run_reference(sc, "f32", projection="b200pressure3", current_volume=1.05, target_volume=1.0, records=True)
+    assert len(ref.records) >= 9
+    for name, values in ref.records.items():          # every record the reference module writes, under the same name
+        assert name in out.records and len(out.records[name]) == len(values), (name, sorted(out.records))
+    assert out.records["Projection_number_projection_iteration"][0] == out.iterations
+    assert out.records["Projection_volume_correct_rhs"] == ref.records["Projection_volume_correct_rhs"]
