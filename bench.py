@@ -2,21 +2,30 @@
 """bench.py — the driver's measurement contract for the pressure-projection hot path.
 
     python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W    the reference's CPU implementation, bounded sample
+    python bench.py --impl reference --steps K --warmup W    the reference's own CPU implementation, measured (never modelled)
 
-A "step" is ONE project() call — fractions, coefficient assembly, multigrid hierarchy, MG-preconditioned CG
-to the reference's default tolerance (Residual=1e-4 relative inf-norm), pressure scatter, velocity update —
-on the workload BASELINE.json quotes the metric on: configs[1], the macsmoke3 buoyant plume on a 256^3
-all-fluid Neumann box (16.8 M unknowns). `value` is grid cells projected per second with the inputs
-resident in HBM (restored from pristine device copies inside the timed region), `e2e` is the same through
-the host-buffer C-ABI call a Shiokaze plugin makes (pinned host buffers, H2D and D2H inside the timed region).
-For N > 1 every rank owns a 256x256x256 z-slab of a 256x256x(256 N) box (weak scaling, the default); with
-`--scaling strong` the n^3 grid itself is cut into N z-slabs (configs[3] flip_splash 512^3 over 1/2/4 GPUs and
-configs[4] liquid_box 1024^3 over 2/4/8 GPUs are quoted that way).
+A "step" is ONE project() call — fractions, coefficient assembly, multigrid hierarchy, MG-preconditioned CG to the
+reference's default tolerance (Residual=1e-4 relative inf-norm), pressure scatter, velocity update. The default workload is
+the north-star target, BASELINE.json configs[2]: macliquid3 dam-break with a solid obstacle on 512^3 (level-set free surface,
+solid volume fractions, 18.0 M unknowns in 13 % of the box). `value` is grid cells projected per second with the inputs
+resident in HBM (restored from pristine device copies inside the timed region); `e2e` is the same through the host-buffer
+C-ABI call a Shiokaze module makes (pinned host buffers, H2D and D2H inside the timed region). At N=1 the line also carries
+`sub_records.smoke_plume_256` (configs[1], the all-fluid Neumann box the round-1 line was quoted on).
+
+N > 1 (weak scaling, the default): every rank owns one 512^3 copy of the scene, stacked in z into a 512x512x(512 N) box.
+`--scaling strong` cuts the n^3 grid itself into N z-slabs (configs[3] flip_splash 512^3 over 1/2/4 GPUs, configs[4] liquid_box
+1024^3 over 2/4/8 GPUs); the default N=8 / N=2,4 lines also carry those as `strong` sub-records. Before timing, every multi-GPU
+run projects two small grids both ways — cut into N slabs and whole on one GPU — and reports the agreement as `parity_vs_1gpu`.
+
+The reference arm runs the UNMODIFIED reference build (oracle/_ref; the oracle port only where that was never built) through
+its own module loader on the SAME scene family at the largest size whose full solve fits the time budget (128^3: its solve
+phase is single-threaded and its iteration count grows with N, so 512^3 would take hours). Every number it prints was
+measured in that run; nothing is scaled. `config.grid` states the grid it ran.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -32,11 +41,14 @@ import numpy as np  # noqa: E402
 
 METRIC = "projection_throughput"
 UNIT = "Mcells/s"
-
-# plain-CG iteration counts of the reference at full size (Residual=1e-4). The reference's "pcg" is plain CG
-# (pcg_solver.h:383) and our fp64 Precond=none path tracks it iteration for iteration (tests/test_gpu_parity.py);
-# the 256^3 entry was also confirmed by a full run of the unmodified reference build (measurement).
-REFERENCE_ITERATIONS = {("smoke_plume", 256): 888}
+REFERENCE_N = 128        # grid of the reference arm / cpu_baseline leg: the largest full solve of the scene family that takes seconds
+WORKLOAD_TEXT = {
+    "dambreak_solid": "macliquid3 dam-break + solid obstacle, level-set free surface and solid fractions (BASELINE configs[2])",
+    "dambreak": "macliquid3 dam-break, level-set free surface (BASELINE configs[0] geometry)",
+    "smoke_plume": "macsmoke3 buoyant plume, all-fluid Neumann box (BASELINE configs[1])",
+    "flip_splash": "FLIP liquid splash, rasterised noisy velocity, shell container (BASELINE configs[3])",
+    "liquid_box": "synthetic half-filled liquid box, hash-noise velocity (BASELINE configs[4])",
+}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -98,9 +110,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, levels_rows, precond: str = "mg", sweeps=(2, 2)):
-    """Algorithmic (minimum necessary) bytes one launch of `kernel` moves, counted on unknown rows
-    (DESIGN.md 'Kernels and their rooflines'). V = CG vector bytes, C = operator coefficient bytes, MG is fp32."""
+def algorithmic_bytes_per_launch(kernel: str, n_rows: float, precision: str, precond: str = "mg"):
+    """Algorithmic (minimum necessary) bytes one launch of `kernel` moves, counted on unknown rows (DESIGN.md sections 3-4).
+    V = CG vector bytes, C = operator coefficient bytes, multigrid is fp32; level l holds n_rows / 8^l rows."""
     V = 4 if precision == "fp32" else 8
     Cc = 8 if precision == "fp64" else 4
     mg = precond == "mg"
@@ -110,14 +122,14 @@ def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, level
     lvl = lvl[:len(lvl) - len(variant)] if variant else lvl
     if lvl and not lvl.isdigit():
         return None                           # gathered coarse levels of a z-slab run ("@g0", ...): tiny, not modelled
-    n = levels_rows[int(lvl)] if lvl else n_rows
-    pre, post = max(1, sweeps[0]), max(0, sweeps[1])
+    n = n_rows / (8 ** int(lvl)) if lvl else n_rows
     # one launch = one FULL red-black sweep: 4 coefficient arrays + b + x_old read, x_new written (fp32);
     # the first pre-sweep does not read x_old, the first post-sweep also reads the coarse correction (1/8 value per cell)
     sweep_bytes = 24.0 if "z" in variant else (28.5 if "p" in variant else 28.0)
     per_row = {
         "cg_init": 4 * V + b0,                # read b ; write x r s (+ b0)
         "spmv_dot": 2 * V + 4 * Cc,           # read s, wx wy wz dd ; write q (s.q fused)
+        "xpay_spmv_dot": (3 * V + 4 + 4 * Cc) if mg else (4 * V + 4 * Cc),   # read z s, wx wy wz dd ; write s q (s = z + beta s fused into the product)
         "axpy2_norm": 6 * V + b0,             # read s q x r ; write x r (+ b0) (norms fused)
         "xpay": (2 * V + 4) if mg else 3 * V, # read z s ; write s
         "dot_rr": V,
@@ -130,7 +142,7 @@ def algorithmic_bytes_per_launch(kernel: str, n_rows: int, precision: str, level
 
 
 def base_tag(k):
-    """"sweep@0p" -> "sweep@0": the variant letters of a profiler tag (z: x_old = 0, p: coarse correction folded in, d: z.r folded in) dropped."""
+    """"sweep@0p" -> "sweep@0": the variant letters of a profiler tag dropped."""
     name, _, lvl = k.partition("@")
     return name + ("@" + lvl.rstrip("zpd") if lvl else "")
 
@@ -138,7 +150,7 @@ def base_tag(k):
 def group_kernels(table, ab):
     """Profiler table {tag: (launches, total ms)} -> {kernel function: launches, ms, algorithmic bytes, variants}. The dominant kernel is the
     kernel FUNCTION with the largest summed time: the sweep variants of one level are template instances of the same k_sweep_tma and count
-    together, each launch with the algorithmic bytes of its own variant (ab(tag) = bytes per launch, None for kernels outside the byte model)."""
+    together, each launch with the algorithmic bytes of its own variant."""
     groups = {}
     for k, (c, t) in table.items():
         if ab(k):
@@ -148,51 +160,82 @@ def group_kernels(table, ab):
     return groups
 
 
+def kernel_source_hash():
+    """Identity of the kernel sources: profiles/traffic.json (ncu DRAM bytes per unknown and launch) is only quoted while it was
+    captured from THESE sources — a stale capture reads as null, never as a number."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "shiokaze_b200", "csrc")
+    for fn in sorted(os.listdir(d)):
+        if fn.endswith((".cuh", ".cu", ".h")):
+            with open(os.path.join(d, fn), "rb") as f:
+                h.update(fn.encode()); h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(groups, dom, rank_rows):
+    """DRAM bytes per launch of the dominant kernel from the ncu --set full capture of this round (tools/ncu_traffic.py writes the table)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+    except Exception:
+        return None, "no profiles/traffic.json"
+    meta = tj.get("_meta", {})
+    if meta.get("kernel_source_hash") != kernel_source_hash():
+        return None, f"profiles/traffic.json is from other kernel sources (set {meta.get('set')}): not quoted"
+    acc, cnt = 0.0, 0
+    for k, v in groups[dom]["variants"].items():
+        ent = tj.get(k) or tj.get(base_tag(k))
+        if not ent:
+            return None, f"no ncu capture of {k} in set {meta.get('set')}"
+        lvl = base_tag(k).partition("@")[2]
+        acc += ent["bytes_per_row"] * rank_rows / (8 ** int(lvl or 0)) * v["launches"]
+        cnt += v["launches"]
+    return acc / cnt, f"ncu --set full, set {meta.get('set')} ({meta.get('workload')}), dram__bytes_read.sum + dram__bytes_write.sum per unknown x this run's unknowns"
+
+
 def build_scene(workload, n, zrange=None):
     from shiokaze_b200 import scenes
     return scenes.BENCH_SCENES[workload](n, zrange=zrange) if zrange else scenes.BENCH_SCENES[workload](n)
 
 
-# ------------------------------------------------------------------------------------------------------
-def reference_sample(workload, n, budget_s, threads):
-    """One bounded sample of the reference's CPU implementation of the path, scaled to the full workload.
+def workload_string(workload, n, mode, residual):
+    return (f"{workload} {n}^3 {mode} ({WORKLOAD_TEXT.get(workload, workload)}), one project() call: fractions + assembly + solve to "
+            f"Residual={residual:g} + velocity update")
 
-    The reference cannot finish the full workload in minutes (256^3: ~16 min, one core in the solve), so a step
-    runs the unmodified reference build (oracle/_ref) on a thin slab of the same scene — n x n x nzs cells around
-    the plume — twice: MaxIterations=0 (every fixed cost: fractions, RCMatrix assembly, the SparseMatrix copy and
-    the dead MIC(0) factorisation) and MaxIterations=m (adds m CG iterations). Cost per cell and per
-    cell-iteration are then scaled to n^3 cells and the reference's full iteration count."""
+
+# ------------------------------------------------------------------------------------------------------
+_REF_SCENES = {}
+
+
+def reference_run(workload, threads, residual):
+    """ONE full project() of the reference's CPU implementation on the `workload` scene at REFERENCE_N^3: the unmodified reference build
+    through its own module loader (oracle/_ref/f32/ref_driver), or — only where that was never built — the dense C port of the same
+    algorithm. Returns measured quantities only."""
     from oracle import refio
-    from shiokaze_b200 import scenes
-    nzs = 8 if budget_s < 20 else 16
-    m = 6
-    z0 = n // 2 - nzs // 2
-    slab = build_scene(workload, n, zrange=(z0, z0 + nzs))
-    sc = scenes.standalone(slab)
-    t0 = time.time()
+    n = REFERENCE_N
+    sc = _REF_SCENES.get((workload, n))
+    if sc is None:
+        sc = _REF_SCENES[(workload, n)] = build_scene(workload, n)
     kind = "reference" if refio.ref_available("f32") else "port"
+    t0 = time.perf_counter()
     if kind == "reference":
-        r0 = refio.run_reference(sc, "f32", flags={"MaxIterations": 0}, threads=threads)
-        r1 = refio.run_reference(sc, "f32", flags={"MaxIterations": m}, threads=threads)
-        fixed_ms = r0.phase_ms.get("projection", r0.ms_project)
-        iter_ms = max(r1.phase_ms.get("linsolve", 0.0) - r0.phase_ms.get("linsolve", 0.0), 1e-9) / m
-        cores = threads
-    else:  # the dense C port of the same algorithm (single thread)
+        r = refio.run_reference(sc, "f32", flags={"Residual": residual}, threads=threads)
+        ms, iters, phases, cores = r.ms_project, r.iterations, r.phase_ms, threads
+    else:
         from oracle import dense_oracle
-        t = time.time(); dense_oracle.project(sc, max_iterations=0); fixed_ms = (time.time() - t) * 1e3
-        t = time.time(); dense_oracle.project(sc, max_iterations=m); iter_ms = max((time.time() - t) * 1e3 - fixed_ms, 1e-9) / m
-        cores = 1
-    scale = n / float(nzs)
-    iters_full = REFERENCE_ITERATIONS.get((workload, n), int(round(888 * n / 256.0)))
-    full_ms = scale * (fixed_ms + iters_full * iter_ms)
-    cells = float(n) ** 3
-    return {
-        "ms_per_solve": full_ms, "value": cells / (full_ms * 1e-3) / 1e6, "kind": kind, "cores": cores,
-        "sample": (f"{workload} {n}x{n}x{nzs} slab of the {n}^3 scene through {'the unmodified reference build (oracle/_ref)' if kind == 'reference' else 'the dense C port (oracle/dense_oracle.c)'}: "
-                   f"fixed cost {fixed_ms:.0f} ms + {iter_ms:.1f} ms per CG iteration on the slab (solve phase is single-threaded in the reference), "
-                   f"scaled x{scale:.0f} cells and to the reference's {iters_full} iterations at {n}^3"),
-        "wall_s": time.time() - t0,
-    }
+        t = time.perf_counter()
+        o = dense_oracle.project(sc, residual=residual)
+        ms, iters, phases, cores = (time.perf_counter() - t) * 1e3, o.iterations, {}, 1
+    return {"ms": ms, "iterations": iters, "phase_ms": phases, "kind": kind, "cores": cores, "n": n, "wall_s": time.perf_counter() - t0,
+            "cells": float(n) ** 3}
+
+
+def reference_sample_text(workload, r, target_n):
+    src = "the unmodified reference build (oracle/_ref, Projection=macpressuresolver3 LinSolver=pcg)" if r["kind"] == "reference" else "the dense C port (oracle/dense_oracle.c)"
+    ph = ", ".join(f"{k} {v:.0f}" for k, v in r["phase_ms"].items())
+    return (f"{workload} {r['n']}^3 — the same scene family as the {target_n}^3 workload at the largest size whose full solve takes seconds — one complete project() "
+            f"through {src}: {r['ms']:.0f} ms, {r['iterations']} CG iterations (phases, ms: {ph}); the solve phase is single-threaded in the reference and its "
+            f"iteration count grows with N, so its throughput at {target_n}^3 is lower than this figure, which is measured, not extrapolated")
 
 
 def run_reference_arm(args):
@@ -200,215 +243,316 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    budget = max(8.0, 150.0 / max(1, args.steps + args.warmup))
     for _ in range(args.warmup):
-        reference_sample(args.workload, args.n, budget, threads)
-    samples = [reference_sample(args.workload, args.n, budget, threads) for _ in range(args.steps)]
-    ms = float(np.mean([s["ms_per_solve"] for s in samples]))
-    copies = 1 if args.scaling == "strong" else args.gpus
-    cells = float(args.n) ** 3 * copies
-    value = cells / (ms * copies * 1e-3) / 1e6  # the reference has no multi-GPU path: N slabs take N times as long
+        reference_run(args.workload, threads, args.residual)
+    t0 = time.perf_counter()
+    runs = [reference_run(args.workload, threads, args.residual) for _ in range(args.steps)]
+    timed_s = time.perf_counter() - t0
+    ms = float(np.mean([r["ms"] for r in runs]))
+    value = runs[0]["cells"] / (ms * 1e-3) / 1e6
+    n = runs[0]["n"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms * copies, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, "cpu"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": samples[0]["cores"], "kind": samples[0]["kind"], "sample": samples[0]["sample"]},
+        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_string(args.workload, n, "on the host CPU", args.residual), "grid": [n, n, n], "sample_of": [args.n] * 3,
+                   "precision": "fp64 matrix and vectors (FLOAT_TYPE=double), Real=float grids", "precond": "pcg (MIC(0), numerically plain CG: pcg_solver.h:383)",
+                   "residual": args.residual, "where": "cpu", "threads": threads,
+                   "note": f"the reference has no GPU and no multi-GPU path; every step is one full reference project() at {n}^3, nothing is scaled to {args.n}^3"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": runs[0]["cores"], "kind": runs[0]["kind"], "sample": reference_sample_text(args.workload, runs[0], args.n),
+                         "iterations": runs[0]["iterations"], "phase_ms": runs[0]["phase_ms"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "timed_region_s": timed_s,
     }
     print(json.dumps(line))
     return 0
 
 
-def config_dict(args, where):
-    strong = args.scaling == "strong"
-    nzg = args.n if strong else args.n * args.gpus
-    return {"workload": f"{args.workload} {args.n}^3 {'cut into z-slabs' if strong else 'per GPU'} ({'macsmoke3 buoyant plume, all-fluid Neumann box' if args.workload == 'smoke_plume' else args.workload}), "
-                        f"one project() call: assembly + MG-PCG solve to Residual={args.residual:g} + velocity update",
-            "grid": [args.n, args.n, nzg], "slab_per_gpu": [args.n, args.n, nzg // args.gpus], "parallelism": f"z-slab x{args.gpus}",
-            "precision": args.precision, "precond": args.precond, "mg_sweeps": [args.pre, args.post], "residual": args.residual,
-            "l2_policy": "inputs (318 MB per step) and solver working set (>1 GB) exceed the 126 MB L2; no explicit flush",
-            "where": where}
-
-
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from shiokaze_b200 import MacPressureSolver3, capi
+class Harness:
+    """One slab (or whole-grid) solver with pristine device copies of its inputs; PyTorch is only the allocator."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
-    if capi.lib().shkz_b200_device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: libshkz_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, torch, dev, sc, nzg, zr, flags, local, connect=None):
+        from shiokaze_b200 import MacPressureSolver3
+        self.torch, self.sc, self.dev = torch, sc, dev
+        self.S = MacPressureSolver3((sc.nx, sc.ny, nzg), sc.dx, device=local, zrange=zr, **flags)
+        if connect:
+            connect(self.S)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.vel0 = [t(v) for v in sc.vel]
+        self.act0 = [t(a) for a in sc.vel_active]
+        self.fluid = t(sc.fluid)
+        self.solid = t(sc.solid) if sc.solid is not None else None
+        self.vel = [torch.empty_like(v) for v in self.vel0]
+        self.act = [torch.empty_like(a) for a in self.act0]
+        self.pres = torch.zeros(sc.fluid.shape, dtype=torch.float32, device=dev)
+        self.pact = torch.zeros(sc.fluid.shape, dtype=torch.uint8, device=dev)
 
-    n = args.n
-    strong = args.scaling == "strong"
-    if strong and n % world:
-        raise SystemExit(f"--scaling strong: n={n} is not divisible by {world} slabs")
-    nzg = n if strong else n * world
-    nzl = nzg // world
-    zr = (rank * nzl, (rank + 1) * nzl)
-    if world > 1:
-        from shiokaze_b200 import dist as sdist
-        sc = sdist.slab_scene(args.workload, n, nzg, zr)
-    else:
-        sc = build_scene(args.workload, n)
-    flags = dict(Precision=args.precision, Precond=args.precond, Residual=args.residual, MGPreSweeps=args.pre, MGPostSweeps=args.post,
-                 CheckEvery=args.check_every)
-    S = MacPressureSolver3((sc.nx, sc.ny, nzg), sc.dx, device=local, zrange=zr, **flags)
-    if world > 1:
-        sdist.connect(S, rank, world)
-
-    # pristine device copies + working set (PyTorch is only the allocator here)
-    def dev_t(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    vel0 = [dev_t(v) for v in sc.vel]
-    act0 = [dev_t(a) for a in sc.vel_active]
-    fluid = dev_t(sc.fluid)
-    solid = dev_t(sc.solid) if sc.solid is not None else None
-    vel = [torch.empty_like(v) for v in vel0]
-    act = [torch.empty_like(a) for a in act0]
-    pres = torch.zeros(sc.fluid.shape, dtype=torch.float32, device=dev)
-    pact = torch.zeros(sc.fluid.shape, dtype=torch.uint8, device=dev)
-
-    def step():
+    def step(self):
         for d in range(3):
-            vel[d].copy_(vel0[d]); act[d].copy_(act0[d])
-        return S.project_device(sc.dt, vel, act, solid, fluid, sc.fluid_levelset, pres, pact)
+            self.vel[d].copy_(self.vel0[d]); self.act[d].copy_(self.act0[d])
+        return self.S.project_device(self.sc.dt, self.vel, self.act, self.solid, self.fluid, self.sc.fluid_levelset, self.pres, self.pact)
 
+    def host_io_bytes(self):
+        sc = self.sc
+        h2d = sum(v.nbytes for v in sc.vel) + sum(a.nbytes for a in sc.vel_active) + sc.fluid.nbytes + (sc.solid.nbytes if sc.solid is not None else 0)
+        d2h = sum(v.nbytes for v in sc.vel) + sum(a.nbytes for a in sc.vel_active) + sc.fluid.nbytes + sc.fluid.size
+        return h2d, d2h
+
+    def close(self):
+        self.S.close()
+
+
+def timed_steps(torch, dist, H, steps, warmup, world, dev, sampler=None):
+    """W untimed + K timed project() calls; barrier + synchronise on both sides, CUDA events, max over ranks."""
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 0)):
-        res = step()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    res = None
+    for _ in range(max(warmup, 0)):
+        res = H.step()
+    if sampler:
         sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches, iters = 0, []
     e0.record()
-    for _ in range(args.steps):
-        res = step()
+    for _ in range(steps):
+        res = H.step()
         launches += res.stats["kernel_launches"] + 6  # + the six restore copies
         iters.append(res.iterations)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    cells_global = float(n) * n * nzg
-    value = cells_global / (ms_step * 1e-3) / 1e6
-    n_rows = res.stats["n_rows_global"] if world > 1 else res.n_rows
-    phase = {k: res.stats[k] for k in ("ms_assemble", "ms_setup", "ms_solve", "ms_update")}
+    return ms_total / steps, res, launches, iters, clocks
 
-    # ---- end to end through the host-buffer C-ABI (what the Shiokaze plugin calls), pinned host memory ----
+
+def e2e_steps(torch, dist, H, steps, warmup, world):
+    """The same step through shkz_b200_project_host: pinned host buffers in, pinned host buffers out, wall clock around the call
+    (the call returns after its last device-to-host copy), max over ranks."""
+    sc = H.sc
+
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.from_numpy(np.zeros(1, a.dtype)).dtype, pin_memory=True)
         t.numpy()[...] = a
         return t
-    h2d = sum(v.nbytes for v in sc.vel) + sum(a.nbytes for a in sc.vel_active) + sc.fluid.nbytes + (sc.solid.nbytes if sc.solid is not None else 0)
-    d2h = sum(v.nbytes for v in sc.vel) + sum(a.nbytes for a in sc.vel_active) + sc.fluid.nbytes + sc.fluid.size
-    e2e_s = 0.0
-    e2e_steps = args.steps if world == 1 else 0   # slab e2e goes through the same call; measured on one GPU
-    if e2e_steps:
-        hv0 = [np.ascontiguousarray(v) for v in sc.vel]
-        ha0 = [np.ascontiguousarray(a) for a in sc.vel_active]
-        hv = [pinned(v) for v in hv0]
-        ha = [pinned(a) for a in ha0]
-        hfluid = pinned(sc.fluid)
-        hsolid = pinned(sc.solid) if sc.solid is not None else None
-        hpres = pinned(np.zeros(sc.fluid.shape, dtype=np.float32))
-        hpact = pinned(np.zeros(sc.fluid.shape, dtype=np.uint8))
-        for it in range(min(2, args.warmup) + e2e_steps):
-            for d in range(3):
-                hv[d].numpy()[...] = hv0[d]; ha[d].numpy()[...] = ha0[d]
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            _, _, e2e_res = S.project(sc.dt, [t.numpy() for t in hv], [t.numpy() for t in ha], hsolid.numpy() if hsolid is not None else None,
-                                      hfluid.numpy(), sc.fluid_levelset, pressure_out=hpres.numpy(), pressure_active_out=hpact.numpy())
-            t1 = time.perf_counter()
-            if it >= min(2, args.warmup):
-                e2e_s += t1 - t0
-        del hv, ha, hfluid, hsolid, hpres, hpact
-    e2e_value = (cells_global * e2e_steps / e2e_s / 1e6) if e2e_s > 0 else None
-
-    # ---- roofline of the dominant kernel: CUDA events around every launch of one extra solve ----
-    roofline = None
-    table = {}
-    if rank == 0 or world > 1:
-        S.profile(True)
+    hv0 = [np.ascontiguousarray(v) for v in sc.vel]
+    ha0 = [np.ascontiguousarray(a) for a in sc.vel_active]
+    hv, ha = [pinned(v) for v in hv0], [pinned(a) for a in ha0]
+    hfluid = pinned(sc.fluid)
+    hsolid = pinned(sc.solid) if sc.solid is not None else None
+    hpres = pinned(np.zeros(sc.fluid.shape, dtype=np.float32))
+    hpact = pinned(np.zeros(sc.fluid.shape, dtype=np.uint8))
+    total, res = 0.0, None
+    w = min(2, warmup)
+    for it in range(w + steps):
         for d in range(3):
-            vel[d].copy_(vel0[d]); act[d].copy_(act0[d])
-        S.project_device(sc.dt, vel, act, solid, fluid, sc.fluid_levelset, pres, pact)
-        table = S.profile_table()
-        S.profile(False)
-    if rank == 0 and table:
-        peak, how = measured_peak()
-        levels_rows = [n_rows / (8 ** l) for l in range(16)]
-        rank_rows = res.n_rows / world        # a slab solver reports the global row count; kernels are timed on rank 0's slab
-        ab = lambda k: algorithmic_bytes_per_launch(k, rank_rows, args.precision, [rank_rows / (8 ** l) for l in range(16)], args.precond, (args.pre, args.post))
-        groups = group_kernels(table, ab)
-        dom = max(groups, key=lambda k: groups[k]["ms"])
-        cnt, tot = groups[dom]["launches"], groups[dom]["ms"]
-        per_launch = groups[dom]["bytes"] / cnt
-        achieved = per_launch / (tot / cnt * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tj = json.load(f)
-            acc = 0.0
-            for k, v in groups[dom]["variants"].items():
-                ent = tj.get(k) or tj.get(base_tag(k))        # a variant without its own capture: the plain kernel of that level
-                lvl = int(base_tag(k).split("@")[1]) if "@" in k else 0
-                acc += ent["bytes_per_row"] * rank_rows / (8 ** lvl) * v["launches"]
-            traffic = acc / cnt
-        except Exception:
-            traffic = None
-        total_profiled = sum(v[1] for v in table.values())
-        alg_total = sum((ab(k) or 0) * v[0] for k, v in table.items())
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": how, "launches": cnt, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_launch": per_launch,
-                    "share_of_step": tot / total_profiled if total_profiled else None, "variants": groups[dom]["variants"],
-                    "solve_whole": {"algorithmic_GB": alg_total / 1e9, "ms": res.stats["ms_solve"], "achieved": alg_total / 1e9 / (res.stats["ms_solve"] * 1e-3),
-                                    "frac": alg_total / 1e9 / (res.stats["ms_solve"] * 1e-3) / peak},
-                    "by_kernel_ms": {k: round(v[1], 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])[:12]}}
+            hv[d].numpy()[...] = hv0[d]; ha[d].numpy()[...] = ha0[d]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        _, _, res = H.S.project(sc.dt, [t.numpy() for t in hv], [t.numpy() for t in ha], hsolid.numpy() if hsolid is not None else None,
+                                hfluid.numpy(), sc.fluid_levelset, pressure_out=hpres.numpy(), pressure_active_out=hpact.numpy())
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=H.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        if it >= w:
+            total += dt
+    return total / steps, res
+
+
+def profile_one_step(H):
+    H.S.profile(True)
+    res = H.step()
+    table = H.S.profile_table()
+    H.S.profile(False)
+    return table, res
+
+
+def roofline_of(table, res, rank_rows, precision, precond):
+    peak, how = measured_peak()
+    ab = lambda k: algorithmic_bytes_per_launch(k, rank_rows, precision, precond)
+    groups = group_kernels(table, ab)
+    if not groups:
+        return None
+    dom = max(groups, key=lambda k: groups[k]["ms"])
+    cnt, tot = groups[dom]["launches"], groups[dom]["ms"]
+    per_launch = groups[dom]["bytes"] / cnt
+    achieved = per_launch / (tot / cnt * 1e-3) / 1e9
+    traffic, traffic_source = ncu_traffic(groups, dom, rank_rows)
+    total_profiled = sum(v[1] for v in table.values())
+    alg_total = sum((ab(k) or 0) * v[0] for k, v in table.items())
+    ms_solve = res.stats["ms_solve"]
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_source, "peak_source": how, "launches": cnt, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_launch": per_launch,
+            "share_of_step": tot / total_profiled if total_profiled else None, "variants": groups[dom]["variants"],
+            "solve_whole": {"algorithmic_GB": alg_total / 1e9, "ms": ms_solve, "achieved": alg_total / 1e9 / (ms_solve * 1e-3),
+                            "frac": alg_total / 1e9 / (ms_solve * 1e-3) / peak,
+                            "what": "every solve kernel of one project(): algorithmic bytes (counted on unknown rows) / CUDA-event time of the solve phase / peak"},
+            "active_tiles": [res.stats.get("active_tiles"), res.stats.get("total_tiles")],
+            "by_kernel_ms": {k: round(v[1], 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])[:16]}}
+
+
+def solve_record(res, n_rows, iters):
+    phase = {k: res.stats[k] for k in ("ms_assemble", "ms_setup", "ms_solve", "ms_update")}
+    return {"iterations": iters[-1], "reresid": res.reresid, "converged": res.converged, "n_rows": int(n_rows),
+            "cell_iters_per_s": n_rows * iters[-1] / (phase["ms_solve"] * 1e-3) if phase["ms_solve"] > 0 else None, **phase}
+
+
+def parity_vs_1gpu(torch, dist, sdist, rank, world, local):
+    """Before timing a multi-GPU run: two small global grids projected cut into `world` slabs AND whole on this rank's own GPU (fp64, Residual=1e-10).
+    Every rank compares its slab of the outputs; the line carries the worst rank. Masks must be equal, velocity within 1e-6 rel. L2."""
+    from shiokaze_b200 import MacPressureSolver3, scenes
+    out = {}
+    ok_all = True
+    for name, make in (("dambreak_solid_64", lambda: scenes.dambreak(64, True)), ("smoke_plume_64", lambda: scenes.smoke_plume(64))):
+        sc = make()
+        flags = dict(Precision="fp64", Precond="mg", Residual=1e-10)
+        W = MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, device=local, **flags)
+        whole = W.project_scene(sc)
+        W.close()
+        k0, k1 = sdist.slab_range(sc.nz, rank, world)
+        part = sdist.split_dense(sc, world)[rank]
+        S = MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, device=local, zrange=(k0, k1), **flags)
+        sdist.connect(S, rank, world)
+        mine = S.project_scene(part)
+        S.close()
+        zs = [slice(k0, k1), slice(k0, k1), slice(k0, k1 + 1)]
+        masks = all(np.array_equal(mine["vel_active"][d], whole["vel_active"][d][zs[d]]) for d in range(3)) and \
+            np.array_equal(mine["pressure_active"], whole["pressure_active"][k0:k1])
+        num = sum(float(((mine["vel"][d].astype(np.float64) - whole["vel"][d][zs[d]]) ** 2).sum()) for d in range(3))
+        den = sum(float((whole["vel"][d].astype(np.float64) ** 2).sum()) for d in range(3))
+        t = torch.tensor([num, 0.0 if masks else 1.0], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        rel = (float(t[0].item()) / den) ** 0.5 if den > 0 else 0.0
+        masks_all = float(t[1].item()) == 0.0
+        ok = masks_all and rel < 1e-6
+        ok_all = ok_all and ok
+        out[name] = {"grid": [sc.nx, sc.ny, sc.nz], "slabs": world, "masks_equal": masks_all, "vel_rel_l2": rel,
+                     "iterations": [mine["result"].iterations, whole["result"].iterations], "ok": ok}
+    out["ok"] = ok_all
+    out["bar"] = "activity masks equal, velocity <= 1e-6 rel. L2 between the slab run and the whole-grid run on one GPU (fp64, Residual=1e-10)"
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from shiokaze_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if capi.lib().shkz_b200_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: libshkz_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sdist = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from shiokaze_b200 import dist as sdist
+
+    flags = dict(Precision=args.precision, Precond=args.precond, Residual=args.residual, MGPreSweeps=args.pre, MGPostSweeps=args.post,
+                 CheckEvery=args.check_every)
+
+    def harness(workload, n, strong):
+        nzg = n if strong else n * world
+        if strong and n % world:
+            raise SystemExit(f"--scaling strong: n={n} is not divisible by {world} slabs")
+        nzl = nzg // world
+        zr = (rank * nzl, (rank + 1) * nzl)
+        sc = sdist.slab_scene(workload, n, nzg, zr) if world > 1 else build_scene(workload, n)
+        return Harness(torch, dev, sc, nzg, zr, flags, local, connect=(lambda S: sdist.connect(S, rank, world)) if world > 1 else None), nzg
+
+    parity = parity_vs_1gpu(torch, dist, sdist, rank, world, local) if world > 1 else None
+
+    n = args.n
+    strong = args.scaling == "strong"
+    H, nzg = harness(args.workload, n, strong)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, res, launches, iters, clocks = timed_steps(torch, dist, H, args.steps, args.warmup, world, dev, sampler)
+    cells_global = float(n) * n * nzg
+    value = cells_global / (ms_step * 1e-3) / 1e6
+    n_rows = res.stats["n_rows_global"] if world > 1 else res.n_rows
+
+    # ---- end to end through the host-buffer C-ABI (what the Shiokaze module calls), pinned host memory, every rank its slab ----
+    h2d, d2h = H.host_io_bytes()
+    e2e_s, e2e_res = e2e_steps(torch, dist, H, args.steps, args.warmup, world)
+    e2e_value = cells_global / e2e_s / 1e6
+
+    # ---- roofline of the dominant kernel: CUDA events around every launch of one extra project() ----
+    table, pres = profile_one_step(H)
+    roofline = roofline_of(table, pres, res.n_rows / world, args.precision, args.precond) if rank == 0 else None
+    H.close()
+    del H
+    torch.cuda.empty_cache()
+
+    # ---- secondary records ----
+    sub = {}
+    if world == 1 and not args.no_sub_records and (args.workload, n) != ("smoke_plume", 256):
+        Hs, _ = harness("smoke_plume", 256, False)
+        ms_s, res_s, _, it_s, _ = timed_steps(torch, dist, Hs, max(5, args.steps // 2), 3, 1, dev)
+        e2e_ss, _ = e2e_steps(torch, dist, Hs, 5, 2, 1)
+        tab_s, pres_s = profile_one_step(Hs)
+        rf = roofline_of(tab_s, pres_s, res_s.n_rows, args.precision, args.precond)
+        sub["smoke_plume_256"] = {"config": workload_string("smoke_plume", 256, "on one GPU", args.residual), "ms_per_step": ms_s,
+                                  "value": 256.0 ** 3 / (ms_s * 1e-3) / 1e6, "unit": UNIT, "e2e_ms_per_step": e2e_ss * 1e3,
+                                  "solve": solve_record(res_s, res_s.n_rows, it_s),
+                                  "roofline": {k: rf[k] for k in ("kernel", "achieved", "peak", "frac", "solve_whole")} if rf else None}
+        Hs.close()
+        del Hs
+        torch.cuda.empty_cache()
+    strong_rec = None
+    if world > 1 and not strong and not args.no_sub_records:
+        # the strong-scaling targets of BASELINE.json ride along: configs[3] (FLIP splash 512^3) on 2 / 4 GPUs, configs[4] (liquid box 1024^3) on 8
+        sw, sn = ("liquid_box", 1024) if world == 8 else ("flip_splash", 512)
+        Hs, _ = harness(sw, sn, True)
+        ms_s, res_s, _, it_s, _ = timed_steps(torch, dist, Hs, 5, 3, world, dev)
+        strong_rec = {"config": workload_string(sw, sn, f"cut into {world} z-slabs", args.residual), "grid": [sn, sn, sn], "ms_per_step": ms_s,
+                      "value": float(sn) ** 3 / (ms_s * 1e-3) / 1e6, "unit": UNIT, "solve": solve_record(res_s, res_s.stats["n_rows_global"], it_s)}
+        Hs.close()
+        del Hs
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        s = reference_sample(args.workload, n, 30.0, os.cpu_count() or 1)
-        cpu_baseline = {"value": s["value"], "unit": UNIT, "cores": s["cores"], "kind": s["kind"], "sample": s["sample"],
-                        "ms_per_solve": s["ms_per_solve"]}
+        r = reference_run(args.workload, os.cpu_count() or 1, args.residual)
+        cpu_baseline = {"value": r["cells"] / (r["ms"] * 1e-3) / 1e6, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                        "sample": reference_sample_text(args.workload, r, n), "ms_per_solve": r["ms"], "grid": [r["n"]] * 3, "iterations": r["iterations"]}
 
     if rank == 0:
+        mode = "cut into z-slabs" if strong else ("per GPU, stacked in z" if world > 1 else "on one GPU")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": {"mixed": "f64", "fp64": "f64", "fp32": "f32"}[args.precision], "data": "synthetic", "config": config_dict(args, "gpu"),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": (e2e_s / e2e_steps * 1e3) if e2e_steps else None,
-                    "ms_h2d": e2e_res.stats["ms_h2d"] if e2e_steps else None, "ms_d2h": e2e_res.stats["ms_d2h"] if e2e_steps else None},
+            "dtype": {"mixed": "f64", "fp64": "f64", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": {"workload": workload_string(args.workload, n, mode, args.residual), "grid": [n, n, nzg], "slab_per_gpu": [n, n, nzg // world],
+                       "parallelism": f"z-slab x{world}", "precision": args.precision, "precond": args.precond, "mg_sweeps": [args.pre, args.post],
+                       "residual": args.residual,
+                       "l2_policy": "inputs and solver working set of one step (GBs at 512^3, > 1 GB at 256^3) exceed the 126 MB L2; no explicit flush",
+                       "where": "gpu"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_s * 1e3,
+                    "ms_h2d": e2e_res.stats["ms_h2d"], "ms_d2h": e2e_res.stats["ms_d2h"],
+                    "what": "shkz_b200_project_host with page-locked host buffers, wall clock around the call, max over ranks"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "solve": {"iterations": iters[-1], "reresid": res.reresid, "converged": res.converged, "n_rows": int(n_rows),
-                      "cell_iters_per_s": n_rows * iters[-1] / (phase["ms_solve"] * 1e-3), **phase},
+            "solve": solve_record(res, n_rows, iters),
         }
+        if sub:
+            line["sub_records"] = sub
+        if strong_rec:
+            line["strong"] = strong_rec
+        if parity is not None:
+            line["parity_vs_1gpu"] = parity
         print(json.dumps(line))
-    S.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -420,8 +564,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="smoke_plume")
-    ap.add_argument("--n", "--grid", dest="n", type=int, default=256, help="grid size n (n^3 cells per GPU, or in total with --scaling strong); --grid is the spelling to use under torchrun, whose own parser finds --n ambiguous")
+    ap.add_argument("--workload", default="dambreak_solid")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=512, help="grid size n (n^3 cells per GPU, or in total with --scaling strong); --grid is the spelling to use under torchrun, whose own parser finds --n ambiguous")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "fp64", "fp32"])
     ap.add_argument("--precond", default="mg", choices=["mg", "none"])
     ap.add_argument("--pre", type=int, default=2)
@@ -430,6 +574,7 @@ def main():
     ap.add_argument("--check-every", type=int, default=4)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: n^3 per GPU (weak) or the n^3 grid cut into N slabs (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least three warm-up steps

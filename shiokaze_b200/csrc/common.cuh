@@ -48,7 +48,7 @@ struct Tiles {
 	const int *count;  // number of active tiles
 	int ntx, nty, ntz; // tile grid of the level
 	int bz;            // planes per tile (even)
-	int balanced;      // how a persistent grid divides the list (TileWalk)
+	int balanced;      // how a persistent grid divides the list (TileWalk): bit 0 element-wise kernels, bit 1 stencil kernels may take the balanced walk
 };
 
 __device__ __forceinline__ void tile_origin(const Tiles &T, int id, int &i0, int &j0, int &kb) {
@@ -71,7 +71,7 @@ struct TileWalk {
 	int u, end; // balanced: next / last plane-pair unit of this CTA; strided: next tile index / number of tiles
 	bool bal;
 	// (with four or more tiles per CTA the strided walk loses little to the last partial round and keeps its locality: measured, all-fluid 512^3)
-	__device__ __forceinline__ TileWalk(const Tiles &T, int ntiles, bool elementwise = false) : bal(elementwise && T.balanced && ntiles < 4 * (int)gridDim.x) {
+	__device__ __forceinline__ TileWalk(const Tiles &T, int ntiles, bool elementwise = false) : bal((T.balanced & (elementwise ? 1 : 2)) && ntiles < 4 * (int)gridDim.x) {
 		if (bal) {
 			const long long tot = (long long)ntiles * (T.bz >> 1);
 			u = (int)(tot * blockIdx.x / gridDim.x);

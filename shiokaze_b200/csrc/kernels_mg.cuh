@@ -604,39 +604,46 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vcycle_tail(TailArgs A, const 
 // Coarse operator = scale * P^T A P (once per projection): coarse face coupling = sum of the four fine
 // couplings crossing the coarse face, coarse dd = sum of the children's dd. Flags the coarse tile of every
 // coarse cell that carries an equation.
-__global__ void __launch_bounds__(256) k_coarsen_operator(Dims df, Dims dc, Tiles Tc, float scale, const float *__restrict__ wx, const float *__restrict__ wy,
-                                                         const float *__restrict__ wz, const float *__restrict__ dd, float *__restrict__ cwx,
-                                                         float *__restrict__ cwy, float *__restrict__ cwz, float *__restrict__ cdd,
-                                                         unsigned char *__restrict__ tile_flags) {
-	const int I = blockIdx.x * blockDim.x + threadIdx.x;
-	const int J = blockIdx.y * blockDim.y + threadIdx.y;
-	const int K = blockIdx.z;
-	if (I >= dc.nx || J >= dc.ny) return;
-	float sx = 0.f, sy = 0.f, sz = 0.f, sd = 0.f;
-	bool live = false;
+// Persistent over the UNION list of the fine level (tiles that hold an unknown now or held one in the previous projection, `U`): the coarse cells under
+// every other fine tile were zero before and stay zero. Block (TX/2, TY/2): one coarse column of the tile's footprint per thread.
+__global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_coarsen_operator(Dims df, Dims dc, Tiles U, Tiles Tc, float scale, const float *__restrict__ wx, const float *__restrict__ wy,
+                                                                         const float *__restrict__ wz, const float *__restrict__ dd, float *__restrict__ cwx,
+                                                                         float *__restrict__ cwy, float *__restrict__ cwz, float *__restrict__ cdd,
+                                                                         unsigned char *__restrict__ tile_flags) {
+	const int ntiles = *U.count;
+	int i0, j0, kb, ke;
+	for (TileWalk w(U, ntiles); w.next(U, df.nzl, i0, j0, kb, ke);) {
+		const int I = (i0 >> 1) + threadIdx.x, J = (j0 >> 1) + threadIdx.y;
+		if (I >= dc.nx || J >= dc.ny) continue;
+		for (int k0 = kb; k0 < ke; k0 += 2) {
+			const int K = k0 >> 1;
+			float sx = 0.f, sy = 0.f, sz = 0.f, sd = 0.f;
+			bool live = false;
 #pragma unroll
-	for (int dk = 0; dk < 2; ++dk)
+			for (int dk = 0; dk < 2; ++dk)
 #pragma unroll
-		for (int dj = 0; dj < 2; ++dj)
+				for (int dj = 0; dj < 2; ++dj)
 #pragma unroll
-			for (int di = 0; di < 2; ++di) {
-				const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
-				if (i >= df.nx || j >= df.ny || k >= df.nzl) continue;
-				const long long c = i + (long long)df.nx * (j + (long long)df.ny * k);
-				const float a = wx[c], bq = wy[c], cq = wz[c], e = dd[c];
-				sd += e;
-				if (!di) sx += a;
-				if (!dj) sy += bq;
-				if (!dk) sz += cq;
-				// a child with an equation has a positive diagonal: its own lower faces, its upper faces, or dd
-				live = live || a > 0.f || bq > 0.f || cq > 0.f || e > 0.f || wx[c + 1] > 0.f || wy[c + df.nx] > 0.f || wz[c + df.plane] > 0.f;
-			}
-	const long long C = I + (long long)dc.nx * (J + (long long)dc.ny * K);
-	cwx[C] = scale * sx;
-	cwy[C] = scale * sy;
-	cwz[C] = scale * sz;
-	cdd[C] = scale * sd;
-	if (live) tile_flags[tile_of(Tc, I, J, K)] = 1;
+					for (int di = 0; di < 2; ++di) {
+						const int i = 2 * I + di, j = 2 * J + dj, k = 2 * K + dk;
+						if (i >= df.nx || j >= df.ny || k >= df.nzl) continue;
+						const long long c = i + (long long)df.nx * (j + (long long)df.ny * k);
+						const float a = wx[c], bq = wy[c], cq = wz[c], e = dd[c];
+						sd += e;
+						if (!di) sx += a;
+						if (!dj) sy += bq;
+						if (!dk) sz += cq;
+						// a child with an equation has a positive diagonal: its own lower faces, its upper faces, or dd
+						live = live || a > 0.f || bq > 0.f || cq > 0.f || e > 0.f || wx[c + 1] > 0.f || wy[c + df.nx] > 0.f || wz[c + df.plane] > 0.f;
+					}
+			const long long C = I + (long long)dc.nx * (J + (long long)dc.ny * K);
+			cwx[C] = scale * sx;
+			cwy[C] = scale * sy;
+			cwz[C] = scale * sz;
+			cdd[C] = scale * sd;
+			if (live) tile_flags[tile_of(Tc, I, J, K)] = 1;
+		}
+	}
 }
 
 // flag the tiles of a level that hold at least one cell with an equation (positive diagonal)
@@ -650,32 +657,38 @@ __global__ void __launch_bounds__(256) k_flag_live_tiles(Dims d, Tiles T, const 
 	if (gs_diag(wx[c], wx[c + 1], wy[c], wy[c + d.nx], wz[c], wz[c + d.plane], dd[c]) > 0.f) tile_flags[tile_of(T, i, j, k)] = 1;
 }
 
-// flags -> ascending id list + count (single CTA; tile grids are at most a few 10^4 entries)
-__global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned char *__restrict__ flags, int n, int *__restrict__ ids, int *__restrict__ count) {
-	__shared__ int warp_sums[32];
-	__shared__ int base;
+// flags -> ascending id list + count (single CTA; tile grids are at most a few 10^4 entries). Also the UNION list: tiles flagged now or in the previous
+// projection (`dirty`), i.e. every tile whose arrays may hold something other than zeros — what the kernels that WRITE a level's arrays walk over —,
+// after which `dirty` becomes the current flags.
+__global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned char *__restrict__ flags, unsigned char *__restrict__ dirty, int n, int *__restrict__ ids,
+                                                       int *__restrict__ count, int *__restrict__ uids, int *__restrict__ ucount) {
+	__shared__ int warp_sums[2][32];
+	__shared__ int base[2];
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	if (tid == 0) base = 0;
+	if (tid < 2) base[tid] = 0;
 	__syncthreads();
 	for (int start = 0; start < n; start += 1024) {
 		const int idx = start + tid;
 		const int f = (idx < n && flags[idx]) ? 1 : 0;
-		const unsigned ballot = __ballot_sync(0xffffffffu, f);
-		const int before = __popc(ballot & ((1u << lane) - 1u));
-		if (lane == 0) warp_sums[wid] = __popc(ballot);
+		const int u = (idx < n && (f || dirty[idx])) ? 1 : 0;
+		const unsigned bf = __ballot_sync(0xffffffffu, f), bu = __ballot_sync(0xffffffffu, u);
+		const unsigned below = (1u << lane) - 1u;
+		if (lane == 0) { warp_sums[0][wid] = __popc(bf); warp_sums[1][wid] = __popc(bu); }
 		__syncthreads();
-		int woff = 0;
-		for (int w = 0; w < wid; ++w) woff += warp_sums[w];
-		if (f) ids[base + woff + before] = idx;
+		int wf = 0, wu = 0;
+		for (int w = 0; w < wid; ++w) { wf += warp_sums[0][w]; wu += warp_sums[1][w]; }
+		if (f) ids[base[0] + wf + __popc(bf & below)] = idx;
+		if (u) uids[base[1] + wu + __popc(bu & below)] = idx;
+		if (idx < n) dirty[idx] = (unsigned char)f;
 		__syncthreads();
-		if (tid == 0) {
+		if (tid < 2) {
 			int tot = 0;
-			for (int w = 0; w < 32; ++w) tot += warp_sums[w];
-			base += tot;
+			for (int w = 0; w < 32; ++w) tot += warp_sums[tid][w];
+			base[tid] += tot;
 		}
 		__syncthreads();
 	}
-	if (tid == 0) *count = base;
+	if (tid == 0) { *count = base[0]; *ucount = base[1]; }
 }
 
 } // namespace shkz

@@ -157,6 +157,10 @@ struct HostLevel {
 	CellArray legacy_r; // residual array of the unfused validation path (allocated on first use)
 	bool own_coef = true, own_b = true; // level 0 may alias CG arrays
 	PlainArray tile_flags, tile_ids, tile_count;
+	// tiles whose arrays may hold something other than zeros: flagged now or in the previous projection (`tile_dirty` = last call's flags). The kernels
+	// that WRITE a level's arrays (assembly, coarsening, pressure scatter) walk this union list; everything outside it is zero and stays zero.
+	PlainArray tile_dirty, tile_uids, tile_ucount;
+	Tiles utiles{};
 	MGLevel view;
 	bool tma = false; // tensor maps built: the level's sweeps run the TMA-staged kernel
 	CUtensorMap map_wx, map_wy, map_wz, map_dd, map_b, map_xa, map_xb;
@@ -239,7 +243,8 @@ struct shkz_b200_solver {
 	Profiler prof;
 	bool have_system = false;
 	bool have_hierarchy = false;
-	bool fractions_stale = false; // closed-form fractions (no solid, no liquid level set): the face arrays were not written by the last project()
+	bool fractions_stale = false; // the face arrays of the fractions were not written by the last project() (they never are: debug_fetch materialises them)
+	const void *last_solid = nullptr; // the caller's device solid grid of the last project() (debug_fetch of the area fractions reads it again)
 	const float *debug_vcycle_result = nullptr;
 	int sweep_mode = 0; // 0: best kernel per level (TMA-staged > quad > scalar); 1: no TMA; 2: scalar only (debug / A-B timing)
 	AsmParams last_asm{};
@@ -261,12 +266,12 @@ void release_precision_arrays(shkz_b200_solver *S) {
 		if (L.own_coef) { L.wx.release(); L.wy.release(); L.wz.release(); L.dd.release(); }
 		if (L.own_b) L.b.release();
 		L.xa.release(); L.xb.release(); L.legacy_r.release();
-		L.tile_flags.release(); L.tile_ids.release(); L.tile_count.release();
+		L.tile_flags.release(); L.tile_ids.release(); L.tile_count.release(); L.tile_dirty.release(); L.tile_uids.release(); L.tile_ucount.release();
 	}
 	for (HostLevel &L : S->glevels) {
 		L.wx.release(); L.wy.release(); L.wz.release(); L.dd.release(); L.b.release();
 		L.xa.release(); L.xb.release(); L.legacy_r.release();
-		L.tile_flags.release(); L.tile_ids.release(); L.tile_count.release();
+		L.tile_flags.release(); L.tile_ids.release(); L.tile_count.release(); L.tile_dirty.release(); L.tile_uids.release(); L.tile_ucount.release();
 	}
 	S->glevels.clear();
 	S->agg_level = -1;
@@ -285,6 +290,7 @@ int pick_bz(const Dims &d) {
 	const long long xy = (long long)((d.nx + TX - 1) / TX) * ((d.ny + TY - 1) / TY);
 	int bz = 32;
 	while (bz > 4 && xy * ((d.nzl + bz - 1) / bz) < 592) bz >>= 1;
+	if (const char *e = getenv("SHKZ_B200_BZ")) { const int v = atoi(e); if (v >= 2 && v <= 64 && !(v & 1) && v < bz) bz = v; } // (experiments)
 	return bz;
 }
 
@@ -303,10 +309,16 @@ int finish_level(HostLevel &L, const Dims &cur, const std::string &n, SlabComm *
 	CKR(L.tile_flags.alloc((size_t)L.tiles_total));
 	CKR(L.tile_ids.alloc((size_t)L.tiles_total * sizeof(int)));
 	CKR(L.tile_count.alloc(sizeof(int)));
+	CKR(L.tile_dirty.alloc((size_t)L.tiles_total));
+	CKR(L.tile_uids.alloc((size_t)L.tiles_total * sizeof(int)));
+	CKR(L.tile_ucount.alloc(sizeof(int)));
 	L.tag_sweep = "sweep@" + n; L.tag_restrict = "residual_restrict@" + n; L.tag_prolong = "prolong_add@" + n;
 	L.tag_coarsen = "coarsen_operator@" + n; L.tag_compact = "compact_tiles@" + n;
 	L.view.d = cur;
-	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz, balanced ? 1 : 0};
+	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz, balanced ? (getenv("SHKZ_B200_STENCIL_BALANCED") ? 3 : 1) : 0};
+	L.utiles = L.view.tiles;
+	L.utiles.ids = static_cast<const int *>(L.tile_uids.base);
+	L.utiles.count = static_cast<const int *>(L.tile_ucount.base);
 	L.view.wx = L.wx.ptr<float>(cur); L.view.wy = L.wy.ptr<float>(cur); L.view.wz = L.wz.ptr<float>(cur); L.view.dd = L.dd.ptr<float>(cur);
 	L.view.b = L.b.ptr<float>(cur); L.view.xa = L.xa.ptr<float>(cur); L.view.xb = L.xb.ptr<float>(cur);
 	L.tma = (cur.nx & 3) == 0 && make_plane_map(&L.map_wx, L.wx.base, cur, ST_ROWS) && make_plane_map(&L.map_wy, L.wy.base, cur, ST_WY_ROWS) &&
@@ -475,8 +487,8 @@ int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
 }
 
 int compact_tiles(shkz_b200_solver *S, HostLevel &H, cudaStream_t stream) {
-	LAUNCH(S, H.tag_compact.c_str(), k_compact_tiles, 1, 1024, stream, static_cast<const unsigned char *>(H.tile_flags.base), H.tiles_total,
-	       static_cast<int *>(H.tile_ids.base), static_cast<int *>(H.tile_count.base));
+	LAUNCH(S, H.tag_compact.c_str(), k_compact_tiles, 1, 1024, stream, static_cast<const unsigned char *>(H.tile_flags.base), static_cast<unsigned char *>(H.tile_dirty.base),
+	       H.tiles_total, static_cast<int *>(H.tile_ids.base), static_cast<int *>(H.tile_count.base), static_cast<int *>(H.tile_uids.base), static_cast<int *>(H.tile_ucount.base));
 	return SHKZ_B200_OK;
 }
 
@@ -535,8 +547,9 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st
 		return SHKZ_B200_OK;
 	}
 	const bool last = (l + 1 == lv.size());
-	const int pre = last ? coarse : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
-	const int post = last ? coarse : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
+	int pre = last ? coarse : (P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps);
+	int post = last ? coarse : (P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps);
+	if (!last && l >= 1) if (const char *e = getenv("SHKZ_B200_COARSE_SWEEPS")) pre = post = atoi(e); // (experiments)
 	float *bufs[2] = {L.xa, L.xb};
 	const float *cur = nullptr;
 	int w = 0;
@@ -744,8 +757,8 @@ int coarsen_levels(shkz_b200_solver *S, std::vector<HostLevel> &lv, bool slab, c
 		HostLevel &HC = lv[l + 1];
 		const MGLevel &C = HC.view;
 		CK(cudaMemsetAsync(HC.tile_flags.base, 0, (size_t)HC.tiles_total, stream));
-		LAUNCH(S, lv[l].tag_coarsen.c_str(), k_coarsen_operator, cell_grid(C.d, 0, 0, 0), cell_block(), stream, F.d, C.d, C.tiles, (float)P.mg_coarse_scale,
-		       (const float *)F.wx, (const float *)F.wy, (const float *)F.wz, (const float *)F.dd, C.wx, C.wy, C.wz, C.dd, static_cast<unsigned char *>(HC.tile_flags.base));
+		LAUNCH_TILES(S, lv[l].tag_coarsen.c_str(), k_coarsen_operator, restrict_block(), lv[l].tiles_total, stream, F.d, C.d, lv[l].utiles, C.tiles, (float)P.mg_coarse_scale,
+		             (const float *)F.wx, (const float *)F.wy, (const float *)F.wz, (const float *)F.dd, C.wx, C.wy, C.wz, C.dd, static_cast<unsigned char *>(HC.tile_flags.base));
 		if (slab) CKR(halo(S, C.d, C.wz, stream));
 		CKR(compact_tiles(S, HC, stream));
 	}
@@ -891,13 +904,11 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	RealT *pres = S->pressure.ptr<RealT>(d);
 	uint8_t *in_rows = S->in_rows.ptr<uint8_t>(d);
 	const RealT *solid = static_cast<const RealT *>(solid_v);
-	FaceGrids<RealT> vel, areas, rhos;
-	ConstFaceGrids<RealT> cvel, careas, crhos;
+	FaceGrids<RealT> vel;
+	ConstFaceGrids<RealT> cvel;
 	FaceMasks masks;
 	for (int dim = 0; dim < 3; ++dim) {
 		vel.p[dim] = static_cast<RealT *>(vel_v[dim]); cvel.p[dim] = vel.p[dim];
-		areas.p[dim] = static_cast<RealT *>(S->areas[dim].base); careas.p[dim] = areas.p[dim];
-		rhos.p[dim] = static_cast<RealT *>(S->rhos[dim].base); crhos.p[dim] = rhos.p[dim];
 		masks.p[dim] = act[dim];
 	}
 	AsmParams A{};
@@ -920,10 +931,10 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	// fluid -> internal array with ghost planes (neighbour slabs fill them)
 	CK(cudaMemcpyAsync(phi, fluid_v, sizeof(RealT) * (size_t)d.ncell, cudaMemcpyDeviceToDevice, stream));
 	CKR(halo(S, d, phi, stream));
-	// without a solid and without a liquid level set every consumer uses the closed form (kernels_assemble.cuh: closed_form_area / _rho): the six face
-	// arrays are only materialised when somebody asks for them (shkz_b200_debug_fetch)
-	S->fractions_stale = !A.have_solid && !A.fluid_levelset;
-	if (!S->fractions_stale) LAUNCH(S, "face_fractions", k_face_fractions<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, solid, (const RealT *)phi, areas, rhos);
+	// a2-a4: the area / liquid fractions are recomputed from the level sets by every kernel that needs them (kernels_assemble.cuh: face_area / face_rho,
+	// closed form without a level set); the six face arrays are only materialised when somebody asks for them (shkz_b200_debug_fetch)
+	S->fractions_stale = true;
+	S->last_solid = solid_v;
 	const bool tension = P.surface_tension != 0.0 && A.fluid_levelset; // (without a level set every rho is 1: no face takes the increment, macpressuresolver3.cpp:104-113)
 	if (tension) {
 		CK(cudaEventRecord(S->ev[8], stream));
@@ -931,7 +942,7 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		if (!curv) { CKR(S->curv.alloc(d, sizeof(RealT))); curv = S->curv.ptr<RealT>(d); }
 		LAUNCH(S, "curvature", k_curvature<RealT>, cell_grid(d, 0, 0, 0), cell_block(), stream, d, A, (const RealT *)phi, curv);
 		CKR(halo(S, d, curv, stream));
-		LAUNCH(S, "surface_tension", k_surface_tension<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)curv, crhos, vel, masks);
+		LAUNCH(S, "surface_tension", k_surface_tension<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)curv, vel, masks);
 		CK(cudaEventRecord(S->ev[9], stream));
 	}
 	{
@@ -939,15 +950,23 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		HostLevel &H0 = S->levels[0];
 		const MGLevel &L0 = H0.view;
 		CK(cudaMemsetAsync(H0.tile_flags.base, 0, (size_t)H0.tiles_total, stream));
-		dim3 bgrid = cell_grid(d, 0, 0, 0); // z extent folded into a loop: ~one wave of blocks
 		{
-			const long long xy = (long long)bgrid.x * bgrid.y, want = (long long)S->num_sms * 32;
-			long long gz = (want + xy - 1) / xy;
-			bgrid.z = (unsigned)(gz < 1 ? 1 : (gz > d.nzl ? d.nzl : gz));
+			// persistent over (tile footprint, plane) units
+			const long long units = (long long)L0.tiles.ntx * L0.tiles.nty * d.nzl;
+#define BUILD_SYSTEM(HS, LS)                                                                                                                                          \
+	do {                                                                                                                                                          \
+		const int bgrid = tile_grid(S, k_build_system<RealT, CoefT, VecT, HS, LS>, dim3(TX, BS_ROWS, 1), (int)(units > (1ll << 30) ? (1ll << 30) : units));       \
+		LAUNCH(S, "build_system", (k_build_system<RealT, CoefT, VecT, HS, LS>), bgrid, dim3(TX, BS_ROWS, 1), stream, d, A, (const RealT *)phi, solid, in_rows,     \
+		       cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->dd.ptr<CoefT>(d), share ? nullptr : L0.wx, share ? nullptr : L0.wy,         \
+		       share ? nullptr : L0.wz, share ? nullptr : L0.dd, S->b.ptr<VecT>(d), L0.tiles, static_cast<unsigned char *>(H0.tile_flags.base),                   \
+		       static_cast<const unsigned char *>(H0.tile_dirty.base), rb, st);                                                                                   \
+	} while (0)
+			if (A.have_solid && A.fluid_levelset) BUILD_SYSTEM(true, true);
+			else if (A.have_solid) BUILD_SYSTEM(true, false);
+			else if (A.fluid_levelset) BUILD_SYSTEM(false, true);
+			else BUILD_SYSTEM(false, false);
+#undef BUILD_SYSTEM
 		}
-		LAUNCH(S, "build_system", (k_build_system<RealT, CoefT, VecT>), bgrid, cell_block(), stream, d, A, (const RealT *)phi, in_rows, careas,
-		       crhos, cvel, S->wx.ptr<CoefT>(d), S->wy.ptr<CoefT>(d), S->wz.ptr<CoefT>(d), S->dd.ptr<CoefT>(d), share ? nullptr : L0.wx,
-		       share ? nullptr : L0.wy, share ? nullptr : L0.wz, share ? nullptr : L0.dd, S->b.ptr<VecT>(d), L0.tiles, static_cast<unsigned char *>(H0.tile_flags.base), rb, st);
 		CKR(compact_tiles(S, H0, stream));
 		CKR(halo(S, d, S->wz.ptr<CoefT>(d), stream));
 		if (!share) CKR(halo(S, d, L0.wz, stream));
@@ -973,10 +992,19 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	if (!S->h_state->has_dirichlet && S->h_state->n_rows && P.precond == SHKZ_B200_PRECOND_MG && P.mg_post_sweeps <= 0) {
 		LAUNCH(S, "sum_rows", k_sum_rows<VecT>, flat_blocks(d.ncell), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows, rb, st);
 	}
-	LAUNCH(S, "store_pressure", (k_store_pressure<RealT, VecT>), (unsigned)((d.ncell + 255) / 256), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows,
-	       (const CGState *)st, pres, static_cast<RealT *>(pressure_v), pressure_active, P.warm_start ? S->p_prev.ptr<VecT>(d) : (VecT *)nullptr);
+	// the caller's grids are cleared wholesale, then written where a tile holds (or held) unknowns
+	if (pressure_v) CK(cudaMemsetAsync(pressure_v, 0, sizeof(RealT) * (size_t)d.ncell, stream));
+	if (pressure_active) CK(cudaMemsetAsync(pressure_active, 0, (size_t)d.ncell, stream));
+	LAUNCH_TILES(S, "store_pressure", (k_store_pressure<RealT, VecT>), dim3(TX, 8, 1), S->levels[0].tiles_total, stream, d, S->levels[0].utiles, (const VecT *)S->x.ptr<VecT>(d),
+	             (const uint8_t *)in_rows, (const CGState *)st, pres, static_cast<RealT *>(pressure_v), pressure_active, P.warm_start ? S->p_prev.ptr<VecT>(d) : (VecT *)nullptr);
 	CKR(halo(S, d, pres, stream));
-	LAUNCH(S, "update_velocity", k_update_velocity<RealT>, cell_grid(d, 1, 1, 1), cell_block(), stream, d, A, (const RealT *)phi, (const RealT *)pres, careas, crhos, vel, masks);
+	{
+		const dim3 ugrid((d.nx + 1 + 31) / 32, (d.ny + 1 + 8 * UV_ROWS - 1) / (8 * UV_ROWS), d.nzl + 1), ublock(32, 8, 1);
+		if (A.have_solid && A.fluid_levelset) LAUNCH(S, "update_velocity", (k_update_velocity<RealT, true, true>), ugrid, ublock, stream, d, A, (const RealT *)phi, solid, (const RealT *)pres, vel, masks);
+		else if (A.have_solid) LAUNCH(S, "update_velocity", (k_update_velocity<RealT, true, false>), ugrid, ublock, stream, d, A, (const RealT *)phi, solid, (const RealT *)pres, vel, masks);
+		else if (A.fluid_levelset) LAUNCH(S, "update_velocity", (k_update_velocity<RealT, false, true>), ugrid, ublock, stream, d, A, (const RealT *)phi, solid, (const RealT *)pres, vel, masks);
+		else LAUNCH(S, "update_velocity", (k_update_velocity<RealT, false, false>), ugrid, ublock, stream, d, A, (const RealT *)phi, solid, (const RealT *)pres, vel, masks);
+	}
 	CK(cudaEventRecord(S->ev[4], stream));
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
@@ -1113,10 +1141,6 @@ int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int
 	if (!S->whole_grid) {
 		tryalloc(S->curv.alloc(d, S->real_bytes, S->arena())); // (a whole grid allocates it on first use)
 		S->arena_mark = S->comm->mark();
-	}
-	for (int dim = 0; dim < 3; ++dim) {
-		tryalloc(S->areas[dim].alloc(face_count(d, dim) * S->real_bytes));
-		tryalloc(S->rhos[dim].alloc(face_count(d, dim) * S->real_bytes));
 	}
 	// reduction scratch: the largest grid any reducing kernel uses
 	{
@@ -1319,14 +1343,18 @@ int shkz_b200_debug_fetch(shkz_b200_solver *S, const char *name, void *dst, size
 	size_t bytes = 0;
 	if (S->fractions_stale && (n.compare(0, 5, "areas") == 0 || n.compare(0, 4, "rhos") == 0)) {
 		const dim3 grid((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, d.nzl + 1), block(32, 8, 1);
+		for (int dim = 0; dim < 3; ++dim) {
+			if (!S->areas[dim].base) CKR(S->areas[dim].alloc(face_count(d, dim) * S->real_bytes));
+			if (!S->rhos[dim].base) CKR(S->rhos[dim].alloc(face_count(d, dim) * S->real_bytes));
+		}
 		if (S->real == SHKZ_B200_REAL_F32) {
 			FaceGrids<float> a, r;
 			for (int dim = 0; dim < 3; ++dim) { a.p[dim] = static_cast<float *>(S->areas[dim].base); r.p[dim] = static_cast<float *>(S->rhos[dim].base); }
-			k_face_fractions<float><<<grid, block>>>(d, S->last_asm, nullptr, S->phi.ptr<float>(d), a, r);
+			k_face_fractions<float><<<grid, block>>>(d, S->last_asm, static_cast<const float *>(S->last_solid), S->phi.ptr<float>(d), a, r);
 		} else {
 			FaceGrids<double> a, r;
 			for (int dim = 0; dim < 3; ++dim) { a.p[dim] = static_cast<double *>(S->areas[dim].base); r.p[dim] = static_cast<double *>(S->rhos[dim].base); }
-			k_face_fractions<double><<<grid, block>>>(d, S->last_asm, nullptr, S->phi.ptr<double>(d), a, r);
+			k_face_fractions<double><<<grid, block>>>(d, S->last_asm, static_cast<const double *>(S->last_solid), S->phi.ptr<double>(d), a, r);
 		}
 		CK(cudaDeviceSynchronize());
 		S->fractions_stale = false;
