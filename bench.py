@@ -110,13 +110,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-def algorithmic_bytes_per_launch(kernel: str, n_rows: float, precision: str, precond: str = "mg"):
+def algorithmic_bytes_per_launch(kernel: str, n_rows: float, precision: str, precond: str = "mg", mid_level=None, tail_level=None):
     """Algorithmic (minimum necessary) bytes one launch of `kernel` moves, counted on unknown rows (DESIGN.md sections 3-4).
     V = CG vector bytes, C = operator coefficient bytes, multigrid is fp32; level l holds n_rows / 8^l rows."""
     V = 4 if precision == "fp32" else 8
     Cc = 8 if precision == "fp64" else 4
     mg = precond == "mg"
     b0 = 4 if (mg and V == 8) else 0          # float copy of r handed to multigrid
+    if kernel in ("vcycle_mid", "vcycle_tail"):
+        # every level from the launch's first one down: V(2,2) = five passes per level (24 + 28 + 28.5 + 28 sweep bytes, 24.5 residual + restriction), x 8/7
+        first = mid_level if kernel == "vcycle_mid" else tail_level
+        return None if first is None or first < 0 else n_rows / (8 ** first) * (24 + 28 + 28.5 + 28 + 24.5) * 8.0 / 7.0
     name, _, lvl = kernel.partition("@")
     variant = lvl.lstrip("0123456789g")       # sweep variants: z (x_old = 0, not read), p (+ coarse correction read), d (+ z.r reduced)
     lvl = lvl[:len(lvl) - len(variant)] if variant else lvl
@@ -379,7 +383,7 @@ def profile_one_step(H):
 
 def roofline_of(table, res, rank_rows, precision, precond):
     peak, how = measured_peak()
-    ab = lambda k: algorithmic_bytes_per_launch(k, rank_rows, precision, precond)
+    ab = lambda k: algorithmic_bytes_per_launch(k, rank_rows, precision, precond, res.stats.get("mg_mid_level"), res.stats.get("mg_tail_level"))
     groups = group_kernels(table, ab)
     if not groups:
         return None

@@ -99,8 +99,12 @@ typedef struct shkz_b200_stats {
 	uint64_t kernel_launches; /* kernels of this library launched by the call */
 	float ms_h2d, ms_assemble, ms_setup, ms_solve, ms_update, ms_d2h, ms_total; /* CUDA-event times */
 	float ms_surftension;   /* part of ms_assemble spent on the surface-tension force (macpressuresolver3.cpp:85-115); 0 without it */
-	uint32_t active_tiles;  /* level-0 tiles (64 x 16 x bz cells) that hold an unknown: what every solve kernel walks over */
+	uint32_t active_tiles;  /* level-0 tiles (64 x 16 x tile_depth cells) that hold an unknown: what every solve kernel walks over */
 	uint32_t total_tiles;
+	int32_t mg_mid_level;   /* first multigrid level of the cooperative mid-V-cycle launch (levels of <= 2^21 cells), -1: none */
+	int32_t mg_tail_level;  /* first level of the shared-memory tail, which runs inside that launch (or alone when mg_mid_level is -1) */
+	uint32_t tile_depth;    /* planes per level-0 tile this projection (chosen on the device: deep tiles for full grids, shallower for liquid scenes) */
+	uint32_t reserved;
 } shkz_b200_stats;
 
 typedef struct shkz_b200_solver shkz_b200_solver; /* opaque */

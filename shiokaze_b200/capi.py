@@ -42,7 +42,8 @@ class Stats(C.Structure):
                 ("reresid", C.c_double), ("rhs_absmax", C.c_double), ("has_dirichlet", C.c_int32), ("mg_levels", C.c_int32),
                 ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_float), ("ms_assemble", C.c_float), ("ms_setup", C.c_float),
                 ("ms_solve", C.c_float), ("ms_update", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
-                ("ms_surftension", C.c_float), ("active_tiles", C.c_uint32), ("total_tiles", C.c_uint32)]
+                ("ms_surftension", C.c_float), ("active_tiles", C.c_uint32), ("total_tiles", C.c_uint32),
+                ("mg_mid_level", C.c_int32), ("mg_tail_level", C.c_int32), ("tile_depth", C.c_uint32), ("reserved", C.c_uint32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -43,13 +43,19 @@ struct CGState {
 // from device memory, so launch geometry (and a captured CUDA graph) never depends on the scene.
 constexpr int TX = 64, TY = 16;
 
+// Tiles are flagged in SLICES of `slice` planes (8, or the level's tile depth where that is smaller); how many slices make a tile — the tile depth bz — is
+// decided per projection ON THE DEVICE by the compaction kernel (k_compact_tiles: deep tiles when the scene fills the grid, shallower ones when a liquid
+// scene leaves a persistent grid with a handful of tiles per CTA), which stores it next to the count. bz != 0 here fixes the depth (z-slab levels, small levels).
 struct Tiles {
-	const int *ids;    // active tile ids, ascending
-	const int *count;  // number of active tiles
-	int ntx, nty, ntz; // tile grid of the level
-	int bz;            // planes per tile (even)
+	const int *ids;    // active tile ids, ascending:  id = tx + ntx * (ty + nty * tz)
+	const int *count;  // [0] number of active tiles  [1] planes per tile chosen for this projection
+	int ntx, nty;      // tile grid of the level in x and y
+	int slice;         // planes per flag slice
+	int bz;            // planes per tile (even); 0: read it from count[1]
 	int balanced;      // how a persistent grid divides the list (TileWalk): bit 0 element-wise kernels, bit 1 stencil kernels may take the balanced walk
 };
+// every tile kernel starts with this: after it T.bz is the depth in force
+__device__ __forceinline__ void resolve_tiles(Tiles &T) { if (T.bz == 0) T.bz = T.count[1]; }
 
 __device__ __forceinline__ void tile_origin(const Tiles &T, int id, int &i0, int &j0, int &kb) {
 	const int tx = id % T.ntx;
@@ -101,7 +107,8 @@ struct TileWalk {
 	}
 };
 
-__device__ __forceinline__ int tile_of(const Tiles &T, int i, int j, int k) { return (i / TX) + T.ntx * ((j / TY) + T.nty * (k / T.bz)); }
+// flag slot (slice) of a cell
+__device__ __forceinline__ int slice_of(const Tiles &T, int i, int j, int k) { return (i / TX) + T.ntx * ((j / TY) + T.nty * (k / T.slice)); }
 
 struct RedBuf {
 	double *partials;      // [blocks][N]

@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(TX *BS_ROWS, 3) k_build_system(Dims d, AsmPara
 	for (long long u = blockIdx.x; u < units; u += gridDim.x) {
 		const int k = (int)(u / per_plane), r = (int)(u - (long long)k * per_plane);
 		const int i0 = (r % T.ntx) * TX, j0 = (r / T.ntx) * TY;
-		const int tile = (r % T.ntx) + T.ntx * ((r / T.ntx) + T.nty * (k / T.bz));
+		const int tile = (r % T.ntx) + T.ntx * ((r / T.ntx) + T.nty * (k / T.slice)); // flag slot (slice) of the unit
 		const int i = i0 + threadIdx.x;
 		RealT pc[CELLS];
 		bool wet = false;
@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(TX * 8) k_store_pressure(Dims d, Tiles U, cons
                                                           const CGState *__restrict__ st, RealT *__restrict__ pressure, RealT *__restrict__ pressure_out,
                                                           uint8_t *__restrict__ active_out, VecT *__restrict__ p_prev) {
 	const double shift = (!st->has_dirichlet && st->n_rows) ? st->sum_x / (double)st->n_rows : 0.0;
+	resolve_tiles(U);
 	const int ntiles = *U.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(U, ntiles, true); w.next(U, d.nzl, i0, j0, kb, ke);) {

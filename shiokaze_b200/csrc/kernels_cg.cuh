@@ -23,6 +23,7 @@ inline dim3 cg_block() { return dim3(TX, CG_BY, 1); }
 template <class VecT, bool WRITE_B0>
 __global__ void __launch_bounds__(TX *CG_BY) k_cg_init(Dims d, Tiles T, const VecT *__restrict__ b, VecT *__restrict__ x, VecT *__restrict__ r,
                                                       VecT *__restrict__ s, float *__restrict__ b0) {
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
@@ -60,6 +61,7 @@ template <class VecT>
 __global__ void __launch_bounds__(TX *CG_BY) k_dot_rr(Dims d, Tiles T, const VecT *__restrict__ r, RedBuf rb, CGState *st) {
 	if (st->done) return;
 	double red[1] = {0.0};
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
@@ -88,6 +90,7 @@ __device__ __forceinline__ void finish_zr(CGState *st, double zr) {
 __global__ void __launch_bounds__(TX *CG_BY) k_dot_zb(Dims d, Tiles T, const float *__restrict__ z, const float *__restrict__ b0, RedBuf rb, CGState *st) {
 	if (st->done) return;
 	double red[1] = {0.0};
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(TX *CG_BY) k_xpay(Dims d, Tiles T, const ZT *_
 	if (st->done) return;
 	VecT *const plo = push_target_lo<VecT>(sp, d.plane, d.nzl), *const phi = push_target_hi<VecT>(sp);
 	const VecT beta = (VecT)st->beta;
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
@@ -137,6 +141,7 @@ __global__ void __launch_bounds__(TX *CG_BY) k_spmv_dot(Dims d, Tiles T, const C
 	if (st->done) return;
 	if (wait_in) block_wait_neighbours(rb.comm, wait_in); // z-slabs: the ghost planes of s, pushed by the neighbours' k_xpay
 	double red[1] = {0.0};
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
@@ -175,6 +180,7 @@ template <class VecT, class CoefT>
 __global__ void __launch_bounds__(TX *CG_BY) k_warm_rhs(Dims d, Tiles T, const CoefT *__restrict__ wx, const CoefT *__restrict__ wy, const CoefT *__restrict__ wz,
                                                        const CoefT *__restrict__ dd, const VecT *__restrict__ p, VecT *__restrict__ b, RedBuf rb, CGState *st) {
 	double red[1] = {0.0};
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__((TX / 4) * TY, 3) k_spmv_dot4(Dims d, Tiles T,
 	if (st->done) return;
 	if (wait_in) block_wait_neighbours(rb.comm, wait_in); // z-slabs: the ghost planes of s, pushed by the neighbours' k_xpay
 	double red[1] = {0.0};
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	const long long nx = d.nx;
 	int i0, j0, kb, ke;
@@ -282,6 +289,7 @@ __global__ void __launch_bounds__(TX *CG_BY) k_axpy2_norm(Dims d, Tiles T, const
 	if (st->done) return;
 	const VecT alpha = (VecT)st->alpha;
 	double red[3] = {0.0, 0.0, 0.0};
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(Dims d, Tiles T, con
 	__shared__ float H[3][TY + 2][TX + 2];
 	const int px = threadIdx.x, ty = threadIdx.y;
 	const int tid = px + (TX / 2) * ty;
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	const long long nx = d.nx, ny = d.ny, plane = d.plane;
 	double red[1] = {0.0};
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep4(Dims d, Tiles T, const
 	const bool colwarp = warp == S4_ROW_WARPS;
 	const int tx = lane & 15, half = lane >> 4;
 	const int r = warp < S4_ROW_WARPS - 1 ? ((warp >> 1) * 4 + (warp & 1) + 2 * half) : TY + half; // row slot of a row-warp thread
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	const long long nx = d.nx, ny = d.ny, plane = d.plane;
 	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -445,6 +447,7 @@ __global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_residual_restrict(Dims 
                                                                           const CGState *__restrict__ st, const CommDev *cm, unsigned long long wait_in) {
 	if (st && st->done) return;
 	if (cm && wait_in) block_wait_neighbours(cm, wait_in); // z-slabs: the ghost planes of x come from the neighbours' last fused sweep
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	const long long nx = d.nx, ny = d.ny, plane = d.plane;
 	int i0, j0, kb, ke;
@@ -477,6 +480,7 @@ __global__ void __launch_bounds__(TX *8) k_prolong_add(Dims d, Tiles T, Dims dc,
                                                       const CGState *__restrict__ st, const SlabPush sp) {
 	if (st && st->done) return;
 	float *const plo = push_target_lo<float>(sp, d.plane, d.nzl), *const phi = push_target_hi<float>(sp);
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(T, ntiles, true); w.next(T, d.nzl, i0, j0, kb, ke);) {
@@ -513,9 +517,8 @@ struct TailArgs {
 	TailLevel L[TAIL_MAX_LEVELS];
 };
 
-__global__ void __launch_bounds__(TAIL_THREADS) k_vcycle_tail(TailArgs A, const CGState *__restrict__ st) {
-	if (st && st->done) return;
-	extern __shared__ float sm[];
+// (one CTA of TAIL_THREADS threads; sm = its dynamic shared memory)
+__device__ __forceinline__ void tail_body(const TailArgs &A, float *sm) {
 	const int tid = threadIdx.x;
 	auto arr = [&](int l, int which) -> float * { return sm + A.L[l].offset + which * A.L[l].stride + (int)A.L[l].d.plane; };
 	// stage the operators; x and the ghost planes of b start at zero
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vcycle_tail(TailArgs A, const 
 		for (int c = tid - plane; c < n - plane; c += TAIL_THREADS) {
 			wx[c] = L.wx[c]; wy[c] = L.wy[c]; wz[c] = L.wz[c]; dd[c] = L.dd[c];
 			x[c] = 0.f;
-			b[c] = (l == 0 && c >= 0 && c < (int)L.d.ncell) ? A.b_in[c] : 0.f;
+			b[c] = (l == 0 && c >= 0 && c < (int)L.d.ncell) ? __ldcg(A.b_in + c) : 0.f; // (L2: inside k_vcycle_mid other SMs have just written it)
 		}
 	}
 	__syncthreads();
@@ -600,6 +603,245 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_vcycle_tail(TailArgs A, const 
 	for (int c = tid; c < (int)A.L[0].d.ncell; c += TAIL_THREADS) A.x_out[c] = x[c];
 }
 
+__global__ void __launch_bounds__(TAIL_THREADS) k_vcycle_tail(TailArgs A, const CGState *__restrict__ st) {
+	if (st && st->done) return;
+	extern __shared__ float sm[];
+	tail_body(A, sm);
+}
+
+// ---- the middle of the V-cycle in ONE cooperative launch -----------------------------------------------------------------
+// Levels that are too large for one CTA's shared memory but far too small to fill the GPU (a few 10^5 unknowns and less: from the third level down on a
+// 512^3 liquid scene, the whole hierarchy of a 64^3 one) used to cost five launches each per V-cycle, every one of them ~12 us of launch latency, pipeline
+// fill and tail for microseconds of work — a quarter of the solve time for a tenth of its bytes. Here ONE launch of one CTA per SM walks all of them down
+// and up again, in place, separated by grid-wide barriers (cooperative launch: every CTA is resident); the data lives in L2. The shared-memory tail runs
+// inside the same launch on CTA 0. Arithmetic is that of the tiled kernels (same atoms, same order): in-place red-black relaxation is what the out-of-place
+// fused sweep computes, so results agree bit for bit with every other path (tests/test_gpu_parity.py).
+//   work item = one row of one plane of one active tile, taken by a warp: lane l relaxes cell i0 + 2 l + (colour offset of the row)
+constexpr int MID_MAX_LEVELS = 8;
+constexpr int MID_THREADS = 1024;
+struct MidLevel {
+	Dims d;
+	Tiles tiles;
+	const float *wx, *wy, *wz, *dd;
+	float *b, *x; // right-hand side, solution (in place)
+};
+struct MidArgs {
+	int nlev;              // levels walked here, finest first
+	int pre, post, coarse; // sweeps (coarse: on the last level when no tail follows)
+	int has_tail;          // the shared-memory tail (TailArgs) continues below the last level
+	int dot;               // finest level is level 0 of the solve: reduce z.b into the CG state at the end
+	unsigned *barrier;     // [0] arrivals, [1] generation
+	MidLevel L[MID_MAX_LEVELS];
+};
+
+// Grid-wide barrier of a cooperative launch: arrivals counted with a release atomic (the CTA's writes, ordered before it by the block barrier, become
+// visible with it), the last arrival resets the counter and publishes the next generation, everybody else polls the generation with acquire loads.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &gen) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned target = ++gen;
+		unsigned prev;
+		asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
+		if (prev == gridDim.x - 1) {
+			asm volatile("st.relaxed.gpu.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+			asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(bar + 1), "r"(target) : "memory");
+		} else {
+			unsigned seen;
+			do {
+				asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 1) : "memory");
+			} while (seen != target);
+		}
+	}
+	__syncthreads();
+}
+
+enum MidMode { MID_ZERO_A, MID_ZERO_B, MID_PLAIN, MID_PROLONG_A, MID_PROLONG_B };
+
+__global__ void __launch_bounds__(MID_THREADS, 1) k_vcycle_mid(const __grid_constant__ MidArgs A, const __grid_constant__ TailArgs TA, RedBuf rb, CGState *st) {
+	if (st && st->done) return;
+	extern __shared__ float sm[];
+	unsigned gen = *reinterpret_cast<volatile unsigned *>(&A.barrier[1]);
+	const int lane = threadIdx.x & 31;
+	__shared__ int s_ntiles[MID_MAX_LEVELS], s_bz[MID_MAX_LEVELS]; // the levels' active-tile counts and tile depths, fetched once
+	if (threadIdx.x < MID_MAX_LEVELS) {
+		const bool have = (int)threadIdx.x < A.nlev;
+		s_ntiles[threadIdx.x] = have ? A.L[threadIdx.x].tiles.count[0] : 0;
+		s_bz[threadIdx.x] = have ? (A.L[threadIdx.x].tiles.bz ? A.L[threadIdx.x].tiles.bz : A.L[threadIdx.x].tiles.count[1]) : 2;
+	}
+	__syncthreads();
+	const long long gwarp = ((long long)blockIdx.x * MID_THREADS + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * MID_THREADS) >> 5;
+
+	// one colour of one red-black sweep on level l; ec / dc: the coarse correction of the PROLONG modes
+	auto relax = [&](int l, int colour, int mode, const float *ec, const Dims &dc) {
+		const MidLevel &L = A.L[l];
+		const Dims &d = L.d;
+		Tiles T = L.tiles;
+		T.bz = s_bz[l];
+		const long long nx = d.nx, ny = d.ny, plane = d.plane;
+		const int ntiles = s_ntiles[l];
+		const long long items = (long long)ntiles * T.bz * TY;
+		auto E = [&](int i, int j, int k) -> float { return __ldcg(ec + ((i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1)))); };
+		for (long long it = gwarp; it < items; it += nwarps) {
+			const int t = (int)(it / (T.bz * TY)), rem = (int)(it - (long long)t * (T.bz * TY));
+			int i0, j0, kb;
+			tile_origin(T, T.ids[t], i0, j0, kb);
+			const int k = kb + rem / TY, j = j0 + rem % TY;
+			if (k >= d.nzl || j >= d.ny) continue;
+			const int i = i0 + 2 * lane + ((colour + j + k + d.k0) & 1);
+			if (i >= d.nx) continue;
+			const long long c = i + nx * (j + ny * k);
+			const float w0 = L.wx[c], w1 = L.wx[c + 1], w2 = L.wy[c], w3 = L.wy[c + nx], w4 = L.wz[c], w5 = L.wz[c + plane], dg = L.dd[c];
+			const float bb = __ldcg(L.b + c);
+			float xn;
+			if (mode == MID_ZERO_A) xn = gs_relax0(w0, w1, w2, w3, w4, w5, dg, bb);
+			else {
+				// every operand in one round trip: a neighbour across a zero coefficient (a wall, whose flat index wraps to another cell of the allocation,
+				// or a cell without an equation) is read like any other — whatever finite value it holds meets an exact zero, as in the tiled kernels
+				float x0 = __ldcg(L.x + c - 1), x1 = __ldcg(L.x + c + 1), x2 = __ldcg(L.x + c - nx), x3 = __ldcg(L.x + c + nx), x4 = __ldcg(L.x + c - plane),
+				      x5 = __ldcg(L.x + c + plane);
+				float xc = mode == MID_ZERO_B ? 0.f : __ldcg(L.x + c);
+				if (mode == MID_PROLONG_A) { // neighbours (the other colour) and the cell itself still lack the coarse correction
+					if (i > 0) x0 += E(i - 1, j, k);
+					if (i + 1 < d.nx) x1 += E(i + 1, j, k);
+					if (j > 0) x2 += E(i, j - 1, k);
+					if (j + 1 < d.ny) x3 += E(i, j + 1, k);
+					if (k > 0) x4 += E(i, j, k - 1);
+					if (k + 1 < d.nzl) x5 += E(i, j, k + 1);
+				}
+				if (mode == MID_PROLONG_A || mode == MID_PROLONG_B) xc += E(i, j, k);
+				xn = gs_relax(w0, w1, w2, w3, w4, w5, dg, bb, x0, x1, x2, x3, x4, x5, xc);
+			}
+			__stcg(L.x + c, xn);
+		}
+	};
+	// coarse b = P^T (b - A x), level l -> l + 1 (bc: the coarse right-hand side, which may be the tail's)
+	auto restrict_to = [&](int l, float *bc, const Dims &dc) {
+		const MidLevel &L = A.L[l];
+		const Dims &d = L.d;
+		Tiles T = L.tiles;
+		T.bz = s_bz[l];
+		const long long nx = d.nx, ny = d.ny, plane = d.plane;
+		const int ntiles = s_ntiles[l];
+		const int per_tile = (T.bz >> 1) * (TY >> 1);
+		const long long items = (long long)ntiles * per_tile;
+		for (long long it = gwarp; it < items; it += nwarps) {
+			const int t = (int)(it / per_tile), rem = (int)(it - (long long)t * per_tile);
+			int i0, j0, kb;
+			tile_origin(T, T.ids[t], i0, j0, kb);
+			const int k = kb + 2 * (rem / (TY >> 1)), J = (j0 >> 1) + rem % (TY >> 1), I = (i0 >> 1) + lane;
+			if (k >= d.nzl || I >= dc.nx || J >= dc.ny) continue;
+			float acc = 0.f;
+#pragma unroll
+			for (int dk = 0; dk < 2; ++dk)
+#pragma unroll
+				for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+					for (int di = 0; di < 2; ++di) {
+						const int i = 2 * I + di, j = 2 * J + dj, kk = k + dk;
+						if (i < d.nx && j < d.ny && kk < d.nzl) {
+							const long long c = i + nx * (j + ny * kk);
+							acc += residual7(L.wx[c], L.wx[c + 1], L.wy[c], L.wy[c + nx], L.wz[c], L.wz[c + plane], L.dd[c], __ldcg(L.b + c), __ldcg(L.x + c), __ldcg(L.x + c - 1),
+							                 __ldcg(L.x + c + 1), __ldcg(L.x + c - nx), __ldcg(L.x + c + nx), __ldcg(L.x + c - plane), __ldcg(L.x + c + plane));
+						}
+					}
+			__stcg(bc + (I + (long long)dc.nx * (J + (long long)dc.ny * (k >> 1))), acc);
+		}
+	};
+	// x += P e on every cell of the active tiles (MGPostSweeps = 0 only: otherwise the first post-sweep folds it in)
+	auto prolong = [&](int l, const float *ec, const Dims &dc) {
+		const MidLevel &L = A.L[l];
+		const Dims &d = L.d;
+		Tiles T = L.tiles;
+		T.bz = s_bz[l];
+		const int ntiles = s_ntiles[l];
+		const long long items = (long long)ntiles * T.bz * TY;
+		for (long long it = gwarp; it < items; it += nwarps) {
+			const int t = (int)(it / (T.bz * TY)), rem = (int)(it - (long long)t * (T.bz * TY));
+			int i0, j0, kb;
+			tile_origin(T, T.ids[t], i0, j0, kb);
+			const int k = kb + rem / TY, j = j0 + rem % TY;
+			if (k >= d.nzl || j >= d.ny) continue;
+			for (int e = 0; e < 2; ++e) {
+				const int i = i0 + 2 * lane + e;
+				if (i >= d.nx) continue;
+				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+				__stcg(L.x + c, __ldcg(L.x + c) + __ldcg(ec + ((i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1)))));
+			}
+		}
+	};
+
+	// ---- descend
+	for (int l = 0; l < A.nlev; ++l) {
+		const bool last = l + 1 == A.nlev && !A.has_tail;
+		const int sweeps = last ? A.coarse : A.pre;
+		for (int sw = 0; sw < sweeps; ++sw) {
+			relax(l, 0, sw == 0 ? MID_ZERO_A : MID_PLAIN, nullptr, A.L[l].d);
+			grid_barrier(A.barrier, gen);
+			relax(l, 1, sw == 0 ? MID_ZERO_B : MID_PLAIN, nullptr, A.L[l].d);
+			grid_barrier(A.barrier, gen);
+		}
+		if (last) break;
+		if (l + 1 < A.nlev) restrict_to(l, A.L[l + 1].b, A.L[l + 1].d);
+		else restrict_to(l, const_cast<float *>(TA.b_in), TA.L[0].d);
+		grid_barrier(A.barrier, gen);
+	}
+	// ---- the shared-memory tail on CTA 0 (the others wait at the barrier)
+	if (A.has_tail) {
+		if (blockIdx.x == 0) tail_body(TA, sm);
+		grid_barrier(A.barrier, gen);
+	}
+	// ---- ascend
+	for (int l = A.nlev - 1; l >= 0; --l) {
+		const bool last = l + 1 == A.nlev && !A.has_tail;
+		const int sweeps = last ? A.coarse : A.post;
+		const float *ec = nullptr;
+		Dims dc = A.L[l].d;
+		if (!last) {
+			if (l + 1 < A.nlev) { ec = A.L[l + 1].x; dc = A.L[l + 1].d; }
+			else { ec = TA.x_out; dc = TA.L[0].d; }
+			if (sweeps == 0) {
+				prolong(l, ec, dc);
+				grid_barrier(A.barrier, gen);
+			}
+		}
+		for (int sw = 0; sw < sweeps; ++sw) {
+			const bool pro = !last && sw == 0;
+			relax(l, 1, pro ? MID_PROLONG_A : MID_PLAIN, ec, dc);
+			grid_barrier(A.barrier, gen);
+			relax(l, 0, pro ? MID_PROLONG_B : MID_PLAIN, ec, dc);
+			grid_barrier(A.barrier, gen);
+		}
+	}
+	if (A.dot) { // level 0 of the solve: rho' = z.b0, beta (pcg_solver.h:286-288)
+		const MidLevel &L = A.L[0];
+		const Dims &d = L.d;
+		Tiles T = L.tiles;
+		T.bz = s_bz[0];
+		const int ntiles = s_ntiles[0];
+		const long long items = (long long)ntiles * T.bz * TY;
+		double red[1] = {0.0};
+		for (long long it = gwarp; it < items; it += nwarps) {
+			const int t = (int)(it / (T.bz * TY)), rem = (int)(it - (long long)t * (T.bz * TY));
+			int i0, j0, kb;
+			tile_origin(T, T.ids[t], i0, j0, kb);
+			const int k = kb + rem / TY, j = j0 + rem % TY;
+			if (k >= d.nzl || j >= d.ny) continue;
+			for (int e = 0; e < 2; ++e) {
+				const int i = i0 + 2 * lane + e;
+				if (i >= d.nx) continue;
+				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
+				red[0] += (double)__ldcg(L.x + c) * (double)__ldcg(L.b + c);
+			}
+		}
+		grid_reduce<1, 0u>(red, rb, [&](double (&tot)[1]) {
+			const double zr = tot[0];
+			st->beta = st->iter == 0 ? 0.0 : zr / st->rho;
+			st->rho = zr;
+			if (zr == 0.0 || zr != zr) st->done = 1;
+		});
+	}
+}
+
 // ---- hierarchy setup -----------------------------------------------------------------------------------------
 // Coarse operator = scale * P^T A P (once per projection): coarse face coupling = sum of the four fine
 // couplings crossing the coarse face, coarse dd = sum of the children's dd. Flags the coarse tile of every
@@ -610,6 +852,7 @@ __global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_coarsen_operator(Dims d
                                                                          const float *__restrict__ wz, const float *__restrict__ dd, float *__restrict__ cwx,
                                                                          float *__restrict__ cwy, float *__restrict__ cwz, float *__restrict__ cdd,
                                                                          unsigned char *__restrict__ tile_flags) {
+	resolve_tiles(U);
 	const int ntiles = *U.count;
 	int i0, j0, kb, ke;
 	for (TileWalk w(U, ntiles); w.next(U, df.nzl, i0, j0, kb, ke);) {
@@ -641,7 +884,7 @@ __global__ void __launch_bounds__((TX / 2) * (TY / 2)) k_coarsen_operator(Dims d
 			cwy[C] = scale * sy;
 			cwz[C] = scale * sz;
 			cdd[C] = scale * sd;
-			if (live) tile_flags[tile_of(Tc, I, J, K)] = 1;
+			if (live) tile_flags[slice_of(Tc, I, J, K)] = 1;
 		}
 	}
 }
@@ -654,23 +897,76 @@ __global__ void __launch_bounds__(256) k_flag_live_tiles(Dims d, Tiles T, const 
 	const int k = blockIdx.z;
 	if (i >= d.nx || j >= d.ny) return;
 	const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-	if (gs_diag(wx[c], wx[c + 1], wy[c], wy[c + d.nx], wz[c], wz[c + d.plane], dd[c]) > 0.f) tile_flags[tile_of(T, i, j, k)] = 1;
+	if (gs_diag(wx[c], wx[c + 1], wy[c], wy[c + d.nx], wz[c], wz[c + d.plane], dd[c]) > 0.f) tile_flags[slice_of(T, i, j, k)] = 1;
 }
 
-// flags -> ascending id list + count (single CTA; tile grids are at most a few 10^4 entries). Also the UNION list: tiles flagged now or in the previous
-// projection (`dirty`), i.e. every tile whose arrays may hold something other than zeros — what the kernels that WRITE a level's arrays walk over —,
-// after which `dirty` becomes the current flags.
-__global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned char *__restrict__ flags, unsigned char *__restrict__ dirty, int n, int *__restrict__ ids,
-                                                       int *__restrict__ count, int *__restrict__ uids, int *__restrict__ ucount) {
+// Slice flags -> the projection's tile lists (single CTA; a level has at most a few 10^4 slices).
+//   * tile depth: `bz_fixed` != 0, or chosen here among bz_max, bz_max / 2, ... down to the slice depth. A persistent sweep CTA spends (bz + 2) plane
+//     steps per tile and the grid of `sweep_grid` CTAs needs ceil(tiles / grid) rounds, so the depth that minimises (bz + 2) * rounds wins (ties: the
+//     deeper one): deep tiles for a grid full of unknowns (fewest halo planes), shallower ones when a liquid scene leaves only a few tiles per CTA
+//     — they fill the waves better and hug the free surface more tightly. A level whose every slice is active keeps bz_max.
+//   * ids / count: active tiles of that depth, ascending; count[1] = the depth (what Tiles::bz == 0 reads).
+//   * uids / ucount: the UNION list — tiles with a slice flagged now or in the previous projection (`dirty`), i.e. every tile whose arrays may hold
+//     something other than zeros: what the kernels that WRITE a level's arrays walk over. Afterwards `dirty` becomes the current flags.
+__global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned char *__restrict__ flags, unsigned char *__restrict__ dirty, int ntx, int nty, int nslices_z, int slice,
+                                                       int bz_max, int bz_fixed, int sweep_grid, int *__restrict__ ids, int *__restrict__ count, int *__restrict__ uids,
+                                                       int *__restrict__ ucount) {
 	__shared__ int warp_sums[2][32];
 	__shared__ int base[2];
+	__shared__ int s_cnt[4], s_bz;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int per_plane = ntx * nty;
+	// ---- the depth
+	if (tid == 0) s_bz = bz_fixed ? bz_fixed : bz_max;
+	if (tid < 4) s_cnt[tid] = 0;
+	__syncthreads();
+	if (!bz_fixed && bz_max > slice) {
+		int ncand = 0;
+		for (int bz = bz_max; bz >= slice && ncand < 4; bz >>= 1) ++ncand;
+		for (int cnd = 0; cnd < ncand; ++cnd) {
+			const int m = (bz_max >> cnd) / slice, ntz = (nslices_z + m - 1) / m;
+			int mine = 0;
+			for (int t = tid; t < per_plane * ntz; t += 1024) {
+				const int tz = t / per_plane, xy = t - tz * per_plane;
+				bool any = false;
+				for (int q = 0; q < m && tz * m + q < nslices_z; ++q) any = any || flags[xy + per_plane * (tz * m + q)];
+				mine += any ? 1 : 0;
+			}
+			for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+			if (lane == 0 && mine) atomicAdd(&s_cnt[cnd], mine);
+		}
+		__syncthreads();
+		if (tid == 0) {
+			const int finest = (bz_max >> (ncand - 1)) / slice; // slices per tile of the shallowest candidate
+			const int total_finest = per_plane * ((nslices_z + finest - 1) / finest);
+			int best = 0;
+			if (s_cnt[ncand - 1] < total_finest) { // (a level that is active everywhere keeps the deepest tiles)
+				long long best_cost = -1;
+				for (int cnd = 0; cnd < ncand; ++cnd) {
+					const int bz = bz_max >> cnd, g = s_cnt[cnd] < sweep_grid ? (s_cnt[cnd] > 0 ? s_cnt[cnd] : 1) : sweep_grid;
+					const long long cost = (long long)(bz + 2) * ((s_cnt[cnd] + g - 1) / g);
+					if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cnd; }
+				}
+			}
+			s_bz = bz_max >> best;
+		}
+		__syncthreads();
+	}
+	const int bz = s_bz, m = bz / slice > 0 ? bz / slice : 1, ntz = (nslices_z + m - 1) / m, n = per_plane * ntz;
 	if (tid < 2) base[tid] = 0;
 	__syncthreads();
+	// ---- the lists
 	for (int start = 0; start < n; start += 1024) {
 		const int idx = start + tid;
-		const int f = (idx < n && flags[idx]) ? 1 : 0;
-		const int u = (idx < n && (f || dirty[idx])) ? 1 : 0;
+		int f = 0, u = 0;
+		if (idx < n) {
+			const int tz = idx / per_plane, xy = idx - tz * per_plane;
+			for (int q = 0; q < m && tz * m + q < nslices_z; ++q) {
+				const int sl = xy + per_plane * (tz * m + q);
+				f |= flags[sl] ? 1 : 0;
+				u |= (flags[sl] || dirty[sl]) ? 1 : 0;
+			}
+		}
 		const unsigned bf = __ballot_sync(0xffffffffu, f), bu = __ballot_sync(0xffffffffu, u);
 		const unsigned below = (1u << lane) - 1u;
 		if (lane == 0) { warp_sums[0][wid] = __popc(bf); warp_sums[1][wid] = __popc(bu); }
@@ -679,7 +975,6 @@ __global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned char *__r
 		for (int w = 0; w < wid; ++w) { wf += warp_sums[0][w]; wu += warp_sums[1][w]; }
 		if (f) ids[base[0] + wf + __popc(bf & below)] = idx;
 		if (u) uids[base[1] + wu + __popc(bu & below)] = idx;
-		if (idx < n) dirty[idx] = (unsigned char)f;
 		__syncthreads();
 		if (tid < 2) {
 			int tot = 0;
@@ -688,7 +983,8 @@ __global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned char *__r
 		}
 		__syncthreads();
 	}
-	if (tid == 0) { *count = base[0]; *ucount = base[1]; }
+	for (int sl = tid; sl < per_plane * nslices_z; sl += 1024) dirty[sl] = flags[sl];
+	if (tid == 0) { count[0] = base[0]; count[1] = bz; ucount[0] = base[1]; ucount[1] = bz; }
 }
 
 } // namespace shkz

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 	const bool producer = tid == S4_THREADS - 1; // last lane of the halo-column warp
 	const int tx = lane & 15, half = lane >> 4;
 	const int r = warp < S4_ROW_WARPS - 1 ? ((warp >> 1) * 4 + (warp & 1) + 2 * half) : TY + half;
+	resolve_tiles(T);
 	const int ntiles = *T.count;
 	const long long nx = d.nx, ny = d.ny, plane = d.plane;
 	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);

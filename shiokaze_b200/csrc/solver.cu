@@ -151,7 +151,9 @@ struct Profiler {
 
 struct HostLevel {
 	Dims d;
-	int bz = 4, tiles_total = 0;
+	int bz = 4, tiles_total = 0; // deepest tile depth of the level; number of flag slices (= the largest number of tiles any depth gives)
+	int slice = 4, nslices_z = 0, ntx = 0, nty = 0;
+	bool adaptive = false;       // tile depth chosen per projection by k_compact_tiles (whole-grid levels with deep tiles)
 	std::string tag_sweep, tag_restrict, tag_prolong, tag_coarsen, tag_compact;
 	CellArray wx, wy, wz, dd, xa, xb, b;
 	CellArray legacy_r; // residual array of the unfused validation path (allocated on first use)
@@ -226,6 +228,9 @@ struct shkz_b200_solver {
 	int gtail_first = -1;
 	size_t gtail_smem = 0;
 	TailArgs gtail_args{};
+	// levels [mid_first, tail_first) run inside ONE cooperative launch together with the tail (k_vcycle_mid, kernels_mg.cuh); -1: no such levels
+	int mid_first = -1, gmid_first = -1;
+	PlainArray mid_barrier;
 	std::map<const void *, int> occupancy; // resident CTAs per SM of each persistent kernel
 	// reductions / control
 	PlainArray partials, counter, state;
@@ -276,6 +281,7 @@ void release_precision_arrays(shkz_b200_solver *S) {
 	S->glevels.clear();
 	S->agg_level = -1;
 	S->gtail_first = -1;
+	S->mid_first = S->gmid_first = -1;
 	S->levels.clear();
 	S->alloc_precision = -1;
 	S->have_system = false;
@@ -304,18 +310,22 @@ int finish_level(HostLevel &L, const Dims &cur, const std::string &n, SlabComm *
 	CKR(L.xa.alloc(cur, sizeof(float), arena));
 	CKR(L.xb.alloc(cur, sizeof(float), arena));
 	L.bz = pick_bz(cur);
-	const int ntx = (cur.nx + TX - 1) / TX, nty = (cur.ny + TY - 1) / TY, ntz = (cur.nzl + L.bz - 1) / L.bz;
-	L.tiles_total = ntx * nty * ntz;
+	L.slice = L.bz < 8 ? L.bz : 8;
+	L.adaptive = balanced && L.bz > L.slice && !getenv("SHKZ_B200_BZ"); // (balanced == whole-grid level)
+	const int ntx = (cur.nx + TX - 1) / TX, nty = (cur.ny + TY - 1) / TY;
+	L.ntx = ntx; L.nty = nty;
+	L.nslices_z = (cur.nzl + L.slice - 1) / L.slice;
+	L.tiles_total = ntx * nty * L.nslices_z;
 	CKR(L.tile_flags.alloc((size_t)L.tiles_total));
 	CKR(L.tile_ids.alloc((size_t)L.tiles_total * sizeof(int)));
-	CKR(L.tile_count.alloc(sizeof(int)));
+	CKR(L.tile_count.alloc(2 * sizeof(int)));
 	CKR(L.tile_dirty.alloc((size_t)L.tiles_total));
 	CKR(L.tile_uids.alloc((size_t)L.tiles_total * sizeof(int)));
-	CKR(L.tile_ucount.alloc(sizeof(int)));
+	CKR(L.tile_ucount.alloc(2 * sizeof(int)));
 	L.tag_sweep = "sweep@" + n; L.tag_restrict = "residual_restrict@" + n; L.tag_prolong = "prolong_add@" + n;
 	L.tag_coarsen = "coarsen_operator@" + n; L.tag_compact = "compact_tiles@" + n;
 	L.view.d = cur;
-	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, ntz, L.bz, balanced ? (getenv("SHKZ_B200_STENCIL_BALANCED") ? 3 : 1) : 0};
+	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, L.slice, L.adaptive ? 0 : L.bz, balanced ? 1 : 0};
 	L.utiles = L.view.tiles;
 	L.utiles.ids = static_cast<const int *>(L.tile_uids.base);
 	L.utiles.count = static_cast<const int *>(L.tile_ucount.base);
@@ -364,6 +374,25 @@ int setup_tail(const std::vector<HostLevel> &lv, int &tail_first, size_t &tail_s
 
 // z-slab solvers: levels this small (largest global extent, or global cell count: a long thin stack of slabs) are gathered and solved
 // redundantly on every rank — a whole-grid kernel on 2 M cells takes ~10 us, a slab sweep never less than two NVLink round trips
+// levels of at most this many cells (dense) leave the tiled kernels for the cooperative mid-V-cycle kernel
+long long mid_max_cells() {
+	static long long v = -1;
+	if (v < 0) {
+		v = 1ll << 21;
+		if (const char *e = getenv("SHKZ_B200_MID_CELLS")) v = atoll(e); // 0 switches the kernel off (A-B timing)
+	}
+	return v;
+}
+int pick_mid_first(const std::vector<HostLevel> &lv, int tail_first, bool allow_level0) {
+	const int end = tail_first >= 0 ? tail_first : (int)lv.size();
+	int first = -1;
+	for (int l = end - 1; l >= (allow_level0 ? 0 : 1); --l) {
+		if (lv[l].d.ncell > mid_max_cells() || end - l > MID_MAX_LEVELS) break;
+		first = l;
+	}
+	return first;
+}
+
 constexpr int AGG_MAX_EXTENT = 64;
 constexpr long long AGG_MAX_CELLS = 1ll << 21;
 
@@ -418,6 +447,12 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 	{
 		const size_t smem = S->tail_smem > S->gtail_smem ? S->tail_smem : S->gtail_smem;
 		if (smem) CK(cudaFuncSetAttribute(k_vcycle_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		if (smem) CK(cudaFuncSetAttribute(k_vcycle_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		S->mid_first = S->whole_grid ? pick_mid_first(S->levels, S->tail_first, true) : -1; // (slab levels exchange halos between sweeps: tiled kernels)
+		S->gmid_first = S->glevels.empty() ? -1 : pick_mid_first(S->glevels, S->gtail_first, false);
+		int coop = 0;
+		if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, S->device) != cudaSuccess || !coop) S->mid_first = S->gmid_first = -1;
+		if (!S->mid_barrier.base) CKR(S->mid_barrier.alloc(64));
 	}
 	S->alloc_precision = precision;
 	S->mg_min_size_built = min_size;
@@ -488,7 +523,8 @@ int halo(shkz_b200_solver *S, const Dims &d, T *p, cudaStream_t st) {
 
 int compact_tiles(shkz_b200_solver *S, HostLevel &H, cudaStream_t stream) {
 	LAUNCH(S, H.tag_compact.c_str(), k_compact_tiles, 1, 1024, stream, static_cast<const unsigned char *>(H.tile_flags.base), static_cast<unsigned char *>(H.tile_dirty.base),
-	       H.tiles_total, static_cast<int *>(H.tile_ids.base), static_cast<int *>(H.tile_count.base), static_cast<int *>(H.tile_uids.base), static_cast<int *>(H.tile_ucount.base));
+	       H.ntx, H.nty, H.nslices_z, H.slice, H.bz, H.adaptive ? 0 : H.bz, 2 * S->num_sms, static_cast<int *>(H.tile_ids.base), static_cast<int *>(H.tile_count.base),
+	       static_cast<int *>(H.tile_uids.base), static_cast<int *>(H.tile_ucount.base));
 	return SHKZ_B200_OK;
 }
 
@@ -533,6 +569,36 @@ int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st
 	HostLevel &H = lv[l];
 	const MGLevel &L = H.view;
 	const int coarse = P.mg_coarse_sweeps < 1 ? 1 : P.mg_coarse_sweeps;
+	const int mid_first = global ? S->gmid_first : S->mid_first;
+	if ((int)l == mid_first && P.mg_gamma <= 1 && S->sweep_mode == 0) {
+		// levels [l, tail_first) and the tail: one cooperative launch, one CTA per SM
+		MidArgs A{};
+		const int end = tail_first >= 0 ? tail_first : (int)lv.size();
+		A.nlev = end - (int)l;
+		A.pre = P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps;
+		A.post = P.mg_post_sweeps < 0 ? 0 : P.mg_post_sweeps;
+		A.coarse = coarse;
+		A.has_tail = tail_first >= 0 ? 1 : 0;
+		A.dot = (dot && l == 0 && !global) ? 1 : 0;
+		A.barrier = static_cast<unsigned *>(S->mid_barrier.base);
+		for (int m = 0; m < A.nlev; ++m) {
+			const MGLevel &V = lv[l + m].view;
+			A.L[m].d = V.d; A.L[m].tiles = V.tiles;
+			A.L[m].wx = V.wx; A.L[m].wy = V.wy; A.L[m].wz = V.wz; A.L[m].dd = V.dd;
+			A.L[m].b = V.b; A.L[m].x = V.xa;
+		}
+		TailArgs T = global ? S->gtail_args : S->tail_args;
+		T.pre = A.pre; T.post = A.post; T.coarse = coarse;
+		RedBuf rb = S->redbuf();
+		void *args[] = {&A, &T, &rb, &st};
+		const size_t smem = A.has_tail ? (global ? S->gtail_smem : S->tail_smem) : 0;
+		const int slot_ = S->prof.begin("vcycle_mid", stream);
+		CK(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k_vcycle_mid), dim3(S->num_sms), dim3(MID_THREADS), args, smem, stream));
+		S->prof.end(slot_, stream);
+		S->launches++;
+		*result = L.xa;
+		return SHKZ_B200_OK;
+	}
 	if ((int)l == tail_first) {
 		TailArgs A = global ? S->gtail_args : S->tail_args;
 		A.pre = P.mg_pre_sweeps < 1 ? 1 : P.mg_pre_sweeps;
@@ -893,6 +959,8 @@ void fill_stats(const shkz_b200_solver *S, shkz_b200_stats *out) {
 	out->has_dirichlet = h.has_dirichlet;
 	out->mg_levels = (int)(S->levels.size() + (S->glevels.empty() ? 0 : S->glevels.size() - 1));
 	out->kernel_launches = S->launches;
+	out->mg_mid_level = S->mid_first;
+	out->mg_tail_level = S->tail_first;
 }
 
 template <class RealT, class VecT, class CoefT>
@@ -1017,9 +1085,13 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		cudaEventElapsedTime(&stats->ms_update, S->ev[3], S->ev[4]);
 		cudaEventElapsedTime(&stats->ms_total, S->ev[0], S->ev[4]);
 		if (tension) cudaEventElapsedTime(&stats->ms_surftension, S->ev[8], S->ev[9]);
-		int nt = 0;
-		if (cudaMemcpy(&nt, S->levels[0].tile_count.base, sizeof nt, cudaMemcpyDeviceToHost) == cudaSuccess) stats->active_tiles = (uint32_t)nt;
-		stats->total_tiles = (uint32_t)S->levels[0].tiles_total;
+		int nt[2] = {0, 0};
+		const HostLevel &H0 = S->levels[0];
+		if (cudaMemcpy(nt, H0.tile_count.base, sizeof nt, cudaMemcpyDeviceToHost) == cudaSuccess && nt[1] > 0) {
+			stats->active_tiles = (uint32_t)nt[0];
+			stats->tile_depth = (uint32_t)nt[1];
+			stats->total_tiles = (uint32_t)(H0.ntx * H0.nty * ((d.nzl + nt[1] - 1) / nt[1]));
+		}
 	}
 	return comm_health(S);
 }
@@ -1180,7 +1252,7 @@ void shkz_b200_destroy(shkz_b200_solver *S) {
 		S->areas[dim].release(); S->rhos[dim].release(); S->st_vel[dim].release(); S->st_act[dim].release();
 	}
 	S->st_solid.release(); S->st_fluid.release(); S->st_pressure.release(); S->st_pact.release();
-	S->partials.release(); S->counter.release(); S->state.release();
+	S->partials.release(); S->counter.release(); S->state.release(); S->mid_barrier.release();
 	if (S->h_state) cudaFreeHost(S->h_state);
 	if (S->events) for (auto &e : S->ev) if (e) cudaEventDestroy(e);
 	S->prof.destroy();
