@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 //
 #include "../../include/shkz_b200.h"
@@ -145,8 +146,12 @@ protected:
 		void *vel_ptr[3] = { vel[0], vel[1], vel[2] };
 		uint8_t *act_ptr[3] = { vel_active[0], vel_active[1], vel_active[2] };
 		shkz_b200_stats stats;
-		if( shkz_b200_project_host(m_solver,dt,vel_ptr,act_ptr,have_solid ? solid_dense : nullptr,fluid_dense,
-				fluid_levelset,&params,pressure,pressure_active,&stats) != SHKZ_B200_OK ) fatal("shkz_b200_project_host");
+		if( m_slabs.empty()) {
+			if( shkz_b200_project_host(m_solver,dt,vel_ptr,act_ptr,have_solid ? solid_dense : nullptr,fluid_dense,
+					fluid_levelset,&params,pressure,pressure_active,&stats) != SHKZ_B200_OK ) fatal("shkz_b200_project_host");
+		} else {
+			project_slabs(dt,vel,vel_active,have_solid ? solid_dense : nullptr,fluid_dense,fluid_levelset,params,pressure,pressure_active,stats);
+		}
 		// the reference's records (macpressuresolver3.cpp:82,114,201,215,236-237,269,271 through scoped_timer::stock -> "<Arg>_<name>", milliseconds), fed
 		// from the CUDA-event times of the phases that replace them: fractions + labelling + assembly are ONE fused phase here (ms_assemble; the surface-tension
 		// part of it is reported separately like the reference does), the multigrid hierarchy is this solver's "build" step, the MG-PCG loop its "linsolve"
@@ -178,6 +183,54 @@ protected:
 		});
 		console::dump( "Done. Took %s\n", timer.stock("scatter").c_str());
 		console::dump( "<<< Projection done. Took %s.\n", timer.stock("projection").c_str());
+	}
+	//
+	// GPUs=N: the grid cut into N equal z-slabs, one CUDA device and one host thread per slab (every call blocks on its own device while the slabs talk
+	// to each other through peer memory inside the kernels: they must run concurrently). z is the slowest index of the dense layout, so a slab of the cell /
+	// x-face / y-face / nodal grids is a contiguous range of the gathered buffers and is handed over in place; only the z-face grids, whose plane between two
+	// slabs belongs to both, go through a per-slab copy.
+	void project_slabs( double dt, Real *vel[DIM3], uint8_t *vel_active[DIM3], const Real *solid, const Real *fluid, bool fluid_levelset,
+				const shkz_b200_params &params, Real *pressure, uint8_t *pressure_active, shkz_b200_stats &stats ) {
+		const int world = (int)m_slabs.size();
+		const size_t nx = m_shape.w, ny = m_shape.h, nzl = m_shape.d / world;
+		const size_t cell_plane = nx*ny, xf_plane = (nx+1)*ny, yf_plane = nx*(ny+1), node_plane = (nx+1)*(ny+1);
+		std::vector<int> rc (world,SHKZ_B200_OK);
+		std::vector<std::string> message (world);
+		std::vector<shkz_b200_stats> slab_stats (world);
+		std::vector<std::thread> threads;
+		for( int r=0; r<world; ++r ) {
+			Real *wz = m_slab_w[r].ensure(cell_plane*(nzl+1));
+			uint8_t *az = m_slab_wact[r].ensure(cell_plane*(nzl+1));
+			std::copy(vel[2]+r*nzl*cell_plane,vel[2]+(r*nzl+nzl+1)*cell_plane,wz);
+			std::copy(vel_active[2]+r*nzl*cell_plane,vel_active[2]+(r*nzl+nzl+1)*cell_plane,az);
+			threads.emplace_back([&,r,wz,az]() {
+				const size_t k0 = r*nzl;
+				void *v[3] = { vel[0]+k0*xf_plane, vel[1]+k0*yf_plane, wz };
+				uint8_t *a[3] = { vel_active[0]+k0*xf_plane, vel_active[1]+k0*yf_plane, az };
+				rc[r] = shkz_b200_project_host(m_slabs[r],dt,v,a,solid ? solid+k0*node_plane : nullptr,fluid+k0*cell_plane,fluid_levelset,&params,
+					pressure+k0*cell_plane,pressure_active+k0*cell_plane,&slab_stats[r]);
+				if( rc[r] != SHKZ_B200_OK ) message[r] = shkz_b200_last_error(); // (the message is thread-local)
+			});
+		}
+		for( auto &t : threads ) t.join();
+		for( int r=0; r<world; ++r ) if( rc[r] != SHKZ_B200_OK ) {
+			console::dump( "<Red>b200pressure3: slab %d of %d failed: %s<Default>\n", r, world, message[r].c_str());
+			exit(-1);
+		}
+		// z faces back: every slab owns its lower planes, the last one also the top plane (the shared planes agree between neighbours)
+		for( int r=0; r<world; ++r ) {
+			const size_t planes = nzl + (r == world-1 ? 1 : 0);
+			std::copy(m_slab_w[r].p,m_slab_w[r].p+planes*cell_plane,vel[2]+r*nzl*cell_plane);
+			std::copy(m_slab_wact[r].p,m_slab_wact[r].p+planes*cell_plane,vel_active[2]+r*nzl*cell_plane);
+		}
+		// every slab reports the same globally reduced solve; phase times are the slowest slab's
+		stats = slab_stats[0];
+		for( int r=1; r<world; ++r ) {
+			stats.ms_h2d = std::max(stats.ms_h2d,slab_stats[r].ms_h2d); stats.ms_assemble = std::max(stats.ms_assemble,slab_stats[r].ms_assemble);
+			stats.ms_setup = std::max(stats.ms_setup,slab_stats[r].ms_setup); stats.ms_solve = std::max(stats.ms_solve,slab_stats[r].ms_solve);
+			stats.ms_update = std::max(stats.ms_update,slab_stats[r].ms_update); stats.ms_d2h = std::max(stats.ms_d2h,slab_stats[r].ms_d2h);
+			stats.ms_total = std::max(stats.ms_total,slab_stats[r].ms_total); stats.kernel_launches += slab_stats[r].kernel_launches;
+		}
 	}
 	//
 	virtual void configure( configuration &config ) override {
@@ -213,7 +266,8 @@ protected:
 		config.get_integer("MGPreSweeps",m_cuda_param.mg_pre_sweeps,"Red-black sweeps before the coarse correction");
 		config.get_integer("MGPostSweeps",m_cuda_param.mg_post_sweeps,"Red-black sweeps after the coarse correction");
 		config.get_double("MGOmega",m_cuda_param.mg_omega,"Relaxation factor of the red-black sweeps (1 = Gauss-Seidel)");
-		config.get_integer("GPU",m_device,"CUDA device index");
+		config.get_integer("GPU",m_device,"CUDA device index (of the first slab when GPUs > 1)");
+		config.get_integer("GPUs",m_gpus,"Number of CUDA devices: the grid is cut into this many equal z-slabs (1, 2, 4 or 8)");
 		m_cuda_param.precision = precision == "fp64" ? SHKZ_B200_PREC_FP64 : (precision == "fp32" ? SHKZ_B200_PREC_FP32 : SHKZ_B200_PREC_MIXED);
 		m_cuda_param.precond = precond == "none" ? SHKZ_B200_PRECOND_NONE : SHKZ_B200_PRECOND_MG;
 	}
@@ -224,9 +278,27 @@ protected:
 	virtual void post_initialize() override {
 		m_pressure.initialize(m_shape);
 		m_target_volume = m_current_volume = m_y_prev = 0.0;
-		if( m_solver ) { shkz_b200_destroy(m_solver); m_solver = nullptr; }
+		release_solvers();
 		const int real = sizeof(Real) == sizeof(double) ? SHKZ_B200_REAL_F64 : SHKZ_B200_REAL_F32;
-		if( shkz_b200_create(m_shape.w,m_shape.h,m_shape.d,m_dx,real,m_device,&m_solver) != SHKZ_B200_OK ) fatal("shkz_b200_create");
+		if( m_gpus <= 1 ) {
+			if( shkz_b200_create(m_shape.w,m_shape.h,m_shape.d,m_dx,real,m_device,&m_solver) != SHKZ_B200_OK ) fatal("shkz_b200_create");
+		} else {
+			if( m_gpus > 8 || m_shape.d % m_gpus ) {
+				console::dump( "<Red>b200pressure3: GPUs=%d needs a z extent (%d) divisible by it, and at most 8 devices.<Default>\n", m_gpus, (int)m_shape.d );
+				exit(-1);
+			}
+			if( m_device+m_gpus > shkz_b200_device_count()) {
+				console::dump( "<Red>b200pressure3: GPUs=%d from device %d, but %d CUDA device(s) visible.<Default>\n", m_gpus, m_device, shkz_b200_device_count());
+				exit(-1);
+			}
+			const int nzl = m_shape.d / m_gpus;
+			m_slabs.assign(m_gpus,nullptr);
+			for( int r=0; r<m_gpus; ++r ) {
+				if( shkz_b200_create_slab(m_shape.w,m_shape.h,m_shape.d,r*nzl,(r+1)*nzl,m_dx,real,m_device+r,&m_slabs[r]) != SHKZ_B200_OK ) fatal("shkz_b200_create_slab");
+			}
+			if( shkz_b200_slab_connect_local(m_slabs.data(),m_gpus) != SHKZ_B200_OK ) fatal("shkz_b200_slab_connect_local");
+			m_slab_w.resize(m_gpus); m_slab_wact.resize(m_gpus);
+		}
 	}
 	virtual const array3<Real> * get_pressure() const override {
 		return &m_pressure;
@@ -234,7 +306,14 @@ protected:
 	virtual ~b200pressure3() {
 		for( int dim : DIMS3 ) { m_hvel[dim].release(); m_hact[dim].release(); }
 		m_hsolid.release(); m_hfluid.release(); m_hpressure.release(); m_hpact.release();
-		if( m_solver ) shkz_b200_destroy(m_solver);
+		release_solvers();
+	}
+	void release_solvers() {
+		if( m_solver ) { shkz_b200_destroy(m_solver); m_solver = nullptr; }
+		for( auto *s : m_slabs ) if( s ) shkz_b200_destroy(s);
+		m_slabs.clear();
+		for( auto &b : m_slab_w ) b.release();
+		for( auto &b : m_slab_wact ) b.release();
 	}
 	//
 	struct Parameters {
@@ -244,6 +323,10 @@ protected:
 	shkz_b200_params m_cuda_param;
 	shkz_b200_solver *m_solver {nullptr};
 	int m_device {0};
+	int m_gpus {1};
+	std::vector<shkz_b200_solver *> m_slabs;   // GPUs > 1: one z-slab solver per device, wired through peer memory
+	std::vector<staging<Real>> m_slab_w;       // ... and the slabs' copies of the z-face grid
+	std::vector<staging<uint8_t>> m_slab_wact;
 	staging<Real> m_hvel[DIM3], m_hsolid, m_hfluid, m_hpressure;
 	staging<uint8_t> m_hact[DIM3], m_hpact;
 	//

@@ -84,3 +84,27 @@ def test_unconnected_slab_refuses_to_project(cuda_device):
         S.project_scene(dist.split_dense(sc, 2)[0])
     assert e.value.code == capi.ERR_STATE
     S.close()
+
+
+@pytest.mark.parametrize("scene", ["dambreak_solid", "smoke"])
+def test_module_gpus_flag_through_the_reference_loader(worlds, scene):
+    """`Projection=b200pressure3 GPUs=N`: the Shiokaze module cuts the grid into N z-slabs, one device and one host thread each
+    (plugin/b200pressure3.cpp: project_slabs) — same host, same sparse grids, against the reference module and against GPUs=1."""
+    import os
+    from oracle import refio
+    if not (refio.ref_available("f32") and os.path.isfile(os.path.join(refio.ref_dir("f32"), "libshiokaze_b200pressure3.so"))):
+        pytest.skip("oracle/_ref (reference build + module) was not shipped to this box")
+    sc = {"dambreak_solid": lambda: scenes.dambreak(64, True), "smoke": lambda: scenes.smoke_plume(48)}[scene]()
+    flags = {"Residual": 1e-10}
+    ref = refio.run_reference(sc, "f32", flags=flags)
+    one = refio.run_reference(sc, "f32", flags={**flags, "Precision": "fp64"}, projection="b200pressure3")
+    for world in worlds:
+        if sc.nz % world:
+            continue
+        many = refio.run_reference(sc, "f32", flags={**flags, "Precision": "fp64", "GPUs": world}, projection="b200pressure3")
+        assert np.array_equal(many.pressure_active, ref.pressure_active)
+        for d in range(3):
+            assert np.array_equal(many.vel_active[d], ref.vel_active[d])
+        assert rel_l2(many.vel, ref.vel) < 1e-3
+        assert rel_l2(many.vel, one.vel) < 1e-6
+        assert abs(many.iterations - one.iterations) <= 1
