@@ -1,0 +1,23 @@
+/*
+ * b200dense.h — the message by which a Shiokaze module asks an array for direct access to its storage.
+ *
+ * array3<T>::const_send_message(B200_DENSE_MESSAGE, &descriptor) forwards to the array's core (include/shiokaze/array/array3.h:125-150); the
+ * b200array3 core (`Array=b200array3`, plugin/b200array3.cpp) fills the descriptor and returns true, every stock core returns false.
+ *   values   nx*ny*nz elements of element_bytes bytes, index i + nx*(j + ny*k) — the dense layout of include/shkz_b200.h. Entries of inactive cells
+ *            are unspecified: a reader that wants array3::operator() semantics writes the background / fill value there first (b200pressure3 does)
+ *   active   one byte per cell, 1 = active (array3::active()): the mask format of the C-ABI
+ *   filled   one byte per cell, 1 = flood-filled; NULL when the array was never flood-filled
+ *   pinned   1: values and active are page-locked (shkz_b200_host_alloc) — the C-ABI copies run at PCIe speed straight from / into them
+ */
+#ifndef SHKZ_B200_DENSE_H
+#define SHKZ_B200_DENSE_H
+#include <stdint.h>
+#define B200_DENSE_MESSAGE "b200:dense"
+typedef struct b200_dense_descriptor {
+	unsigned nx, ny, nz, element_bytes;
+	void *values;
+	uint8_t *active;
+	const uint8_t *filled;
+	int pinned;
+} b200_dense_descriptor;
+#endif

@@ -29,6 +29,7 @@
 #include <vector>
 //
 #include "../../include/shkz_b200.h"
+#include "b200dense.h"
 //
 SHKZ_USING_NAMESPACE
 //
@@ -88,6 +89,34 @@ protected:
 		});
 	}
 	//
+	// Zero-copy view of a grid whose core is b200array3 (`Array=b200array3`, plugin/b200array3.cpp): its value buffer and its one-byte-per-cell activity
+	// mask ARE the dense buffers the C-ABI takes, page-locked. Entries of inactive cells are first rewritten to what array3::operator() returns for them
+	// (fill value inside, background outside: array3.h:796-801) — a plain threaded sweep over memory instead of one std::function call per cell.
+	static bool dense_view( const array3<Real> &a, Real *&values, uint8_t *&active ) {
+		b200_dense_descriptor d;
+		if( ! a.const_send_message(B200_DENSE_MESSAGE,&d) || ! d.pinned || d.element_bytes != sizeof(Real) || ! d.values ) return false;
+		Real *v = static_cast<Real *>(d.values);
+		const size_t plane = (size_t)d.nx*d.ny;
+		const Real background = a.get_background_value();
+		Real fill = background;
+		if( d.filled ) { // (the fill value has no getter: read it where it shows, at the first filled inactive cell)
+			for( size_t n=0; n<plane*d.nz; ++n ) if( d.filled[n] && ! d.active[n] ) {
+				fill = a((int)(n%d.nx),(int)((n%plane)/d.nx),(int)(n/plane));
+				break;
+			}
+		}
+		const unsigned nthreads = std::max(1u,std::min((unsigned)NUM_THREAD,d.nz));
+		std::vector<std::thread> pool;
+		for( unsigned t=0; t<nthreads; ++t ) pool.emplace_back([&,t]() {
+			for( size_t n=plane*(d.nz*(size_t)t/nthreads); n<plane*(d.nz*(size_t)(t+1)/nthreads); ++n ) {
+				if( ! d.active[n] ) v[n] = (d.filled && d.filled[n]) ? fill : background;
+			}
+		});
+		for( auto &t : pool ) t.join();
+		values = v; active = d.active;
+		return true;
+	}
+	//
 	virtual void project( double dt,
 				macarray3<Real> &velocity,
 				const array3<Real> &solid,
@@ -101,22 +130,28 @@ protected:
 		// Host -> dense buffers
 		timer.tick(); console::dump( "Gathering dense buffers..." );
 		Real *vel[DIM3], *solid_dense (nullptr), *fluid_dense;
-		uint8_t *vel_active[DIM3];
+		uint8_t *vel_active[DIM3], *unused (nullptr);
+		bool vel_in_place[DIM3];
 		for( int dim : DIMS3 ) {
-			const size_t nf = velocity[dim].shape().count();
-			vel[dim] = m_hvel[dim].ensure(nf);
-			vel_active[dim] = m_hact[dim].ensure(nf);
-			gather(velocity[dim],vel[dim],vel_active[dim]);
+			vel_in_place[dim] = dense_view(velocity[dim],vel[dim],vel_active[dim]); // b200array3 grids are read and written where they live
+			if( ! vel_in_place[dim] ) {
+				const size_t nf = velocity[dim].shape().count();
+				vel[dim] = m_hvel[dim].ensure(nf);
+				vel_active[dim] = m_hact[dim].ensure(nf);
+				gather(velocity[dim],vel[dim],vel_active[dim]);
+			}
 		}
-		fluid_dense = m_hfluid.ensure(m_shape.count());
-		gather(fluid,fluid_dense,nullptr);
+		if( ! dense_view(fluid,fluid_dense,unused)) {
+			fluid_dense = m_hfluid.ensure(m_shape.count());
+			gather(fluid,fluid_dense,nullptr);
+		}
 		const bool fluid_levelset = array_utility3::levelset_exist(fluid);
 		bool have_solid = array_utility3::levelset_exist(solid);
 		if( have_solid && solid.shape() != m_shape.nodal()) {
 			console::dump( "<Red>b200pressure3: a solid level set must be nodal (shape+1).<Default>\n" );
 			exit(-1);
 		}
-		if( have_solid ) {
+		if( have_solid && ! dense_view(solid,solid_dense,unused)) {
 			solid_dense = m_hsolid.ensure(solid.shape().count());
 			gather(solid,solid_dense,nullptr);
 		}
@@ -141,8 +176,13 @@ protected:
 		//
 		// The CUDA path
 		timer.tick(); console::dump( "Solving on the GPU...");
-		Real *pressure = m_hpressure.ensure(m_shape.count());
-		uint8_t *pressure_active = m_hpact.ensure(m_shape.count());
+		Real *pressure (nullptr);
+		uint8_t *pressure_active (nullptr);
+		const bool pressure_in_place = dense_view(m_pressure,pressure,pressure_active); // (the call overwrites every value and every activity byte)
+		if( ! pressure_in_place ) {
+			pressure = m_hpressure.ensure(m_shape.count());
+			pressure_active = m_hpact.ensure(m_shape.count());
+		}
 		void *vel_ptr[3] = { vel[0], vel[1], vel[2] };
 		uint8_t *act_ptr[3] = { vel_active[0], vel_active[1], vel_active[2] };
 		shkz_b200_stats stats;
@@ -170,17 +210,21 @@ protected:
 		timer.tick(); console::dump( "Scattering results...");
 		// (exactly the row set is activated, macpressuresolver3.cpp:245-248; parallel_all + it.set() is the reference's own way of
 		// filling a grid in parallel, e.g. macutility3.cpp:341-349)
-		m_pressure.clear();
-		m_pressure.parallel_all([&]( int i, int j, int k, auto &it ) {
-			const size_t n = i + m_shape.w * (j + m_shape.h * (size_t)k);
-			if( pressure_active[n] ) it.set(pressure[n]);
-		});
-		velocity.parallel_actives([&]( int dim, int i, int j, int k, auto &it, int tn ) {
+		if( ! pressure_in_place ) {
+			m_pressure.clear();
+			m_pressure.parallel_all([&]( int i, int j, int k, auto &it ) {
+				const size_t n = i + m_shape.w * (j + m_shape.h * (size_t)k);
+				if( pressure_active[n] ) it.set(pressure[n]);
+			});
+		}
+		for( int dim : DIMS3 ) if( ! vel_in_place[dim] ) {
 			const shape3 s = velocity[dim].shape();
-			const size_t n = i + s.w * (j + s.h * (size_t)k);
-			if( vel_active[dim][n] ) it.set(vel[dim][n]);
-			else it.set_off();
-		});
+			velocity[dim].parallel_actives([&]( int i, int j, int k, auto &it, int tn ) {
+				const size_t n = i + s.w * (j + s.h * (size_t)k);
+				if( vel_active[dim][n] ) it.set(vel[dim][n]);
+				else it.set_off();
+			});
+		}
 		console::dump( "Done. Took %s\n", timer.stock("scatter").c_str());
 		console::dump( "<<< Projection done. Took %s.\n", timer.stock("projection").c_str());
 	}

@@ -77,3 +77,23 @@ def test_module_emits_the_reference_records(cuda_device):
         assert name in out.records and len(out.records[name]) == len(values), (name, sorted(out.records))
     assert out.records["Projection_number_projection_iteration"][0] == out.iterations
     assert out.records["Projection_volume_correct_rhs"] == ref.records["Projection_volume_correct_rhs"]
+
+
+@pytest.mark.parametrize("scene", ["dambreak_solid", "smoke", "flip"])
+def test_dense_array_core_is_a_zero_copy_bridge(cuda_device, scene):
+    """`Array=b200array3`: the host's grids live in page-locked dense buffers and b200pressure3 hands them to the C-ABI in place (no gather / scatter).
+    Same host, same module, default tiledarray3 grids vs b200array3 grids: the GPU sees the same dense inputs, so the outputs are the same bits."""
+    import os
+    if not (have_plugin("f32") and os.path.isfile(os.path.join(refio.ref_dir("f32"), "libshiokaze_b200array3.so"))):
+        pytest.skip("oracle/_ref (reference build + modules) was not shipped to this box")
+    sc = {"dambreak_solid": lambda: scenes.dambreak(40, True), "smoke": lambda: scenes.smoke_plume(32), "flip": lambda: scenes.flip_splash(40)}[scene]()
+    tiled = refio.run_reference(sc, "f32", projection="b200pressure3")
+    dense = refio.run_reference(sc, "f32", projection="b200pressure3", flags={"Array": "b200array3"}, repeat=2)
+    assert 'Loaded "b200array3.so"' in dense.stdout
+    assert dense.iterations == tiled.iterations
+    for d in range(3):
+        assert np.array_equal(dense.vel[d], tiled.vel[d]) and np.array_equal(dense.vel_active[d], tiled.vel_active[d])
+    assert np.array_equal(dense.pressure, tiled.pressure) and np.array_equal(dense.pressure_active, tiled.pressure_active)
+    ref = refio.run_reference(sc, "f32")
+    assert np.array_equal(dense.pressure_active, ref.pressure_active)
+    assert rel_l2(dense.vel, ref.vel) < 2e-3
