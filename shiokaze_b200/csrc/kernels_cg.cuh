@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(TX *CG_BY) k_xpay(Dims d, Tiles T, const ZT *_
 		for (int k = kb; k < ke; ++k)
 			for (int j = j0 + threadIdx.y; j < je; j += CG_BY) {
 				const long long c = i + (long long)d.nx * (j + (long long)d.ny * k);
-				const VecT v = (VecT)z[c] + beta * s[c];
+				const VecT v = fma(beta, s[c], (VecT)z[c]); // (an explicit fused multiply-add: k_xpay_spmv_tma forms the same value)
 				s[c] = v;
 				if (k == 0 && plo) plo[c] = v;
 				if (k == d.nzl - 1 && phi) phi[c - (long long)k * d.plane] = v;

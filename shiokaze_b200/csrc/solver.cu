@@ -19,6 +19,7 @@
 #include "kernels_legacy.cuh" // one-launch-per-colour validation kernels: only in the test-hook build of the library
 #endif
 #include "kernels_mg_tma.cuh"
+#include "kernels_cg_tma.cuh"
 #include "slab_comm.h"
 
 using namespace shkz;
@@ -184,17 +185,18 @@ EncodeTiledFn encode_tiled() {
 	return fn;
 }
 
-// 3-D map of a cell array WITH its ghost planes (z coordinate = plane + 1), box = ST_W columns x rows x 1 plane, zero fill outside
-bool make_plane_map(CUtensorMap *map, void *base, const Dims &d, int rows) {
+// 3-D map of a cell array WITH its ghost planes (z coordinate = plane + 1), box = cols x rows x 1 plane of float / double elements, zero fill outside
+bool make_box_map(CUtensorMap *map, void *base, const Dims &d, size_t elem, int cols, int rows) {
 	EncodeTiledFn enc = encode_tiled();
 	if (!enc || !base) return false;
 	const cuuint64_t dims[3] = {(cuuint64_t)d.nx, (cuuint64_t)d.ny, (cuuint64_t)d.nzl + 2};
-	const cuuint64_t strides[2] = {(cuuint64_t)d.nx * sizeof(float), (cuuint64_t)d.plane * sizeof(float)};
-	const cuuint32_t box[3] = {(cuuint32_t)ST_W, (cuuint32_t)rows, 1u};
+	const cuuint64_t strides[2] = {(cuuint64_t)d.nx * elem, (cuuint64_t)d.plane * elem};
+	const cuuint32_t box[3] = {(cuuint32_t)cols, (cuuint32_t)rows, 1u};
 	const cuuint32_t estr[3] = {1u, 1u, 1u};
-	return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-	           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+	return enc(map, elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+bool make_plane_map(CUtensorMap *map, void *base, const Dims &d, int rows) { return make_box_map(map, base, d, sizeof(float), ST_W, rows); }
 
 } // namespace
 
@@ -214,6 +216,9 @@ struct shkz_b200_solver {
 	int alloc_precision = -1;
 	CellArray wx, wy, wz, dd; // CoefT
 	CellArray b, x, r, s, q;    // VecT
+	CellArray s2;               // VecT: the other direction buffer of the fused xpay + product kernel (k_xpay_spmv_tma writes s_new out of place)
+	bool spmv_tma = false;      // tensor maps of that kernel built (whole grid, float coefficients, nx % 4 == 0)
+	SpmvMaps spmv_maps{};
 	CellArray p_prev;           // VecT: WarmStart=Yes — the previous call's pressure per cell (allocated on first use)
 	bool poisoned = false;      // the last solve ended on a non-finite scalar: the solver's persistent vectors are re-zeroed before the next one
 	std::vector<HostLevel> levels;
@@ -266,7 +271,8 @@ struct shkz_b200_solver {
 namespace {
 
 void release_precision_arrays(shkz_b200_solver *S) {
-	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd, &S->b, &S->x, &S->r, &S->s, &S->q, &S->p_prev}) a->release();
+	for (CellArray *a : {&S->wx, &S->wy, &S->wz, &S->dd, &S->b, &S->x, &S->r, &S->s, &S->q, &S->p_prev, &S->s2}) a->release();
+	S->spmv_tma = false;
 	for (HostLevel &L : S->levels) {
 		if (L.own_coef) { L.wx.release(); L.wy.release(); L.wz.release(); L.dd.release(); }
 		if (L.own_b) L.b.release();
@@ -453,6 +459,18 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 		int coop = 0;
 		if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, S->device) != cudaSuccess || !coop) S->mid_first = S->gmid_first = -1;
 		if (!S->mid_barrier.base) CKR(S->mid_barrier.alloc(64));
+	}
+	// the fused direction update + product (kernels_cg_tma.cuh): whole grids with float coefficients whose rows are whole quads
+	S->spmv_tma = false;
+	if (S->whole_grid && sizeof(CoefT) == sizeof(float) && (d.nx & 3) == 0 && !getenv("SHKZ_B200_NO_SPMV_TMA")) {
+		using SS = SpmvStage<VecT>;
+		CKR(S->s2.alloc(d, sizeof(VecT), arena));
+		HostLevel &L0 = S->levels[0];
+		SpmvMaps &M = S->spmv_maps;
+		S->spmv_tma = make_box_map(&M.s[0], S->s.base, d, sizeof(VecT), SS::SW, SS::SROWS) && make_box_map(&M.s[1], S->s2.base, d, sizeof(VecT), SS::SW, SS::SROWS) &&
+		              make_box_map(&M.z[0], L0.xa.base, d, sizeof(float), SS::ZW, SS::SROWS) && make_box_map(&M.z[1], L0.xb.base, d, sizeof(float), SS::ZW, SS::SROWS) &&
+		              make_box_map(&M.wx, S->wx.base, d, sizeof(float), SS::WXW, TY) && make_box_map(&M.wy, S->wy.base, d, sizeof(float), TX, SS::WYROWS) &&
+		              make_box_map(&M.wz, S->wz.base, d, sizeof(float), TX, TY) && make_box_map(&M.dd, S->dd.base, d, sizeof(float), TX, TY);
 	}
 	S->alloc_precision = precision;
 	S->mg_min_size_built = min_size;
@@ -873,7 +891,7 @@ int comm_health(shkz_b200_solver *S) {
 // wipe everything such a solve may have touched before the next one.
 int scrub_after_nonfinite(shkz_b200_solver *S, cudaStream_t stream) {
 	if (!S->poisoned) return SHKZ_B200_OK;
-	for (CellArray *a : {&S->x, &S->r, &S->s, &S->q, &S->p_prev})
+	for (CellArray *a : {&S->x, &S->r, &S->s, &S->s2, &S->q, &S->p_prev})
 		if (a->base) CK(cudaMemsetAsync(a->base, 0, a->bytes, stream));
 	for (std::vector<HostLevel> *lv : {&S->levels, &S->glevels})
 		for (HostLevel &L : *lv) {
@@ -895,6 +913,8 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	const Tiles T = H0.view.tiles;
 	const int tt = H0.tiles_total;
 	VecT *b = S->b.ptr<VecT>(d), *x = S->x.ptr<VecT>(d), *r = S->r.ptr<VecT>(d), *s = S->s.ptr<VecT>(d), *q = S->q.ptr<VecT>(d);
+	VecT *sbuf[2] = {s, S->s2.ptr<VecT>(d)};
+	int scur = 0; // which of the two direction buffers holds s
 	const CoefT *wx = S->wx.ptr<CoefT>(d), *wy = S->wy.ptr<CoefT>(d), *wz = S->wz.ptr<CoefT>(d), *dd = S->dd.ptr<CoefT>(d);
 	const bool mg = P.precond == SHKZ_B200_PRECOND_MG;
 	constexpr bool kFloatVec = sizeof(VecT) == sizeof(float);
@@ -916,6 +936,18 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	while (it < P.max_iterations) {
 		for (unsigned c = 0; c < batch && it < P.max_iterations; ++c, ++it) {
 			// z-slabs: k_xpay stores the boundary planes of s into the neighbours' ghost planes, the product waits for theirs
+			if (mg && S->spmv_tma && S->sweep_mode == 0 && sizeof(CoefT) == sizeof(float)) {
+				// s_new = z + beta s and q = A s_new in ONE TMA-staged launch, s_new into the other direction buffer
+				const int zin = z == H0.view.xb ? 1 : 0;
+				LAUNCH_TILES_SMEM(S, "xpay_spmv_dot", (k_xpay_spmv_tma<VecT>), dim3(SPMV_TMA_THREADS, 1, 1), tt, SpmvStage<VecT>::SMEM, stream, d, T, S->spmv_maps, scur, zin,
+				                  (const VecT *)sbuf[scur], z, sbuf[scur ^ 1], q, rb, st);
+				scur ^= 1;
+				s = sbuf[scur];
+				if (kFloatVec) LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, false>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
+				else LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, true>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
+				CKR(vcycle(S, 0, P, st, stream, true, &z));
+				continue;
+			}
 			const SlabPush sp = S->whole_grid ? SlabPush{} : slab_push(S, d, s);
 			if (mg) LAUNCH_TILES(S, "xpay", (k_xpay<VecT, float>), cg_block(), tt, stream, d, T, z, s, (const CGState *)st, sp);
 			else LAUNCH_TILES(S, "xpay", (k_xpay<VecT, VecT>), cg_block(), tt, stream, d, T, (const VecT *)r, s, (const CGState *)st, sp);
