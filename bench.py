@@ -381,7 +381,8 @@ def profile_one_step(H):
     return table, res
 
 
-def roofline_of(table, res, rank_rows, precision, precond):
+def roofline_of(table, res, rank_rows, precision, precond, ms_solve):
+    """table: per-kernel CUDA-event times of ONE profiled project(); ms_solve: solve phase of an UNprofiled step (events around every launch slow the step down)."""
     peak, how = measured_peak()
     ab = lambda k: algorithmic_bytes_per_launch(k, rank_rows, precision, precond, res.stats.get("mg_mid_level"), res.stats.get("mg_tail_level"))
     groups = group_kernels(table, ab)
@@ -394,7 +395,6 @@ def roofline_of(table, res, rank_rows, precision, precond):
     traffic, traffic_source = ncu_traffic(groups, dom, rank_rows)
     total_profiled = sum(v[1] for v in table.values())
     alg_total = sum((ab(k) or 0) * v[0] for k, v in table.items())
-    ms_solve = res.stats["ms_solve"]
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": traffic_source, "peak_source": how, "launches": cnt, "avg_launch_ms": tot / cnt, "algorithmic_bytes_per_launch": per_launch,
             "share_of_step": tot / total_profiled if total_profiled else None, "variants": groups[dom]["variants"],
@@ -496,7 +496,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: CUDA events around every launch of one extra project() ----
     table, pres = profile_one_step(H)
-    roofline = roofline_of(table, pres, res.n_rows / world, args.precision, args.precond) if rank == 0 else None
+    roofline = roofline_of(table, pres, res.n_rows / world, args.precision, args.precond, res.stats["ms_solve"]) if rank == 0 else None
     H.close()
     del H
     torch.cuda.empty_cache()
@@ -508,7 +508,7 @@ def run_ours(args):
         ms_s, res_s, _, it_s, _ = timed_steps(torch, dist, Hs, max(5, args.steps // 2), 3, 1, dev)
         e2e_ss, _ = e2e_steps(torch, dist, Hs, 5, 2, 1)
         tab_s, pres_s = profile_one_step(Hs)
-        rf = roofline_of(tab_s, pres_s, res_s.n_rows, args.precision, args.precond)
+        rf = roofline_of(tab_s, pres_s, res_s.n_rows, args.precision, args.precond, res_s.stats["ms_solve"])
         sub["smoke_plume_256"] = {"config": workload_string("smoke_plume", 256, "on one GPU", args.residual), "ms_per_step": ms_s,
                                   "value": 256.0 ** 3 / (ms_s * 1e-3) / 1e6, "unit": UNIT, "e2e_ms_per_step": e2e_ss * 1e3,
                                   "solve": solve_record(res_s, res_s.n_rows, it_s),

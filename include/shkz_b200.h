@@ -85,6 +85,9 @@ typedef struct shkz_b200_params {
 	int32_t warm_start;           /* WarmStart (No): solve for the correction to the previous call's pressure, macpressuresolver3.cpp:221-242
 	                                 (kept per CELL by the solver; the reference keeps it per row number) */
 	double mg_omega;              /* relaxation factor of the red-black sweeps, 0 < omega < 2 (1 = Gauss-Seidel; default 1.15) */
+	int32_t extrapolate_width;    /* > 0: project() ends with shkz_b200_extrapolate_constrain on the velocity it still holds on the device (default 0: the
+	                                 host's own macutility3::extrapolate_and_constrain_velocity call does it, as with the reference module) */
+	int32_t reserved;
 } shkz_b200_params;
 
 typedef struct shkz_b200_stats {
@@ -154,6 +157,20 @@ int shkz_b200_project_host(shkz_b200_solver *solver, double dt, void *const vel[
 int shkz_b200_project_device(shkz_b200_solver *solver, double dt, void *const vel[3], uint8_t *const vel_active[3],
                              const void *solid, const void *fluid, int fluid_levelset, const shkz_b200_params *params,
                              void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats, void *cuda_stream);
+
+/*
+ * The step the simulators run right after every projection (src/liquid/macliquid3.cpp:309-319, src/smoke/macsmoke3.cpp:294), SURVEY.md 8f rank 3:
+ *     macutility3::extrapolate_and_constrain_velocity(solid, velocity, width)        src/utility/macutility3.cpp:89-93
+ *       = macarray_extrapolator3::extrapolate(velocity, width)                       include/shiokaze/array/macarray_extrapolator3.h:49-53
+ *         (width rounds: every inactive face next to an active one becomes active with the mean of its active neighbours, array_extrapolator3.h:51-82)
+ *       + macutility3::constrain_velocity(solid, velocity)                           src/utility/macutility3.cpp:61-88
+ *         (faces inside the solid lose the velocity component that points into it; wall faces may not point outwards; nothing at all without a solid level set)
+ * vel / vel_active in place, same dense layouts as project(); solid = nodal level set or NULL (the host's levelset_exist(solid) is false). Results are
+ * the reference's, bit for bit (tests/test_gpu_post.py). Whole-grid solvers only. params.extrapolate_width > 0 makes project() end with this step.
+ */
+int shkz_b200_extrapolate_constrain_device(shkz_b200_solver *solver, void *const vel[3], uint8_t *const vel_active[3], const void *solid, int width,
+                                           void *cuda_stream);
+int shkz_b200_extrapolate_constrain_host(shkz_b200_solver *solver, void *const vel[3], uint8_t *const vel_active[3], const void *solid, int width);
 
 /*
  * Page-locked host memory for the buffers handed to shkz_b200_project_host: the H2D / D2H copies then run at PCIe speed (pageable

@@ -99,13 +99,18 @@ void dump_dense( FILE *fp, const array3<Real> &a, bool with_active ) {
 int main( int argc, const char *argv[] ) {
 	//
 	std::string in_path, out_path;
-	bool dump_fractions (false);
+	bool dump_fractions (false), skip_project (false);
+	int extrapolate_constrain (-1);
 	for( int i=1; i<argc; ++i ) {
 		if( ! std::strncmp(argv[i],"in=",3)) in_path = argv[i]+3;
 		if( ! std::strncmp(argv[i],"out=",4)) out_path = argv[i]+4;
 		if( ! std::strcmp(argv[i],"DumpFractions=1")) dump_fractions = true;
 		// RecordDir=<existing directory>: console::write records (src/core/console.cpp:259-281) land in <dir>/record/<name>.out, as under ./run with Log=
 		if( ! std::strncmp(argv[i],"RecordDir=",10)) console::set_root_path(argv[i]+10);
+		// RefExtrapolate=<width>: after the projection, the step the simulators run next (macliquid3.cpp:309-319) through the REFERENCE's macutility3:
+		// extrapolate_and_constrain_velocity(solid,velocity,width). RefSkipProject=1: that step alone, on the input velocity.
+		if( ! std::strncmp(argv[i],"RefExtrapolate=",15)) extrapolate_constrain = std::atoi(argv[i]+15);
+		if( ! std::strcmp(argv[i],"RefSkipProject=1")) skip_project = true;
 	}
 	if( in_path.empty() || out_path.empty()) {
 		std::fprintf(stderr,"usage: ref_driver in=<scene> out=<result> [DumpFractions=1] [RecordDir=<dir>] [Projection=<module>] [flag=value ...]\n");
@@ -177,8 +182,9 @@ int main( int argc, const char *argv[] ) {
 		}
 		if( h.target_volume ) H.proj->set_target_volume(h.current_volume,h.target_volume);
 		double t0 = utility::get_milliseconds();
-		H.proj->project(h.dt,H.velocity,H.solid,H.fluid,h.surface_tension);
+		if( ! skip_project ) H.proj->project(h.dt,H.velocity,H.solid,H.fluid,h.surface_tension);
 		ms_last = utility::get_milliseconds()-t0;
+		if( extrapolate_constrain >= 0 ) H.util->extrapolate_and_constrain_velocity(H.solid,H.velocity,extrapolate_constrain);
 		ms_sum += ms_last;
 	}
 	std::printf("REFDRIVER project_ms_last=%.3f project_ms_mean=%.3f repeat=%d sizeof_Real=%d\n",ms_last,ms_sum/repeat,repeat,(int)sizeof(Real));

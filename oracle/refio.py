@@ -125,7 +125,7 @@ def _phase_times(text: str) -> dict:
 def run_reference(scene, real: str = "f32", flags: Optional[dict] = None, dump_fractions: bool = False,
                   repeat: int = 1, threads: Optional[int] = None, projection: Optional[str] = None,
                   current_volume: float = 0.0, target_volume: float = 0.0, extra_lib_dirs=(),
-                  timeout: Optional[float] = None, records: bool = False) -> RefResult:
+                  timeout: Optional[float] = None, records: bool = False, extrapolate: Optional[int] = None, skip_project: bool = False) -> RefResult:
     """One project() call of the reference (or of any drop-in module named by `projection`)."""
     d = ref_dir(real)
     if not ref_available(real):
@@ -142,6 +142,10 @@ def run_reference(scene, real: str = "f32", flags: Optional[dict] = None, dump_f
             argv.append(f"Threads={threads}")
         if records:
             argv.append(f"RecordDir={tmp}")
+        if extrapolate is not None:   # the reference's macutility3::extrapolate_and_constrain_velocity after (or, skip_project, instead of) the projection
+            argv.append(f"RefExtrapolate={int(extrapolate)}")
+        if skip_project:
+            argv.append("RefSkipProject=1")
         for k, v in (flags or {}).items():
             argv.append(f"{k}={v}")
         env = dict(os.environ)

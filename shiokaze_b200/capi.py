@@ -19,7 +19,7 @@ IPC_BYTES = 128
 EXPORTS = [
     "shkz_b200_abi_version", "shkz_b200_last_error", "shkz_b200_default_params", "shkz_b200_device_count",
     "shkz_b200_create", "shkz_b200_create_slab", "shkz_b200_destroy", "shkz_b200_project_host",
-    "shkz_b200_project_device", "shkz_b200_resolve", "shkz_b200_host_alloc", "shkz_b200_host_free", "shkz_b200_slab_export",
+    "shkz_b200_project_device", "shkz_b200_extrapolate_constrain_device", "shkz_b200_extrapolate_constrain_host", "shkz_b200_resolve", "shkz_b200_host_alloc", "shkz_b200_host_free", "shkz_b200_slab_export",
     "shkz_b200_slab_connect", "shkz_b200_slab_connect_local", "shkz_b200_debug_fetch", "shkz_b200_profile_enable", "shkz_b200_profile_count",
     "shkz_b200_profile_get", "shkz_b200_debug_vcycle",
     "shkz_b200_csr_last_error", "shkz_b200_csr_default_params", "shkz_b200_csr_create", "shkz_b200_csr_destroy", "shkz_b200_csr_solve_host",
@@ -34,7 +34,8 @@ class Params(C.Structure):
                 ("max_iterations", C.c_uint32), ("precond", C.c_int32), ("precision", C.c_int32),
                 ("mg_pre_sweeps", C.c_int32), ("mg_post_sweeps", C.c_int32), ("mg_coarse_sweeps", C.c_int32),
                 ("mg_min_size", C.c_int32), ("check_every", C.c_int32), ("mg_coarse_scale", C.c_double),
-                ("mg_gamma", C.c_int32), ("warm_start", C.c_int32), ("mg_omega", C.c_double)]
+                ("mg_gamma", C.c_int32), ("warm_start", C.c_int32), ("mg_omega", C.c_double),
+                ("extrapolate_width", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -94,6 +95,8 @@ def lib(test_hooks: bool = False):
     proj = [vp, C.c_double, C.POINTER(vp), C.POINTER(vp), vp, vp, C.c_int, C.POINTER(Params), vp, vp, C.POINTER(Stats)]
     L.shkz_b200_project_host.argtypes = proj
     L.shkz_b200_project_device.argtypes = proj + [vp]
+    L.shkz_b200_extrapolate_constrain_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, C.c_int, vp]
+    L.shkz_b200_extrapolate_constrain_host.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, C.c_int]
     L.shkz_b200_resolve.argtypes = [vp, C.POINTER(Params), C.POINTER(Stats), vp]
     L.shkz_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.shkz_b200_host_free.argtypes = [vp]

@@ -20,6 +20,7 @@
 #endif
 #include "kernels_mg_tma.cuh"
 #include "kernels_cg_tma.cuh"
+#include "kernels_post.cuh"
 #include "slab_comm.h"
 
 using namespace shkz;
@@ -244,6 +245,8 @@ struct shkz_b200_solver {
 	unsigned last_iterations = 0; // of the previous solve: sizes the first batch of iterations before the host looks
 	// host-call staging (device)
 	PlainArray st_vel[3], st_act[3], st_solid, st_fluid, st_pressure, st_pact;
+	// extrapolation + solid constraint after the projection (kernels_post.cuh): the other activity mask of the rounds, the velocity before the constraint
+	PlainArray post_act[3], post_vel[3], post_mask[3];
 	// slab communicator (nullptr on a whole grid)
 	SlabComm *comm = nullptr;
 	size_t arena_mark = 0; // arena fill level after the creation-time arrays
@@ -400,7 +403,7 @@ int pick_mid_first(const std::vector<HostLevel> &lv, int tail_first, bool allow_
 }
 
 constexpr int AGG_MAX_EXTENT = 64;
-constexpr long long AGG_MAX_CELLS = 1ll << 21;
+constexpr long long AGG_MAX_CELLS = 1ll << 23;
 
 template <class VecT, class CoefT>
 int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_params &P) {
@@ -995,6 +998,9 @@ void fill_stats(const shkz_b200_solver *S, shkz_b200_stats *out) {
 	out->mg_tail_level = S->tail_first;
 }
 
+template <class RealT>
+int post_impl(shkz_b200_solver *S, void *const vel_v[3], uint8_t *const act[3], const void *solid_v, int width, cudaStream_t stream);
+
 template <class RealT, class VecT, class CoefT>
 int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *const act[3], const void *solid_v, const void *fluid_v, int fluid_levelset,
                  const shkz_b200_params &P, void *pressure_v, uint8_t *pressure_active, shkz_b200_stats *stats, cudaStream_t stream) {
@@ -1105,6 +1111,7 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		else if (A.fluid_levelset) LAUNCH(S, "update_velocity", (k_update_velocity<RealT, false, true>), ugrid, ublock, stream, d, A, (const RealT *)phi, solid, (const RealT *)pres, vel, masks);
 		else LAUNCH(S, "update_velocity", (k_update_velocity<RealT, false, false>), ugrid, ublock, stream, d, A, (const RealT *)phi, solid, (const RealT *)pres, vel, masks);
 	}
+	if (P.extrapolate_width > 0) CKR((post_impl<RealT>(S, vel_v, act, solid_v, P.extrapolate_width, stream))); // (part of ms_update)
 	CK(cudaEventRecord(S->ev[4], stream));
 	CK(cudaStreamSynchronize(stream));
 	CK(cudaGetLastError());
@@ -1126,6 +1133,45 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		}
 	}
 	return comm_health(S);
+}
+
+// macutility3::extrapolate_and_constrain_velocity (src/utility/macutility3.cpp:89-93) on device arrays, in place
+template <class RealT>
+int post_impl(shkz_b200_solver *S, void *const vel_v[3], uint8_t *const act[3], const void *solid_v, int width, cudaStream_t stream) {
+	const Dims &d = S->d;
+	if (!S->whole_grid) return fail(SHKZ_B200_ERR_STATE, "extrapolate_constrain: whole-grid solvers only");
+	const dim3 block(32, 8, 1);
+	for (int dim = 0; dim < 3; ++dim) {
+		const int w = d.nx + (dim == 0), h = d.ny + (dim == 1), dz = d.nzl + (dim == 2);
+		const size_t nf = face_count(d, dim);
+		if (width > 0 && !S->post_act[dim].base) CKR(S->post_act[dim].alloc(nf));
+		uint8_t *cur = act[dim], *other = static_cast<uint8_t *>(S->post_act[dim].base);
+		const dim3 grid((w + 31) / 32, (h + 7) / 8, dz);
+		for (int round = 0; round < width; ++round) {
+			LAUNCH(S, "extrapolate", k_extrapolate_round<RealT>, grid, block, stream, w, h, dz, static_cast<RealT *>(vel_v[dim]), (const uint8_t *)cur, other);
+			uint8_t *t = cur; cur = other; other = t;
+		}
+		if (cur != act[dim]) CK(cudaMemcpyAsync(act[dim], cur, nf, cudaMemcpyDeviceToDevice, stream));
+	}
+	if (solid_v) { // levelset_exist(solid): the caller passes NULL otherwise, and then not even the wall rule applies (macutility3.cpp:66)
+		ConstFaceGrids<RealT> vs;
+		FaceMasks as;
+		for (int dim = 0; dim < 3; ++dim) {
+			const size_t nf = face_count(d, dim);
+			if (!S->post_vel[dim].base) { CKR(S->post_vel[dim].alloc(nf * sizeof(RealT))); CKR(S->post_mask[dim].alloc(nf)); }
+			CK(cudaMemcpyAsync(S->post_vel[dim].base, vel_v[dim], nf * sizeof(RealT), cudaMemcpyDeviceToDevice, stream));
+			CK(cudaMemcpyAsync(S->post_mask[dim].base, act[dim], nf, cudaMemcpyDeviceToDevice, stream));
+			vs.p[dim] = static_cast<const RealT *>(S->post_vel[dim].base);
+			as.p[dim] = static_cast<uint8_t *>(S->post_mask[dim].base);
+		}
+		for (int dim = 0; dim < 3; ++dim) {
+			const int w = d.nx + (dim == 0), h = d.ny + (dim == 1), dz = d.nzl + (dim == 2);
+			LAUNCH(S, "constrain_velocity", k_constrain_velocity<RealT>, dim3((w + 31) / 32, (h + 7) / 8, dz), block, stream, d, S->dx, dim, static_cast<const RealT *>(solid_v), vs, as,
+			       static_cast<RealT *>(vel_v[dim]), (const uint8_t *)act[dim]);
+		}
+	}
+	CK(cudaGetLastError());
+	return SHKZ_B200_OK;
 }
 
 typedef int (*project_fn)(shkz_b200_solver *, double, void *const[3], uint8_t *const[3], const void *, const void *, int, const shkz_b200_params &, void *,
@@ -1282,6 +1328,7 @@ void shkz_b200_destroy(shkz_b200_solver *S) {
 	S->phi.release(); S->pressure.release(); S->curv.release(); S->in_rows.release();
 	for (int dim = 0; dim < 3; ++dim) {
 		S->areas[dim].release(); S->rhos[dim].release(); S->st_vel[dim].release(); S->st_act[dim].release();
+		S->post_act[dim].release(); S->post_vel[dim].release(); S->post_mask[dim].release();
 	}
 	S->st_solid.release(); S->st_fluid.release(); S->st_pressure.release(); S->st_pact.release();
 	S->partials.release(); S->counter.release(); S->state.release(); S->mid_barrier.release();
@@ -1370,6 +1417,56 @@ static int project_host_impl(shkz_b200_solver *S, double dt, void *const vel[3],
 		cudaEventElapsedTime(&stats->ms_d2h, S->ev[7], S->ev[0]);
 		stats->ms_total += stats->ms_h2d + stats->ms_d2h;
 	}
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_extrapolate_constrain_device(shkz_b200_solver *S, void *const vel[3], uint8_t *const vel_active[3], const void *solid, int width, void *cuda_stream) {
+	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	if (!vel || !vel_active) return fail(SHKZ_B200_ERR_ARG, "vel / vel_active must not be NULL");
+	for (int dim = 0; dim < 3; ++dim)
+		if (!vel[dim] || !vel_active[dim]) return fail(SHKZ_B200_ERR_ARG, "vel[%d] / vel_active[%d] is NULL", dim, dim);
+	if (width < 0) return fail(SHKZ_B200_ERR_ARG, "width must be >= 0");
+	CKR(device_ready(S->device));
+	CK(cudaSetDevice(S->device));
+	cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+	S->launches = 0;
+	const int rc = S->real == SHKZ_B200_REAL_F64 ? post_impl<double>(S, vel, vel_active, solid, width, stream) : post_impl<float>(S, vel, vel_active, solid, width, stream);
+	if (rc != SHKZ_B200_OK) return rc;
+	CK(cudaStreamSynchronize(stream));
+	CK(cudaGetLastError());
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_extrapolate_constrain_host(shkz_b200_solver *S, void *const vel[3], uint8_t *const vel_active[3], const void *solid, int width) {
+	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	if (!vel || !vel_active) return fail(SHKZ_B200_ERR_ARG, "vel / vel_active must not be NULL");
+	CKR(device_ready(S->device));
+	CK(cudaSetDevice(S->device));
+	const Dims &d = S->d;
+	const size_t rb = S->real_bytes, nodal = (size_t)(d.nx + 1) * (d.ny + 1) * (d.nzl + 1);
+	cudaStream_t stream = nullptr;
+	void *dvel[3];
+	uint8_t *dact[3];
+	for (int dim = 0; dim < 3; ++dim) {
+		if (!vel[dim] || !vel_active[dim]) return fail(SHKZ_B200_ERR_ARG, "vel[%d] / vel_active[%d] is NULL", dim, dim);
+		const size_t nf = face_count(d, dim);
+		if (!S->st_vel[dim].base) { CKR(S->st_vel[dim].alloc(nf * rb)); CKR(S->st_act[dim].alloc(nf)); }
+		CK(cudaMemcpyAsync(S->st_vel[dim].base, vel[dim], nf * rb, cudaMemcpyHostToDevice, stream));
+		CK(cudaMemcpyAsync(S->st_act[dim].base, vel_active[dim], nf, cudaMemcpyHostToDevice, stream));
+		dvel[dim] = S->st_vel[dim].base;
+		dact[dim] = static_cast<uint8_t *>(S->st_act[dim].base);
+	}
+	if (solid) {
+		if (!S->st_solid.base) CKR(S->st_solid.alloc(nodal * rb));
+		CK(cudaMemcpyAsync(S->st_solid.base, solid, nodal * rb, cudaMemcpyHostToDevice, stream));
+	}
+	CKR(shkz_b200_extrapolate_constrain_device(S, dvel, dact, solid ? S->st_solid.base : nullptr, width, stream));
+	for (int dim = 0; dim < 3; ++dim) {
+		const size_t nf = face_count(d, dim);
+		CK(cudaMemcpyAsync(vel[dim], S->st_vel[dim].base, nf * rb, cudaMemcpyDeviceToHost, stream));
+		CK(cudaMemcpyAsync(vel_active[dim], S->st_act[dim].base, nf, cudaMemcpyDeviceToHost, stream));
+	}
+	CK(cudaStreamSynchronize(stream));
 	return SHKZ_B200_OK;
 }
 

@@ -219,11 +219,21 @@ protected:
 		}
 		for( int dim : DIMS3 ) if( ! vel_in_place[dim] ) {
 			const shape3 s = velocity[dim].shape();
-			velocity[dim].parallel_actives([&]( int i, int j, int k, auto &it, int tn ) {
-				const size_t n = i + s.w * (j + s.h * (size_t)k);
-				if( vel_active[dim][n] ) it.set(vel[dim][n]);
-				else it.set_off();
-			});
+			if( params.extrapolate_width > 0 ) {
+				// the extrapolation ACTIVATES faces around the active set (array_extrapolator3.h:51-82): every face is visited
+				velocity[dim].parallel_all([&]( int i, int j, int k, auto &it, int tn ) {
+					const size_t n = i + s.w * (j + s.h * (size_t)k);
+					if( vel_active[dim][n] ) it.set(vel[dim][n]);
+					else if( it.active()) it.set_off();
+				});
+			} else {
+				// the projection itself never activates a face (macpressuresolver3.cpp:252-268): the active ones are enough
+				velocity[dim].parallel_actives([&]( int i, int j, int k, auto &it, int tn ) {
+					const size_t n = i + s.w * (j + s.h * (size_t)k);
+					if( vel_active[dim][n] ) it.set(vel[dim][n]);
+					else it.set_off();
+				});
+			}
 		}
 		console::dump( "Done. Took %s\n", timer.stock("scatter").c_str());
 		console::dump( "<<< Projection done. Took %s.\n", timer.stock("projection").c_str());
@@ -310,6 +320,7 @@ protected:
 		config.get_integer("MGPreSweeps",m_cuda_param.mg_pre_sweeps,"Red-black sweeps before the coarse correction");
 		config.get_integer("MGPostSweeps",m_cuda_param.mg_post_sweeps,"Red-black sweeps after the coarse correction");
 		config.get_double("MGOmega",m_cuda_param.mg_omega,"Relaxation factor of the red-black sweeps (1 = Gauss-Seidel)");
+		config.get_integer("ExtrapolateWidth",m_cuda_param.extrapolate_width,"> 0: finish project() with the velocity extrapolation + solid constraint on the device (macutility3::extrapolate_and_constrain_velocity)");
 		config.get_integer("GPU",m_device,"CUDA device index (of the first slab when GPUs > 1)");
 		config.get_integer("GPUs",m_gpus,"Number of CUDA devices: the grid is cut into this many equal z-slabs (1, 2, 4 or 8)");
 		m_cuda_param.precision = precision == "fp64" ? SHKZ_B200_PREC_FP64 : (precision == "fp32" ? SHKZ_B200_PREC_FP32 : SHKZ_B200_PREC_MIXED);

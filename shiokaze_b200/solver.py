@@ -80,6 +80,7 @@ class MacPressureSolver3:
             elif key == "CheckEvery": p.check_every = int(value)
             elif key == "MGGamma": p.mg_gamma = int(value)
             elif key == "MGOmega": p.mg_omega = float(value)
+            elif key == "ExtrapolateWidth": p.extrapolate_width = int(value)
             else:
                 raise KeyError(f"unknown flag {key}")
 
@@ -162,6 +163,18 @@ class MacPressureSolver3:
                                                        pressure_active.data_ptr() if pressure_active is not None else None,
                                                        C.byref(st), stream or None))
         return self._finish(st)
+
+    def extrapolate_and_constrain_velocity(self, solid, velocity, velocity_active, width: int):
+        """macutility3::extrapolate_and_constrain_velocity (src/utility/macutility3.cpp:89-93) in place on numpy arrays; solid: nodal level set
+        or None (the host's levelset_exist(solid) is false)."""
+        rt = self.np_real
+        for v, a, shp in zip(velocity, velocity_active, self.face_shapes()):
+            assert v.dtype == rt and v.flags.c_contiguous and v.shape == shp and a.dtype == np.uint8 and a.flags.c_contiguous and a.shape == shp
+        if solid is not None:
+            assert solid.dtype == rt and solid.flags.c_contiguous and solid.shape == (self.nzl + 1, self.ny + 1, self.nx + 1)
+        vp = (C.c_void_p * 3)(*[v.ctypes.data for v in velocity])
+        ap = (C.c_void_p * 3)(*[a.ctypes.data for a in velocity_active])
+        self._ck(self._L.shkz_b200_extrapolate_constrain_host(self._h, vp, ap, solid.ctypes.data if solid is not None else None, int(width)))
 
     def resolve(self, stream: int = 0) -> ProjectionResult:
         """Repeat only the linear solve of the last project() (same matrix and right-hand side)."""
