@@ -155,7 +155,7 @@ struct HostLevel {
 	Dims d;
 	int bz = 4, tiles_total = 0; // deepest tile depth of the level; number of flag slices (= the largest number of tiles any depth gives)
 	int slice = 4, nslices_z = 0, ntx = 0, nty = 0;
-	bool adaptive = false;       // tile depth chosen per projection by k_compact_tiles (whole-grid levels with deep tiles)
+	bool adaptive = false;       // tile depth chosen per projection by k_compact_tiles (levels with deep tiles)
 	std::string tag_sweep, tag_restrict, tag_prolong, tag_coarsen, tag_compact;
 	CellArray wx, wy, wz, dd, xa, xb, b;
 	CellArray legacy_r; // residual array of the unfused validation path (allocated on first use)
@@ -320,7 +320,7 @@ int finish_level(HostLevel &L, const Dims &cur, const std::string &n, SlabComm *
 	CKR(L.xb.alloc(cur, sizeof(float), arena));
 	L.bz = pick_bz(cur);
 	L.slice = L.bz < 8 ? L.bz : 8;
-	L.adaptive = balanced && L.bz > L.slice && !getenv("SHKZ_B200_BZ"); // (balanced == whole-grid level)
+	L.adaptive = L.bz > L.slice && !getenv("SHKZ_B200_BZ"); // (z-slab levels too: every rank picks the depth that suits its own slab)
 	const int ntx = (cur.nx + TX - 1) / TX, nty = (cur.ny + TY - 1) / TY;
 	L.ntx = ntx; L.nty = nty;
 	L.nslices_z = (cur.nzl + L.slice - 1) / L.slice;
