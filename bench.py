@@ -511,6 +511,7 @@ def run_ours(args):
         rf = roofline_of(tab_s, pres_s, res_s.n_rows, args.precision, args.precond, res_s.stats["ms_solve"])
         sub["smoke_plume_256"] = {"config": workload_string("smoke_plume", 256, "on one GPU", args.residual), "ms_per_step": ms_s,
                                   "value": 256.0 ** 3 / (ms_s * 1e-3) / 1e6, "unit": UNIT, "e2e_ms_per_step": e2e_ss * 1e3,
+                                  "e2e_value": 256.0 ** 3 / e2e_ss / 1e6,
                                   "solve": solve_record(res_s, res_s.n_rows, it_s),
                                   "roofline": {k: rf[k] for k in ("kernel", "achieved", "peak", "frac", "solve_whole")} if rf else None}
         Hs.close()
@@ -544,9 +545,14 @@ def run_ours(args):
                        "residual": args.residual,
                        "l2_policy": "inputs and solver working set of one step (GBs at 512^3, > 1 GB at 256^3) exceed the 126 MB L2; no explicit flush",
                        "where": "gpu"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_s * 1e3,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_res.stats["h2d_bytes"]) * world,
+                    "d2h_bytes_per_step": int(e2e_res.stats["d2h_bytes"]) * world, "ms_per_step": e2e_s * 1e3,
                     "ms_h2d": e2e_res.stats["ms_h2d"], "ms_d2h": e2e_res.stats["ms_d2h"],
-                    "what": "shkz_b200_project_host with page-locked host buffers, wall clock around the call, max over ranks"},
+                    "host_copies": "sparse" if e2e_res.stats["host_copies"] else "dense",
+                    "whole_array_bytes_per_step": [h2d * world, d2h * world],
+                    "what": "shkz_b200_project_host with page-locked host buffers, wall clock around the call, max over ranks; bytes = what the call moved over PCIe "
+                            "as counted by the library (stats.h2d_bytes / d2h_bytes, rank 0 x ranks): on a liquid scene only the level set, the masks, and the "
+                            "velocity / solid nodes / pressure around wet cells travel (csrc/kernels_xfer.cuh); whole_array_bytes_per_step = every array whole"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "solve": solve_record(res, n_rows, iters),
         }

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SHKZ_B200_ABI_VERSION 2
+#define SHKZ_B200_ABI_VERSION 3
 
 enum shkz_b200_status {
 	SHKZ_B200_OK = 0,
@@ -107,7 +107,9 @@ typedef struct shkz_b200_stats {
 	int32_t mg_mid_level;   /* first multigrid level of the cooperative mid-V-cycle launch (levels of <= 2^21 cells), -1: none */
 	int32_t mg_tail_level;  /* first level of the shared-memory tail, which runs inside that launch (or alone when mg_mid_level is -1) */
 	uint32_t tile_depth;    /* planes per level-0 tile this projection (chosen on the device: deep tiles for full grids, shallower for liquid scenes) */
-	uint32_t reserved;
+	uint32_t host_copies;   /* shkz_b200_project_host: 0 = whole arrays through the copy engines, 1 = sparse (only what the projection touches, moved by kernels) */
+	uint64_t h2d_bytes;     /* shkz_b200_project_host: bytes that crossed PCIe towards the device ... */
+	uint64_t d2h_bytes;     /* ... and back to the host, this call */
 } shkz_b200_stats;
 
 typedef struct shkz_b200_solver shkz_b200_solver; /* opaque */
@@ -149,6 +151,14 @@ void shkz_b200_destroy(shkz_b200_solver *solver);
  * Grid element type is float or double as chosen at creation. `_host` takes host pointers and does
  * the H2D / D2H copies itself; `_device` takes device pointers on the solver's GPU and runs on
  * `cuda_stream` (a cudaStream_t, NULL = default stream), returning after the stream has been synchronised.
+ *
+ * `_host` on a liquid scene (fluid_levelset != 0) whose buffers are ALL page-locked (shkz_b200_host_alloc, cudaHostAlloc, cudaHostRegister) moves only
+ * what the projection touches: the liquid level set and the activity masks travel whole, velocity and solid nodes only around wet cells (fluid < 0),
+ * and only the faces that were active on input and the pressure tiles that hold (or held, in the previous call) unknowns are written back — by
+ * the library's own kernels addressing the host buffers directly (stats.host_copies = 1, stats.h2d_bytes / d2h_bytes say what moved). The buffers
+ * end up byte for byte as with whole-array copies, under one assumption: between two calls that pass the SAME pressure / pressure_active pointers
+ * the caller does not write into them (cells off the current and the previous row set are not rewritten; the first call with a new pointer clears
+ * the whole grid). Environment SHKZ_B200_HOST_COPIES=dense forces whole-array copies.
  */
 int shkz_b200_project_host(shkz_b200_solver *solver, double dt, void *const vel[3], uint8_t *const vel_active[3],
                            const void *solid, const void *fluid, int fluid_levelset, const shkz_b200_params *params,

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libshkz_b200.so")
 HOOKS_LIB_PATH = os.path.join(HERE, "_build", "libshkz_b200_testhooks.so")  # same sources + -DSHKZ_B200_TEST_HOOKS (tests only)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_COMM, ERR_STATE = range(6)
 PRECOND_NONE, PRECOND_MG = 0, 1
@@ -44,7 +44,8 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_float), ("ms_assemble", C.c_float), ("ms_setup", C.c_float),
                 ("ms_solve", C.c_float), ("ms_update", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
                 ("ms_surftension", C.c_float), ("active_tiles", C.c_uint32), ("total_tiles", C.c_uint32),
-                ("mg_mid_level", C.c_int32), ("mg_tail_level", C.c_int32), ("tile_depth", C.c_uint32), ("reserved", C.c_uint32)]
+                ("mg_mid_level", C.c_int32), ("mg_tail_level", C.c_int32), ("tile_depth", C.c_uint32), ("host_copies", C.c_uint32),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

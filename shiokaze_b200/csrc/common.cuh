@@ -52,7 +52,7 @@ struct Tiles {
 	int ntx, nty;      // tile grid of the level in x and y
 	int slice;         // planes per flag slice
 	int bz;            // planes per tile (even); 0: read it from count[1]
-	int balanced;      // how a persistent grid divides the list (TileWalk): bit 0 element-wise kernels, bit 1 stencil kernels may take the balanced walk
+	int balanced;      // how a persistent grid divides the list (TileWalk): bit 0 element-wise kernels, bit 1 stencil kernels may take the balanced walk; bit 2: hybrid walk
 };
 // every tile kernel starts with this: after it T.bz is the depth in force
 __device__ __forceinline__ void resolve_tiles(Tiles &T) { if (T.bz == 0) T.bz = T.count[1]; }
@@ -76,18 +76,40 @@ __device__ __forceinline__ void tile_origin(const Tiles &T, int id, int &i0, int
 struct TileWalk {
 	int u, end; // balanced: next / last plane-pair unit of this CTA; strided: next tile index / number of tiles
 	bool bal;
+	int tail_u, tail_end; // hybrid: the plane-pair units of the last, partial round that follow the strided part
 	// (with four or more tiles per CTA the strided walk loses little to the last partial round and keeps its locality: measured, all-fluid 512^3)
-	__device__ __forceinline__ TileWalk(const Tiles &T, int ntiles, bool elementwise = false) : bal((T.balanced & (elementwise ? 1 : 2)) && ntiles < 4 * (int)gridDim.x) {
+	//   hybrid     (whole-grid levels) the strided walk covers the WHOLE rounds only — the first floor(n / G) * G tiles —, and the tiles of the last, partial round
+	//              are cut into plane pairs and divided evenly like the balanced walk does: a liquid scene at 512^3 has 1384 level-0 tiles for 296 CTAs, i.e. 4.68
+	//              rounds that used to cost 5 (level 1: 173 tiles, a single round with 123 idle CTAs). Measured (B200, 512^3): k_residual_restrict -17 % (dam-break) / -18 % (FLIP)
+	//              on level 0 and -56 % on level 1, k_xpay_spmv_tma -1..-7 %; k_sweep_tma is the exception (+3..5 % on liquid scenes: each piece pays its two halo planes
+	//              and the fill of the three-stage pipeline) and passes hybrid = false.
+	__device__ __forceinline__ TileWalk(const Tiles &T, int ntiles, bool elementwise = false, bool hybrid = true)
+	    : bal((T.balanced & (elementwise ? 1 : 2)) && ntiles < 4 * (int)gridDim.x), tail_u(0), tail_end(0) {
+		const int G = (int)gridDim.x, b = (int)blockIdx.x;
 		if (bal) {
 			const long long tot = (long long)ntiles * (T.bz >> 1);
-			u = (int)(tot * blockIdx.x / gridDim.x);
-			end = (int)(tot * (blockIdx.x + 1) / gridDim.x);
+			u = (int)(tot * b / G);
+			end = (int)(tot * (b + 1) / G);
 		} else {
-			u = (int)blockIdx.x;
+			u = b;
 			end = ntiles;
+			if (hybrid && (T.balanced & 4)) {
+				const int full = (ntiles / G) * G, U = T.bz >> 1;
+				const long long tot = (long long)(ntiles - full) * U, first = (long long)full * U;
+				if (tot > 0) {
+					end = full;
+					tail_u = (int)(first + tot * b / G);
+					tail_end = (int)(first + tot * (b + 1) / G);
+				}
+			}
 		}
 	}
 	__device__ __forceinline__ bool next(const Tiles &T, int nzl, int &i0, int &j0, int &kb, int &ke) {
+		if (!bal && u >= end && tail_u < tail_end) { // the strided rounds are done: on to this CTA's share of the partial round
+			bal = true;
+			u = tail_u;
+			end = tail_end;
+		}
 		while (u < end) {
 			if (!bal) {
 				tile_origin(T, T.ids[u], i0, j0, kb);

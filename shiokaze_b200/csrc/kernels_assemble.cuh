@@ -18,6 +18,7 @@ struct AsmParams {
 	int apply_rhs_correct;
 	int dx_pow2;   // dx is an exact power of two: x / dx == x * inv_dx bit for bit
 	double inv_dx;
+	int off_mark;  // what k_update_velocity stores into the mask of a face it switches off: 0, or kernels_xfer.cuh's marker when the host copies are sparse
 };
 
 // x / dx with the reference's rounding; a multiplication when that is exact
@@ -467,7 +468,7 @@ __device__ __forceinline__ void finish_face(const AsmParams &P, int pd, int n_di
 		// (:263-264: fluid at the face's own cell for the lower wall = the clamped cell a; at the cell below for the upper wall = the clamped cell b)
 		if (pd == 0 && pha < (RealT)0) vel[f] = (RealT)0;
 		else if (pd == n_dim && phb < (RealT)0) vel[f] = (RealT)0;
-		else { active[f] = 0; vel[f] = (RealT)0; } // set_off(): reads back as the background 0
+		else { active[f] = (uint8_t)P.off_mark; vel[f] = (RealT)0; } // set_off(): reads back as the background 0
 	}
 }
 

@@ -73,22 +73,36 @@ __global__ void __launch_bounds__(SPMV_TMA_THREADS, 2) k_xpay_spmv_tma(Dims d, T
 	unsigned loads_done = 0;
 	const CUtensorMap *map_s = &M.s[s_in], *map_z = &M.z[z_in];
 
-	int i0, j0, kb, ke;
-	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
+	// The walk looks one tile ahead and the loads of all the CTA's tiles form one stream (load n -> stage n % 3, requested as soon as load n-3 has been
+	// consumed), so the first planes of the next tile arrive while the last steps of this one run (k_sweep_tma, kernels_mg_tma.cuh, does the same).
+	TileWalk w(T, ntiles);
+	int i0, j0, kb, ke, ni0 = 0, nj0 = 0, nkb = 0, nke = 0;
+	bool have = w.next(T, d.nzl, i0, j0, kb, ke);
+	unsigned issued = 0; // (producer) loads requested so far
+	while (have) {
+		const bool nhave = w.next(T, d.nzl, ni0, nj0, nkb, nke);
 		const unsigned base = loads_done; // load index of plane kb
+		const unsigned cur_n = (unsigned)(ke - kb + 1), next_n = nhave ? (unsigned)(nke - nkb + 1) : 0u;
 		auto stage_of = [&](int p) -> unsigned char * { return stage_base + ((base + (unsigned)(p - kb)) % 3) * SS::BYTES; };
-		auto issue = [&](int p) {
-			const unsigned n = base + (unsigned)(p - kb);
+		auto issue_at = [&](int ti0, int tj0, int p, unsigned n) {
 			unsigned char *sp = stage_base + (n % 3) * SS::BYTES;
 			unsigned long long *bar = &full[n % 3];
 			fence_proxy_async();
 			mbar_expect_tx(bar, SS::TX_BYTES);
-			tma_load_3d(sp + SS::OFF_S, map_s, bar, i0 - SS::SX0, j0 - 1, p + 1);
-			tma_load_3d(sp + SS::OFF_Z, map_z, bar, i0 - SS::ZX0, j0 - 1, p + 1);
-			tma_load_3d(sp + SS::OFF_WX, &M.wx, bar, i0, j0, p + 1);
-			tma_load_3d(sp + SS::OFF_WY, &M.wy, bar, i0, j0, p + 1);
-			tma_load_3d(sp + SS::OFF_WZ, &M.wz, bar, i0, j0, p + 1);
-			tma_load_3d(sp + SS::OFF_DD, &M.dd, bar, i0, j0, p + 1);
+			tma_load_3d(sp + SS::OFF_S, map_s, bar, ti0 - SS::SX0, tj0 - 1, p + 1);
+			tma_load_3d(sp + SS::OFF_Z, map_z, bar, ti0 - SS::ZX0, tj0 - 1, p + 1);
+			tma_load_3d(sp + SS::OFF_WX, &M.wx, bar, ti0, tj0, p + 1);
+			tma_load_3d(sp + SS::OFF_WY, &M.wy, bar, ti0, tj0, p + 1);
+			tma_load_3d(sp + SS::OFF_WZ, &M.wz, bar, ti0, tj0, p + 1);
+			tma_load_3d(sp + SS::OFF_DD, &M.dd, bar, ti0, tj0, p + 1);
+		};
+		auto pump = [&](unsigned consumed) { // (producer) request every load whose stage is free
+			while (issued < consumed + 3 && issued < base + cur_n + next_n) {
+				const unsigned idx = issued - base;
+				if (idx < cur_n) issue_at(i0, j0, kb + (int)idx, issued);
+				else issue_at(ni0, nj0, nkb + (int)(idx - cur_n), issued);
+				++issued;
+			}
 		};
 		auto wait_plane = [&](int p) {
 			const unsigned n = base + (unsigned)(p - kb);
@@ -100,11 +114,7 @@ __global__ void __launch_bounds__(SPMV_TMA_THREADS, 2) k_xpay_spmv_tma(Dims d, T
 			const float zz = reinterpret_cast<const float *>(sp + SS::OFF_Z)[r * SS::ZW + SS::ZX0 + c];
 			return fma(beta, so, (VecT)zz);
 		};
-		if (producer) { // planes kb .. ke (the last one is only read for the z neighbour above the tile)
-			issue(kb);
-			if (kb + 1 <= ke) issue(kb + 1);
-			if (kb + 2 <= ke) issue(kb + 2);
-		}
+		if (producer) pump(base); // planes kb .. ke (the last one is only read for the z neighbour above the tile)
 
 		const int i = i0 + 4 * tx, j = j0 + ty;
 		const bool valid = !ringwarp && i < d.nx && j < d.ny;
@@ -123,6 +133,14 @@ __global__ void __launch_bounds__(SPMV_TMA_THREADS, 2) k_xpay_spmv_tma(Dims d, T
 			sc = V4<VecT>{snew_at(sp, ty + 1, 4 * tx), snew_at(sp, ty + 1, 4 * tx + 1), snew_at(sp, ty + 1, 4 * tx + 2), snew_at(sp, ty + 1, 4 * tx + 3)};
 		}
 		for (int p = kb; p < ke; ++p) {
+			if (p + 1 == ke && nhave && !ringwarp) { // the next tile starts with direct loads of its plane kb-1: have them in L2 by then
+				const int pi = ni0 + 4 * tx, pj = nj0 + ty;
+				if (pi < d.nx && pj < d.ny) {
+					const long long c = pi + nx * pj + plane * (nkb - 1);
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(s_old + c));
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(z + c));
+				}
+			}
 			wait_plane(p + 1);
 			const unsigned char *P = stage_of(p), *N = stage_of(p + 1);
 			V4<VecT> sp4{0, 0, 0, 0};
@@ -161,10 +179,12 @@ __global__ void __launch_bounds__(SPMV_TMA_THREADS, 2) k_xpay_spmv_tma(Dims d, T
 				red[0] += (double)sc.a * (double)v.a + (double)sc.b * (double)v.b + (double)sc.c * (double)v.c + (double)sc.d * (double)v.d;
 			}
 			sm = sc; sc = sp4;
-			__syncthreads(); // stage p and the shared plane are free
-			if (producer && p + 3 <= ke) issue(p + 3);
+			__syncthreads(); // stage p and the shared plane are free (after the last step: the stage of plane ke too)
+			if (producer) pump(p + 1 == ke ? base + cur_n : base + (unsigned)(p - kb) + 1u);
 		}
-		loads_done = base + (unsigned)(ke - kb + 1);
+		loads_done = base + cur_n;
+		have = nhave;
+		i0 = ni0; j0 = nj0; kb = nkb; ke = nke;
 	}
 	grid_reduce<1, 0u>(red, rb, [&](double (&t)[1]) {
 		st->sz = t[0];

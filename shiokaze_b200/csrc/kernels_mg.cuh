@@ -502,6 +502,7 @@ __global__ void __launch_bounds__(TX *8) k_prolong_add(Dims d, Tiles T, Dims dc,
 constexpr int TAIL_MAX_LEVELS = 12;
 constexpr int TAIL_THREADS = 1024;
 constexpr int TAIL_ARRAYS = 6; // wx wy wz dd x b
+constexpr int TAIL_SLOTS = 4;  // pairs of x-adjacent cells a thread may own on one tail level (setup_tail keeps larger levels out of the tail)
 
 struct TailLevel {
 	Dims d;
@@ -533,14 +534,45 @@ __device__ __forceinline__ void tail_body(const TailArgs &A, float *sm) {
 		}
 	}
 	__syncthreads();
-	auto half = [&](int l, int color, bool zero_x) {
+	// Relaxation of one colour. The cells of a level are walked as PAIRS along x (hx = ceil(nx / 2) pairs per row): pair slot q = tid + TAIL_THREADS * m belongs
+	// to this thread, the colour picks which cell of the pair — every thread of a warp works, on every pass (a walk over all cells that skips the other colour
+	// keeps half of each warp idle). load_slots() resolves the thread's slots of a level once per visit (the index divisions are as expensive as the relaxation
+	// itself); only the threads that own a slot take part in the level's barriers: a named barrier over those warps, or none at all when one warp does the
+	// whole level (the 4^3 bottom of the hierarchy, 16 sweeps per V-cycle).
+	__shared__ int s_cells[TAIL_SLOTS][TAIL_THREADS]; // (shared, not registers: 1024 threads leave 64 registers each) per slot: flat index of the pair's first cell | bit 29: the pair has no second cell (odd nx, last pair) | bit 30: (j + k + k0) & 1; -1: no such slot
+	int n_active = 0;       // threads with a slot, rounded up to whole warps
+	auto load_slots = [&](int l) {
 		const Dims &d = A.L[l].d;
-		const int nx = d.nx, plane = (int)d.plane, n = (int)d.ncell;
+		const int hx = (d.nx + 1) >> 1, slots = hx * d.ny * d.nzl;
+		n_active = min(TAIL_THREADS, (slots + 31) & ~31);
+#pragma unroll
+		for (int m = 0; m < TAIL_SLOTS; ++m) {
+			const int q = tid + TAIL_THREADS * m;
+			int v = -1;
+			if (q < slots) {
+				const int rowi = q / hx, p2 = q - rowi * hx, k = rowi / d.ny, j = rowi - k * d.ny;
+				v = (d.nx * rowi + 2 * p2) | ((2 * p2 + 1 >= d.nx) ? (1 << 29) : 0) | (((j + k + d.k0) & 1) << 30);
+			}
+			s_cells[m][tid] = v;
+		}
+	};
+	auto level_sync = [&]() {
+		if (n_active <= 32) __syncwarp();
+		else if (n_active < TAIL_THREADS) asm volatile("bar.sync 1, %0;" ::"r"(n_active) : "memory");
+		else __syncthreads();
+	};
+	auto half = [&](int l, int color, bool zero_x) { // (threads without a slot never get here)
+		const Dims &d = A.L[l].d;
+		const int nx = d.nx, plane = (int)d.plane;
 		const float *wx = arr(l, 0), *wy = arr(l, 1), *wz = arr(l, 2), *dd = arr(l, 3), *b = arr(l, 5);
 		float *x = arr(l, 4);
-		for (int c = tid; c < n; c += TAIL_THREADS) {
-			const int k = c / plane, rem = c - k * plane, j = rem / nx, i = rem - j * nx;
-			if (((i + j + k + d.k0) & 1) != color) continue;
+#pragma unroll 1
+		for (int m = 0; m < TAIL_SLOTS; ++m) {
+			const int sc = s_cells[m][tid];
+			if (sc < 0) break;
+			const int second = (color + (sc >> 30)) & 1; // which cell of the pair has this colour
+			if (second && (sc & (1 << 29))) continue;
+			const int c = (sc & 0xffffff) + second;
 			const float w0 = wx[c], w1 = wx[c + 1], w2 = wy[c], w3 = wy[c + nx], w4 = wz[c], w5 = wz[c + plane];
 			// (a neighbour across a zero coefficient — a wall, whose flat index wraps to a cell of the SAME colour — is not read: the product is an
 			// exact zero either way, and the in-place update then never reads a value another thread may be writing)
@@ -548,15 +580,21 @@ __device__ __forceinline__ void tail_body(const TailArgs &A, float *sm) {
 			              : gs_relax(w0, w1, w2, w3, w4, w5, dd[c], b[c], w0 != 0.f ? x[c - 1] : 0.f, w1 != 0.f ? x[c + 1] : 0.f, w2 != 0.f ? x[c - nx] : 0.f,
 			                         w3 != 0.f ? x[c + nx] : 0.f, w4 != 0.f ? x[c - plane] : 0.f, w5 != 0.f ? x[c + plane] : 0.f, x[c]);
 		}
+		level_sync();
+	};
+	// `sweeps` red-black sweeps of level l, first colour `c0`; zero: x starts from zero. Ends with a block barrier.
+	auto smooth = [&](int l, int sweeps, int c0, bool zero) {
+		load_slots(l);
+		if (tid < n_active)
+			for (int sw = 0; sw < sweeps; ++sw) {
+				half(l, c0, zero && sw == 0);
+				half(l, c0 ^ 1, false);
+			}
 		__syncthreads();
 	};
 	for (int l = 0; l < A.nlev; ++l) { // descend
 		const bool last = l + 1 == A.nlev;
-		const int sweeps = last ? A.coarse : A.pre;
-		for (int sw = 0; sw < sweeps; ++sw) {
-			half(l, 0, sw == 0);
-			half(l, 1, false);
-		}
+		smooth(l, last ? A.coarse : A.pre, 0, true);
 		if (last) break;
 		const Dims &d = A.L[l].d, &dc = A.L[l + 1].d;
 		const int nx = d.nx, ny = d.ny, plane = (int)d.plane;
@@ -593,11 +631,7 @@ __device__ __forceinline__ void tail_body(const TailArgs &A, float *sm) {
 			}
 			__syncthreads();
 		}
-		const int sweeps = last ? A.coarse : A.post;
-		for (int sw = 0; sw < sweeps; ++sw) {
-			half(l, 1, false);
-			half(l, 0, false);
-		}
+		smooth(l, last ? A.coarse : A.post, 1, false);
 	}
 	const float *x = arr(0, 4);
 	for (int c = tid; c < (int)A.L[0].d.ncell; c += TAIL_THREADS) A.x_out[c] = x[c];

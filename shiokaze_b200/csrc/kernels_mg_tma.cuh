@@ -110,33 +110,26 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 
 	for (int pass = 0; pass < (slab_ghosts ? 2 : 1); ++pass) {
 	if (SLAB && pass == 1) block_wait_neighbours(sl.cm, sl.seq_half); // the neighbours' half-updated planes are in the ghost planes of x_old
+	// The loads of a CTA form ONE stream over all its tiles (planes kb-1 .. ke+1 of the first, then of the next, ...): load n lands in stage n % 3, and the producer
+	// requests a load as soon as the one three before it has been consumed. The halo-column warp, which holds the producer, looks one tile ahead, so while the
+	// last two steps of a tile run, the first planes of the NEXT tile are already on their way (a tile of a liquid scene is 8-16 planes deep: the pipeline
+	// fill was ~8 % of it). The row warps know nothing of this — they wait on the same mbarriers as before, which have simply completed earlier.
+	TileWalk w(T, ntiles, false, false); // (whole tiles only: see TileWalk)
+	auto fetch = [&](TileWalk &tw, int &ti0, int &tj0, int &tkb, int &tke) -> bool {
+		while (tw.next(T, d.nzl, ti0, tj0, tkb, tke))
+			if (!(slab_ghosts && (tkb < 2 || tke + 1 >= d.nzl) != (pass == 1))) return true; // pass 0: tiles that read no ghost plane; pass 1: the others
+		return false;
+	};
 	int i0, j0, kb, ke;
-	for (TileWalk w(T, ntiles); w.next(T, d.nzl, i0, j0, kb, ke);) {
-		if (slab_ghosts && (kb < 2 || ke + 1 >= d.nzl) != (pass == 1)) continue; // pass 0: tiles that read no ghost plane; pass 1: the others
+	unsigned issued = loads_done; // (producer) loads requested so far
+	while (fetch(w, i0, j0, kb, ke)) {
 		const unsigned base = loads_done;           // load index of plane kb-1
-		auto issue = [&](int p) {                   // producer: fill the stage of plane p
-			const unsigned n = base + (unsigned)(p - (kb - 1));
-			float *sp = stage_base + (n % ST_STAGES) * ST_FLOATS;
-			unsigned long long *bar = &full[n % ST_STAGES];
-			fence_proxy_async(); // the stage's previous contents were read through the generic proxy
-			mbar_expect_tx(bar, ZERO_X ? ST_TX_BYTES_NOX : ST_TX_BYTES);
-			if (!ZERO_X) tma_load_3d(sp + ST_XO, &M.xo, bar, i0 - 4, j0 - 2, p + 1);
-			tma_load_3d(sp + ST_WY, &M.wy, bar, i0 - 4, j0 - 1, p + 1);
-			tma_load_3d(sp + ST_WX, &M.wx, bar, i0 - 4, j0 - 1, p + 1);
-			tma_load_3d(sp + ST_WZ, &M.wz, bar, i0 - 4, j0 - 1, p + 1);
-			tma_load_3d(sp + ST_DD, &M.dd, bar, i0 - 4, j0 - 1, p + 1);
-			tma_load_3d(sp + ST_B, &M.b, bar, i0 - 4, j0 - 1, p + 1);
-		};
+		const unsigned cur_n = (unsigned)(ke - kb + 3);
 		auto stage_of = [&](int p) -> const float * { return stage_base + ((base + (unsigned)(p - (kb - 1))) % ST_STAGES) * ST_FLOATS; };
 		auto wait_plane = [&](int p) {
 			const unsigned n = base + (unsigned)(p - (kb - 1));
 			mbar_wait(&full[n % ST_STAGES], (n / ST_STAGES) & 1u);
 		};
-		if (producer) {
-			issue(kb - 1);
-			issue(kb);
-			issue(kb + 1);
-		}
 		// PROLONG: x_old + P e_coarse is formed IN the stage. As soon as the box of plane p+2 has landed (one step before anybody
 		// needs it) every row-warp thread adds the coarse correction to its OWN quad of it — the only part of that plane it reads
 		// before the next block barrier — and the halo-column warp does the rim (rows 0 and 19, quads 0 and 17 of the other rows),
@@ -155,6 +148,35 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 		};
 
 		if (colwarp) {
+			// ---- the producer's view of the load stream: this tile and the next
+			TileWalk peek = w;
+			int ni0 = 0, nj0 = 0, nkb = 0, nke = 0;
+			const bool nhave = fetch(peek, ni0, nj0, nkb, nke);
+			const unsigned next_n = nhave ? (unsigned)(nke - nkb + 3) : 0u;
+			auto issue_at = [&](int ti0, int tj0, int p, unsigned n) { // fill stage n % 3 with plane p of the tile at (ti0, tj0)
+				float *sp = stage_base + (n % ST_STAGES) * ST_FLOATS;
+				unsigned long long *bar = &full[n % ST_STAGES];
+				fence_proxy_async(); // the stage's previous contents were read through the generic proxy
+				mbar_expect_tx(bar, ZERO_X ? ST_TX_BYTES_NOX : ST_TX_BYTES);
+				if (!ZERO_X) tma_load_3d(sp + ST_XO, &M.xo, bar, ti0 - 4, tj0 - 2, p + 1);
+				tma_load_3d(sp + ST_WY, &M.wy, bar, ti0 - 4, tj0 - 1, p + 1);
+				tma_load_3d(sp + ST_WX, &M.wx, bar, ti0 - 4, tj0 - 1, p + 1);
+				tma_load_3d(sp + ST_WZ, &M.wz, bar, ti0 - 4, tj0 - 1, p + 1);
+				tma_load_3d(sp + ST_DD, &M.dd, bar, ti0 - 4, tj0 - 1, p + 1);
+				tma_load_3d(sp + ST_B, &M.b, bar, ti0 - 4, tj0 - 1, p + 1);
+			};
+			// request every load whose stage is free: `consumed` loads of the stream have been read for the last time
+			auto pump = [&](unsigned consumed) {
+				while (issued < consumed + ST_STAGES && issued < base + cur_n + next_n) {
+					const unsigned idx = issued - base;
+					if (idx < cur_n) issue_at(i0, j0, kb - 1 + (int)idx, issued);
+					else issue_at(ni0, nj0, nkb - 1 + (int)(idx - cur_n), issued);
+					++issued;
+				}
+			};
+			// after the block barrier of step p the stage of plane p is free (the last step also reads plane ke+1 for the last time)
+			auto consumed_after = [&](int p) -> unsigned { return p == ke ? base + cur_n : base + (unsigned)(p - (kb - 1)) + 1u; };
+			if (producer) pump(base);
 			// ---- halo columns (stage columns 3 and TX+4) of the TY tile rows: one cell per lane and plane
 			const int side = lane >> 4, cc = side ? TX + 4 : 3, rr = (lane & 15) + 1; // stage column, row slot
 			const int ci = i0 - 4 + cc, cj = j0 - 1 + rr;
@@ -213,14 +235,11 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 				}
 				H[(p + 3) % 3][rr][cc] = cv ? h : 0.f;
 				__syncthreads();
-				if (producer && p + 3 <= ke + 1) issue(p + 3); // the stage of plane p is free: every phase-1 read of it is behind the barrier
+				if (producer) pump(consumed_after(p)); // the stage of plane p is free: every phase-1 read of it is behind the barrier
 				if (fix) rim_add(p + 2, e_rim);
 				xm = xc; xc = xp;
 			}
-			loads_done = base + (unsigned)(ke - kb + 3);
-			__syncthreads();
-			continue;
-		}
+		} else {
 
 		const int i = i0 + 4 * tx, j = j0 - 1 + r;
 		const bool valid = i < d.nx && j >= 0 && j < d.ny;
@@ -317,7 +336,8 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 			wz_cur = wz_next;
 			prv = cur;
 		}
-		loads_done = base + (unsigned)(ke - kb + 3);
+		}
+		loads_done = base + cur_n;
 		__syncthreads();
 	}
 	}

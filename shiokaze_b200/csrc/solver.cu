@@ -21,6 +21,7 @@
 #include "kernels_mg_tma.cuh"
 #include "kernels_cg_tma.cuh"
 #include "kernels_post.cuh"
+#include "kernels_xfer.cuh"
 #include "slab_comm.h"
 
 using namespace shkz;
@@ -245,6 +246,14 @@ struct shkz_b200_solver {
 	unsigned last_iterations = 0; // of the previous solve: sizes the first batch of iterations before the host looks
 	// host-call staging (device)
 	PlainArray st_vel[3], st_act[3], st_solid, st_fluid, st_pressure, st_pact;
+	// sparse host copies (kernels_xfer.cuh): flags / list / count of the wet transfer blocks, byte counter of the face push, their pinned mirror
+	PlainArray xf_flags, xf_list, xf_count, xf_pushed;
+	unsigned long long *h_xf = nullptr; // pinned: [0] wet blocks [1] bytes pushed
+	cudaStream_t copy_stream = nullptr; // non-blocking: the activity masks travel behind the solve
+	bool xfer_sparse = false;           // set around the project_impl of a sparse host call: the caller's pressure grids are host memory written by k_store_pressure
+	                                    // over the union tile list (no wholesale clear), the masks arrive on copy_stream (ev[11]), switched-off faces are marked
+	const void *last_host_pressure = nullptr, *last_host_pact = nullptr; // the grids the previous sparse call wrote: everything off its tiles is known to be zero there
+	uint64_t project_serial = 0, host_serial = ~0ull; // ... provided no other projection ran on this solver in between
 	// extrapolation + solid constraint after the projection (kernels_post.cuh): the other activity mask of the rounds, the velocity before the constraint
 	PlainArray post_act[3], post_vel[3], post_mask[3];
 	// slab communicator (nullptr on a whole grid)
@@ -292,6 +301,7 @@ void release_precision_arrays(shkz_b200_solver *S) {
 	S->gtail_first = -1;
 	S->mid_first = S->gmid_first = -1;
 	S->levels.clear();
+	S->last_host_pressure = S->last_host_pact = nullptr; // (the union tile lists start over)
 	S->alloc_precision = -1;
 	S->have_system = false;
 	S->have_hierarchy = false;
@@ -334,7 +344,7 @@ int finish_level(HostLevel &L, const Dims &cur, const std::string &n, SlabComm *
 	L.tag_sweep = "sweep@" + n; L.tag_restrict = "residual_restrict@" + n; L.tag_prolong = "prolong_add@" + n;
 	L.tag_coarsen = "coarsen_operator@" + n; L.tag_compact = "compact_tiles@" + n;
 	L.view.d = cur;
-	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, L.slice, L.adaptive ? 0 : L.bz, balanced ? 1 : 0};
+	L.view.tiles = Tiles{static_cast<const int *>(L.tile_ids.base), static_cast<const int *>(L.tile_count.base), ntx, nty, L.slice, L.adaptive ? 0 : L.bz, balanced ? (getenv("SHKZ_B200_NO_HYBRID") ? 1 : 5) : 0}; // (the variable: A-B timing)
 	L.utiles = L.view.tiles;
 	L.utiles.ids = static_cast<const int *>(L.tile_uids.base);
 	L.utiles.count = static_cast<const int *>(L.tile_ucount.base);
@@ -359,6 +369,7 @@ int setup_tail(const std::vector<HostLevel> &lv, int &tail_first, size_t &tail_s
 		const Dims &dl = lv[first - 1].d;
 		const size_t add = (size_t)TAIL_ARRAYS * (size_t)(dl.ncell + 2 * dl.plane) * sizeof(float);
 		if (bytes + add > limit) break;
+		if ((long long)((dl.nx + 1) / 2) * dl.ny * dl.nzl > (long long)TAIL_SLOTS * TAIL_THREADS) break; // tail_body: at most TAIL_SLOTS cell pairs per thread
 		bytes += add;
 		--first;
 	}
@@ -1024,6 +1035,8 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 	A.second_order_fluid = P.second_order_fluid; A.second_order_solid = P.second_order_solid;
 	A.have_solid = solid != nullptr; A.fluid_levelset = fluid_levelset;
 	A.apply_rhs_correct = P.apply_rhs_correct;
+	A.off_mark = S->xfer_sparse ? XFER_OFF_MARK : 0;
+	S->project_serial++;
 	{
 		int e = 0;
 		A.dx_pow2 = frexp(S->dx, &e) == 0.5 ? 1 : 0;
@@ -1099,11 +1112,13 @@ int project_impl(shkz_b200_solver *S, double dt, void *const vel_v[3], uint8_t *
 		LAUNCH(S, "sum_rows", k_sum_rows<VecT>, flat_blocks(d.ncell), 256, stream, d, (const VecT *)S->x.ptr<VecT>(d), (const uint8_t *)in_rows, rb, st);
 	}
 	// the caller's grids are cleared wholesale, then written where a tile holds (or held) unknowns
-	if (pressure_v) CK(cudaMemsetAsync(pressure_v, 0, sizeof(RealT) * (size_t)d.ncell, stream));
-	if (pressure_active) CK(cudaMemsetAsync(pressure_active, 0, (size_t)d.ncell, stream));
+	// (a sparse host call passes the caller's page-locked grids here: off the union list they already hold zeros, shkz_b200.h)
+	if (pressure_v && !S->xfer_sparse) CK(cudaMemsetAsync(pressure_v, 0, sizeof(RealT) * (size_t)d.ncell, stream));
+	if (pressure_active && !S->xfer_sparse) CK(cudaMemsetAsync(pressure_active, 0, (size_t)d.ncell, stream));
 	LAUNCH_TILES(S, "store_pressure", (k_store_pressure<RealT, VecT>), dim3(TX, 8, 1), S->levels[0].tiles_total, stream, d, S->levels[0].utiles, (const VecT *)S->x.ptr<VecT>(d),
 	             (const uint8_t *)in_rows, (const CGState *)st, pres, static_cast<RealT *>(pressure_v), pressure_active, P.warm_start ? S->p_prev.ptr<VecT>(d) : (VecT *)nullptr);
 	CKR(halo(S, d, pres, stream));
+	if (S->xfer_sparse) CK(cudaStreamWaitEvent(stream, S->ev[11], 0)); // the activity masks, uploaded on copy_stream behind the solve
 	{
 		const dim3 ugrid((d.nx + 1 + 31) / 32, (d.ny + 1 + 8 * UV_ROWS - 1) / (8 * UV_ROWS), d.nzl + 1), ublock(32, 8, 1);
 		if (A.have_solid && A.fluid_levelset) LAUNCH(S, "update_velocity", (k_update_velocity<RealT, true, true>), ugrid, ublock, stream, d, A, (const RealT *)phi, solid, (const RealT *)pres, vel, masks);
@@ -1201,6 +1216,82 @@ int check_params(const shkz_b200_params *p, shkz_b200_params &out) {
 	if (out.precision < 0 || out.precision > 2) return fail(SHKZ_B200_ERR_ARG, "unknown precision %d", out.precision);
 	if (!(out.mg_coarse_scale > 0.0)) return fail(SHKZ_B200_ERR_ARG, "mg_coarse_scale must be > 0");
 	if (!(out.mg_omega > 0.0 && out.mg_omega < 2.0)) return fail(SHKZ_B200_ERR_ARG, "mg_omega must be in (0, 2)");
+	return SHKZ_B200_OK;
+}
+
+// device-visible address of a page-locked host buffer; nullptr for pageable memory (and for NULL)
+static void *mapped_host(const void *p) {
+	if (!p) return nullptr;
+	cudaPointerAttributes a{};
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+// The sparse upload of a host call (kernels_xfer.cuh), after the liquid level set has been copied into its staging array: flag the wet transfer blocks, and — unless
+// they are most of the grid — pull velocity and solid nodes around them straight out of the caller's page-locked buffers and send the masks after them on
+// copy_stream. *sparse = false leaves everything but the level set to the whole-array copies. pulled = bytes read from host memory by k_pull_slices.
+template <class RealT>
+static int host_sparse_upload(shkz_b200_solver *S, void *const hvel[3], uint8_t *const vel_active[3], const void *hsolid, cudaStream_t stream, bool *sparse, uint64_t *pulled) {
+	const Dims &d = S->d;
+	XferGeom g{};
+	g.ntx = (d.nx + TX - 1) / TX; g.nty = (d.ny + TY - 1) / TY;
+	g.slice = d.nzl < 8 ? d.nzl : 8;
+	g.nslices_z = (d.nzl + g.slice - 1) / g.slice;
+	const size_t nslices = (size_t)g.ntx * g.nty * g.nslices_z;
+	if (!S->xf_flags.base) {
+		CKR(S->xf_flags.alloc(nslices * sizeof(int)));
+		CKR(S->xf_list.alloc(nslices * sizeof(int)));
+		CKR(S->xf_count.alloc(sizeof(int)));
+		CKR(S->xf_pushed.alloc(sizeof(unsigned long long)));
+		CK(cudaHostAlloc(reinterpret_cast<void **>(&S->h_xf), 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+		CK(cudaStreamCreateWithFlags(&S->copy_stream, cudaStreamNonBlocking));
+	}
+	CK(cudaMemsetAsync(S->xf_flags.base, 0, nslices * sizeof(int), stream));
+	CK(cudaMemsetAsync(S->xf_count.base, 0, sizeof(int), stream));
+	const long long units = (long long)g.ntx * g.nty * d.nzl;
+	const int fgrid = (int)(units < 8ll * S->num_sms ? units : 8ll * S->num_sms);
+	LAUNCH(S, "flag_wet_slices", k_flag_wet_slices<RealT>, fgrid, dim3(TX, 4, 1), stream, d, g, static_cast<const RealT *>(S->st_fluid.base), static_cast<int *>(S->xf_flags.base),
+	       static_cast<int *>(S->xf_list.base), static_cast<int *>(S->xf_count.base));
+	S->h_xf[0] = 0;
+	CK(cudaMemcpyAsync(&S->h_xf[0], S->xf_count.base, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	const size_t wet = (size_t)(S->h_xf[0] & 0xffffffffull);
+	*sparse = 2 * wet <= nslices; // (beyond that the copy engines' whole-array streams are the faster way)
+	if (!*sparse) return SHKZ_B200_OK;
+	if (wet) {
+		ConstFaceGrids<RealT> hv;
+		FaceGrids<RealT> dv;
+		for (int dim = 0; dim < 3; ++dim) {
+			hv.p[dim] = static_cast<const RealT *>(hvel[dim]);
+			dv.p[dim] = static_cast<RealT *>(S->st_vel[dim].base);
+		}
+		const int pgrid = (int)(wet < 8ull * S->num_sms ? wet : 8ull * S->num_sms);
+		LAUNCH(S, "pull_slices", k_pull_slices<RealT>, pgrid, 256, stream, d, g, static_cast<const int *>(S->xf_list.base), static_cast<const int *>(S->xf_count.base), hv, dv,
+		       static_cast<const RealT *>(hsolid), static_cast<RealT *>(S->st_solid.base));
+	}
+	const uint64_t per_block = (uint64_t)((TX + 1) * TY * g.slice + TX * (TY + 1) * g.slice + TX * TY * (g.slice + 1) + (hsolid ? (TX + 1) * (TY + 1) * (g.slice + 1) : 0));
+	*pulled = (uint64_t)wet * per_block * sizeof(RealT); // (blocks on the grid's upper edges are smaller: an upper bound by a few percent)
+	// the masks are first needed by the velocity update: they cross PCIe after the pull and behind assembly and solve
+	CK(cudaEventRecord(S->ev[10], stream));
+	CK(cudaStreamWaitEvent(S->copy_stream, S->ev[10], 0));
+	for (int dim = 0; dim < 3; ++dim) CK(cudaMemcpyAsync(S->st_act[dim].base, vel_active[dim], face_count(d, dim), cudaMemcpyHostToDevice, S->copy_stream));
+	CK(cudaEventRecord(S->ev[11], S->copy_stream));
+	return SHKZ_B200_OK;
+}
+
+template <class RealT>
+static int host_sparse_download(shkz_b200_solver *S, void *const hvel[3], uint8_t *const hact[3], cudaStream_t stream) {
+	const Dims &d = S->d;
+	CK(cudaMemsetAsync(S->xf_pushed.base, 0, sizeof(unsigned long long), stream));
+	for (int dim = 0; dim < 3; ++dim) {
+		const long long nf = (long long)face_count(d, dim);
+		LAUNCH(S, "push_faces", k_push_faces<RealT>, flat_blocks((nf + 3) / 4), 256, stream, nf, static_cast<const RealT *>(S->st_vel[dim].base),
+		       static_cast<uint8_t *>(S->st_act[dim].base), static_cast<RealT *>(hvel[dim]), hact[dim], static_cast<unsigned long long *>(S->xf_pushed.base));
+	}
+	CK(cudaMemcpyAsync(&S->h_xf[1], S->xf_pushed.base, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
 	return SHKZ_B200_OK;
 }
 
@@ -1331,8 +1422,11 @@ void shkz_b200_destroy(shkz_b200_solver *S) {
 		S->post_act[dim].release(); S->post_vel[dim].release(); S->post_mask[dim].release();
 	}
 	S->st_solid.release(); S->st_fluid.release(); S->st_pressure.release(); S->st_pact.release();
+	S->xf_flags.release(); S->xf_list.release(); S->xf_count.release(); S->xf_pushed.release();
 	S->partials.release(); S->counter.release(); S->state.release(); S->mid_barrier.release();
 	if (S->h_state) cudaFreeHost(S->h_state);
+	if (S->h_xf) cudaFreeHost(S->h_xf);
+	if (S->copy_stream) cudaStreamDestroy(S->copy_stream);
 	if (S->events) for (auto &e : S->ev) if (e) cudaEventDestroy(e);
 	S->prof.destroy();
 	delete S;
@@ -1374,48 +1468,123 @@ int shkz_b200_project_host(shkz_b200_solver *S, double dt, void *const vel[3], u
 static int project_host_impl(shkz_b200_solver *S, double dt, void *const vel[3], uint8_t *const vel_active[3], const void *solid, const void *fluid,
                              int fluid_levelset, const shkz_b200_params *params, void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats) {
 	if (!vel || !vel_active || !fluid) return fail(SHKZ_B200_ERR_ARG, "vel / vel_active / fluid must not be NULL");
+	for (int dim = 0; dim < 3; ++dim)
+		if (!vel[dim] || !vel_active[dim]) return fail(SHKZ_B200_ERR_ARG, "vel[%d] / vel_active[%d] is NULL", dim, dim);
+	shkz_b200_params P;
+	CKR(check_params(params, P));
 	CKR(device_ready(S->device));
 	CK(cudaSetDevice(S->device));
 	const Dims &d = S->d;
 	const size_t rb = S->real_bytes;
 	const size_t nodal = (size_t)(d.nx + 1) * (d.ny + 1) * (d.nzl + 1);
+	const size_t ncell = (size_t)d.ncell;
 	cudaStream_t stream = nullptr;
 	void *dvel[3];
 	uint8_t *dact[3];
-	CK(cudaEventRecord(S->ev[5], stream));
 	for (int dim = 0; dim < 3; ++dim) {
-		if (!vel[dim] || !vel_active[dim]) return fail(SHKZ_B200_ERR_ARG, "vel[%d] / vel_active[%d] is NULL", dim, dim);
 		const size_t nf = face_count(d, dim);
 		if (!S->st_vel[dim].base) { CKR(S->st_vel[dim].alloc(nf * rb)); CKR(S->st_act[dim].alloc(nf)); }
-		CK(cudaMemcpyAsync(S->st_vel[dim].base, vel[dim], nf * rb, cudaMemcpyHostToDevice, stream));
-		CK(cudaMemcpyAsync(S->st_act[dim].base, vel_active[dim], nf, cudaMemcpyHostToDevice, stream));
 		dvel[dim] = S->st_vel[dim].base;
 		dact[dim] = static_cast<uint8_t *>(S->st_act[dim].base);
 	}
-	if (!S->st_fluid.base) { CKR(S->st_fluid.alloc((size_t)d.ncell * rb)); CKR(S->st_pressure.alloc((size_t)d.ncell * rb)); CKR(S->st_pact.alloc((size_t)d.ncell)); }
-	CK(cudaMemcpyAsync(S->st_fluid.base, fluid, (size_t)d.ncell * rb, cudaMemcpyHostToDevice, stream));
-	if (solid) {
-		if (!S->st_solid.base) CKR(S->st_solid.alloc(nodal * rb));
-		CK(cudaMemcpyAsync(S->st_solid.base, solid, nodal * rb, cudaMemcpyHostToDevice, stream));
+	if (!S->st_fluid.base) { CKR(S->st_fluid.alloc(ncell * rb)); CKR(S->st_pressure.alloc(ncell * rb)); CKR(S->st_pact.alloc(ncell)); }
+	if (solid && !S->st_solid.base) CKR(S->st_solid.alloc(nodal * rb));
+
+	// Sparse copies (kernels_xfer.cuh) need a liquid level set (without one every cell is wet), nothing that reads the velocity away from wet cells
+	// (surface tension walks the masks early, the extrapolation fills the whole band), and every buffer addressable from the device.
+	void *mvel[3] = {nullptr, nullptr, nullptr}, *mact[3] = {nullptr, nullptr, nullptr}, *msolid = nullptr, *mpres = nullptr, *mpact = nullptr;
+	bool sparse = fluid_levelset && P.surface_tension == 0.0 && P.extrapolate_width <= 0;
+	if (const char *e = getenv("SHKZ_B200_HOST_COPIES")) sparse = sparse && strcmp(e, "dense") != 0;
+	if (sparse) {
+		for (int dim = 0; dim < 3 && sparse; ++dim) sparse = (mvel[dim] = mapped_host(vel[dim])) && (mact[dim] = mapped_host(vel_active[dim]));
+		if (sparse && solid) sparse = (msolid = mapped_host(solid)) != nullptr;
+		if (sparse && pressure) sparse = (mpres = mapped_host(pressure)) != nullptr;
+		if (sparse && pressure_active) sparse = (mpact = mapped_host(pressure_active)) != nullptr;
 	}
+	uint64_t h2d = 0, d2h = 0, pulled = 0;
+	S->launches = 0;
+	CK(cudaEventRecord(S->ev[5], stream));
+	CK(cudaMemcpyAsync(S->st_fluid.base, fluid, ncell * rb, cudaMemcpyHostToDevice, stream));
+	h2d += ncell * rb;
+	if (sparse) {
+		if (S->real == SHKZ_B200_REAL_F32) CKR((host_sparse_upload<float>(S, mvel, vel_active, msolid, stream, &sparse, &pulled)));
+		else CKR((host_sparse_upload<double>(S, mvel, vel_active, msolid, stream, &sparse, &pulled)));
+	}
+	for (int dim = 0; dim < 3; ++dim) h2d += face_count(d, dim);
+	if (sparse) {
+		h2d += pulled;
+		// everything off the tiles the previous sparse call wrote is zero in the caller's pressure grids — if they are the same grids and no other projection
+		// has moved the solver's tile lists since; otherwise clear them once
+		const bool known = S->host_serial == S->project_serial;
+		if (pressure && !(known && S->last_host_pressure == mpres)) {
+			if (rb == 4) LAUNCH(S, "fill_zero", k_fill_zero<float>, flat_blocks((long long)ncell), 256, stream, static_cast<float *>(mpres), (long long)ncell);
+			else LAUNCH(S, "fill_zero", k_fill_zero<double>, flat_blocks((long long)ncell), 256, stream, static_cast<double *>(mpres), (long long)ncell);
+			d2h += ncell * rb;
+		}
+		if (pressure_active && !(known && S->last_host_pact == mpact)) {
+			LAUNCH(S, "fill_zero", k_fill_zero<uint8_t>, flat_blocks((long long)ncell), 256, stream, static_cast<uint8_t *>(mpact), (long long)ncell);
+			d2h += ncell;
+		}
+	} else {
+		for (int dim = 0; dim < 3; ++dim) {
+			const size_t nf = face_count(d, dim);
+			CK(cudaMemcpyAsync(S->st_vel[dim].base, vel[dim], nf * rb, cudaMemcpyHostToDevice, stream));
+			CK(cudaMemcpyAsync(S->st_act[dim].base, vel_active[dim], nf, cudaMemcpyHostToDevice, stream));
+			h2d += nf * rb;
+		}
+		if (solid) {
+			CK(cudaMemcpyAsync(S->st_solid.base, solid, nodal * rb, cudaMemcpyHostToDevice, stream));
+			h2d += nodal * rb;
+		}
+	}
+	S->last_host_pressure = S->last_host_pact = nullptr;
 	CK(cudaEventRecord(S->ev[6], stream));
-	int rc = shkz_b200_project_device(S, dt, dvel, dact, solid ? S->st_solid.base : nullptr, S->st_fluid.base, fluid_levelset, params, S->st_pressure.base,
-	                                  static_cast<uint8_t *>(S->st_pact.base), stats, stream);
-	if (rc != SHKZ_B200_OK) return rc;
-	CK(cudaEventRecord(S->ev[6 + 1], stream));
-	for (int dim = 0; dim < 3; ++dim) {
-		const size_t nf = face_count(d, dim);
-		CK(cudaMemcpyAsync(vel[dim], S->st_vel[dim].base, nf * rb, cudaMemcpyDeviceToHost, stream));
-		CK(cudaMemcpyAsync(vel_active[dim], S->st_act[dim].base, nf, cudaMemcpyDeviceToHost, stream));
+	const uint64_t setup_launches = S->launches;
+	S->xfer_sparse = sparse;
+	int rc = shkz_b200_project_device(S, dt, dvel, dact, solid ? S->st_solid.base : nullptr, S->st_fluid.base, fluid_levelset, params, sparse ? mpres : S->st_pressure.base,
+	                                  sparse ? static_cast<uint8_t *>(mpact) : static_cast<uint8_t *>(S->st_pact.base), stats, stream);
+	S->xfer_sparse = false;
+	if (rc != SHKZ_B200_OK) {
+		if (sparse) cudaStreamSynchronize(S->copy_stream); // (nothing of this call may still be reading the caller's buffers)
+		return rc;
 	}
-	if (pressure) CK(cudaMemcpyAsync(pressure, S->st_pressure.base, (size_t)d.ncell * rb, cudaMemcpyDeviceToHost, stream));
-	if (pressure_active) CK(cudaMemcpyAsync(pressure_active, S->st_pact.base, (size_t)d.ncell, cudaMemcpyDeviceToHost, stream));
+	CK(cudaEventRecord(S->ev[6 + 1], stream));
+	const uint64_t before_push = S->launches;
+	if (sparse) {
+		if (S->real == SHKZ_B200_REAL_F32) CKR((host_sparse_download<float>(S, mvel, reinterpret_cast<uint8_t *const *>(mact), stream)));
+		else CKR((host_sparse_download<double>(S, mvel, reinterpret_cast<uint8_t *const *>(mact), stream)));
+	} else {
+		for (int dim = 0; dim < 3; ++dim) {
+			const size_t nf = face_count(d, dim);
+			CK(cudaMemcpyAsync(vel[dim], S->st_vel[dim].base, nf * rb, cudaMemcpyDeviceToHost, stream));
+			CK(cudaMemcpyAsync(vel_active[dim], S->st_act[dim].base, nf, cudaMemcpyDeviceToHost, stream));
+			d2h += nf * (rb + 1);
+		}
+		if (pressure) { CK(cudaMemcpyAsync(pressure, S->st_pressure.base, ncell * rb, cudaMemcpyDeviceToHost, stream)); d2h += ncell * rb; }
+		if (pressure_active) { CK(cudaMemcpyAsync(pressure_active, S->st_pact.base, ncell, cudaMemcpyDeviceToHost, stream)); d2h += ncell; }
+	}
 	CK(cudaEventRecord(S->ev[0], stream));
 	CK(cudaStreamSynchronize(stream));
+	if (sparse) {
+		d2h += S->h_xf[1];
+		int nu[2] = {0, 0};
+		const HostLevel &H0 = S->levels[0];
+		CK(cudaMemcpy(nu, H0.tile_ucount.base, sizeof nu, cudaMemcpyDeviceToHost)); // union tiles k_store_pressure wrote, and their depth
+		uint64_t cells = (uint64_t)nu[0] * TX * TY * (uint64_t)(nu[1] > 0 ? nu[1] : H0.bz);
+		if (cells > ncell) cells = ncell;
+		d2h += cells * ((pressure ? rb : 0) + (pressure_active ? 1 : 0));
+		S->last_host_pressure = mpres;
+		S->last_host_pact = mpact;
+		S->host_serial = S->project_serial;
+	}
 	if (stats) {
 		cudaEventElapsedTime(&stats->ms_h2d, S->ev[5], S->ev[6]);
 		cudaEventElapsedTime(&stats->ms_d2h, S->ev[7], S->ev[0]);
 		stats->ms_total += stats->ms_h2d + stats->ms_d2h;
+		stats->host_copies = sparse ? 1 : 0;
+		stats->h2d_bytes = h2d;
+		stats->d2h_bytes = d2h;
+		stats->kernel_launches += setup_launches + (S->launches - before_push);
 	}
 	return SHKZ_B200_OK;
 }

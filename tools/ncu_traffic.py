@@ -1,7 +1,7 @@
 """profiles/traffic.json from an `ncu --set full` capture of one project() (runs here, no GPU): DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per
 unknown and launch of the level-0 solve kernels, keyed by the profiler tags bench.py uses, stamped with the hash of the kernel sources they were captured from
 (bench.py quotes the table only while that hash matches).
-usage: python tools/ncu_traffic.py <capture.ncu-rep> <n_rows of the captured workload> <set name> <workload text> [summary.csv]"""
+usage: python tools/ncu_traffic.py <capture.ncu-rep | capture_raw.csv> <n_rows of the captured workload> <set name> <workload text> [summary.csv]"""
 import csv, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,7 +12,8 @@ bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
 rep, rows_n, set_name, workload = sys.argv[1], float(sys.argv[2]), sys.argv[3], sys.argv[4]
 summary = sys.argv[5] if len(sys.argv) > 5 else None
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
-txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# (a capture of a whole solve at 512^3 is > 64 MB, more than gpurun brings back: the box reduces it with `ncu -i X.ncu-rep --page raw --csv > X_raw.csv`)
+txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 idx = {h: i for i, h in enumerate(rows[0])}
 units = rows[1]
