@@ -47,10 +47,16 @@ struct SpmvMaps { // tensor maps of the operands, box shapes as in SpmvStage
 
 constexpr int SPMV_TMA_THREADS = 32 * 9; // 8 warps own the tile's 16 x 16 quads, the ninth forms the halo ring of s_new
 
-template <class VecT>
+// SLAB (z-slab solvers): nothing of s ever crosses NVLink. The ghost planes of z arrive with the V-cycle's last sweep (its boundary planes of x_new go straight into
+// the neighbours' ghost planes; this kernel waits for that exchange, `wait_in`, in its prologue), and every rank keeps the ghost planes of s itself:
+// s_new(ghost) = z(ghost) + beta s_old(ghost) is the arithmetic the neighbour applies to the same bits on its own boundary plane, so the copies agree bit for bit —
+// the tiles at the bottom / top of the slab store the value they form for plane -1 / nzl anyway. One exchange per iteration less than k_xpay (push) + k_spmv_dot4 (wait).
+template <class VecT, bool SLAB>
 __global__ void __launch_bounds__(SPMV_TMA_THREADS, 2) k_xpay_spmv_tma(Dims d, Tiles T, const __grid_constant__ SpmvMaps M, int s_in, int z_in, const VecT *__restrict__ s_old,
-                                                                      const float *__restrict__ z, VecT *__restrict__ s_new, VecT *__restrict__ q, RedBuf rb, CGState *st) {
+                                                                      const float *__restrict__ z, VecT *__restrict__ s_new, VecT *__restrict__ q, RedBuf rb, CGState *st,
+                                                                      unsigned long long wait_in) {
 	if (st->done) return;
+	if (SLAB && wait_in) block_wait_neighbours(rb.comm, wait_in);
 	using SS = SpmvStage<VecT>;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	unsigned char *stage_base = smem_raw;
@@ -126,6 +132,7 @@ __global__ void __launch_bounds__(SPMV_TMA_THREADS, 2) k_xpay_spmv_tma(Dims d, T
 			const V4<VecT> so = ldv4(s_old + c);
 			const float4 zz = *reinterpret_cast<const float4 *>(z + c);
 			sm = V4<VecT>{fma(beta, so.a, (VecT)zz.x), fma(beta, so.b, (VecT)zz.y), fma(beta, so.c, (VecT)zz.z), fma(beta, so.d, (VecT)zz.w)};
+			if (SLAB && kb == 0) stv4(s_new + c, sm); // the lower ghost plane of s, kept by this rank itself
 		}
 		wait_plane(kb);
 		if (!ringwarp) {
@@ -182,6 +189,7 @@ __global__ void __launch_bounds__(SPMV_TMA_THREADS, 2) k_xpay_spmv_tma(Dims d, T
 			__syncthreads(); // stage p and the shared plane are free (after the last step: the stage of plane ke too)
 			if (producer) pump(p + 1 == ke ? base + cur_n : base + (unsigned)(p - kb) + 1u);
 		}
+		if (SLAB && ke == d.nzl && valid) stv4(s_new + row + plane * ke, sc); // (sc now holds s_new of plane ke: the upper ghost plane)
 		loads_done = base + cur_n;
 		have = nhave;
 		i0 = ni0; j0 = nj0; kb = nkb; ke = nke;

@@ -238,12 +238,23 @@ struct SlabSweep {
 };
 
 // start of a fused slab sweep: every thread of the grid takes quads of the two boundary planes (nx % 4 == 0, 1-D blocks)
-template <int FIRST, bool ZERO_X>
-__device__ __forceinline__ void slab_push_half_planes(const Dims &d, const SlabSweep &sl, const float *__restrict__ xo) {
+// PROLONG: x_old is "x_old + P e_coarse" everywhere it is read — on the boundary planes, their in-slab neighbours and the ghost planes beyond them (the coarse
+// correction `ec` has valid ghost planes: pushed by the coarse level's last sweep, or simply the next planes of the gathered global level). The half-updated
+// planes that leave here carry relaxed values on the first colour and the PLAIN x_old, without the correction, on the second: a ghost plane must read the same on
+// its second-colour cells before and after the neighbour's half-updated plane lands on it (that is what makes reading it while it lands race-free), so the
+// correction of those cells is added by whoever reads them — here for the planes beyond the boundary, in the stage for the tiles (k_sweep_tma: add_quad).
+template <int FIRST, bool ZERO_X, bool PROLONG>
+__device__ __forceinline__ void slab_push_half_planes(const Dims &d, const SlabSweep &sl, const float *__restrict__ xo, const float *__restrict__ ec, const Dims &dc) {
 	const CommDev *cm = sl.cm;
 	const long long nx = d.nx, plane = d.plane, quads = plane >> 2, nth = (long long)gridDim.x * blockDim.x;
 	const int qx = d.nx >> 2;
 	const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+	auto EC = [&](int i, int j, int k) -> long long { return (i >> 1) + (long long)dc.nx * ((j >> 1) + (long long)dc.ny * (k >> 1)); };
+	auto add4 = [&](float4 &v, int i, int j, int k) { // + P e on an aligned quad inside the grid's x / y extent (k may be a ghost plane)
+		if (j < 0 || j >= d.ny) return;
+		const float2 e = __ldcg(reinterpret_cast<const float2 *>(ec + EC(i, j, k)));
+		v.x += e.x; v.y += e.x; v.z += e.y; v.w += e.y;
+	};
 	for (int side = 0; side < 2; ++side) {
 		char *peer = side ? cm->hi : cm->lo;
 		if (!peer) continue;
@@ -257,14 +268,24 @@ __device__ __forceinline__ void slab_push_half_planes(const Dims &d, const SlabS
 			Q.wy = ld4(sl.wy + c); Q.wyu = ld4(sl.wy + c + nx);
 			Q.wz = ld4(sl.wz + c); Q.dd = ld4(sl.dd + c); Q.b = ld4(sl.b + c);
 			const float4 wzu = ld4(sl.wz + c + plane);
-			float4 x = zero4, xd = zero4, xu = zero4, zm = zero4, zp = zero4;
+			float4 x = zero4, xd = zero4, xu = zero4, zm = zero4, zp = zero4, x_plain = zero4;
 			float xl = 0.f, xr = 0.f;
 			if (!ZERO_X) { // (the plane beyond the boundary is a ghost plane: read it where the neighbour's stores land, in L2)
 				x = ld4cg(xo + c); xl = __ldcg(xo + c - 1); xr = __ldcg(xo + c + 4);
 				xd = ld4cg(xo + c - nx); xu = ld4cg(xo + c + nx); zm = ld4cg(xo + c - plane); zp = ld4cg(xo + c + plane);
+				x_plain = x;
+				if (PROLONG) {
+					add4(x, i, j, p); add4(xd, i, j - 1, p); add4(xu, i, j + 1, p); add4(zm, i, j, p - 1); add4(zp, i, j, p + 1);
+					if (i > 0) xl += __ldcg(ec + EC(i - 1, j, p));
+					if (i + 4 < d.nx) xr += __ldcg(ec + EC(i + 4, j, p));
+				}
 			}
 			const int a1 = (FIRST + j + p + d.k0) & 1;
-			const float4 h = a1 == 0 ? relax_quad<0, ZERO_X>(Q, wzu, x, xl, xr, xd, xu, zm, zp) : relax_quad<1, ZERO_X>(Q, wzu, x, xl, xr, xd, xu, zm, zp);
+			float4 h = a1 == 0 ? relax_quad<0, ZERO_X>(Q, wzu, x, xl, xr, xd, xu, zm, zp) : relax_quad<1, ZERO_X>(Q, wzu, x, xl, xr, xd, xu, zm, zp);
+			if (PROLONG) { // the cells of the OTHER colour leave as they are in memory, without the correction (see above)
+				if (a1 == 0) { h.y = x_plain.y; h.w = x_plain.w; }
+				else { h.x = x_plain.x; h.z = x_plain.z; }
+			}
 			*reinterpret_cast<float4 *>(dst + (c - plane * p)) = h;
 		}
 	}

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 	float *push_lo = nullptr, *push_hi = nullptr; // neighbours' ghost planes of x_new that take the own boundary planes
 	if constexpr (SLAB) {
 		if (sl.wait_in) block_wait_neighbours(sl.cm, sl.wait_in);
-		slab_push_half_planes<FIRST, ZERO_X>(d, sl, xo);
+		slab_push_half_planes<FIRST, ZERO_X, PROLONG>(d, sl, xo, ec, dc);
 		if (sl.seq_out) {
 			if (sl.cm->lo) push_lo = reinterpret_cast<float *>(sl.cm->lo + sl.off_xn) + (long long)(d.nzl + 1) * plane;
 			if (sl.cm->hi) push_hi = reinterpret_cast<float *>(sl.cm->hi + sl.off_xn);
@@ -143,7 +143,15 @@ __global__ void __launch_bounds__(S4_THREADS, 2) k_sweep_tma(Dims d, Tiles T, co
 		auto add_quad = [&](int pz, int rowi, int c4, float2 e) {
 			float4 *cell = reinterpret_cast<float4 *>(stage_base + ((base + (unsigned)(pz - (kb - 1))) % ST_STAGES) * ST_FLOATS + ST_XO + rowi * ST_W + 4 * c4);
 			float4 v = *cell;
-			v.x += e.x; v.y += e.x; v.z += e.y; v.w += e.y;
+			if (SLAB && (pz < 0 || pz >= d.nzl)) {
+				// a ghost plane of a z-slab holds the neighbour's half-updated plane by the time a tile reads it: relaxed values on the first colour, the plain
+				// x_old on the second (slab_push_half_planes) — only the latter still lacks the correction
+				const int par0 = (j0 - 2 + rowi + pz + d.k0) & 1; // colour of the quad's cells 0 and 2 (its first column is a multiple of 4)
+				if (par0 != FIRST) { v.x += e.x; v.z += e.y; }
+				else { v.y += e.x; v.w += e.y; }
+			} else {
+				v.x += e.x; v.y += e.x; v.z += e.y; v.w += e.y;
+			}
 			*cell = v;
 		};
 

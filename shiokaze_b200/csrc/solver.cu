@@ -476,7 +476,8 @@ int ensure_precision_arrays(shkz_b200_solver *S, int precision, const shkz_b200_
 	}
 	// the fused direction update + product (kernels_cg_tma.cuh): whole grids with float coefficients whose rows are whole quads
 	S->spmv_tma = false;
-	if (S->whole_grid && sizeof(CoefT) == sizeof(float) && (d.nx & 3) == 0 && !getenv("SHKZ_B200_NO_SPMV_TMA")) {
+	// (z-slabs too — k_xpay_spmv_tma<SLAB> — unless the whole problem is gathered from level 0 on: its V-cycle result then lives in the global arrays)
+	if ((S->whole_grid || (S->agg_level != 0 && !getenv("SHKZ_B200_NO_SLAB_SPMV_TMA"))) && sizeof(CoefT) == sizeof(float) && (d.nx & 3) == 0 && !getenv("SHKZ_B200_NO_SPMV_TMA")) {
 		using SS = SpmvStage<VecT>;
 		CKR(S->s2.alloc(d, sizeof(VecT), arena));
 		HostLevel &L0 = S->levels[0];
@@ -572,12 +573,10 @@ void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, floa
 		SweepMaps maps;
 		maps.wx = H.map_wx; maps.wy = H.map_wy; maps.wz = H.map_wz; maps.dd = H.map_dd; maps.b = H.map_b;
 		maps.xo = xo == L.xb ? H.map_xb : H.map_xa;
-		if constexpr (!PROLONG) {
-			if (slab_ghosts) { // z-slab: the same kernel also moves the sweep's halo planes
-				LAUNCH_TILES_SMEM(S, tag.c_str(), (k_sweep_tma<FIRST, ZERO_X, false, DOT, true>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
-				                  L.tiles, maps, xo, xn, ec, dc, sl, S->redbuf(), st);
-				return;
-			}
+		if (slab_ghosts) { // z-slab: the same kernel also moves the sweep's halo planes
+			LAUNCH_TILES_SMEM(S, tag.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT, true>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
+			                  L.tiles, maps, xo, xn, ec, dc, sl, S->redbuf(), st);
+			return;
 		}
 		LAUNCH_TILES_SMEM(S, tag.c_str(), (k_sweep_tma<FIRST, ZERO_X, PROLONG, DOT, false>), dim3(S4_THREADS, 1, 1), H.tiles_total, SWEEP_TMA_SMEM, stream, L.d,
 		                  L.tiles, maps, xo, xn, ec, dc, sl, S->redbuf(), st);
@@ -591,7 +590,7 @@ void launch_sweep(shkz_b200_solver *S, const HostLevel &H, const float *xo, floa
 
 // One V-cycle on level l and below, right-hand side in the level's b. *result = buffer holding the solution.
 // dot: also reduce (solution . b) into the CG state (level 0 only).
-int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result);
+int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result, bool push_result = false);
 
 // global = true: the gathered coarse hierarchy of a z-slab solver (whole-grid semantics on every rank)
 int vcycle(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result, bool global = false) {
@@ -727,7 +726,8 @@ void settle_pending(shkz_b200_solver *S, cudaStream_t stream) {
 // residual), so the boundary planes of x_new travel too. Levels swept by the TMA kernel do all of it in ONE launch
 // (SlabSweep, kernels_mg.cuh); the others keep the three-launch form (half-plane push + wait, sweep, halo push + wait).
 template <int FIRST>
-int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, float *xn, bool dot, CGState *st, cudaStream_t stream, bool push_out) {
+int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, float *xn, bool dot, CGState *st, cudaStream_t stream, bool push_out,
+               const float *ec = nullptr, const Dims *dcp = nullptr) { // ec != nullptr (TMA levels only): x_old + P e_coarse folded into this sweep
 	const MGLevel &L = H.view;
 	const Dims none{};
 	const size_t off = S->comm->offset_of(reinterpret_cast<const char *>(xo) - (size_t)L.d.plane * sizeof(float));
@@ -741,6 +741,8 @@ int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, 
 		sl.seq_out = push_out ? S->comm->next_exchange() : 0ull;
 		sl.wx = L.wx; sl.wy = L.wy; sl.wz = L.wz; sl.dd = L.dd; sl.b = L.b;
 		if (zero_x) launch_sweep<FIRST, true, false, false>(S, H, xo, xn, nullptr, none, st, stream, sl);
+		else if (ec && dot) launch_sweep<FIRST, false, true, true>(S, H, xo, xn, ec, *dcp, st, stream, sl);
+		else if (ec) launch_sweep<FIRST, false, true, false>(S, H, xo, xn, ec, *dcp, st, stream, sl);
 		else if (dot) launch_sweep<FIRST, false, false, true>(S, H, xo, xn, nullptr, none, st, stream, sl);
 		else launch_sweep<FIRST, false, false, false>(S, H, xo, xn, nullptr, none, st, stream, sl);
 		S->pending_wait = sl.seq_out;
@@ -762,7 +764,8 @@ int slab_sweep(shkz_b200_solver *S, HostLevel &H, bool zero_x, const float *xo, 
 	return push_out ? halo(S, L.d, xn, stream) : SHKZ_B200_OK;
 }
 
-int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result) {
+// push_result: the caller folds this level's result into its first post-sweep and reads its ghost planes: the last sweep pushes its boundary planes too
+int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGState *st, cudaStream_t stream, bool dot, const float **result, bool push_result) {
 	HostLevel &H = S->levels[l];
 	const MGLevel &L = H.view;
 	if ((int)l == S->agg_level) {
@@ -782,6 +785,9 @@ int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGStat
 	float *bufs[2] = {L.xa, L.xb};
 	const float *cur = nullptr;
 	int w = 0;
+	bool fold = false;
+	const float *fold_ec = nullptr;
+	Dims fold_dc{};
 	for (int sw = 0; sw < pre; ++sw) {
 		// the very first sweep starts from x = 0: the "old" buffer is only a landing place for the neighbours' boundary planes
 		CKR(slab_sweep<0>(S, H, sw == 0, sw == 0 ? bufs[w ^ 1] : cur, bufs[w], false, st, stream, true));
@@ -794,16 +800,24 @@ int vcycle_slab(shkz_b200_solver *S, size_t l, const shkz_b200_params &P, CGStat
 		             (const float *)L.wz, (const float *)L.dd, (const float *)L.b, cur, C.d, C.b, (const CGState *)st, S->comm->device_view(), S->pending_wait);
 		S->pending_wait = 0;
 		const float *ec = nullptr;
-		CKR(vcycle_slab(S, l + 1, P, st, stream, false, &ec));
-		// (the correction's boundary planes travel with the kernel that writes them; whoever reads the ghost planes next waits)
-		const SlabPush sp = post > 0 ? slab_push(S, L.d, bufs[w]) : SlabPush{};
-		LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, C.d, ec, cur, bufs[w], (const CGState *)st, sp);
-		if (sp.cm) S->pending_wait = sp.seq;
-		cur = bufs[w];
-		w ^= 1;
+		// levels swept by the TMA kernel fold "x + P e" into the first post-sweep, ghost planes included (k_sweep_tma<PROLONG, SLAB>): no k_prolong_add launch
+		fold = post > 0 && H.tma && S->sweep_mode == 0 && !getenv("SHKZ_B200_NO_SLAB_PROLONG");
+		CKR(vcycle_slab(S, l + 1, P, st, stream, false, &ec, fold));
+		fold_ec = ec; fold_dc = C.d;
+		if (!fold) {
+			// (the correction's boundary planes travel with the kernel that writes them; whoever reads the ghost planes next waits)
+			const SlabPush sp = post > 0 ? slab_push(S, L.d, bufs[w]) : SlabPush{};
+			LAUNCH_TILES(S, H.tag_prolong.c_str(), k_prolong_add, dim3(TX, 8, 1), H.tiles_total, stream, L.d, L.tiles, C.d, ec, cur, bufs[w], (const CGState *)st, sp);
+			if (sp.cm) S->pending_wait = sp.seq;
+			cur = bufs[w];
+			w ^= 1;
+		}
 	}
 	for (int sw = 0; sw < post; ++sw) {
-		CKR(slab_sweep<1>(S, H, false, cur, bufs[w], dot && sw + 1 == post, st, stream, sw + 1 < post));
+		// (the last sweep of the whole V-cycle pushes its boundary planes too when the fused direction update + product reads the ghost planes of z)
+		const bool pro = fold && sw == 0;
+		CKR(slab_sweep<1>(S, H, false, cur, bufs[w], dot && sw + 1 == post, st, stream, sw + 1 < post || (dot && l == 0 && S->spmv_tma) || push_result,
+		                  pro ? fold_ec : nullptr, pro ? &fold_dc : nullptr));
 		cur = bufs[w];
 		w ^= 1;
 	}
@@ -950,11 +964,17 @@ int solve(shkz_b200_solver *S, const shkz_b200_params &P, cudaStream_t stream) {
 	while (it < P.max_iterations) {
 		for (unsigned c = 0; c < batch && it < P.max_iterations; ++c, ++it) {
 			// z-slabs: k_xpay stores the boundary planes of s into the neighbours' ghost planes, the product waits for theirs
-			if (mg && S->spmv_tma && S->sweep_mode == 0 && sizeof(CoefT) == sizeof(float)) {
+			if (mg && S->spmv_tma && S->sweep_mode == 0 && sizeof(CoefT) == sizeof(float) && (S->whole_grid || (P.mg_post_sweeps > 0 && (z == H0.view.xa || z == H0.view.xb)))) {
 				// s_new = z + beta s and q = A s_new in ONE TMA-staged launch, s_new into the other direction buffer
 				const int zin = z == H0.view.xb ? 1 : 0;
-				LAUNCH_TILES_SMEM(S, "xpay_spmv_dot", (k_xpay_spmv_tma<VecT>), dim3(SPMV_TMA_THREADS, 1, 1), tt, SpmvStage<VecT>::SMEM, stream, d, T, S->spmv_maps, scur, zin,
-				                  (const VecT *)sbuf[scur], z, sbuf[scur ^ 1], q, rb, st);
+				if (S->whole_grid) {
+					LAUNCH_TILES_SMEM(S, "xpay_spmv_dot", (k_xpay_spmv_tma<VecT, false>), dim3(SPMV_TMA_THREADS, 1, 1), tt, SpmvStage<VecT>::SMEM, stream, d, T, S->spmv_maps, scur, zin,
+					                  (const VecT *)sbuf[scur], z, sbuf[scur ^ 1], q, rb, st, 0ull);
+				} else { // z-slab: the ghost planes of z come with the V-cycle's last sweep (vcycle_slab pushes them for this kernel)
+					LAUNCH_TILES_SMEM(S, "xpay_spmv_dot", (k_xpay_spmv_tma<VecT, true>), dim3(SPMV_TMA_THREADS, 1, 1), tt, SpmvStage<VecT>::SMEM, stream, d, T, S->spmv_maps, scur, zin,
+					                  (const VecT *)sbuf[scur], z, sbuf[scur ^ 1], q, rb, st, S->pending_wait);
+					S->pending_wait = 0;
+				}
 				scur ^= 1;
 				s = sbuf[scur];
 				if (kFloatVec) LAUNCH_TILES(S, "axpy2_norm", (k_axpy2_norm<VecT, false, false>), cg_block(), tt, stream, d, T, (const VecT *)s, (const VecT *)q, x, r, b0, rb, st);
@@ -1241,14 +1261,7 @@ static int host_sparse_upload(shkz_b200_solver *S, void *const hvel[3], uint8_t 
 	g.slice = d.nzl < 8 ? d.nzl : 8;
 	g.nslices_z = (d.nzl + g.slice - 1) / g.slice;
 	const size_t nslices = (size_t)g.ntx * g.nty * g.nslices_z;
-	if (!S->xf_flags.base) {
-		CKR(S->xf_flags.alloc(nslices * sizeof(int)));
-		CKR(S->xf_list.alloc(nslices * sizeof(int)));
-		CKR(S->xf_count.alloc(sizeof(int)));
-		CKR(S->xf_pushed.alloc(sizeof(unsigned long long)));
-		CK(cudaHostAlloc(reinterpret_cast<void **>(&S->h_xf), 2 * sizeof(unsigned long long), cudaHostAllocDefault));
-		CK(cudaStreamCreateWithFlags(&S->copy_stream, cudaStreamNonBlocking));
-	}
+	if (nslices * sizeof(int) > S->xf_flags.bytes || !S->h_xf || !S->copy_stream) return fail(SHKZ_B200_ERR_STATE, "sparse host copies: bookkeeping arrays missing");
 	CK(cudaMemsetAsync(S->xf_flags.base, 0, nslices * sizeof(int), stream));
 	CK(cudaMemsetAsync(S->xf_count.base, 0, sizeof(int), stream));
 	const long long units = (long long)g.ntx * g.nty * d.nzl;
@@ -1272,8 +1285,26 @@ static int host_sparse_upload(shkz_b200_solver *S, void *const hvel[3], uint8_t 
 		LAUNCH(S, "pull_slices", k_pull_slices<RealT>, pgrid, 256, stream, d, g, static_cast<const int *>(S->xf_list.base), static_cast<const int *>(S->xf_count.base), hv, dv,
 		       static_cast<const RealT *>(hsolid), static_cast<RealT *>(S->st_solid.base));
 	}
+	if (!S->whole_grid) {
+		// z-slab: the z faces of plane 0 and plane nzl are shared with the neighbouring slabs and finished by BOTH sides (the host keeps the upper slab's copy):
+		// one of them may lie between a dry cell of this slab and a wet cell of the neighbour, which no block of this slab's list covers. Those two face planes
+		// and the node planes their area fractions read travel whole (a few MB).
+		const size_t rbs = sizeof(RealT), fplane = (size_t)d.plane, nplane = (size_t)(d.nx + 1) * (d.ny + 1);
+		const RealT *hw = static_cast<const RealT *>(hvel[2]);
+		RealT *dw = static_cast<RealT *>(S->st_vel[2].base);
+		CK(cudaMemcpyAsync(dw, hw, fplane * rbs, cudaMemcpyHostToDevice, stream));
+		CK(cudaMemcpyAsync(dw + fplane * d.nzl, hw + fplane * d.nzl, fplane * rbs, cudaMemcpyHostToDevice, stream));
+		*pulled += 2 * fplane * rbs;
+		if (hsolid) {
+			const RealT *hs = static_cast<const RealT *>(hsolid);
+			RealT *ds = static_cast<RealT *>(S->st_solid.base);
+			CK(cudaMemcpyAsync(ds, hs, nplane * rbs, cudaMemcpyHostToDevice, stream));
+			CK(cudaMemcpyAsync(ds + nplane * d.nzl, hs + nplane * d.nzl, nplane * rbs, cudaMemcpyHostToDevice, stream));
+			*pulled += 2 * nplane * rbs;
+		}
+	}
 	const uint64_t per_block = (uint64_t)((TX + 1) * TY * g.slice + TX * (TY + 1) * g.slice + TX * TY * (g.slice + 1) + (hsolid ? (TX + 1) * (TY + 1) * (g.slice + 1) : 0));
-	*pulled = (uint64_t)wet * per_block * sizeof(RealT); // (blocks on the grid's upper edges are smaller: an upper bound by a few percent)
+	*pulled += (uint64_t)wet * per_block * sizeof(RealT); // (blocks on the grid's upper edges are smaller: an upper bound by a few percent)
 	// the masks are first needed by the velocity update: they cross PCIe after the pull and behind assembly and solve
 	CK(cudaEventRecord(S->ev[10], stream));
 	CK(cudaStreamWaitEvent(S->copy_stream, S->ev[10], 0));
@@ -1390,6 +1421,18 @@ int shkz_b200_create_slab(int nx, int ny, int nz, int k0, int k1, double dx, int
 		tryalloc(S->partials.alloc(S->max_blocks * 4 * sizeof(double)));
 		tryalloc(S->counter.alloc(64));
 		tryalloc(S->state.alloc(sizeof(CGState)));
+	}
+	// bookkeeping of the sparse host copies (kernels_xfer.cuh). Allocated HERE, not on first use: a page-locked allocation synchronises every device of the
+	// process, and a z-slab solver's first host call may run while a neighbouring slab's kernel already spins on this rank (one process, N host threads).
+	{
+		const size_t nslices = (size_t)((d.nx + TX - 1) / TX) * ((d.ny + TY - 1) / TY) * ((d.nzl + 7) / 8 + 1);
+		tryalloc(S->xf_flags.alloc(nslices * sizeof(int)));
+		tryalloc(S->xf_list.alloc(nslices * sizeof(int)));
+		tryalloc(S->xf_count.alloc(sizeof(int)));
+		tryalloc(S->xf_pushed.alloc(sizeof(unsigned long long)));
+		if (rc == SHKZ_B200_OK && cudaHostAlloc(reinterpret_cast<void **>(&S->h_xf), 2 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess)
+			rc = fail(SHKZ_B200_ERR_CUDA, "cudaHostAlloc failed");
+		if (rc == SHKZ_B200_OK && cudaStreamCreateWithFlags(&S->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail(SHKZ_B200_ERR_CUDA, "cudaStreamCreate failed");
 	}
 	if (rc == SHKZ_B200_OK && cudaMallocHost((void **)&S->h_state, sizeof(CGState)) != cudaSuccess) rc = fail(SHKZ_B200_ERR_CUDA, "cudaMallocHost failed");
 	if (rc == SHKZ_B200_OK) {

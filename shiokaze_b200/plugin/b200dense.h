@@ -20,4 +20,15 @@ typedef struct b200_dense_descriptor {
 	const uint8_t *filled;
 	int pinned;
 } b200_dense_descriptor;
+
+#ifdef __cplusplus
+#include <cstdlib>
+// Every Shiokaze module of this repository carries one of these. CUDA loads a kernel's code lazily, on its first launch, and that load takes a process-wide
+// driver lock and may wait for the launching context to drain. With `GPUs=N` the module drives N devices from N host threads of ONE process, and its kernels wait
+// for each other across devices: a thread that holds the loader lock while its device spins on a neighbour, whose host thread in turn needs that lock to launch
+// the kernel the spin is waiting for, is a deadlock (seen as a rare 20 s communicator time-out in the first projection of a run). Loading everything when the
+// context is created removes the lock from the solve. Runs when the module is dlopen'ed, i.e. before the first CUDA call of a Shiokaze host; a value the
+// user has set is kept.
+namespace { struct b200_eager_cuda_modules { b200_eager_cuda_modules() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); } } b200_eager_cuda_modules_instance; }
+#endif
 #endif

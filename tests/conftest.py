@@ -5,6 +5,9 @@ import sys
 import numpy as np
 import pytest
 
+# one process driving several GPUs from several threads (shiokaze_b200/dist.py: run_per_slab) must not load kernels lazily in the middle of a solve whose
+# kernels wait for each other across devices (see shiokaze_b200/plugin/b200dense.h); set before anything initialises CUDA
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

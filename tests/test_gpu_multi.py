@@ -108,3 +108,26 @@ def test_module_gpus_flag_through_the_reference_loader(worlds, scene):
         assert rel_l2(many.vel, ref.vel) < 1e-3
         assert rel_l2(many.vel, one.vel) < 1e-6
         assert abs(many.iterations - one.iterations) <= 1
+
+
+@pytest.mark.parametrize("scene", ["dambreak_solid", "flip", "blobs"])
+def test_module_slabs_on_the_dense_array_core(worlds, scene):
+    """`GPUs=N` together with `Array=b200array3`: every slab solver is handed a z-range of the host's own page-locked grids in place (the z-face grids
+    through a per-slab copy), several projections in a row on the same grids — the sparse host copies (csrc/kernels_xfer.cuh) of N solvers at once."""
+    import os
+    from oracle import refio
+    if not (refio.ref_available("f32") and os.path.isfile(os.path.join(refio.ref_dir("f32"), "libshiokaze_b200array3.so"))):
+        pytest.skip("oracle/_ref (reference build + modules) was not shipped to this box")
+    # ("blobs": liquid surfaces that cross the slab boundaries at an angle — wet cells of one slab facing dry cells of the other)
+    sc = {"dambreak_solid": lambda: scenes.dambreak(64, True), "flip": lambda: scenes.flip_splash(96), "blobs": lambda: scenes.random_blobs(48, 40, 32, seed=7)}[scene]()
+    flags = {"Array": "b200array3", "Residual": 1e-10, "Precision": "fp64"}
+    one = refio.run_reference(sc, "f32", projection="b200pressure3", flags=flags, repeat=3)
+    for world in worlds:
+        if sc.nz % world:
+            continue
+        many = refio.run_reference(sc, "f32", projection="b200pressure3", flags={**flags, "GPUs": world}, repeat=3)
+        assert np.array_equal(many.pressure_active, one.pressure_active)
+        for d in range(3):
+            assert np.array_equal(many.vel_active[d], one.vel_active[d])
+        assert rel_l2(many.vel, one.vel) < 1e-6
+        assert abs(many.iterations - one.iterations) <= 1

@@ -18,11 +18,25 @@ for sc, prec in cases:
         a = S.debug_vcycle(0); b = S.debug_vcycle(2); print("   vcycle fused == scalar:", np.array_equal(a, b), flush=True)
     S.close()
 if mode == "mem":
+    # the sparse host-copy kernels (k_flag_wet_slices / k_pull_slices / k_push_faces, k_store_pressure into host memory): page-locked buffers, two scenes in a row
+    import ctypes as C
+    from shiokaze_b200 import capi
+    L = capi.lib(); held = []
+    def pinned(a):
+        p = C.c_void_p(); capi.check(L.shkz_b200_host_alloc(a.nbytes, C.byref(p))); held.append(p)
+        v = np.frombuffer((C.c_ubyte * a.nbytes).from_address(p.value), dtype=a.dtype).reshape(a.shape); v[...] = a; return v
+    S = MacPressureSolver3((72, 72, 72), 1.0 / 72)
+    pres, pact = pinned(np.zeros((72, 72, 72), np.float32)), pinned(np.zeros((72, 72, 72), np.uint8))
+    for sc in (scenes.dambreak(72, True), scenes.flip_splash(72)):
+        _, _, res = S.project(sc.dt, [pinned(v) for v in sc.vel], [pinned(a) for a in sc.vel_active], pinned(sc.solid), pinned(sc.fluid), sc.fluid_levelset, pressure_out=pres, pressure_active_out=pact)
+        print("sparse host copies", sc.name, res.iterations, res.converged, res.stats["host_copies"], res.stats["h2d_bytes"], res.stats["d2h_bytes"], flush=True)
+    S.close()
+    for p in held: L.shkz_b200_host_free(p)
     n = 24; I = sp.identity(n); T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n))
     A = (sp.kron(sp.kron(T, I), I) + sp.kron(sp.kron(I, T), I) + sp.kron(sp.kron(I, I), T)).tocsr()
     C = B200CG(Residual=1e-8); x, r = C.solve(A, None, None, np.ones(A.shape[0])); print("csr ell", r.count, r.converged)
     B = sp.random(400, 400, density=0.2, random_state=1, format="csr"); W = (B @ B.T + sp.identity(400)).tocsr()
     x, r = C.solve(W, None, None, np.ones(400)); print("csr wide", r.count, r.converged, r.stats["ell_width"]); C.close()
 PY
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san_case.py mem > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|vcycle|csr|mixed|fp32|fp64" gpurun_out/sanitizer_memcheck.log | tail -14
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/san_case.py mem > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|vcycle|csr|mixed|fp32|fp64|sparse host" gpurun_out/sanitizer_memcheck.log | tail -14
 timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python /tmp/san_case.py race > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|hazard|vcycle|mixed|fp32" gpurun_out/sanitizer_racecheck.log | sort | uniq -c | sort -rn | head -12
