@@ -14,7 +14,7 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 out, rows_n, reps = sys.argv[1], float(sys.argv[2]), sys.argv[3:]
 header, units, lines, traffic = None, None, [], {}
 for rep in reps:
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     idx = {h: i for i, h in enumerate(rows[0])}
     header = ["Kernel Name"] + COLS
