@@ -169,6 +169,14 @@ int shkz_b200_project_device(shkz_b200_solver *solver, double dt, void *const ve
                              void *pressure, uint8_t *pressure_active, shkz_b200_stats *stats, void *cuda_stream);
 
 /*
+ * Optional: allocate, now, everything the next project() with these parameters would allocate on first use (precision-dependent arrays, multigrid hierarchy,
+ * and — host_buffers != 0 — the device staging arrays of shkz_b200_project_host; have_solid: a solid level set will be passed). One process that drives several
+ * z-slab solvers from several threads calls this for every solver BEFORE starting the threads (plugin/b200pressure3.cpp does): a device allocation made while peer
+ * access is enabled waits for the peer devices, and a peer whose kernel is already spinning on this rank's planes never becomes idle.
+ */
+int shkz_b200_prepare(shkz_b200_solver *solver, const shkz_b200_params *params, int host_buffers, int have_solid);
+
+/*
  * The step the simulators run right after every projection (src/liquid/macliquid3.cpp:309-319, src/smoke/macsmoke3.cpp:294), SURVEY.md 8f rank 3:
  *     macutility3::extrapolate_and_constrain_velocity(solid, velocity, width)        src/utility/macutility3.cpp:89-93
  *       = macarray_extrapolator3::extrapolate(velocity, width)                       include/shiokaze/array/macarray_extrapolator3.h:49-53

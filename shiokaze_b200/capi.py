@@ -19,7 +19,7 @@ IPC_BYTES = 128
 EXPORTS = [
     "shkz_b200_abi_version", "shkz_b200_last_error", "shkz_b200_default_params", "shkz_b200_device_count",
     "shkz_b200_create", "shkz_b200_create_slab", "shkz_b200_destroy", "shkz_b200_project_host",
-    "shkz_b200_project_device", "shkz_b200_extrapolate_constrain_device", "shkz_b200_extrapolate_constrain_host", "shkz_b200_resolve", "shkz_b200_host_alloc", "shkz_b200_host_free", "shkz_b200_slab_export",
+    "shkz_b200_project_device", "shkz_b200_prepare", "shkz_b200_extrapolate_constrain_device", "shkz_b200_extrapolate_constrain_host", "shkz_b200_resolve", "shkz_b200_host_alloc", "shkz_b200_host_free", "shkz_b200_slab_export",
     "shkz_b200_slab_connect", "shkz_b200_slab_connect_local", "shkz_b200_debug_fetch", "shkz_b200_profile_enable", "shkz_b200_profile_count",
     "shkz_b200_profile_get", "shkz_b200_debug_vcycle",
     "shkz_b200_csr_last_error", "shkz_b200_csr_default_params", "shkz_b200_csr_create", "shkz_b200_csr_destroy", "shkz_b200_csr_solve_host",
@@ -96,6 +96,7 @@ def lib(test_hooks: bool = False):
     proj = [vp, C.c_double, C.POINTER(vp), C.POINTER(vp), vp, vp, C.c_int, C.POINTER(Params), vp, vp, C.POINTER(Stats)]
     L.shkz_b200_project_host.argtypes = proj
     L.shkz_b200_project_device.argtypes = proj + [vp]
+    L.shkz_b200_prepare.argtypes = [vp, C.POINTER(Params), C.c_int, C.c_int]
     L.shkz_b200_extrapolate_constrain_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, C.c_int, vp]
     L.shkz_b200_extrapolate_constrain_host.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, C.c_int]
     L.shkz_b200_resolve.argtypes = [vp, C.POINTER(Params), C.POINTER(Stats), vp]

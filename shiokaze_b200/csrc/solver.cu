@@ -1239,6 +1239,19 @@ int check_params(const shkz_b200_params *p, shkz_b200_params &out) {
 	return SHKZ_B200_OK;
 }
 
+// device staging arrays of the host-buffer entry points (allocated on first use, or ahead of time by shkz_b200_prepare)
+static int ensure_host_staging(shkz_b200_solver *S, bool have_solid) {
+	const Dims &d = S->d;
+	const size_t rb = S->real_bytes, ncell = (size_t)d.ncell, nodal = (size_t)(d.nx + 1) * (d.ny + 1) * (d.nzl + 1);
+	for (int dim = 0; dim < 3; ++dim) {
+		const size_t nf = face_count(d, dim);
+		if (!S->st_vel[dim].base) { CKR(S->st_vel[dim].alloc(nf * rb)); CKR(S->st_act[dim].alloc(nf)); }
+	}
+	if (!S->st_fluid.base) { CKR(S->st_fluid.alloc(ncell * rb)); CKR(S->st_pressure.alloc(ncell * rb)); CKR(S->st_pact.alloc(ncell)); }
+	if (have_solid && !S->st_solid.base) CKR(S->st_solid.alloc(nodal * rb));
+	return SHKZ_B200_OK;
+}
+
 // device-visible address of a page-locked host buffer; nullptr for pageable memory (and for NULL)
 static void *mapped_host(const void *p) {
 	if (!p) return nullptr;
@@ -1524,14 +1537,11 @@ static int project_host_impl(shkz_b200_solver *S, double dt, void *const vel[3],
 	cudaStream_t stream = nullptr;
 	void *dvel[3];
 	uint8_t *dact[3];
+	CKR(ensure_host_staging(S, solid != nullptr));
 	for (int dim = 0; dim < 3; ++dim) {
-		const size_t nf = face_count(d, dim);
-		if (!S->st_vel[dim].base) { CKR(S->st_vel[dim].alloc(nf * rb)); CKR(S->st_act[dim].alloc(nf)); }
 		dvel[dim] = S->st_vel[dim].base;
 		dact[dim] = static_cast<uint8_t *>(S->st_act[dim].base);
 	}
-	if (!S->st_fluid.base) { CKR(S->st_fluid.alloc(ncell * rb)); CKR(S->st_pressure.alloc(ncell * rb)); CKR(S->st_pact.alloc(ncell)); }
-	if (solid && !S->st_solid.base) CKR(S->st_solid.alloc(nodal * rb));
 
 	// Sparse copies (kernels_xfer.cuh) need a liquid level set (without one every cell is wet), nothing that reads the velocity away from wet cells
 	// (surface tension walks the masks early, the extrapolation fills the whole band), and every buffer addressable from the device.
@@ -1629,6 +1639,21 @@ static int project_host_impl(shkz_b200_solver *S, double dt, void *const vel[3],
 		stats->d2h_bytes = d2h;
 		stats->kernel_launches += setup_launches + (S->launches - before_push);
 	}
+	return SHKZ_B200_OK;
+}
+
+int shkz_b200_prepare(shkz_b200_solver *S, const shkz_b200_params *params, int host_buffers, int have_solid) {
+	if (!S) return fail(SHKZ_B200_ERR_ARG, "solver is NULL");
+	shkz_b200_params P;
+	CKR(check_params(params, P));
+	CKR(device_ready(S->device));
+	CK(cudaSetDevice(S->device));
+	if (P.precision == SHKZ_B200_PREC_FP64) CKR((ensure_precision_arrays<double, double>(S, P.precision, P)));
+	else if (P.precision == SHKZ_B200_PREC_MIXED) CKR((ensure_precision_arrays<double, float>(S, P.precision, P)));
+	else CKR((ensure_precision_arrays<float, float>(S, P.precision, P)));
+	if (P.warm_start && !S->p_prev.base) CKR(S->p_prev.alloc(S->d, P.precision == SHKZ_B200_PREC_FP32 ? sizeof(float) : sizeof(double), S->arena()));
+	if (host_buffers) CKR(ensure_host_staging(S, have_solid != 0));
+	CK(cudaDeviceSynchronize());
 	return SHKZ_B200_OK;
 }
 

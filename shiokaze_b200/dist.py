@@ -141,4 +141,7 @@ def run_per_slab(calls):
 
 
 def project_local(solvers: Sequence, slab_scenes: Sequence["scenes.Scene"], **kw) -> List[dict]:
+    # one process, several devices: everything a first call allocates is allocated before any slab's kernels start waiting for its neighbours (shkz_b200_prepare)
+    for s, sc in zip(solvers, slab_scenes):
+        s.prepare(host_buffers=True, have_solid=sc.solid is not None)
     return run_per_slab([(lambda s=s, sc=sc: s.project_scene(sc, **kw)) for s, sc in zip(solvers, slab_scenes)])

@@ -251,6 +251,10 @@ protected:
 		std::vector<int> rc (world,SHKZ_B200_OK);
 		std::vector<std::string> message (world);
 		std::vector<shkz_b200_stats> slab_stats (world);
+		// everything a first call allocates is allocated here, slab by slab, before any slab's kernels start waiting for its neighbours (shkz_b200.h)
+		for( int r=0; r<world; ++r ) {
+			if( shkz_b200_prepare(m_slabs[r],&params,1,solid != nullptr) != SHKZ_B200_OK ) fatal("shkz_b200_prepare");
+		}
 		std::vector<std::thread> threads;
 		for( int r=0; r<world; ++r ) {
 			Real *wz = m_slab_w[r].ensure(cell_plane*(nzl+1));

@@ -138,6 +138,10 @@ class MacPressureSolver3:
                                                      pressure.ctypes.data, pact.ctypes.data, C.byref(st)))
         return pressure, pact, self._finish(st)
 
+    def prepare(self, host_buffers: bool = True, have_solid: bool = True):
+        """shkz_b200_prepare: allocate now what the next project() with the current flags would allocate on first use."""
+        self._ck(self._L.shkz_b200_prepare(self._h, C.byref(self.params), int(host_buffers), int(have_solid)))
+
     def project_scene(self, scene, surface_tension: Optional[float] = None):
         """Convenience for tests: run a scenes.Scene through project() on copies; returns dict of outputs."""
         rt = self.np_real
