@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SHKZ_B200_ABI_VERSION 3
+#define SHKZ_B200_ABI_VERSION 4
 
 enum shkz_b200_status {
 	SHKZ_B200_OK = 0,
@@ -253,6 +253,54 @@ void shkz_b200_csr_destroy(shkz_b200_csr *solver);
 /* Solve A x = rhs (host pointers; x is overwritten, the start vector is 0 as in pcg_solver.h:249). */
 int shkz_b200_csr_solve_host(shkz_b200_csr *solver, uint64_t n, const int64_t *rowptr /* n+1 */, const int32_t *col, const double *val,
                              const double *rhs, double *x, const shkz_b200_csr_params *params, shkz_b200_csr_stats *stats);
+
+/* ---- the step BEFORE the projection: advection on the MAC grid (first part) ------------------------------------
+ * Replaces macadvection3_interface::advect_vector / advect_scalar (include/shiokaze/advection/macadvection3_interface.h:52-71) as implemented by the
+ * reference's `macadvection3` module (src/advection/macadvection3.cpp): semi-Lagrangian back-tracing with trilinear (array_interpolator3.h:50-105) or
+ * sixth-order WENO (WENO3.h, WENO.h) interpolation, and the MacCormack scheme on top of it (forward, backward with -dt, correction limited to the
+ * min / max of the eight corner values; first-order inside `trim_narrowband` cells of the liquid surface). The simulators call both right before
+ * project(): src/liquid/macliquid3.cpp:343-346 (the level set through maclevelsetsurfacetracker3.cpp:51, then the velocity), src/smoke/macsmoke3.cpp:274,281
+ * (density, velocity). The Shiokaze module on top is shiokaze_b200/plugin/b200advection3.cpp (`Advection=b200advection3`). Results are the reference's, bit for bit
+ * (tests/test_gpu_advect.py). Same dense layouts as project(); whole grids only.
+ *   - a velocity grid is read through its activity mask: inactive faces read as 0, the background value of the simulators' velocity grids;
+ *   - cell grids (q, fluid) are read densely: every entry holds what array3::operator() returns (active value / flood-fill value / background);
+ *   - only ACTIVE entries of u / q are written; the activity itself never changes (macadvection3.cpp:71-72, :195-196).
+ * advect_vector: the reference traces the field with ITSELF — its `velocity` argument is not used (macadvection3.cpp:79) — hence no such argument here.
+ * fluid: the liquid level set (a smoke solver passes its constant grid); may be NULL when maccormack == 0. */
+typedef struct shkz_b200_advect_params {
+	uint32_t struct_size;       /* = sizeof(shkz_b200_advect_params) */
+	int32_t maccormack;         /* MacCormack (Yes, macadvection3.cpp:286) */
+	int32_t weno;               /* WENO (No, :287): WENO3::interpolate, order 6, instead of trilinear interpolation */
+	uint32_t trim_narrowband;   /* TrimNarrowBand (1, :288) */
+	double scalar_background;   /* advect_scalar with MacCormack: array3::get_background_value() of q — what the forward result, a freshly borrowed grid of
+	                               q's type (:245), reads off the active set when the backward pass interpolates in it (a level set: +halfwidth; density: 0) */
+} shkz_b200_advect_params;
+
+typedef struct shkz_b200_advect_stats {
+	uint64_t kernel_launches;
+	uint64_t h2d_bytes, d2h_bytes;       /* `_host` entry points */
+	float ms_h2d, ms_advect, ms_d2h;     /* CUDA-event times */
+	float reserved;
+} shkz_b200_advect_stats;
+
+typedef struct shkz_b200_advect shkz_b200_advect; /* opaque: work arrays (forward result, limiter record) and host staging, reused across calls */
+
+const char *shkz_b200_advect_last_error(void);
+void shkz_b200_advect_default_params(shkz_b200_advect_params *params);
+/* Replaces macadvection3::initialize(shape,dx) (macadvection3.cpp:63-67). real: shkz_b200_real. */
+int shkz_b200_advect_create(int nx, int ny, int nz, double dx, int real, int device, shkz_b200_advect **out);
+void shkz_b200_advect_destroy(shkz_b200_advect *advect);
+/* u in/out (face grids), u_active their activity. `_device`: device pointers on the handle's GPU, runs on cuda_stream, returns after synchronising it. */
+int shkz_b200_advect_vector_host(shkz_b200_advect *advect, double dt, void *const u[3], const uint8_t *const u_active[3], const void *fluid,
+                                 const shkz_b200_advect_params *params, shkz_b200_advect_stats *stats);
+int shkz_b200_advect_vector_device(shkz_b200_advect *advect, double dt, void *const u[3], const uint8_t *const u_active[3], const void *fluid,
+                                   const shkz_b200_advect_params *params, shkz_b200_advect_stats *stats, void *cuda_stream);
+/* q in/out (cell grid) carried by vel; `fluid` may be the grid q was copied from (a level set carried by itself, maclevelsetsurfacetracker3.cpp:49-51). */
+int shkz_b200_advect_scalar_host(shkz_b200_advect *advect, double dt, void *q, const uint8_t *q_active, const void *const vel[3],
+                                 const uint8_t *const vel_active[3], const void *fluid, const shkz_b200_advect_params *params, shkz_b200_advect_stats *stats);
+int shkz_b200_advect_scalar_device(shkz_b200_advect *advect, double dt, void *q, const uint8_t *q_active, const void *const vel[3],
+                                   const uint8_t *const vel_active[3], const void *fluid, const shkz_b200_advect_params *params, shkz_b200_advect_stats *stats,
+                                   void *cuda_stream);
 
 /* ---- per-kernel timing (CUDA events around every launch; slows the call down, never on by default) ----
  * enable(1) resets the accumulators; entries are "<kernel>" or "<kernel>@<multigrid level>". */

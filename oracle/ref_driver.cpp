@@ -23,6 +23,8 @@
 #include <shiokaze/array/macarray3.h>
 #include <shiokaze/array/shared_array_core3.h>
 #include <shiokaze/projection/macproject3_interface.h>
+#include <shiokaze/advection/macadvection3_interface.h>
+#include <shiokaze/array/shared_array3.h>
 #include <shiokaze/utility/macutility3_interface.h>
 #include <shiokaze/utility/utility.h>
 #include <cmath>
@@ -53,6 +55,7 @@ struct host : public recursive_configurable {
 	macarray3<Real> velocity{this};
 	macproject3_driver proj{this,"macpressuresolver3"};
 	macutility3_driver util{this,"macutility3"};
+	macadvection3_driver adv{this,"macadvection3"};
 	shape3 shape;
 	double dx;
 	host( const scene_header &h ) {
@@ -101,6 +104,7 @@ int main( int argc, const char *argv[] ) {
 	std::string in_path, out_path;
 	bool dump_fractions (false), skip_project (false);
 	int extrapolate_constrain (-1);
+	std::string advect_mode;
 	for( int i=1; i<argc; ++i ) {
 		if( ! std::strncmp(argv[i],"in=",3)) in_path = argv[i]+3;
 		if( ! std::strncmp(argv[i],"out=",4)) out_path = argv[i]+4;
@@ -111,6 +115,14 @@ int main( int argc, const char *argv[] ) {
 		// extrapolate_and_constrain_velocity(solid,velocity,width). RefSkipProject=1: that step alone, on the input velocity.
 		if( ! std::strncmp(argv[i],"RefExtrapolate=",15)) extrapolate_constrain = std::atoi(argv[i]+15);
 		if( ! std::strcmp(argv[i],"RefSkipProject=1")) skip_project = true;
+		// RefAdvect=vector|density|levelset: INSTEAD of the projection, one call of the step the simulators run right before it, through whichever module
+		// `Advection=<name>` selects (default: the reference's macadvection3), with the scene's dt:
+		//   vector    advect_vector(velocity, copy of velocity, fluid, dt)                      src/liquid/macliquid3.cpp:345-346, src/smoke/macsmoke3.cpp:280-281
+		//   density   advect_scalar(q, velocity, fluid, dt), q = a sparse cell grid (background 0) built from the scene: active where the y-face of the same
+		//             index is, with that face's value                                          src/smoke/macsmoke3.cpp:274
+		//   levelset  advect_scalar(fluid, velocity, copy of fluid, dt)                         src/surfacetracker/maclevelsetsurfacetracker3.cpp:49-51
+		// The advected scalar is dumped in the result's pressure slot.
+		if( ! std::strncmp(argv[i],"RefAdvect=",10)) advect_mode = argv[i]+10;
 	}
 	if( in_path.empty() || out_path.empty()) {
 		std::fprintf(stderr,"usage: ref_driver in=<scene> out=<result> [DumpFractions=1] [RecordDir=<dir>] [Projection=<module>] [flag=value ...]\n");
@@ -169,6 +181,7 @@ int main( int argc, const char *argv[] ) {
 	std::fclose(fp);
 	//
 	double ms_last (0.0), ms_sum (0.0);
+	array3<Real> scalar; // RefAdvect=density
 	for( int rep=0; rep<repeat; ++rep ) {
 		H.velocity.initialize(shape);
 		for( int dim : DIMS3 ) {
@@ -182,7 +195,29 @@ int main( int argc, const char *argv[] ) {
 		}
 		if( h.target_volume ) H.proj->set_target_volume(h.current_volume,h.target_volume);
 		double t0 = utility::get_milliseconds();
-		if( ! skip_project ) H.proj->project(h.dt,H.velocity,H.solid,H.fluid,h.surface_tension);
+		if( ! advect_mode.empty()) {
+			if( advect_mode == "vector" ) {
+				shared_macarray3<Real> velocity_save(H.velocity);
+				t0 = utility::get_milliseconds();
+				H.adv->advect_vector(H.velocity,velocity_save(),H.fluid,h.dt,"velocity");
+			} else if( advect_mode == "density" ) {
+				scalar.initialize(shape);
+				const shape3 fs = shape.face(1);
+				scalar.parallel_all([&]( int i, int j, int k, auto &it ) {
+					size_t n = fs.encode(i,j,k);
+					if( vel_active[1][n] ) it.set(vel[1][n]);
+				});
+				t0 = utility::get_milliseconds();
+				H.adv->advect_scalar(scalar,H.velocity,H.fluid,h.dt,"density");
+			} else if( advect_mode == "levelset" ) {
+				shared_array3<Real> fluid_save(H.fluid);
+				t0 = utility::get_milliseconds();
+				H.adv->advect_scalar(H.fluid,H.velocity,fluid_save(),h.dt,"levelset");
+			} else {
+				std::fprintf(stderr,"ref_driver: RefAdvect=%s ?\n",advect_mode.c_str());
+				return 2;
+			}
+		} else if( ! skip_project ) H.proj->project(h.dt,H.velocity,H.solid,H.fluid,h.surface_tension);
 		ms_last = utility::get_milliseconds()-t0;
 		if( extrapolate_constrain >= 0 ) H.util->extrapolate_and_constrain_velocity(H.solid,H.velocity,extrapolate_constrain);
 		ms_sum += ms_last;
@@ -198,7 +233,9 @@ int main( int argc, const char *argv[] ) {
 	double ms[2] = {ms_last,ms_sum/repeat};
 	std::fwrite(ms,sizeof(double),2,out);
 	for( int dim : DIMS3 ) dump_dense(out,H.velocity[dim],true);
-	dump_dense(out,*H.proj->get_pressure(),true);
+	if( advect_mode == "density" ) dump_dense(out,scalar,true);
+	else if( advect_mode == "levelset" ) dump_dense(out,H.fluid,true);
+	else dump_dense(out,*H.proj->get_pressure(),true);
 	dump_dense(out,H.fluid,true);
 	dump_dense(out,H.solid,true);
 	int32_t has_fractions = dump_fractions ? 1 : 0;

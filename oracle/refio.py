@@ -125,7 +125,8 @@ def _phase_times(text: str) -> dict:
 def run_reference(scene, real: str = "f32", flags: Optional[dict] = None, dump_fractions: bool = False,
                   repeat: int = 1, threads: Optional[int] = None, projection: Optional[str] = None,
                   current_volume: float = 0.0, target_volume: float = 0.0, extra_lib_dirs=(),
-                  timeout: Optional[float] = None, records: bool = False, extrapolate: Optional[int] = None, skip_project: bool = False) -> RefResult:
+                  timeout: Optional[float] = None, records: bool = False, extrapolate: Optional[int] = None, skip_project: bool = False,
+                  advect: Optional[str] = None, advection: Optional[str] = None) -> RefResult:
     """One project() call of the reference (or of any drop-in module named by `projection`)."""
     d = ref_dir(real)
     if not ref_available(real):
@@ -146,6 +147,10 @@ def run_reference(scene, real: str = "f32", flags: Optional[dict] = None, dump_f
             argv.append(f"RefExtrapolate={int(extrapolate)}")
         if skip_project:
             argv.append("RefSkipProject=1")
+        if advect:   # INSTEAD of the projection: one advect_vector ("vector") / advect_scalar ("density", "levelset") call of the module `advection` names
+            argv.append(f"RefAdvect={advect}")   # (default: the reference's macadvection3); the advected scalar comes back in the pressure slot
+        if advection:
+            argv.append(f"Advection={advection}")
         for k, v in (flags or {}).items():
             argv.append(f"{k}={v}")
         env = dict(os.environ)

@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libshkz_b200.so")
 HOOKS_LIB_PATH = os.path.join(HERE, "_build", "libshkz_b200_testhooks.so")  # same sources + -DSHKZ_B200_TEST_HOOKS (tests only)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_COMM, ERR_STATE = range(6)
 PRECOND_NONE, PRECOND_MG = 0, 1
@@ -23,6 +23,8 @@ EXPORTS = [
     "shkz_b200_slab_connect", "shkz_b200_slab_connect_local", "shkz_b200_debug_fetch", "shkz_b200_profile_enable", "shkz_b200_profile_count",
     "shkz_b200_profile_get", "shkz_b200_debug_vcycle",
     "shkz_b200_csr_last_error", "shkz_b200_csr_default_params", "shkz_b200_csr_create", "shkz_b200_csr_destroy", "shkz_b200_csr_solve_host",
+    "shkz_b200_advect_last_error", "shkz_b200_advect_default_params", "shkz_b200_advect_create", "shkz_b200_advect_destroy",
+    "shkz_b200_advect_vector_host", "shkz_b200_advect_vector_device", "shkz_b200_advect_scalar_host", "shkz_b200_advect_scalar_device",
 ]
 CSR_PRECOND_NONE, CSR_PRECOND_JACOBI = 0, 1
 
@@ -60,6 +62,19 @@ class CsrStats(C.Structure):
     _fields_ = [("iterations", C.c_uint32), ("converged", C.c_int32), ("reresid", C.c_double), ("rhs_absmax", C.c_double),
                 ("ell_width", C.c_int32), ("reserved", C.c_int32), ("kernel_launches", C.c_uint64), ("ms_h2d", C.c_float),
                 ("ms_solve", C.c_float), ("ms_d2h", C.c_float), ("reserved2", C.c_float)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
+
+
+class AdvectParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("maccormack", C.c_int32), ("weno", C.c_int32), ("trim_narrowband", C.c_uint32),
+                ("scalar_background", C.c_double)]
+
+
+class AdvectStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("ms_h2d", C.c_float),
+                ("ms_advect", C.c_float), ("ms_d2h", C.c_float), ("reserved", C.c_float)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
@@ -118,6 +133,18 @@ def lib(test_hooks: bool = False):
     L.shkz_b200_csr_destroy.argtypes = [vp]
     L.shkz_b200_csr_destroy.restype = None
     L.shkz_b200_csr_solve_host.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(CsrParams), C.POINTER(CsrStats)]
+    L.shkz_b200_advect_last_error.restype = C.c_char_p
+    L.shkz_b200_advect_default_params.argtypes = [C.POINTER(AdvectParams)]
+    L.shkz_b200_advect_default_params.restype = None
+    L.shkz_b200_advect_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(vp)]
+    L.shkz_b200_advect_destroy.argtypes = [vp]
+    L.shkz_b200_advect_destroy.restype = None
+    adv_v = [vp, C.c_double, C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(AdvectParams), C.POINTER(AdvectStats)]
+    adv_s = [vp, C.c_double, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(AdvectParams), C.POINTER(AdvectStats)]
+    L.shkz_b200_advect_vector_host.argtypes = adv_v
+    L.shkz_b200_advect_vector_device.argtypes = adv_v + [vp]
+    L.shkz_b200_advect_scalar_host.argtypes = adv_s
+    L.shkz_b200_advect_scalar_device.argtypes = adv_s + [vp]
     _libs[test_hooks] = L
     return L
 
@@ -131,6 +158,11 @@ def check(code, L=None):
 def check_csr(code):
     if code != OK:
         raise ShkzError(code, lib().shkz_b200_csr_last_error().decode(errors="replace"))
+
+
+def check_advect(code):
+    if code != OK:
+        raise ShkzError(code, lib().shkz_b200_advect_last_error().decode(errors="replace"))
 
 
 def default_params() -> Params:

@@ -1,0 +1,99 @@
+"""The advection kernels' source, compiled once more for the HOST (csrc/advect.cu -DSHKZ_B200_ADVECT_HOSTCHECK -> oracle/_build/libadvect_hostcheck.so: plain
+loops over the same __host__ __device__ bodies), against the unmodified reference's macadvection3 module run through its own loader (oracle/ref_driver
+RefAdvect=...). Runs where the reference build exists (this container); it pins the restatement bit for bit before any GPU time is spent.
+tests/test_gpu_advect.py holds the product — the CUDA kernels behind the C-ABI — to the same bar on the GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from advect_util import advect_scenes, density_of, fluid_active
+from oracle import refio
+from shiokaze_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_build", "libadvect_hostcheck.so")
+SCENES = advect_scenes()
+FLAGS = [{}, {"MacCormack": "No"}, {"WENO": "Yes"}, {"WENO": "Yes", "MacCormack": "No"}, {"TrimNarrowBand": 3}]
+
+
+def hostcheck():
+    if not refio.ref_available("f32"):
+        pytest.skip("oracle/_ref (the reference build) is not here")
+    src = os.path.join(ROOT, "shiokaze_b200", "csrc", "advect.cu")
+    if not os.path.isfile(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.run(["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-extended-lambda", "--fmad=false",
+                        "-Xcompiler", "-fPIC,-O3,-ffp-contract=off", "-DSHKZ_B200_ADVECT_HOSTCHECK", "-shared", "-o", LIB, src, "-lcudart"], check=True)
+    return C.CDLL(LIB)
+
+
+def params(flags, background=0.0):
+    p = capi.AdvectParams()
+    p.struct_size = C.sizeof(p)
+    p.maccormack = 0 if flags.get("MacCormack") == "No" else 1
+    p.weno = 1 if flags.get("WENO") == "Yes" else 0
+    p.trim_narrowband = int(flags.get("TrimNarrowBand", 1))
+    p.scalar_background = background
+    return p
+
+
+def ptrs(arrays):
+    return (C.c_void_p * 3)(*[a.ctypes.data for a in arrays])
+
+
+@pytest.mark.parametrize("flags", FLAGS, ids=lambda f: "-".join(f"{k}{v}" for k, v in f.items()) or "default")
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_restatement_of_advect_vector_equals_the_reference(name, flags, real):
+    L = hostcheck()
+    if real == "f64" and (flags or name not in ("dambreak_solid", "smoke")):
+        pytest.skip("Real=double: default flags on two scenes")
+    sc = SCENES[name]()
+    ref = refio.run_reference(sc, real, flags=flags, advect="vector")
+    dt = np.float64 if real == "f64" else np.float32
+    u = [np.ascontiguousarray(v, dtype=dt).copy() for v in sc.vel]
+    act = [np.ascontiguousarray(a, dtype=np.uint8) for a in sc.vel_active]
+    fluid = np.ascontiguousarray(sc.fluid, dtype=dt)
+    p = params(flags)
+    L.shkz_b200_hostcheck_advect_vector(sc.nx, sc.ny, sc.nz, C.c_double(sc.dx), 1 if real == "f64" else 0, C.c_double(sc.dt), ptrs(u), ptrs(act), C.c_void_p(fluid.ctypes.data), C.byref(p))
+    moved = 0
+    for d in range(3):
+        assert np.array_equal(ref.vel_active[d], act[d])
+        on = act[d] != 0
+        diff = u[d].astype(np.float64)[on] != ref.vel[d][on]
+        assert not diff.any(), (name, flags, d, int(diff.sum()), int(on.sum()), float(np.abs(u[d].astype(np.float64)[on] - ref.vel[d][on]).max()))
+        moved += int((u[d][on] != sc.vel[d][on].astype(dt)).sum())
+    assert moved > 0
+
+
+@pytest.mark.parametrize("flags", FLAGS, ids=lambda f: "-".join(f"{k}{v}" for k, v in f.items()) or "default")
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("mode", ["density", "levelset"])
+def test_restatement_of_advect_scalar_equals_the_reference(name, flags, mode):
+    L = hostcheck()
+    sc = SCENES[name]()
+    if mode == "levelset" and sc.fluid_raw is None:
+        pytest.skip("no liquid level set in a smoke scene")
+    ref = refio.run_reference(sc, "f32", flags=flags, advect=mode)
+    if mode == "density":
+        q, qa = density_of(sc)
+        background = 0.0
+    else:
+        q, qa = sc.fluid.astype(np.float32).copy(), fluid_active(sc)
+        background = float(np.float32(sc.band))
+    q = np.ascontiguousarray(q).copy()
+    q_in = q.copy()
+    vel = [np.ascontiguousarray(v, dtype=np.float32) for v in sc.vel]
+    act = [np.ascontiguousarray(a, dtype=np.uint8) for a in sc.vel_active]
+    fluid = np.ascontiguousarray(sc.fluid, dtype=np.float32)
+    p = params(flags, background)
+    L.shkz_b200_hostcheck_advect_scalar(sc.nx, sc.ny, sc.nz, C.c_double(sc.dx), 0, C.c_double(sc.dt), C.c_void_p(q.ctypes.data), C.c_void_p(qa.ctypes.data), ptrs(vel), ptrs(act),
+                                        C.c_void_p(fluid.ctypes.data), C.byref(p))
+    assert np.array_equal(ref.pressure_active, qa)
+    on = qa != 0
+    diff = q.astype(np.float64)[on] != ref.pressure[on]
+    assert not diff.any(), (name, flags, mode, int(diff.sum()), int(on.sum()), float(np.abs(q.astype(np.float64)[on] - ref.pressure[on]).max()))
+    assert (q[on] != q_in[on]).any()

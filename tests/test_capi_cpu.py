@@ -100,7 +100,36 @@ def test_csr_entry_points_refuse_without_a_device_and_check_arguments():
             B200CG()
 
 
-@pytest.mark.parametrize("flags,module", [({"Projection": "b200pressure3"}, "b200pressure3.so"), ({"LinSolver": "b200cg"}, "b200cg.so")])
+def test_advect_entry_points_refuse_without_a_device_and_check_arguments():
+    L = capi.lib()
+    p = capi.AdvectParams()
+    L.shkz_b200_advect_default_params(C.byref(p))
+    assert p.struct_size == C.sizeof(capi.AdvectParams)
+    assert p.maccormack == 1 and p.weno == 0 and p.trim_narrowband == 1 and p.scalar_background == 0.0      # macadvection3.cpp:285-289
+    h = C.c_void_p()
+    assert L.shkz_b200_advect_create(8, 8, 8, 0.125, capi.REAL_F32, 0, None) == capi.ERR_ARG
+    assert L.shkz_b200_advect_create(8, 1, 8, 0.125, capi.REAL_F32, 0, C.byref(h)) == capi.ERR_ARG
+    assert L.shkz_b200_advect_create(8, 8, 8, -1.0, capi.REAL_F32, 0, C.byref(h)) == capi.ERR_ARG
+    assert L.shkz_b200_advect_vector_host(None, 0.1, None, None, None, None, None) == capi.ERR_ARG
+    assert L.shkz_b200_advect_scalar_host(None, 0.1, None, None, None, None, None, None, None) == capi.ERR_ARG
+    if L.shkz_b200_device_count() == 0:
+        assert L.shkz_b200_advect_create(8, 8, 8, 0.125, capi.REAL_F32, 0, C.byref(h)) == capi.ERR_NO_DEVICE and not h.value
+        assert b"no CPU fallback" in L.shkz_b200_advect_last_error()
+        from shiokaze_b200 import MacAdvection3
+        with pytest.raises(capi.ShkzError):
+            MacAdvection3((8, 8, 8), 0.125)
+
+
+def test_host_build_of_the_advection_source_is_test_infrastructure_only():
+    """csrc/advect.cu carries a host-loop harness behind -DSHKZ_B200_ADVECT_HOSTCHECK (tests/test_advect_cpu.py builds it into oracle/_build): the product
+    library must not export it."""
+    L = capi.lib()
+    for sym in ("shkz_b200_hostcheck_advect_vector", "shkz_b200_hostcheck_advect_scalar"):
+        assert not hasattr(L, sym), sym
+
+
+@pytest.mark.parametrize("flags,module", [({"Projection": "b200pressure3"}, "b200pressure3.so"), ({"LinSolver": "b200cg"}, "b200cg.so"),
+                                          ({"Advection": "b200advection3", "RefAdvect": "vector"}, "b200advection3.so")])
 def test_shiokaze_modules_load_under_the_reference_loader_and_refuse_without_a_device(flags, module):
     """The drop-in boundary without a GPU: the reference's own host (oracle/ref_driver) dlopens our module by name, casts it to the
     interface, configures it — and the module then stops the run with the library's no-device error instead of computing anything."""

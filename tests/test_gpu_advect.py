@@ -1,0 +1,155 @@
+"""The step before the projection on the device (first part; csrc/advect.cu): advect_vector / advect_scalar through the C-ABI against the
+reference's own macadvection3 module (src/advection/macadvection3.cpp), driven through the reference's loader by oracle/ref_driver (RefAdvect=...).
+The floating-point expressions are restated as written and compiled without contraction: the bar is bit-exact, on every flag combination of the module
+(MacCormack, WENO, TrimNarrowBand), Real=float and Real=double. Size-independent properties cover the sizes the reference does not run in seconds."""
+import os
+
+import numpy as np
+import pytest
+
+from advect_util import advect_scenes, density_of, fluid_active, swirl
+from oracle import refio
+from shiokaze_b200 import MacAdvection3, scenes
+
+pytestmark = pytest.mark.gpu
+
+SCENES = advect_scenes()
+FLAGS = [{}, {"MacCormack": "No"}, {"WENO": "Yes"}, {"WENO": "Yes", "MacCormack": "No"}, {"TrimNarrowBand": 3}]
+IDS = lambda f: "-".join(f"{k}{v}" for k, v in f.items()) or "default"  # noqa: E731
+
+
+def need_ref(real="f32"):
+    if not refio.ref_available(real):
+        pytest.skip("oracle/_ref (the reference build) was not shipped to this box")
+
+
+def same_bits(ours, ref64, on, what):
+    diff = ours.astype(np.float64)[on] != ref64[on]
+    assert not diff.any(), (what, int(diff.sum()), int(on.sum()), float(np.abs(ours.astype(np.float64)[on] - ref64[on]).max()))
+
+
+@pytest.mark.parametrize("flags", FLAGS, ids=IDS)
+@pytest.mark.parametrize("name", list(SCENES))
+def test_advect_vector_equals_the_reference_bit_for_bit(cuda_device, name, flags):
+    need_ref()
+    sc = SCENES[name]()
+    ref = refio.run_reference(sc, "f32", flags=flags, advect="vector")
+    A = MacAdvection3(sc.shape, sc.dx, **flags)
+    out = A.advect_vector(sc.vel, sc.vel_active, sc.fluid, sc.dt)
+    assert A.last_stats["kernel_launches"] >= 2
+    A.close()
+    moved = 0
+    for d in range(3):
+        on = sc.vel_active[d] != 0
+        assert np.array_equal(ref.vel_active[d] != 0, on)
+        same_bits(out[d], ref.vel[d], on, (name, flags, d))
+        assert np.array_equal(out[d][~on], sc.vel[d][~on])      # inactive faces are not written
+        moved += int((out[d][on] != sc.vel[d][on]).sum())
+    assert moved > 0
+
+
+@pytest.mark.parametrize("name", ["dambreak_solid", "smoke"])
+@pytest.mark.parametrize("flags", [{}, {"WENO": "Yes"}], ids=IDS)
+def test_advect_vector_real_double(cuda_device, name, flags):
+    need_ref("f64")
+    sc = SCENES[name]()
+    ref = refio.run_reference(sc, "f64", flags=flags, advect="vector")
+    A = MacAdvection3(sc.shape, sc.dx, real="f64", **flags)
+    out = A.advect_vector(sc.vel, sc.vel_active, sc.fluid, sc.dt)
+    A.close()
+    for d in range(3):
+        same_bits(out[d], ref.vel[d], sc.vel_active[d] != 0, (name, flags, d))
+
+
+@pytest.mark.parametrize("flags", FLAGS, ids=IDS)
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("mode", ["density", "levelset"])
+def test_advect_scalar_equals_the_reference_bit_for_bit(cuda_device, name, flags, mode):
+    need_ref()
+    sc = SCENES[name]()
+    if mode == "levelset" and sc.fluid_raw is None:
+        pytest.skip("no liquid level set in a smoke scene")
+    ref = refio.run_reference(sc, "f32", flags=flags, advect=mode)
+    if mode == "density":
+        q, qa = density_of(sc)
+        background = 0.0
+    else:   # the level set carried by itself (maclevelsetsurfacetracker3.cpp:49-51): `fluid` is the grid q was copied from
+        q, qa = sc.fluid.astype(np.float32), fluid_active(sc)
+        background = float(np.float32(sc.band))
+    A = MacAdvection3(sc.shape, sc.dx, **flags)
+    out = A.advect_scalar(q, qa, sc.vel, sc.vel_active, sc.fluid, sc.dt, background=background)
+    A.close()
+    on = qa != 0
+    assert np.array_equal(ref.pressure_active != 0, on)
+    same_bits(out, ref.pressure, on, (name, flags, mode))
+    assert np.array_equal(out[~on], q[~on])
+    assert (out[on] != q[on]).any()
+
+
+def test_module_is_a_drop_in_through_the_reference_loader(cuda_device):
+    """`Advection=b200advection3` loaded by the reference's own module loader (oracle/ref_driver) against `Advection=macadvection3`: same bits, all three calls."""
+    need_ref()
+    if not os.path.isfile(os.path.join(refio.ref_dir("f32"), "libshiokaze_b200advection3.so")):
+        pytest.skip("the Shiokaze module was not built (needs the reference headers)")
+    for name, flags in (("dambreak_solid", {}), ("flip", {"WENO": "Yes"}), ("smoke", {"MacCormack": "No"})):
+        sc = SCENES[name]()
+        for mode in ("vector", "density", "levelset"):
+            if mode == "levelset" and sc.fluid_raw is None:
+                continue
+            ref = refio.run_reference(sc, "f32", flags=flags, advect=mode)
+            mod = refio.run_reference(sc, "f32", flags=flags, advect=mode, advection="b200advection3")
+            for d in range(3):
+                assert np.array_equal(mod.vel_active[d], ref.vel_active[d])
+                assert np.array_equal(mod.vel[d], ref.vel[d]), (name, mode, d)
+            assert np.array_equal(mod.pressure_active, ref.pressure_active)
+            assert np.array_equal(mod.pressure, ref.pressure), (name, mode)
+
+
+def test_properties_at_a_size_the_reference_does_not_run_in_seconds(cuda_device):
+    """256^3, liquid scene: a field at rest stays what it is; a uniform field is carried onto itself away from the walls; the limiter keeps every value inside
+    the range of the input; two calls give the same bits."""
+    n = 256
+    sc = scenes.dambreak(n, True)
+    A = MacAdvection3(sc.shape, sc.dx)
+    rest = [np.zeros_like(v) for v in sc.vel]
+    out = A.advect_vector(rest, sc.vel_active, sc.fluid, 0.5)
+    assert all(not o.any() for o in out)
+    uni = [np.where(a != 0, np.float32(c), np.float32(0)) for a, c in zip(sc.vel_active, (0.25, -0.5, 0.125))]
+    out = A.advect_vector(uni, sc.vel_active, sc.fluid, 2.0 * sc.dx)     # carried by up to one cell
+    for d, c in enumerate((0.25, -0.5, 0.125)):
+        on = sc.vel_active[d] != 0
+        assert float(np.abs(out[d][on]).max()) <= abs(c) * (1 + 1e-6)
+        inner = on.copy()
+        for ax in range(3):                                               # faces whose 3-neighbourhood is all active: the stencil never meets a 0
+            for sh in (-3, -2, -1, 1, 2, 3):
+                inner &= np.roll(on, sh, axis=ax)
+        inner[:4] = inner[-4:] = False; inner[:, :4] = inner[:, -4:] = False; inner[:, :, :4] = inner[:, :, -4:] = False
+        assert inner.any()
+        assert float(np.abs(out[d][inner] - np.float32(c)).max()) <= 2e-6 * abs(c)
+    sw = swirl(sc, 3.0)
+    out1 = A.advect_vector(sw.vel, sw.vel_active, sw.fluid, sw.dt)
+    out2 = A.advect_vector(sw.vel, sw.vel_active, sw.fluid, sw.dt)
+    lo, hi = min(float(v.min()) for v in sw.vel), max(float(v.max()) for v in sw.vel)
+    for d in range(3):
+        assert np.array_equal(out1[d], out2[d])
+        assert lo <= float(out1[d].min()) and float(out1[d].max()) <= hi
+    A.close()
+
+
+def test_argument_errors(cuda_device):
+    import ctypes as C
+    from shiokaze_b200 import capi
+    L = capi.lib()
+    h = C.c_void_p()
+    assert L.shkz_b200_advect_create(1, 8, 8, 0.1, 0, 0, C.byref(h)) == capi.ERR_ARG
+    assert L.shkz_b200_advect_create(8, 8, 8, 0.1, 7, 0, C.byref(h)) == capi.ERR_ARG
+    assert L.shkz_b200_advect_vector_host(None, 0.1, None, None, None, None, None) == capi.ERR_ARG
+    A = MacAdvection3((8, 8, 8), 0.125)
+    with pytest.raises(ValueError):
+        A.advect_vector([np.zeros((8, 8, 8), np.float32)] * 3, [np.zeros((8, 8, 8), np.uint8)] * 3, None, 0.1)
+    sc = scenes.smoke_plume(8)
+    with pytest.raises(capi.ShkzError):   # MacCormack needs the liquid level set
+        A.advect_vector(sc.vel, sc.vel_active, None, 0.1)
+    A.configure(MacCormack="No")
+    A.advect_vector(sc.vel, sc.vel_active, None, 0.1)
+    A.close()
