@@ -405,6 +405,94 @@ def roofline_of(table, res, rank_rows, precision, precond, ms_solve):
             "by_kernel_ms": {k: round(v[1], 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])[:16]}}
 
 
+# ---- the step before the projection (first part): advect_vector on the bench scene -----------------------------------------------
+# Algorithmic bytes per ACTIVE face of one MacCormack advect_vector (csrc/advect.cu), Real = float: forward kernel reads u (4) + mask (1) and, per
+# cell, the level set (4/3 per face), writes the forward value (4) and the limiter record min / max / narrow-band flag (4 + 4 + 1); backward + limiter kernel
+# reads the forward value (4), mask (1), the record (9) and u (4), writes u (4). Stencil neighbours are re-reads of the same arrays (cache hits) and get no credit.
+ADVECT_BYTES_PER_ACTIVE_FACE = (4 + 1 + 4.0 / 3.0 + 4 + 9) + (4 + 1 + 9 + 4 + 4)
+
+
+def advect_dt(sc, cells=2.0):
+    """Time step that carries the scene's fastest face over `cells` cells (the simulators run at CFL 1-3; the projection scenes' dt moves a dam-break by 0.35)."""
+    vmax = max(float(np.abs(v).max()) for v in sc.vel)
+    return cells * sc.dx / vmax if vmax > 0 else sc.dt
+
+
+def reference_advect(workload, threads):
+    """ONE advect_vector of the unmodified reference module (oracle/_ref, Advection=macadvection3) on the workload's scene at REFERENCE_N^3, all host threads."""
+    from oracle import refio
+    import dataclasses
+    if not refio.ref_available("f32"):
+        return None
+    n = REFERENCE_N
+    sc = _REF_SCENES.get((workload, n))
+    if sc is None:
+        sc = _REF_SCENES[(workload, n)] = build_scene(workload, n)
+    r = refio.run_reference(dataclasses.replace(sc, dt=advect_dt(sc)), "f32", threads=threads, advect="vector")
+    faces = float(sum(int(a.sum()) for a in sc.vel_active))
+    return {"ms": r.ms_project, "active_faces": faces, "n": n, "cores": threads}
+
+
+def advect_sub_record(torch, dev, local, sc, workload, n, steps, with_cpu):
+    from shiokaze_b200 import MacAdvection3
+    A = MacAdvection3(sc.shape, sc.dx, device=local)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    u0, act, fluid = [t(v) for v in sc.vel], [t(a) for a in sc.vel_active], t(sc.fluid)
+    u = [torch.empty_like(v) for v in u0]
+    dt = advect_dt(sc)
+    faces = float(sum(int(a.sum()) for a in sc.vel_active))
+
+    def step():
+        for d in range(3):
+            u[d].copy_(u0[d])
+        return A.advect_vector_device([x.data_ptr() for x in u], [x.data_ptr() for x in act], fluid.data_ptr(), dt)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_kernels, launches = 0.0, 0
+    e0.record()
+    for _ in range(steps):
+        st = step()
+        ms_kernels += st["ms_advect"]
+        launches += st["kernel_launches"] + 3
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / steps
+    ms_kernels /= steps
+    # end to end: the call the Shiokaze module makes, page-locked host grids in and out
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hu, ha, hf = [pin(v) for v in sc.vel], [pin(a) for a in sc.vel_active], pin(sc.fluid)
+    import ctypes as C
+    from shiokaze_b200 import capi
+    e2e = []
+    for it in range(2 + 3):
+        for d in range(3):
+            hu[d].copy_(torch.from_numpy(sc.vel[d]))
+        stt = capi.AdvectStats()
+        t0 = time.perf_counter()
+        capi.check_advect(capi.lib().shkz_b200_advect_vector_host(A._h, dt, (C.c_void_p * 3)(*[x.data_ptr() for x in hu]), (C.c_void_p * 3)(*[x.data_ptr() for x in ha]),
+                                                                 hf.data_ptr(), C.byref(A.params), C.byref(stt)))
+        if it >= 2:
+            e2e.append(time.perf_counter() - t0)
+    A.close()
+    peak, peak_src = measured_peak()
+    alg = ADVECT_BYTES_PER_ACTIVE_FACE * faces
+    rec = {"config": f"advect_vector (MacCormack, trilinear: the reference's defaults) of the {workload} {n}^3 velocity, dt = 2 cells of the fastest face; "
+                     f"{int(faces)} active faces of {sum(v.size for v in sc.vel)}",
+           "ms_per_step": ms_step, "value": faces / (ms_step * 1e-3) / 1e6, "unit": "Mfaces/s (active faces)", "gpu_launches_per_step": launches // steps,
+           "e2e_ms_per_step": float(np.mean(e2e)) * 1e3, "e2e_h2d_bytes": int(stt.h2d_bytes), "e2e_d2h_bytes": int(stt.d2h_bytes),
+           "roofline": {"bound": "hbm", "kernel": "k_advect_faces (forward + record, backward + limiter)", "achieved": alg / (ms_kernels * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": alg / (ms_kernels * 1e-3) / 1e9 / peak, "peak_source": peak_src, "kernels_ms": ms_kernels,
+                        "algorithmic_bytes_per_active_face": ADVECT_BYTES_PER_ACTIVE_FACE, "traffic": None}}
+    if with_cpu:
+        r = reference_advect(workload, os.cpu_count() or 1)
+        if r:
+            rec["cpu_baseline"] = {"value": r["active_faces"] / (r["ms"] * 1e-3) / 1e6, "unit": "Mfaces/s (active faces)", "cores": r["cores"], "kind": "reference",
+                                   "sample": f"{workload} {r['n']}^3, one advect_vector of the unmodified reference module (oracle/_ref, Advection=macadvection3): {r['ms']:.0f} ms, measured"}
+    return rec
+
+
 def solve_record(res, n_rows, iters):
     phase = {k: res.stats[k] for k in ("ms_assemble", "ms_setup", "ms_solve", "ms_update")}
     return {"iterations": iters[-1], "reresid": res.reresid, "converged": res.converged, "n_rows": int(n_rows),
@@ -497,12 +585,20 @@ def run_ours(args):
     # ---- roofline of the dominant kernel: CUDA events around every launch of one extra project() ----
     table, pres = profile_one_step(H)
     roofline = roofline_of(table, pres, res.n_rows / world, args.precision, args.precond, res.stats["ms_solve"]) if rank == 0 else None
+    main_scene = H.sc
     H.close()
     del H
     torch.cuda.empty_cache()
 
     # ---- secondary records ----
     sub = {}
+    if world == 1 and not args.no_sub_records:
+        try:
+            sub[f"advect_vector_{n}"] = advect_sub_record(torch, dev, local, main_scene, args.workload, n, max(5, args.steps // 2), not args.no_cpu_baseline)
+        except Exception as e:   # a secondary record never takes the headline line down with it
+            sub[f"advect_vector_{n}"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
+    del main_scene
     if world == 1 and not args.no_sub_records and (args.workload, n) != ("smoke_plume", 256):
         Hs, _ = harness("smoke_plume", 256, False)
         ms_s, res_s, _, it_s, _ = timed_steps(torch, dist, Hs, max(5, args.steps // 2), 3, 1, dev)

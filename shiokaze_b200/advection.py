@@ -86,6 +86,22 @@ class MacAdvection3:
         self.last_stats = st.asdict()
         return qq
 
+    def advect_vector_device(self, u_ptrs, act_ptrs, fluid_ptr, dt: float, stream=None):
+        """shkz_b200_advect_vector_device on raw device pointers (three face grids in/out, their masks, the level set or None) on this object's GPU."""
+        st = capi.AdvectStats()
+        capi.check_advect(capi.lib().shkz_b200_advect_vector_device(self._h, float(dt), (C.c_void_p * 3)(*u_ptrs), (C.c_void_p * 3)(*act_ptrs), fluid_ptr,
+                                                                   C.byref(self.params), C.byref(st), stream))
+        self.last_stats = st.asdict()
+        return self.last_stats
+
+    def advect_scalar_device(self, q_ptr, qact_ptr, vel_ptrs, vact_ptrs, fluid_ptr, dt: float, background: float = 0.0, stream=None):
+        self.params.scalar_background = float(background)
+        st = capi.AdvectStats()
+        capi.check_advect(capi.lib().shkz_b200_advect_scalar_device(self._h, float(dt), q_ptr, qact_ptr, (C.c_void_p * 3)(*vel_ptrs), (C.c_void_p * 3)(*vact_ptrs),
+                                                                   fluid_ptr, C.byref(self.params), C.byref(st), stream))
+        self.last_stats = st.asdict()
+        return self.last_stats
+
     def close(self):
         if getattr(self, "_h", None):
             capi.lib().shkz_b200_advect_destroy(self._h)

@@ -74,8 +74,9 @@ template <class RealT> struct Mac {
 	const uint8_t *a[3];
 };
 // macarray3::operator() on a face inside the grid: the active value, else the background value 0
-template <class RealT> HD RealT face_read(const Mac<RealT> &F, const Grid &g, int dim, int i, int j, int k) {
+template <class RealT, bool MASKED = true> HD RealT face_read(const Mac<RealT> &F, const Grid &g, int dim, int i, int j, int k) {
 	const long long n = i + (long long)fw(g, dim) * (j + (long long)fh(g, dim) * k);
+	if (!MASKED) return F.v[dim][n];
 	return F.a[dim][n] ? F.v[dim][n] : (RealT)0;
 }
 HD int clampi(int v, int n) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); }
@@ -117,6 +118,15 @@ template <class RealT, class Read> HD RealT trilinear(const Stencil &S, Read rea
 #pragma unroll
 	for (int n = 0; n < 8; ++n)
 		if (S.coef[n]) value = (RealT)((double)value + (double)read(S.i + (n & 1), S.j + ((n >> 1) & 1), S.k + (n >> 2)) * S.coef[n]);
+	return value;
+}
+
+// (the same accumulation over eight values already in registers, in stencil order)
+template <class RealT> HD RealT trilinear_corners(const Stencil &S, const RealT corner[8]) {
+	RealT value = (RealT)0;
+#pragma unroll
+	for (int n = 0; n < 8; ++n)
+		if (S.coef[n]) value = (RealT)((double)value + (double)corner[n] * S.coef[n]);
 	return value;
 }
 
@@ -174,24 +184,26 @@ template <class Read> HD double weno3d(int w, int h, int d, double px, double py
 	return weno6(tz, vvv);
 }
 
-// macarray3::convert_to_full, face version (macarray3.h:350-372), at the ACTIVE face (dim; i,j,k): the face's own component, the mean of the four surrounding
+// macarray3::convert_to_full, face version (macarray3.h:350-372), at the ACTIVE face (DIM; i,j,k): the face's own component, the mean of the four surrounding
 // faces for the two others (indices clamped into that component's grid, inactive faces contribute the background 0), summed in double in the order
-// (0,0) (0,1) (1,0) (1,1) of (step along dim, step along the component), /4, rounded to Real.
-template <class RealT> HD void face_full_velocity(const Mac<RealT> &F, const Grid &g, int dim, int i, int j, int k, RealT ur[3]) {
+// (0,0) (0,1) (1,0) (1,1) of (step along DIM, step along the component), /4, rounded to Real.
+// MASKED = false: the field holds zeros on its inactive faces (the forward result, written by this file), no mask lookups. DIM is a template parameter so
+// that no array of pointers is ever indexed at run time (that would move the kernel parameters into local memory: the first version ran at the speed of L1).
+template <class RealT, int DIM, bool MASKED> HD void face_full_velocity(const Mac<RealT> &F, const Grid &g, int i, int j, int k, RealT ur[3]) {
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
 		double u = 0.0;
-		if (c == dim) u = (double)face_read(F, g, c, i, j, k);
+		if (c == DIM) u = (double)F.v[c][i + (long long)fw(g, c) * (j + (long long)fh(g, c) * k)];
 		else {
 			const int w = fw(g, c), h = fh(g, c), d = fd(g, c);
-			const int pi = i - (dim == 0), pj = j - (dim == 1), pk = k - (dim == 2);
+			const int pi = i - (DIM == 0), pj = j - (DIM == 1), pk = k - (DIM == 2);
 #pragma unroll
 			for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
 				for (int jj = 0; jj < 2; ++jj) {
-					const int qi = clampi(pi + ii * (dim == 0) + jj * (c == 0), w), qj = clampi(pj + ii * (dim == 1) + jj * (c == 1), h),
-					          qk = clampi(pk + ii * (dim == 2) + jj * (c == 2), d);
-					u += (double)face_read(F, g, c, qi, qj, qk);
+					const int qi = clampi(pi + ii * (DIM == 0) + jj * (c == 0), w), qj = clampi(pj + ii * (DIM == 1) + jj * (c == 1), h),
+					          qk = clampi(pk + ii * (DIM == 2) + jj * (c == 2), d);
+					u += (double)face_read<RealT, MASKED>(F, g, c, qi, qj, qk);
 				}
 			u /= 4.0;
 		}
@@ -228,7 +240,8 @@ template <> struct Limits<double> {
 };
 
 // ---- faces ------------------------------------------------------------------------------------------------------------------------------------------
-// One thread per face of the three grids (blockIdx.z walks the planes of the x-, then y-, then z-faces); inactive faces leave at once.
+// One thread per face of the three grids (blockIdx.y walks the planes of the x-, then y-, then z-faces); an inactive face only gets the zero a forward
+// result carries there.
 //   COMBINE = false: advect_semiLagrangian_u(in = F, dt) -> out; RECORD: also the limiter's record (min, max over the eight corners, narrow-band flag)
 //   COMBINE = true : the backward pass (F = the forward result, called with -dt) and the limiter (macadvection3.cpp:163-178) in one go: out is the final
 //                    field; `orig` = the field before the advection (only this face of it is read, so `out` may be `orig`)
@@ -236,77 +249,69 @@ template <class RealT> struct FaceRecord {
 	RealT *mn[3], *mx[3];
 	uint8_t *nb[3];
 };
-template <class RealT, bool WENO, bool RECORD, bool COMBINE>
+template <class RealT, bool WENO, bool RECORD, bool COMBINE, int DIM>
 HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *__restrict__ fluid, double band, const FaceRecord<RealT> &R, const Mac<RealT> &orig,
-                    RealT *out, int dim, int i, int j, int k) {
-	const int w = fw(g, dim), h = fh(g, dim), d = fd(g, dim);
+                    RealT *out, int i, int j, int k) {
+	constexpr bool MASKED = !COMBINE; // the backward pass reads the forward result, which carries zeros on inactive faces
+	const int w = fw(g, DIM), h = fh(g, DIM), d = fd(g, DIM);
 	const long long n = i + (long long)w * (j + (long long)h * k);
 	RealT ur[3];
-	face_full_velocity(F, g, dim, i, j, k, ur);
+	face_full_velocity<RealT, DIM, MASKED>(F, g, i, j, k, ur);
 	const bool still = ur[0] == (RealT)0 && ur[1] == (RealT)0 && ur[2] == (RealT)0; // vec::empty()
-	auto read = [&](int a, int b, int c) -> RealT { return face_read(F, g, dim, a, b, c); };
+	auto read = [&](int a, int b, int c) -> RealT { return face_read<RealT, MASKED>(F, g, DIM, a, b, c); };
+	const RealT own = F.v[DIM][n];
 	RealT value;
+	RealT corner[8]; // the eight values of the trilinear stencil, kept for the limiter's min / max when its (double-precision) position lands in the same cell
+	int ci = -1, cj = -1, ck = -1;
 	if (!still) {
 		// p = vec3d(i,j,k) - dt*u/dx with u a vec3<Real>: (Real)(u*dt), then (Real)(that/dx), subtracted in double (macadvection3.cpp:86)
-		double p[3];
-		const int idx[3] = {i, j, k};
-#pragma unroll
-		for (int c = 0; c < 3; ++c) {
-			RealT t = (RealT)((double)ur[c] * dt);
-			t = (RealT)((double)t / g.dx);
-			p[c] = (double)idx[c] - (double)t;
-		}
-		if (WENO) value = (RealT)weno3d(w, h, d, p[0], p[1], p[2], read);
+		RealT tx = (RealT)((double)ur[0] * dt), ty = (RealT)((double)ur[1] * dt), tz = (RealT)((double)ur[2] * dt);
+		tx = (RealT)((double)tx / g.dx); ty = (RealT)((double)ty / g.dx); tz = (RealT)((double)tz / g.dx);
+		const double px = (double)i - (double)tx, py = (double)j - (double)ty, pz = (double)k - (double)tz;
+		if (WENO) value = (RealT)weno3d(w, h, d, px, py, pz, read);
 		else {
 			Stencil S;
-			make_stencil(w, h, d, p[0], p[1], p[2], S);
-			value = (RealT)(double)trilinear<RealT>(S, read);
+			make_stencil(w, h, d, px, py, pz, S);
+			ci = S.i; cj = S.j; ck = S.k;
+#pragma unroll
+			for (int e = 0; e < 8; ++e) corner[e] = read(S.i + (e & 1), S.j + ((e >> 1) & 1), S.k + (e >> 2));
+			value = trilinear_corners<RealT>(S, corner);
 		}
-	} else value = F.v[dim][n];
-	bool within_narrowband = false;
-	double min_value = 0.0, max_value = 0.0;
+	} else value = own;
 	if (RECORD) {
 		// (macadvection3.cpp:99-139) here u is read back as a vec3d: the position is formed in double throughout
 		auto fluid_read = [&](int a, int b, int c) -> RealT { return fluid[a + (long long)g.nx * (b + (long long)g.ny * c)]; };
-		const int idx[3] = {i, j, k};
-		double fp[3];
+		double min_value, max_value;
+		double fx = (double)i + 0.5 * (DIM != 0), fy = (double)j + 0.5 * (DIM != 1), fz = (double)k + 0.5 * (DIM != 2);
 		if (!still) {
-			double p[3];
-#pragma unroll
-			for (int c = 0; c < 3; ++c) {
-				const double t = (double)ur[c] * dt / g.dx;
-				p[c] = (double)idx[c] - t;
-				fp[c] = ((double)idx[c] + 0.5 * (dim != c)) - t;
-			}
+			const double tx = (double)ur[0] * dt / g.dx, ty = (double)ur[1] * dt / g.dx, tz = (double)ur[2] * dt / g.dx;
+			fx = fx - tx; fy = fy - ty; fz = fz - tz;
 			Stencil S;
-			make_stencil(w, h, d, p[0], p[1], p[2], S);
+			clamp_position(w, h, d, (double)i - tx, (double)j - ty, (double)k - tz, S);
+			const bool same = S.i == ci && S.j == cj && S.k == ck;
 			min_value = DBL_MAX;
 			max_value = DBL_MIN;
 #pragma unroll
 			for (int e = 0; e < 8; ++e) {
-				const double v = (double)read(S.i + (e & 1), S.j + ((e >> 1) & 1), S.k + (e >> 2));
+				const double v = (double)(same ? corner[e] : read(S.i + (e & 1), S.j + ((e >> 1) & 1), S.k + (e >> 2)));
 				min_value = std_min(min_value, v);
 				max_value = std_max(max_value, v);
 			}
-		} else {
-#pragma unroll
-			for (int c = 0; c < 3; ++c) fp[c] = (double)idx[c] + 0.5 * (dim != c);
-			min_value = max_value = (double)F.v[dim][n];
-		}
+		} else min_value = max_value = (double)own;
 		Stencil Sf;
-		make_stencil(g.nx, g.ny, g.nz, fp[0] - 0.5, fp[1] - 0.5, fp[2] - 0.5, Sf);
-		within_narrowband = (double)trilinear<RealT>(Sf, fluid_read) > band;
-		R.mn[dim][n] = (RealT)min_value;
-		R.mx[dim][n] = (RealT)max_value;
-		R.nb[dim][n] = within_narrowband ? 1 : 0;
+		make_stencil(g.nx, g.ny, g.nz, fx - 0.5, fy - 0.5, fz - 0.5, Sf);
+		const bool within_narrowband = (double)trilinear<RealT>(Sf, fluid_read) > band;
+		R.mn[DIM][n] = (RealT)min_value;
+		R.mx[DIM][n] = (RealT)max_value;
+		R.nb[DIM][n] = within_narrowband ? 1 : 0;
 	}
 	if (COMBINE) {
 		// `value` is velocity_1 (the forward result traced back), F is velocity_0, orig the field before (macadvection3.cpp:163-178)
-		if (R.nb[dim][n]) value = F.v[dim][n];
+		if (R.nb[DIM][n]) value = own;
 		else {
-			const double lo = (double)R.mn[dim][n], hi = (double)R.mx[dim][n];
-			const double vel0 = (double)F.v[dim][n];
-			const RealT diff = orig.v[dim][n] - value;
+			const double lo = (double)R.mn[DIM][n], hi = (double)R.mx[DIM][n];
+			const double vel0 = (double)own;
+			const RealT diff = orig.v[DIM][n] - value;
 			const double correction = 0.5 * (double)diff;
 			if (vel0 + correction < lo) value = (RealT)lo;
 			else if (vel0 + correction > hi) value = (RealT)hi;
@@ -314,6 +319,23 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 		}
 	}
 	out[n] = value;
+}
+// (run-time direction -> the three instances; `act`: the activity of the field's faces. An inactive face of a forward result is written as 0, which is what
+// lets the backward pass read that field without mask lookups.)
+template <class RealT, bool WENO, bool RECORD, bool COMBINE>
+HD void advect_face_any(const Grid &g, const Mac<RealT> &F, double dt, const RealT *__restrict__ fluid, double band, const FaceRecord<RealT> &R, const Mac<RealT> &orig,
+                        RealT *out0, RealT *out1, RealT *out2, int dim, int i, int j, int k) {
+	const long long n = i + (long long)fw(g, dim) * (j + (long long)fh(g, dim) * k);
+	if (dim == 0) {
+		if (orig.a[0][n]) advect_face<RealT, WENO, RECORD, COMBINE, 0>(g, F, dt, fluid, band, R, orig, out0, i, j, k);
+		else if (!COMBINE) out0[n] = (RealT)0;
+	} else if (dim == 1) {
+		if (orig.a[1][n]) advect_face<RealT, WENO, RECORD, COMBINE, 1>(g, F, dt, fluid, band, R, orig, out1, i, j, k);
+		else if (!COMBINE) out1[n] = (RealT)0;
+	} else {
+		if (orig.a[2][n]) advect_face<RealT, WENO, RECORD, COMBINE, 2>(g, F, dt, fluid, band, R, orig, out2, i, j, k);
+		else if (!COMBINE) out2[n] = (RealT)0;
+	}
 }
 template <class RealT, bool WENO, bool RECORD, bool COMBINE>
 __global__ void __launch_bounds__(ADV_THREADS) k_advect_faces(Grid g, Mac<RealT> F, double dt, const RealT *__restrict__ fluid, double band, FaceRecord<RealT> R,
@@ -323,8 +345,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advect_faces(Grid g, Mac<RealT>
 	const int w = fw(g, dim), h = fh(g, dim);
 	const long long m = (long long)blockIdx.x * ADV_THREADS + threadIdx.x;
 	if (m >= (long long)w * h) return;
-	if (!F.a[dim][m + (long long)w * h * kz]) return;
-	advect_face<RealT, WENO, RECORD, COMBINE>(g, F, dt, fluid, band, R, orig, dim == 0 ? out0 : (dim == 1 ? out1 : out2), dim, (int)(m % w), (int)(m / w), kz);
+	advect_face_any<RealT, WENO, RECORD, COMBINE>(g, F, dt, fluid, band, R, orig, out0, out1, out2, dim, (int)(m % w), (int)(m / w), kz);
 }
 
 // ---- cells ------------------------------------------------------------------------------------------------------------------------------------------
@@ -348,10 +369,15 @@ HD void advect_cell(const Grid &g, const RealT *__restrict__ q, const uint8_t *_
 	const double p[3] = {(double)i - (double)ur[0] * dt / g.dx, (double)j - (double)ur[1] * dt / g.dx, (double)k - (double)ur[2] * dt / g.dx};
 	RealT value;
 	Stencil S;
+	RealT corner[8];
 	if (!still) {
-		if (!WENO || RECORD) make_stencil(g.nx, g.ny, g.nz, p[0], p[1], p[2], S);
+		if (!WENO || RECORD) {
+			make_stencil(g.nx, g.ny, g.nz, p[0], p[1], p[2], S);
+#pragma unroll
+			for (int e = 0; e < 8; ++e) corner[e] = read(S.i + (e & 1), S.j + ((e >> 1) & 1), S.k + (e >> 2));
+		}
 		if (WENO) value = (RealT)weno3d(g.nx, g.ny, g.nz, p[0], p[1], p[2], read);
-		else value = (RealT)(double)trilinear<RealT>(S, read);
+		else value = trilinear_corners<RealT>(S, corner);
 	} else value = q[n];
 	if (RECORD) {
 		auto fluid_read = [&](int a, int b, int c) -> RealT { return fluid[a + (long long)g.nx * (b + (long long)g.ny * c)]; };
@@ -362,7 +388,7 @@ HD void advect_cell(const Grid &g, const RealT *__restrict__ q, const uint8_t *_
 			max_value = Limits<RealT>::min();
 #pragma unroll
 			for (int e = 0; e < 8; ++e) {
-				const double v = (double)read(S.i + (e & 1), S.j + ((e >> 1) & 1), S.k + (e >> 2));
+				const double v = (double)corner[e];
 				min_value = std_min(min_value, v);
 				max_value = std_max(max_value, v);
 			}
@@ -765,14 +791,14 @@ void hostcheck_vector(const Grid &g, double dt, RealT *const u[3], const uint8_t
 			for (int k = 0; k < fd(g, dim); ++k)
 				for (int j = 0; j < fh(g, dim); ++j)
 					for (int i = 0; i < fw(g, dim); ++i)
-						if (act[dim][i + (size_t)fw(g, dim) * (j + (size_t)fh(g, dim) * k)]) body(dim, i, j, k);
+						body(dim, i, j, k);
 	};
 	if (P.maccormack) {
-		sweep([&](int dim, int i, int j, int k) { advect_face<RealT, WENO, true, false>(g, U, dt, fluid, band, R, U, fwd[dim].data(), dim, i, j, k); });
-		sweep([&](int dim, int i, int j, int k) { advect_face<RealT, WENO, false, true>(g, F0, -dt, fluid, band, R, U, u[dim], dim, i, j, k); });
+		sweep([&](int dim, int i, int j, int k) { advect_face_any<RealT, WENO, true, false>(g, U, dt, fluid, band, R, U, fwd[0].data(), fwd[1].data(), fwd[2].data(), dim, i, j, k); });
+		sweep([&](int dim, int i, int j, int k) { advect_face_any<RealT, WENO, false, true>(g, F0, -dt, fluid, band, R, U, u[0], u[1], u[2], dim, i, j, k); });
 	} else {
-		sweep([&](int dim, int i, int j, int k) { advect_face<RealT, WENO, false, false>(g, U, dt, fluid, band, R, U, fwd[dim].data(), dim, i, j, k); });
-		sweep([&](int dim, int i, int j, int k) { const size_t n = i + (size_t)fw(g, dim) * (j + (size_t)fh(g, dim) * k); u[dim][n] = fwd[dim][n]; });
+		sweep([&](int dim, int i, int j, int k) { advect_face_any<RealT, WENO, false, false>(g, U, dt, fluid, band, R, U, fwd[0].data(), fwd[1].data(), fwd[2].data(), dim, i, j, k); });
+		sweep([&](int dim, int i, int j, int k) { const size_t n = i + (size_t)fw(g, dim) * (j + (size_t)fh(g, dim) * k); if (act[dim][n]) u[dim][n] = fwd[dim][n]; });
 	}
 }
 template <class RealT, bool WENO>

@@ -113,10 +113,21 @@ protected:
 		});
 		return v;
 	}
-	// the advected values go back onto the active entries; the activity never changes (macadvection3.cpp:71-72, :195-196)
-	static void write_back( array3<Real> &a, const view &v ) {
+	// the advected values go back onto the active entries; the activity never changes (macadvection3.cpp:71-72, :195-196).
+	// reset: do what the reference does to its output — clear(), then activate and set (:193-196). On the tiled core clear() also drops the flood-fill
+	// state of a level set (cells inside the liquid read the background value afterwards, until the tracker's redistancing fills again,
+	// maclevelsetsurfacetracker3.cpp:55): a dense read of the grid after the call then agrees with the reference everywhere, not only on the active set.
+	static void write_back( array3<Real> &a, const view &v, bool reset=false ) {
 		if( v.in_place ) return;
 		const shape3 sh = a.shape();
+		if( reset ) {
+			a.clear();
+			a.parallel_all([&]( int i, int j, int k, auto &it ) {
+				const size_t n = i + sh.w * (j + sh.h * (size_t)k);
+				if( v.active[n] ) it.set(v.values[n]);
+			});
+			return;
+		}
 		a.parallel_actives([&]( int i, int j, int k, auto &it ) {
 			it.set(v.values[i + sh.w * (j + sh.h * (size_t)k)]);
 		});
@@ -142,7 +153,7 @@ protected:
 		P.scalar_background = scalar.get_background_value();
 		shkz_b200_advect_stats st;
 		if( shkz_b200_advect_scalar_host(m_advect,dt,q.values,q.active,vel_ptr,act_ptr,f.values,&P,&st) != SHKZ_B200_OK ) fatal("shkz_b200_advect_scalar_host");
-		write_back(scalar,q);
+		write_back(scalar,q,scalar.is_levelset());
 		console::dump( "Done. Took %s (h2d %.2f, kernels %.2f, d2h %.2f msec)\n", timer.stock((m_param.maccormack ? "maccormack_cell_" : "semilagrangian_cell_")+name).c_str(), st.ms_h2d, st.ms_advect, st.ms_d2h);
 	}
 	//
