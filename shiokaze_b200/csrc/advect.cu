@@ -320,32 +320,28 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 	}
 	out[n] = value;
 }
-// (run-time direction -> the three instances; `act`: the activity of the field's faces. An inactive face of a forward result is written as 0, which is what
-// lets the backward pass read that field without mask lookups.)
-template <class RealT, bool WENO, bool RECORD, bool COMBINE>
-HD void advect_face_any(const Grid &g, const Mac<RealT> &F, double dt, const RealT *__restrict__ fluid, double band, const FaceRecord<RealT> &R, const Mac<RealT> &orig,
-                        RealT *out0, RealT *out1, RealT *out2, int dim, int i, int j, int k) {
-	const long long n = i + (long long)fw(g, dim) * (j + (long long)fh(g, dim) * k);
-	if (dim == 0) {
-		if (orig.a[0][n]) advect_face<RealT, WENO, RECORD, COMBINE, 0>(g, F, dt, fluid, band, R, orig, out0, i, j, k);
-		else if (!COMBINE) out0[n] = (RealT)0;
-	} else if (dim == 1) {
-		if (orig.a[1][n]) advect_face<RealT, WENO, RECORD, COMBINE, 1>(g, F, dt, fluid, band, R, orig, out1, i, j, k);
-		else if (!COMBINE) out1[n] = (RealT)0;
-	} else {
-		if (orig.a[2][n]) advect_face<RealT, WENO, RECORD, COMBINE, 2>(g, F, dt, fluid, band, R, orig, out2, i, j, k);
-		else if (!COMBINE) out2[n] = (RealT)0;
-	}
+// An inactive face of a forward result is written as 0, which is what lets the backward pass read that field without mask lookups. `orig.a`: the activity.
+template <class RealT, bool WENO, bool RECORD, bool COMBINE, int DIM>
+HD void advect_face_or_zero(const Grid &g, const Mac<RealT> &F, double dt, const RealT *__restrict__ fluid, double band, const FaceRecord<RealT> &R,
+                            const Mac<RealT> &orig, RealT *out, int i, int j, int k) {
+	const long long n = i + (long long)fw(g, DIM) * (j + (long long)fh(g, DIM) * k);
+	if (orig.a[DIM][n]) advect_face<RealT, WENO, RECORD, COMBINE, DIM>(g, F, dt, fluid, band, R, orig, out, i, j, k);
+	else if (!COMBINE) out[n] = (RealT)0;
 }
+// A block takes ADV_TY rows of one plane of one face grid (blockIdx.y walks the planes of the x-, then y-, then z-faces), 64 threads walk along each row:
+// no index divisions, coalesced mask bytes, and a row without an active face costs its mask bytes (and, in a forward pass, its zeros) only — on a liquid scene
+// seven faces of eight are inactive, and with one thread per face their index arithmetic was most of the kernel.
+constexpr int ADV_TX = 64, ADV_TY = 4;
 template <class RealT, bool WENO, bool RECORD, bool COMBINE>
-__global__ void __launch_bounds__(ADV_THREADS) k_advect_faces(Grid g, Mac<RealT> F, double dt, const RealT *__restrict__ fluid, double band, FaceRecord<RealT> R,
-                                                               Mac<RealT> orig, RealT *out0, RealT *out1, RealT *out2) {
+__global__ void __launch_bounds__(ADV_TX *ADV_TY) k_advect_faces(Grid g, Mac<RealT> F, double dt, const RealT *__restrict__ fluid, double band, FaceRecord<RealT> R,
+                                                                  Mac<RealT> orig, RealT *out0, RealT *out1, RealT *out2) {
 	int kz = blockIdx.y, dim = 0;
 	if (kz >= g.nz) { kz -= g.nz; dim = 1; if (kz >= g.nz) { kz -= g.nz; dim = 2; } }
-	const int w = fw(g, dim), h = fh(g, dim);
-	const long long m = (long long)blockIdx.x * ADV_THREADS + threadIdx.x;
-	if (m >= (long long)w * h) return;
-	advect_face_any<RealT, WENO, RECORD, COMBINE>(g, F, dt, fluid, band, R, orig, out0, out1, out2, dim, (int)(m % w), (int)(m / w), kz);
+	const int j = blockIdx.x * ADV_TY + threadIdx.y;
+	if (j >= fh(g, dim)) return;
+	if (dim == 0) for (int i = threadIdx.x; i < g.nx + 1; i += ADV_TX) advect_face_or_zero<RealT, WENO, RECORD, COMBINE, 0>(g, F, dt, fluid, band, R, orig, out0, i, j, kz);
+	else if (dim == 1) for (int i = threadIdx.x; i < g.nx; i += ADV_TX) advect_face_or_zero<RealT, WENO, RECORD, COMBINE, 1>(g, F, dt, fluid, band, R, orig, out1, i, j, kz);
+	else for (int i = threadIdx.x; i < g.nx; i += ADV_TX) advect_face_or_zero<RealT, WENO, RECORD, COMBINE, 2>(g, F, dt, fluid, band, R, orig, out2, i, j, kz);
 }
 
 // ---- cells ------------------------------------------------------------------------------------------------------------------------------------------
@@ -416,12 +412,13 @@ HD void advect_cell(const Grid &g, const RealT *__restrict__ q, const uint8_t *_
 	out[n] = value;
 }
 template <class RealT, bool WENO, bool RECORD, bool COMBINE>
-__global__ void __launch_bounds__(ADV_THREADS) k_advect_cells(Grid g, const RealT *__restrict__ q, const uint8_t *__restrict__ qa, Mac<RealT> V, double dt,
-                                                               const RealT *__restrict__ fluid, double band, RealT *__restrict__ mn, RealT *__restrict__ mx,
-                                                               uint8_t *__restrict__ nb, const RealT *orig, RealT *out, RealT background) {
-	const long long m = (long long)blockIdx.x * ADV_THREADS + threadIdx.x;
-	if (m >= (long long)g.nx * g.ny) return;
-	advect_cell<RealT, WENO, RECORD, COMBINE>(g, q, qa, V, dt, fluid, band, mn, mx, nb, orig, out, background, (int)(m % g.nx), (int)(m / g.nx), (int)blockIdx.y);
+__global__ void __launch_bounds__(ADV_TX *ADV_TY) k_advect_cells(Grid g, const RealT *__restrict__ q, const uint8_t *__restrict__ qa, Mac<RealT> V, double dt,
+                                                                  const RealT *__restrict__ fluid, double band, RealT *__restrict__ mn, RealT *__restrict__ mx,
+                                                                  uint8_t *__restrict__ nb, const RealT *orig, RealT *out, RealT background) {
+	const int j = blockIdx.x * ADV_TY + threadIdx.y;
+	if (j >= g.ny) return;
+	for (int i = threadIdx.x; i < g.nx; i += ADV_TX)
+		advect_cell<RealT, WENO, RECORD, COMBINE>(g, q, qa, V, dt, fluid, band, mn, mx, nb, orig, out, background, i, j, (int)blockIdx.y);
 }
 
 // out[n] = src[n] on active entries (the plain semi-Lagrangian result goes back into the caller's grid)
@@ -503,22 +500,21 @@ int vector_device(shkz_b200_advect *A, double dt, void *const u[3], const uint8_
 		R.mn[dim] = static_cast<RealT *>(A->mn[dim].p); R.mx[dim] = static_cast<RealT *>(A->mx[dim].p); R.nb[dim] = static_cast<uint8_t *>(A->nb[dim].p);
 	}
 	RealT *f0 = static_cast<RealT *>(A->fwd[0].p), *f1 = static_cast<RealT *>(A->fwd[1].p), *f2 = static_cast<RealT *>(A->fwd[2].p);
-	const long long widest = (long long)(g.nx + 1) * (g.ny + 1);
-	const dim3 grid((unsigned)((widest + ADV_THREADS - 1) / ADV_THREADS), (unsigned)(3 * g.nz + 1));
+	const dim3 grid((unsigned)((g.ny + 1 + ADV_TY - 1) / ADV_TY), (unsigned)(3 * g.nz + 1)), block(ADV_TX, ADV_TY);
 	const RealT *fl = static_cast<const RealT *>(fluid);
 	const double band = -g.dx * (double)P.trim_narrowband;
 	if (P.maccormack) {
 		if (P.weno) {
-			k_advect_faces<RealT, true, true, false><<<grid, ADV_THREADS, 0, s>>>(g, U, dt, fl, band, R, U, f0, f1, f2);
-			k_advect_faces<RealT, true, false, true><<<grid, ADV_THREADS, 0, s>>>(g, F0, -dt, fl, band, R, U, (RealT *)u[0], (RealT *)u[1], (RealT *)u[2]);
+			k_advect_faces<RealT, true, true, false><<<grid, block, 0, s>>>(g, U, dt, fl, band, R, U, f0, f1, f2);
+			k_advect_faces<RealT, true, false, true><<<grid, block, 0, s>>>(g, F0, -dt, fl, band, R, U, (RealT *)u[0], (RealT *)u[1], (RealT *)u[2]);
 		} else {
-			k_advect_faces<RealT, false, true, false><<<grid, ADV_THREADS, 0, s>>>(g, U, dt, fl, band, R, U, f0, f1, f2);
-			k_advect_faces<RealT, false, false, true><<<grid, ADV_THREADS, 0, s>>>(g, F0, -dt, fl, band, R, U, (RealT *)u[0], (RealT *)u[1], (RealT *)u[2]);
+			k_advect_faces<RealT, false, true, false><<<grid, block, 0, s>>>(g, U, dt, fl, band, R, U, f0, f1, f2);
+			k_advect_faces<RealT, false, false, true><<<grid, block, 0, s>>>(g, F0, -dt, fl, band, R, U, (RealT *)u[0], (RealT *)u[1], (RealT *)u[2]);
 		}
 		A->launches += 2;
 	} else {
-		if (P.weno) k_advect_faces<RealT, true, false, false><<<grid, ADV_THREADS, 0, s>>>(g, U, dt, fl, band, R, U, f0, f1, f2);
-		else k_advect_faces<RealT, false, false, false><<<grid, ADV_THREADS, 0, s>>>(g, U, dt, fl, band, R, U, f0, f1, f2);
+		if (P.weno) k_advect_faces<RealT, true, false, false><<<grid, block, 0, s>>>(g, U, dt, fl, band, R, U, f0, f1, f2);
+		else k_advect_faces<RealT, false, false, false><<<grid, block, 0, s>>>(g, U, dt, fl, band, R, U, f0, f1, f2);
 		for (int dim = 0; dim < 3; ++dim) {
 			const long long nf = (long long)face_count(g, dim);
 			k_copy_active<RealT><<<(unsigned)((nf + ADV_THREADS - 1) / ADV_THREADS), ADV_THREADS, 0, s>>>(nf, F0.v[dim], act[dim], (RealT *)u[dim]);
@@ -542,20 +538,20 @@ int scalar_device(shkz_b200_advect *A, double dt, void *q, const uint8_t *qact, 
 	uint8_t *nb = static_cast<uint8_t *>(A->nb[3].p);
 	const RealT *fl = static_cast<const RealT *>(fluid);
 	const double band = -g.dx * (double)P.trim_narrowband;
-	const dim3 grid((unsigned)(((long long)g.nx * g.ny + ADV_THREADS - 1) / ADV_THREADS), (unsigned)g.nz);
+	const dim3 grid((unsigned)((g.ny + ADV_TY - 1) / ADV_TY), (unsigned)g.nz), block(ADV_TX, ADV_TY);
 	const RealT bg = (RealT)P.scalar_background;
 	if (P.maccormack) {
 		if (P.weno) {
-			k_advect_cells<RealT, true, true, false><<<grid, ADV_THREADS, 0, s>>>(g, qq, qact, V, dt, fl, band, mn, mx, nb, qq, q0, bg);
-			k_advect_cells<RealT, true, false, true><<<grid, ADV_THREADS, 0, s>>>(g, q0, qact, V, -dt, fl, band, mn, mx, nb, qq, qq, bg);
+			k_advect_cells<RealT, true, true, false><<<grid, block, 0, s>>>(g, qq, qact, V, dt, fl, band, mn, mx, nb, qq, q0, bg);
+			k_advect_cells<RealT, true, false, true><<<grid, block, 0, s>>>(g, q0, qact, V, -dt, fl, band, mn, mx, nb, qq, qq, bg);
 		} else {
-			k_advect_cells<RealT, false, true, false><<<grid, ADV_THREADS, 0, s>>>(g, qq, qact, V, dt, fl, band, mn, mx, nb, qq, q0, bg);
-			k_advect_cells<RealT, false, false, true><<<grid, ADV_THREADS, 0, s>>>(g, q0, qact, V, -dt, fl, band, mn, mx, nb, qq, qq, bg);
+			k_advect_cells<RealT, false, true, false><<<grid, block, 0, s>>>(g, qq, qact, V, dt, fl, band, mn, mx, nb, qq, q0, bg);
+			k_advect_cells<RealT, false, false, true><<<grid, block, 0, s>>>(g, q0, qact, V, -dt, fl, band, mn, mx, nb, qq, qq, bg);
 		}
 		A->launches += 2;
 	} else {
-		if (P.weno) k_advect_cells<RealT, true, false, false><<<grid, ADV_THREADS, 0, s>>>(g, qq, qact, V, dt, fl, band, mn, mx, nb, qq, q0, bg);
-		else k_advect_cells<RealT, false, false, false><<<grid, ADV_THREADS, 0, s>>>(g, qq, qact, V, dt, fl, band, mn, mx, nb, qq, q0, bg);
+		if (P.weno) k_advect_cells<RealT, true, false, false><<<grid, block, 0, s>>>(g, qq, qact, V, dt, fl, band, mn, mx, nb, qq, q0, bg);
+		else k_advect_cells<RealT, false, false, false><<<grid, block, 0, s>>>(g, qq, qact, V, dt, fl, band, mn, mx, nb, qq, q0, bg);
 		k_copy_active<RealT><<<(unsigned)((nc + ADV_THREADS - 1) / ADV_THREADS), ADV_THREADS, 0, s>>>((long long)nc, q0, qact, qq);
 		A->launches += 2;
 	}
@@ -773,6 +769,13 @@ int shkz_b200_advect_scalar_host(shkz_b200_advect *A, double dt, void *q, const 
 // product: nothing in shiokaze_b200/ loads it.
 #include <vector>
 namespace {
+template <class RealT, bool WENO, bool RECORD, bool COMBINE>
+void advect_face_any(const Grid &g, const Mac<RealT> &F, double dt, const RealT *fluid, double band, const FaceRecord<RealT> &R, const Mac<RealT> &orig, RealT *out0,
+                     RealT *out1, RealT *out2, int dim, int i, int j, int k) {
+	if (dim == 0) advect_face_or_zero<RealT, WENO, RECORD, COMBINE, 0>(g, F, dt, fluid, band, R, orig, out0, i, j, k);
+	else if (dim == 1) advect_face_or_zero<RealT, WENO, RECORD, COMBINE, 1>(g, F, dt, fluid, band, R, orig, out1, i, j, k);
+	else advect_face_or_zero<RealT, WENO, RECORD, COMBINE, 2>(g, F, dt, fluid, band, R, orig, out2, i, j, k);
+}
 template <class RealT, bool WENO>
 void hostcheck_vector(const Grid &g, double dt, RealT *const u[3], const uint8_t *const act[3], const RealT *fluid, const shkz_b200_advect_params &P) {
 	std::vector<RealT> fwd[3], mn[3], mx[3];

@@ -6,6 +6,7 @@ import os
 
 import numpy as np
 import pytest
+from scipy.ndimage import minimum_filter
 
 from advect_util import advect_scenes, density_of, fluid_active, swirl
 from oracle import refio
@@ -119,11 +120,7 @@ def test_properties_at_a_size_the_reference_does_not_run_in_seconds(cuda_device)
     for d, c in enumerate((0.25, -0.5, 0.125)):
         on = sc.vel_active[d] != 0
         assert float(np.abs(out[d][on]).max()) <= abs(c) * (1 + 1e-6)
-        inner = on.copy()
-        for ax in range(3):                                               # faces whose 3-neighbourhood is all active: the stencil never meets a 0
-            for sh in (-3, -2, -1, 1, 2, 3):
-                inner &= np.roll(on, sh, axis=ax)
-        inner[:4] = inner[-4:] = False; inner[:, :4] = inner[:, -4:] = False; inner[:, :, :4] = inner[:, :, -4:] = False
+        inner = minimum_filter(on.astype(np.uint8), size=7, mode="constant", cval=0) != 0   # every face within three cells is active: no stencil meets a 0
         assert inner.any()
         assert float(np.abs(out[d][inner] - np.float32(c)).max()) <= 2e-6 * abs(c)
     sw = swirl(sc, 3.0)
