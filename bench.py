@@ -165,12 +165,13 @@ def group_kernels(table, ab):
 
 
 def kernel_source_hash():
-    """Identity of the kernel sources: profiles/traffic.json (ncu DRAM bytes per unknown and launch) is only quoted while it was
-    captured from THESE sources — a stale capture reads as null, never as a number."""
+    """Identity of the projection's kernel sources: profiles/traffic.json (ncu DRAM bytes per unknown and launch) is only quoted while it was
+    captured from THESE sources — a stale capture reads as null, never as a number. (advect.cu is a translation unit of its own and holds none of the
+    kernels the table is about.)"""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "shiokaze_b200", "csrc")
     for fn in sorted(os.listdir(d)):
-        if fn.endswith((".cuh", ".cu", ".h")):
+        if fn.endswith((".cuh", ".cu", ".h")) and fn != "advect.cu":
             with open(os.path.join(d, fn), "rb") as f:
                 h.update(fn.encode()); h.update(f.read())
     return h.hexdigest()[:16]

@@ -29,6 +29,7 @@
 #include <string.h>
 
 #include <cfloat>
+#include <cmath>
 #include <string>
 
 #include "../../include/shkz_b200.h"
@@ -63,7 +64,15 @@ constexpr int ADV_THREADS = 256;
 struct Grid {
 	int nx, ny, nz;
 	double dx;
+	double inv_dx; // != 0: dx is a power of two and x / dx == x * inv_dx bit for bit (scaling by a power of two is exact); 0: divide
 };
+__host__ __device__ __forceinline__ double over_dx(const Grid &g, double x) { return g.inv_dx != 0.0 ? x * g.inv_dx : x / g.dx; }
+inline Grid make_grid(int nx, int ny, int nz, double dx) {
+	Grid g{nx, ny, nz, dx, 0.0};
+	int e = 0;
+	if (frexp(dx, &e) == 0.5 && e > -500 && e < 500) g.inv_dx = ldexp(1.0, 1 - e);
+	return g;
+}
 __host__ __device__ __forceinline__ int fw(const Grid &g, int dim) { return g.nx + (dim == 0); }
 __host__ __device__ __forceinline__ int fh(const Grid &g, int dim) { return g.ny + (dim == 1); }
 __host__ __device__ __forceinline__ int fd(const Grid &g, int dim) { return g.nz + (dim == 2); }
@@ -75,7 +84,7 @@ template <class RealT> struct Mac {
 };
 // macarray3::operator() on a face inside the grid: the active value, else the background value 0
 template <class RealT, bool MASKED = true> HD RealT face_read(const Mac<RealT> &F, const Grid &g, int dim, int i, int j, int k) {
-	const long long n = i + (long long)fw(g, dim) * (j + (long long)fh(g, dim) * k);
+	const long long n = i + (long long)fw(g, dim) * (long long)(j + fh(g, dim) * k); // (rows x planes fits an int: one widening multiply)
 	if (!MASKED) return F.v[dim][n];
 	return F.a[dim][n] ? F.v[dim][n] : (RealT)0;
 }
@@ -193,7 +202,7 @@ template <class RealT, int DIM, bool MASKED> HD void face_full_velocity(const Ma
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
 		double u = 0.0;
-		if (c == DIM) u = (double)F.v[c][i + (long long)fw(g, c) * (j + (long long)fh(g, c) * k)];
+		if (c == DIM) u = (double)F.v[c][i + (long long)fw(g, c) * (long long)(j + fh(g, c) * k)];
 		else {
 			const int w = fw(g, c), h = fh(g, c), d = fd(g, c);
 			const int pi = i - (DIM == 0), pj = j - (DIM == 1), pk = k - (DIM == 2);
@@ -217,8 +226,8 @@ template <class RealT> HD void cell_full_velocity(const Mac<RealT> &F, const Gri
 	int valid = 0;
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
-		const long long w = fw(g, c), h = fh(g, c);
-		const long long n0 = i + w * (j + h * k), n1 = (i + (c == 0)) + w * ((j + (c == 1)) + h * (k + (c == 2)));
+		const int w = fw(g, c), h = fh(g, c);
+		const long long n0 = i + (long long)w * (long long)(j + h * k), n1 = (i + (c == 0)) + (long long)w * (long long)((j + (c == 1)) + h * (k + (c == 2)));
 		int wsum = 0;
 		double value = 0.0;
 		if (F.a[c][n0]) { value += (double)F.v[c][n0]; ++wsum; }
@@ -254,7 +263,7 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
                     RealT *out, int i, int j, int k) {
 	constexpr bool MASKED = !COMBINE; // the backward pass reads the forward result, which carries zeros on inactive faces
 	const int w = fw(g, DIM), h = fh(g, DIM), d = fd(g, DIM);
-	const long long n = i + (long long)w * (j + (long long)h * k);
+	const long long n = i + (long long)w * (long long)(j + h * k);
 	RealT ur[3];
 	face_full_velocity<RealT, DIM, MASKED>(F, g, i, j, k, ur);
 	const bool still = ur[0] == (RealT)0 && ur[1] == (RealT)0 && ur[2] == (RealT)0; // vec::empty()
@@ -266,7 +275,7 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 	if (!still) {
 		// p = vec3d(i,j,k) - dt*u/dx with u a vec3<Real>: (Real)(u*dt), then (Real)(that/dx), subtracted in double (macadvection3.cpp:86)
 		RealT tx = (RealT)((double)ur[0] * dt), ty = (RealT)((double)ur[1] * dt), tz = (RealT)((double)ur[2] * dt);
-		tx = (RealT)((double)tx / g.dx); ty = (RealT)((double)ty / g.dx); tz = (RealT)((double)tz / g.dx);
+		tx = (RealT)over_dx(g, (double)tx); ty = (RealT)over_dx(g, (double)ty); tz = (RealT)over_dx(g, (double)tz);
 		const double px = (double)i - (double)tx, py = (double)j - (double)ty, pz = (double)k - (double)tz;
 		if (WENO) value = (RealT)weno3d(w, h, d, px, py, pz, read);
 		else {
@@ -280,11 +289,11 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 	} else value = own;
 	if (RECORD) {
 		// (macadvection3.cpp:99-139) here u is read back as a vec3d: the position is formed in double throughout
-		auto fluid_read = [&](int a, int b, int c) -> RealT { return fluid[a + (long long)g.nx * (b + (long long)g.ny * c)]; };
+		auto fluid_read = [&](int a, int b, int c) -> RealT { return fluid[a + (long long)g.nx * (long long)(b + g.ny * c)]; };
 		double min_value, max_value;
 		double fx = (double)i + 0.5 * (DIM != 0), fy = (double)j + 0.5 * (DIM != 1), fz = (double)k + 0.5 * (DIM != 2);
 		if (!still) {
-			const double tx = (double)ur[0] * dt / g.dx, ty = (double)ur[1] * dt / g.dx, tz = (double)ur[2] * dt / g.dx;
+			const double tx = over_dx(g, (double)ur[0] * dt), ty = over_dx(g, (double)ur[1] * dt), tz = over_dx(g, (double)ur[2] * dt);
 			fx = fx - tx; fy = fy - ty; fz = fz - tz;
 			Stencil S;
 			clamp_position(w, h, d, (double)i - tx, (double)j - ty, (double)k - tz, S);
@@ -324,7 +333,7 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 template <class RealT, bool WENO, bool RECORD, bool COMBINE, int DIM>
 HD void advect_face_or_zero(const Grid &g, const Mac<RealT> &F, double dt, const RealT *__restrict__ fluid, double band, const FaceRecord<RealT> &R,
                             const Mac<RealT> &orig, RealT *out, int i, int j, int k) {
-	const long long n = i + (long long)fw(g, DIM) * (j + (long long)fh(g, DIM) * k);
+	const long long n = i + (long long)fw(g, DIM) * (long long)(j + fh(g, DIM) * k);
 	if (orig.a[DIM][n]) advect_face<RealT, WENO, RECORD, COMBINE, DIM>(g, F, dt, fluid, band, R, orig, out, i, j, k);
 	else if (!COMBINE) out[n] = (RealT)0;
 }
@@ -351,7 +360,7 @@ template <class RealT, bool WENO, bool RECORD, bool COMBINE>
 HD void advect_cell(const Grid &g, const RealT *__restrict__ q, const uint8_t *__restrict__ qa, const Mac<RealT> &V, double dt, const RealT *__restrict__ fluid,
                     double band, RealT *__restrict__ mn, RealT *__restrict__ mx, uint8_t *__restrict__ nb, const RealT *orig, RealT *out, RealT background,
                     int i, int j, int k) {
-	const long long n = i + (long long)g.nx * (j + (long long)g.ny * k);
+	const long long n = i + (long long)g.nx * (long long)(j + g.ny * k);
 	if (!qa[n]) {
 		// the forward result q_0 is a freshly borrowed grid of q_in's type (macadvection3.cpp:245): off the active set it reads its background value — not
 		// the flood-fill value a level set reads inside the liquid —, and the backward pass interpolates in it
@@ -361,8 +370,8 @@ HD void advect_cell(const Grid &g, const RealT *__restrict__ q, const uint8_t *_
 	RealT ur[3];
 	cell_full_velocity(V, g, i, j, k, ur);
 	const bool still = ur[0] == (RealT)0 && ur[1] == (RealT)0 && ur[2] == (RealT)0;
-	auto read = [&](int a, int b, int c) -> RealT { return q[a + (long long)g.nx * (b + (long long)g.ny * c)]; };
-	const double p[3] = {(double)i - (double)ur[0] * dt / g.dx, (double)j - (double)ur[1] * dt / g.dx, (double)k - (double)ur[2] * dt / g.dx};
+	auto read = [&](int a, int b, int c) -> RealT { return q[a + (long long)g.nx * (long long)(b + g.ny * c)]; };
+	const double p[3] = {(double)i - over_dx(g, (double)ur[0] * dt), (double)j - over_dx(g, (double)ur[1] * dt), (double)k - over_dx(g, (double)ur[2] * dt)};
 	RealT value;
 	Stencil S;
 	RealT corner[8];
@@ -376,7 +385,7 @@ HD void advect_cell(const Grid &g, const RealT *__restrict__ q, const uint8_t *_
 		else value = trilinear_corners<RealT>(S, corner);
 	} else value = q[n];
 	if (RECORD) {
-		auto fluid_read = [&](int a, int b, int c) -> RealT { return fluid[a + (long long)g.nx * (b + (long long)g.ny * c)]; };
+		auto fluid_read = [&](int a, int b, int c) -> RealT { return fluid[a + (long long)g.nx * (long long)(b + g.ny * c)]; };
 		double min_value, max_value;
 		bool within_narrowband;
 		if (!still) {
@@ -585,7 +594,7 @@ int shkz_b200_advect_create(int nx, int ny, int nz, double dx, int real, int dev
 	CK(cudaSetDevice(device));
 	shkz_b200_advect *A = new shkz_b200_advect;
 	A->device = device;
-	A->g.nx = nx; A->g.ny = ny; A->g.nz = nz; A->g.dx = dx;
+	A->g = make_grid(nx, ny, nz, dx);
 	A->real = real;
 	A->rb = real == SHKZ_B200_REAL_F64 ? 8 : 4;
 	for (auto &e : A->ev)
@@ -830,7 +839,7 @@ void hostcheck_scalar(const Grid &g, double dt, RealT *q, const uint8_t *qa, con
 } // namespace
 extern "C" int shkz_b200_hostcheck_advect_vector(int nx, int ny, int nz, double dx, int real, double dt, void *const u[3], const uint8_t *const act[3], const void *fluid,
                                                  const shkz_b200_advect_params *params) {
-	Grid g{nx, ny, nz, dx};
+	const Grid g = make_grid(nx, ny, nz, dx);
 	const shkz_b200_advect_params &P = *params;
 	if (real == SHKZ_B200_REAL_F64) {
 		double *uu[3] = {(double *)u[0], (double *)u[1], (double *)u[2]};
@@ -843,7 +852,7 @@ extern "C" int shkz_b200_hostcheck_advect_vector(int nx, int ny, int nz, double 
 }
 extern "C" int shkz_b200_hostcheck_advect_scalar(int nx, int ny, int nz, double dx, int real, double dt, void *q, const uint8_t *qa, const void *const vel[3],
                                                  const uint8_t *const vact[3], const void *fluid, const shkz_b200_advect_params *params) {
-	Grid g{nx, ny, nz, dx};
+	const Grid g = make_grid(nx, ny, nz, dx);
 	const shkz_b200_advect_params &P = *params;
 	if (real == SHKZ_B200_REAL_F64) {
 		const double *vv[3] = {(const double *)vel[0], (const double *)vel[1], (const double *)vel[2]};
