@@ -85,8 +85,9 @@ template <class RealT> struct Mac {
 // macarray3::operator() on a face inside the grid: the active value, else the background value 0
 template <class RealT, bool MASKED = true> HD RealT face_read(const Mac<RealT> &F, const Grid &g, int dim, int i, int j, int k) {
 	const long long n = i + (long long)fw(g, dim) * (long long)(j + fh(g, dim) * k); // (rows x planes fits an int: one widening multiply)
-	if (!MASKED) return F.v[dim][n];
-	return F.a[dim][n] ? F.v[dim][n] : (RealT)0;
+	const RealT v = F.v[dim][n]; // (requested together with the mask byte, not after it: the entry exists whether the face is active or not)
+	if (!MASKED) return v;
+	return F.a[dim][n] ? v : (RealT)0;
 }
 HD int clampi(int v, int n) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); }
 // std::min / std::max as the reference's library defines them (the first argument wins a tie: signed zeros keep their place)
@@ -269,6 +270,10 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 	const bool still = ur[0] == (RealT)0 && ur[1] == (RealT)0 && ur[2] == (RealT)0; // vec::empty()
 	auto read = [&](int a, int b, int c) -> RealT { return face_read<RealT, MASKED>(F, g, DIM, a, b, c); };
 	const RealT own = F.v[DIM][n];
+	// (the limiter's operands do not depend on anything computed here: requested up front, they arrive under the interpolation)
+	RealT rec_lo = (RealT)0, rec_hi = (RealT)0, before = (RealT)0;
+	uint8_t rec_nb = 0;
+	if (COMBINE) { rec_nb = R.nb[DIM][n]; rec_lo = R.mn[DIM][n]; rec_hi = R.mx[DIM][n]; before = orig.v[DIM][n]; }
 	RealT value;
 	RealT corner[8]; // the eight values of the trilinear stencil, kept for the limiter's min / max when its (double-precision) position lands in the same cell
 	int ci = -1, cj = -1, ck = -1;
@@ -316,11 +321,11 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 	}
 	if (COMBINE) {
 		// `value` is velocity_1 (the forward result traced back), F is velocity_0, orig the field before (macadvection3.cpp:163-178)
-		if (R.nb[DIM][n]) value = own;
+		if (rec_nb) value = own;
 		else {
-			const double lo = (double)R.mn[DIM][n], hi = (double)R.mx[DIM][n];
+			const double lo = (double)rec_lo, hi = (double)rec_hi;
 			const double vel0 = (double)own;
-			const RealT diff = orig.v[DIM][n] - value;
+			const RealT diff = before - value;
 			const double correction = 0.5 * (double)diff;
 			if (vel0 + correction < lo) value = (RealT)lo;
 			else if (vel0 + correction > hi) value = (RealT)hi;
@@ -342,7 +347,7 @@ HD void advect_face_or_zero(const Grid &g, const Mac<RealT> &F, double dt, const
 // seven faces of eight are inactive, and with one thread per face their index arithmetic was most of the kernel.
 constexpr int ADV_TX = 64, ADV_TY = 4;
 template <class RealT, bool WENO, bool RECORD, bool COMBINE>
-__global__ void __launch_bounds__(ADV_TX *ADV_TY) k_advect_faces(Grid g, Mac<RealT> F, double dt, const RealT *__restrict__ fluid, double band, FaceRecord<RealT> R,
+__global__ void __launch_bounds__(ADV_TX *ADV_TY, 4) k_advect_faces(Grid g, Mac<RealT> F, double dt, const RealT *__restrict__ fluid, double band, FaceRecord<RealT> R,
                                                                   Mac<RealT> orig, RealT *out0, RealT *out1, RealT *out2) {
 	int kz = blockIdx.y, dim = 0;
 	if (kz >= g.nz) { kz -= g.nz; dim = 1; if (kz >= g.nz) { kz -= g.nz; dim = 2; } }
