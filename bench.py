@@ -483,6 +483,7 @@ def advect_sub_record(torch, dev, local, sc, workload, n, steps, with_cpu):
                      f"{int(faces)} active faces of {sum(v.size for v in sc.vel)}",
            "ms_per_step": ms_step, "value": faces / (ms_step * 1e-3) / 1e6, "unit": "Mfaces/s (active faces)", "gpu_launches_per_step": launches // steps,
            "e2e_ms_per_step": float(np.mean(e2e)) * 1e3, "e2e_h2d_bytes": int(stt.h2d_bytes), "e2e_d2h_bytes": int(stt.d2h_bytes),
+           "e2e_host_copies": "sparse" if stt.host_copies else "dense",
            "roofline": {"bound": "hbm", "kernel": "k_advect_faces (forward + record, backward + limiter)", "achieved": alg / (ms_kernels * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": alg / (ms_kernels * 1e-3) / 1e9 / peak, "peak_source": peak_src, "kernels_ms": ms_kernels,
                         "algorithmic_bytes_per_active_face": ADVECT_BYTES_PER_ACTIVE_FACE, "traffic": None}}

@@ -280,7 +280,7 @@ typedef struct shkz_b200_advect_stats {
 	uint64_t kernel_launches;
 	uint64_t h2d_bytes, d2h_bytes;       /* `_host` entry points */
 	float ms_h2d, ms_advect, ms_d2h;     /* CUDA-event times */
-	float reserved;
+	uint32_t host_copies;                /* advect_vector_host: 0 = whole arrays through the copy engines, 1 = sparse (masks whole, values of active faces by kernels) */
 } shkz_b200_advect_stats;
 
 typedef struct shkz_b200_advect shkz_b200_advect; /* opaque: work arrays (forward result, limiter record) and host staging, reused across calls */
@@ -290,7 +290,10 @@ void shkz_b200_advect_default_params(shkz_b200_advect_params *params);
 /* Replaces macadvection3::initialize(shape,dx) (macadvection3.cpp:63-67). real: shkz_b200_real. */
 int shkz_b200_advect_create(int nx, int ny, int nz, double dx, int real, int device, shkz_b200_advect **out);
 void shkz_b200_advect_destroy(shkz_b200_advect *advect);
-/* u in/out (face grids), u_active their activity. `_device`: device pointers on the handle's GPU, runs on cuda_stream, returns after synchronising it. */
+/* u in/out (face grids), u_active their activity. `_device`: device pointers on the handle's GPU, runs on cuda_stream, returns after synchronising it.
+ * `_host` with page-locked u[3] (shkz_b200_host_alloc, cudaHostAlloc: what Array=b200array3 hands over) on a scene where at most half of the faces are active
+ * moves the masks whole and the VALUES OF ACTIVE FACES ONLY, both ways, by kernels that address the host buffers directly (an inactive face reads as 0 and is
+ * never written, so nothing else matters); stats.host_copies / h2d_bytes / d2h_bytes say what moved. SHKZ_B200_HOST_COPIES=dense forces whole arrays. */
 int shkz_b200_advect_vector_host(shkz_b200_advect *advect, double dt, void *const u[3], const uint8_t *const u_active[3], const void *fluid,
                                  const shkz_b200_advect_params *params, shkz_b200_advect_stats *stats);
 int shkz_b200_advect_vector_device(shkz_b200_advect *advect, double dt, void *const u[3], const uint8_t *const u_active[3], const void *fluid,

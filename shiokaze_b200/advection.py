@@ -72,6 +72,22 @@ class MacAdvection3:
         self.last_stats = st.asdict()
         return v
 
+    def advect_vector_inplace(self, u, u_active, fluid, dt: float):
+        """The same call on the caller's own buffers (contiguous arrays of this object's dtype, e.g. numpy views of page-locked memory: the library then moves
+        only the values of active faces, include/shkz_b200.h). u is overwritten on its active faces."""
+        for d in range(3):
+            if not (u[d].flags.c_contiguous and u[d].dtype == self.dtype and u[d].shape == self.face_shape(d)):
+                raise ValueError(f"face grid {d}: a contiguous {self.dtype} array of shape {self.face_shape(d)} is needed")
+            if not (u_active[d].flags.c_contiguous and u_active[d].dtype == np.uint8 and u_active[d].shape == self.face_shape(d)):
+                raise ValueError(f"face mask {d}: a contiguous uint8 array of shape {self.face_shape(d)} is needed")
+        fl = None if fluid is None else self._cells(fluid, self.dtype)
+        st = capi.AdvectStats()
+        capi.check_advect(capi.lib().shkz_b200_advect_vector_host(self._h, float(dt), (C.c_void_p * 3)(*[x.ctypes.data for x in u]),
+                                                                 (C.c_void_p * 3)(*[x.ctypes.data for x in u_active]), None if fl is None else fl.ctypes.data,
+                                                                 C.byref(self.params), C.byref(st)))
+        self.last_stats = st.asdict()
+        return self.last_stats
+
     def advect_scalar(self, q, q_active, vel, vel_active, fluid, dt: float, background: float = 0.0):
         """macadvection3_interface::advect_scalar(scalar, velocity, fluid, dt). background = scalar.get_background_value()
         (what the MacCormack forward result reads off the active set). Returns the advected cell grid (a new array)."""

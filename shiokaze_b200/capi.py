@@ -74,7 +74,7 @@ class AdvectParams(C.Structure):
 
 class AdvectStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("ms_h2d", C.c_float),
-                ("ms_advect", C.c_float), ("ms_d2h", C.c_float), ("reserved", C.c_float)]
+                ("ms_advect", C.c_float), ("ms_d2h", C.c_float), ("host_copies", C.c_uint32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}

@@ -26,6 +26,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cfloat>
@@ -441,6 +442,38 @@ template <class RealT> __global__ void __launch_bounds__(ADV_THREADS) k_copy_act
 	if (n < count && act[n]) dst[n] = src[n];
 }
 
+// ---- sparse host copies of advect_vector_host (page-locked buffers: the GPU addresses them directly) -------------------------------------------------
+// An advection reads the VALUES of active faces only (an inactive face reads as 0 whatever its entry holds) and writes active faces only, so on a liquid scene
+// — one face in eight active — the masks travel whole and the values by these kernels: four faces per thread, 16-byte accesses where all four are active.
+__global__ void __launch_bounds__(256) k_count_active(long long n, const uint8_t *__restrict__ act, unsigned long long *__restrict__ total) {
+	unsigned c = 0;
+	for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < (n + 3) >> 2; q += (long long)gridDim.x * blockDim.x) {
+		const long long f = q << 2;
+		if (f + 3 < n) { const uchar4 m = *reinterpret_cast<const uchar4 *>(act + f); c += (m.x != 0) + (m.y != 0) + (m.z != 0) + (m.w != 0); }
+		else for (long long e = f; e < n; ++e) c += act[e] != 0;
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
+}
+// dst[f] = src[f] on active faces (pull: src = host, dst = device staging; push: the other way round)
+template <class RealT>
+__global__ void __launch_bounds__(256) k_move_active(long long n, const uint8_t *__restrict__ act, const RealT *__restrict__ src, RealT *__restrict__ dst) {
+	const bool vec_ok = sizeof(RealT) == 4 && ((reinterpret_cast<unsigned long long>(src) | reinterpret_cast<unsigned long long>(dst)) & 15ull) == 0ull;
+	for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < (n + 3) >> 2; q += (long long)gridDim.x * blockDim.x) {
+		const long long f = q << 2;
+		if (f + 3 < n) {
+			const uchar4 m = *reinterpret_cast<const uchar4 *>(act + f);
+			if (!(m.x | m.y | m.z | m.w)) continue;
+			if (vec_ok && m.x && m.y && m.z && m.w) { *reinterpret_cast<float4 *>(dst + f) = *reinterpret_cast<const float4 *>(src + f); continue; }
+			if (m.x) dst[f] = src[f];
+			if (m.y) dst[f + 1] = src[f + 1];
+			if (m.z) dst[f + 2] = src[f + 2];
+			if (m.w) dst[f + 3] = src[f + 3];
+		} else for (long long e = f; e < n; ++e) if (act[e]) dst[e] = src[e];
+	}
+}
+
 struct Buf {
 	void *p = nullptr;
 	size_t bytes = 0;
@@ -471,7 +504,7 @@ struct shkz_b200_advect {
 	// work arrays of the MacCormack scheme (device): forward result, limiter record — faces [0..2], cells [3]
 	Buf fwd[4], mn[4], mx[4], nb[4];
 	// staging of the `_host` entry points
-	Buf st_val[4], st_act[4], st_fluid;
+	Buf st_val[4], st_act[4], st_fluid, st_count;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint64_t launches = 0;
 };
@@ -480,6 +513,17 @@ namespace {
 
 size_t face_count(const Grid &g, int dim) { return (size_t)fw(g, dim) * fh(g, dim) * fd(g, dim); }
 size_t cell_count(const Grid &g) { return (size_t)g.nx * g.ny * g.nz; }
+
+// device-visible address of a page-locked host buffer; nullptr for pageable memory
+void *mapped_host(const void *p) {
+	if (!p) return nullptr;
+	cudaPointerAttributes a{};
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
 
 int device_ready(int device) {
 	int n = 0;
@@ -615,7 +659,7 @@ void shkz_b200_advect_destroy(shkz_b200_advect *A) {
 	if (!A) return;
 	cudaSetDevice(A->device);
 	for (int n = 0; n < 4; ++n) { A->fwd[n].release(); A->mn[n].release(); A->mx[n].release(); A->nb[n].release(); A->st_val[n].release(); A->st_act[n].release(); }
-	A->st_fluid.release();
+	A->st_fluid.release(); A->st_count.release();
 	for (auto &e : A->ev) if (e) cudaEventDestroy(e);
 	delete A;
 }
@@ -680,20 +724,53 @@ int shkz_b200_advect_vector_host(shkz_b200_advect *A, double dt, void *const u[3
 	CK(cudaSetDevice(A->device));
 	cudaStream_t s = nullptr;
 	const Grid &g = A->g;
-	void *du[3];
+	void *du[3], *hmap[3];
 	const uint8_t *da[3];
 	uint64_t h2d = 0, d2h = 0;
+	const char *mode = getenv("SHKZ_B200_HOST_COPIES");
+	bool sparse = !(mode && !strcmp(mode, "dense"));
+	for (int dim = 0; dim < 3; ++dim) {
+		hmap[dim] = mapped_host(u[dim]);
+		if (!hmap[dim]) sparse = false;
+	}
 	CK(cudaEventRecord(A->ev[2], s));
 	for (int dim = 0; dim < 3; ++dim) {
 		const size_t nf = face_count(g, dim);
 		CKR(A->st_val[dim].need(nf * A->rb));
 		CKR(A->st_act[dim].need(nf));
-		CK(cudaMemcpyAsync(A->st_val[dim].p, u[dim], nf * A->rb, cudaMemcpyHostToDevice, s));
 		CK(cudaMemcpyAsync(A->st_act[dim].p, u_active[dim], nf, cudaMemcpyHostToDevice, s));
 		du[dim] = A->st_val[dim].p;
 		da[dim] = static_cast<const uint8_t *>(A->st_act[dim].p);
-		h2d += nf * (A->rb + 1);
+		h2d += nf;
 	}
+	uint64_t n_active = 0, n_faces = 0;
+	if (sparse) { // how many faces are active decides: above half of them the copy engines move whole arrays faster than kernels move the active entries
+		CKR(A->st_count.need(sizeof(unsigned long long)));
+		CK(cudaMemsetAsync(A->st_count.p, 0, sizeof(unsigned long long), s));
+		for (int dim = 0; dim < 3; ++dim) {
+			const long long nf = (long long)face_count(g, dim);
+			k_count_active<<<148 * 8, 256, 0, s>>>(nf, da[dim], static_cast<unsigned long long *>(A->st_count.p));
+			n_faces += nf;
+		}
+		A->launches += 3;
+		unsigned long long c = 0;
+		CK(cudaMemcpyAsync(&c, A->st_count.p, sizeof c, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		n_active = c;
+		if (2 * n_active > n_faces) sparse = false;
+	}
+	for (int dim = 0; dim < 3; ++dim) {
+		const long long nf = (long long)face_count(g, dim);
+		if (sparse) {
+			if (A->real == SHKZ_B200_REAL_F64) k_move_active<double><<<148 * 8, 256, 0, s>>>(nf, da[dim], static_cast<const double *>(hmap[dim]), static_cast<double *>(du[dim]));
+			else k_move_active<float><<<148 * 8, 256, 0, s>>>(nf, da[dim], static_cast<const float *>(hmap[dim]), static_cast<float *>(du[dim]));
+			++A->launches;
+		} else {
+			CK(cudaMemcpyAsync(du[dim], u[dim], nf * A->rb, cudaMemcpyHostToDevice, s));
+			h2d += nf * A->rb;
+		}
+	}
+	if (sparse) h2d += n_active * A->rb;
 	if (fluid) {
 		CKR(A->st_fluid.need(cell_count(g) * A->rb));
 		CK(cudaMemcpyAsync(A->st_fluid.p, fluid, cell_count(g) * A->rb, cudaMemcpyHostToDevice, s));
@@ -706,15 +783,25 @@ int shkz_b200_advect_vector_host(shkz_b200_advect *A, double dt, void *const u[3
 	CK(cudaEventElapsedTime(&ms_h2d, A->ev[2], A->ev[3]));
 	CK(cudaEventRecord(A->ev[2], s));
 	for (int dim = 0; dim < 3; ++dim) {
-		const size_t nf = face_count(g, dim);
-		CK(cudaMemcpyAsync(u[dim], A->st_val[dim].p, nf * A->rb, cudaMemcpyDeviceToHost, s));
-		d2h += nf * A->rb;
+		const long long nf = (long long)face_count(g, dim);
+		if (sparse) {
+			if (A->real == SHKZ_B200_REAL_F64) k_move_active<double><<<148 * 8, 256, 0, s>>>(nf, da[dim], static_cast<const double *>(du[dim]), static_cast<double *>(hmap[dim]));
+			else k_move_active<float><<<148 * 8, 256, 0, s>>>(nf, da[dim], static_cast<const float *>(du[dim]), static_cast<float *>(hmap[dim]));
+			++A->launches;
+		} else {
+			CK(cudaMemcpyAsync(u[dim], du[dim], nf * A->rb, cudaMemcpyDeviceToHost, s));
+			d2h += nf * A->rb;
+		}
 	}
+	if (sparse) d2h += n_active * A->rb;
+	CK(cudaGetLastError());
 	CK(cudaEventRecord(A->ev[3], s));
 	CK(cudaStreamSynchronize(s));
 	CK(cudaEventElapsedTime(&ms_d2h, A->ev[2], A->ev[3]));
 	if (stats) {
 		*stats = st;
+		stats->kernel_launches += sparse ? 9 : 0;
+		stats->host_copies = sparse ? 1 : 0;
 		stats->ms_h2d = ms_h2d; stats->ms_d2h = ms_d2h; stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
 	}
 	return SHKZ_B200_OK;

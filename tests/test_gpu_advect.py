@@ -87,6 +87,49 @@ def test_advect_scalar_equals_the_reference_bit_for_bit(cuda_device, name, flags
     assert (out[on] != q[on]).any()
 
 
+@pytest.mark.parametrize("name", ["dambreak_solid", "flip", "smoke"])
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_sparse_host_copies_equal_whole_array_copies(cuda_device, name, real, monkeypatch):
+    """Page-locked buffers: on a liquid scene only the masks and the values of active faces cross PCIe (stats say so) and the caller's buffers end up byte for
+    byte as with whole-array copies — inactive entries untouched, whatever they held; an all-active scene keeps whole-array copies."""
+    from test_gpu_host_sparse import Pinned
+    sc = SCENES[name]()
+    dtype = np.float64 if real == "f64" else np.float32
+    rng = np.random.default_rng(4)
+    junk = [np.where(a != 0, v, rng.standard_normal(v.shape)).astype(dtype) for v, a in zip(sc.vel, sc.vel_active)]   # inactive entries hold anything
+    P = Pinned()
+    try:
+        A = MacAdvection3(sc.shape, sc.dx, real=real)
+        u = [P.like(v) for v in junk]
+        act = [P.like(a.astype(np.uint8)) for a in sc.vel_active]
+        st = A.advect_vector_inplace(u, act, sc.fluid, sc.dt)
+        monkeypatch.setenv("SHKZ_B200_HOST_COPIES", "dense")
+        w = [v.copy() for v in junk]
+        st_dense = A.advect_vector_inplace(w, [a.astype(np.uint8) for a in sc.vel_active], sc.fluid, sc.dt)
+        monkeypatch.delenv("SHKZ_B200_HOST_COPIES")
+        A.close()
+        faces = sum(v.size for v in sc.vel)
+        active = sum(int(a.sum()) for a in sc.vel_active)
+        assert st_dense["host_copies"] == 0 and st_dense["d2h_bytes"] == faces * dtype().itemsize
+        if 2 * active <= faces:
+            assert st["host_copies"] == 1 and st["d2h_bytes"] == active * dtype().itemsize
+            assert st["h2d_bytes"] == faces + active * dtype().itemsize + sc.fluid.size * dtype().itemsize
+        else:
+            assert st["host_copies"] == 0
+        for d in range(3):
+            assert np.array_equal(u[d], w[d]), (name, real, d)
+            off = sc.vel_active[d] == 0
+            assert np.array_equal(u[d][off], junk[d][off])
+        ref = MacAdvection3(sc.shape, sc.dx, real=real)
+        out = ref.advect_vector(sc.vel, sc.vel_active, sc.fluid, sc.dt)   # zeros on the inactive entries instead of junk: same active values
+        ref.close()
+        for d in range(3):
+            on = sc.vel_active[d] != 0
+            assert np.array_equal(u[d][on], out[d][on])
+    finally:
+        P.free()
+
+
 def test_module_is_a_drop_in_through_the_reference_loader(cuda_device):
     """`Advection=b200advection3` loaded by the reference's own module loader (oracle/ref_driver) against `Advection=macadvection3`: same bits, all three calls."""
     need_ref()
