@@ -64,7 +64,8 @@ protected:
 	struct slot { staging<Real> values; staging<uint8_t> active; };
 	//
 	// What array3::operator() returns for every cell (active value / flood-fill value / background, array3.h:796-801), plus the activity mask
-	view dense( const array3<Real> &a, slot &s, bool want_active ) const {
+	// dense_read = false (velocity grids): the kernels read a velocity through its mask, what the inactive entries hold is never looked at — no rewrite of them
+	view dense( const array3<Real> &a, slot &s, bool want_active, bool dense_read=true ) const {
 		view v;
 		const shape3 sh = a.shape();
 		const size_t total = sh.count();
@@ -74,7 +75,7 @@ protected:
 			const size_t plane = (size_t)d.nx*d.ny;
 			const Real background = a.get_background_value();
 			Real fill = background;
-			if( d.filled ) {
+			if( d.filled && dense_read ) {
 				for( size_t n=0; n<total; ++n ) if( d.filled[n] && ! d.active[n] ) {
 					fill = a((int)(n%d.nx),(int)((n%plane)/d.nx),(int)(n/plane));
 					break;
@@ -82,7 +83,7 @@ protected:
 			}
 			const unsigned nthreads = std::max(1u,std::min((unsigned)NUM_THREAD,d.nz));
 			std::vector<std::thread> pool;
-			for( unsigned t=0; t<nthreads; ++t ) pool.emplace_back([&,t]() {
+			if( dense_read ) for( unsigned t=0; t<nthreads; ++t ) pool.emplace_back([&,t]() {
 				for( size_t n=plane*(d.nz*(size_t)t/nthreads); n<plane*(d.nz*(size_t)(t+1)/nthreads); ++n ) {
 					if( ! d.active[n] ) p[n] = (d.filled && d.filled[n]) ? fill : background;
 				}
@@ -146,7 +147,7 @@ protected:
 		void *vel_ptr[DIM3];
 		const uint8_t *act_ptr[DIM3];
 		for( int dim : DIMS3 ) {
-			vel[dim] = dense(velocity[dim],m_slot[dim],true);
+			vel[dim] = dense(velocity[dim],m_slot[dim],true,false);
 			vel_ptr[dim] = vel[dim].values; act_ptr[dim] = vel[dim].active;
 		}
 		shkz_b200_advect_params P = m_param;
@@ -167,7 +168,7 @@ protected:
 		void *vel_ptr[DIM3];
 		const uint8_t *act_ptr[DIM3];
 		for( int dim : DIMS3 ) {
-			vel[dim] = dense(u[dim],m_slot[dim],true);
+			vel[dim] = dense(u[dim],m_slot[dim],true,false);
 			vel_ptr[dim] = vel[dim].values; act_ptr[dim] = vel[dim].active;
 		}
 		shkz_b200_advect_stats st;
