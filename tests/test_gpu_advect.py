@@ -49,6 +49,26 @@ def test_advect_vector_equals_the_reference_bit_for_bit(cuda_device, name, flags
     assert moved > 0
 
 
+@pytest.mark.parametrize("case", [("dambreak_solid", 128, {}), ("dambreak_solid", 96, {"WENO": "Yes"}), ("flip_splash", 128, {}), ("smoke_plume", 96, {})], ids=lambda c: f"{c[0]}{c[1]}{IDS(c[2])}")
+def test_bit_exact_at_sizes_the_reference_still_runs_in_seconds(cuda_device, case):
+    """128^3 / 96^3 (many blocks per plane, rows longer than one walk of a block's 64 threads, multi-cell displacements across block borders): velocity, and the
+    level set carried by itself, against the reference module run live."""
+    need_ref()
+    workload, n, flags = case
+    sc = swirl(scenes.BENCH_SCENES[workload](n), 3.0, seed=21)
+    ref = refio.run_reference(sc, "f32", flags=flags, advect="vector")
+    A = MacAdvection3(sc.shape, sc.dx, **flags)
+    out = A.advect_vector(sc.vel, sc.vel_active, sc.fluid, sc.dt)
+    for d in range(3):
+        same_bits(out[d], ref.vel[d], sc.vel_active[d] != 0, (case, d))
+    if sc.fluid_raw is not None:
+        ref = refio.run_reference(sc, "f32", flags=flags, advect="levelset")
+        qa = fluid_active(sc)
+        q = A.advect_scalar(sc.fluid, qa, sc.vel, sc.vel_active, sc.fluid, sc.dt, background=float(np.float32(sc.band)))
+        same_bits(q, ref.pressure, qa != 0, (case, "levelset"))
+    A.close()
+
+
 @pytest.mark.parametrize("name", ["dambreak_solid", "smoke"])
 @pytest.mark.parametrize("flags", [{}, {"WENO": "Yes"}], ids=IDS)
 def test_advect_vector_real_double(cuda_device, name, flags):
