@@ -53,3 +53,18 @@ def density_of(sc):
     act = sc.vel_active[1][:, :sc.ny, :].copy()
     val = np.where(act != 0, sc.vel[1][:, :sc.ny, :], np.float32(0)).astype(np.float32)
     return val, act
+
+
+# flag combinations of the committed fixtures (tests/golden/advect_<scene>.npz, written by tests/golden/make_golden_advect.py from the reference build)
+GOLDEN_FLAGS = [{}, {"MacCormack": "No"}, {"WENO": "Yes"}, {"WENO": "Yes", "MacCormack": "No"}, {"TrimNarrowBand": 3}]
+
+
+def flag_key(flags):
+    return "-".join(f"{k}{v}" for k, v in flags.items()) or "default"
+
+
+def load_golden(name):
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"advect_{name}.npz")
+    return np.load(path)
+

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from advect_util import advect_scenes, density_of, fluid_active
+from advect_util import GOLDEN_FLAGS, advect_scenes, density_of, flag_key, fluid_active, load_golden
 from oracle import refio
 from shiokaze_b200 import capi
 
@@ -19,9 +19,11 @@ SCENES = advect_scenes()
 FLAGS = [{}, {"MacCormack": "No"}, {"WENO": "Yes"}, {"WENO": "Yes", "MacCormack": "No"}, {"TrimNarrowBand": 3}]
 
 
-def hostcheck():
-    if not refio.ref_available("f32"):
+def hostcheck(need_reference=True):
+    if need_reference and not refio.ref_available("f32"):
         pytest.skip("oracle/_ref (the reference build) is not here")
+    if not os.path.isfile("/usr/local/cuda/bin/nvcc") and not os.path.isfile(LIB):
+        pytest.skip("no nvcc to build the host harness with")
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)   # (no-op when __graft_entry__.build() already made it)
     return C.CDLL(LIB)
 
@@ -93,3 +95,43 @@ def test_restatement_of_advect_scalar_equals_the_reference(name, flags, mode):
     diff = q.astype(np.float64)[on] != ref.pressure[on]
     assert not diff.any(), (name, flags, mode, int(diff.sum()), int(on.sum()), float(np.abs(q.astype(np.float64)[on] - ref.pressure[on]).max()))
     assert (q[on] != q_in[on]).any()
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_host_build_equals_the_committed_goldens(name):
+    """tests/golden/advect_<scene>.npz (outputs of the reference build, tests/golden/make_golden_advect.py) against the host build of the kernel source: every
+    flag combination, velocity and both scalars. Needs no reference: this is what pins the restatement on a box that has only the repository."""
+    L = hostcheck(need_reference=False)
+    sc = SCENES[name]()
+    G = load_golden(name)
+    vel = [np.ascontiguousarray(v, dtype=np.float32) for v in sc.vel]
+    act = [np.ascontiguousarray(a, dtype=np.uint8) for a in sc.vel_active]
+    fluid = np.ascontiguousarray(sc.fluid, dtype=np.float32)
+    for flags in GOLDEN_FLAGS:
+        key = flag_key(flags)
+        u = [v.copy() for v in vel]
+        p = params(flags)
+        L.shkz_b200_hostcheck_advect_vector(sc.nx, sc.ny, sc.nz, C.c_double(sc.dx), 0, C.c_double(sc.dt), ptrs(u), ptrs(act), C.c_void_p(fluid.ctypes.data), C.byref(p))
+        for d in range(3):
+            assert np.array_equal(u[d][act[d] != 0], G[f"{key}/vector{d}"]), (name, key, d)
+        for mode in ("density", "levelset"):
+            if f"{key}/{mode}" not in G:
+                continue
+            q, qa = density_of(sc) if mode == "density" else (sc.fluid.astype(np.float32).copy(), fluid_active(sc))
+            q = np.ascontiguousarray(q).copy()
+            p = params(flags, 0.0 if mode == "density" else float(np.float32(sc.band)))
+            L.shkz_b200_hostcheck_advect_scalar(sc.nx, sc.ny, sc.nz, C.c_double(sc.dx), 0, C.c_double(sc.dt), C.c_void_p(q.ctypes.data), C.c_void_p(qa.ctypes.data), ptrs(vel),
+                                                ptrs(act), C.c_void_p(fluid.ctypes.data), C.byref(p))
+            assert np.array_equal(q[qa != 0], G[f"{key}/{mode}"]), (name, key, mode)
+
+
+def test_committed_goldens_are_what_the_reference_build_gives():
+    if not refio.ref_available("f32"):
+        pytest.skip("oracle/_ref (the reference build) is not here")
+    sc = SCENES["blobs"]()
+    G = load_golden("blobs")
+    for flags in ({}, {"WENO": "Yes"}):
+        r = refio.run_reference(sc, "f32", flags=flags, advect="vector")
+        for d in range(3):
+            assert np.array_equal(r.vel[d][sc.vel_active[d] != 0].astype(np.float32), G[f"{flag_key(flags)}/vector{d}"])
+

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 from scipy.ndimage import minimum_filter
 
-from advect_util import advect_scenes, density_of, fluid_active, swirl
+from advect_util import GOLDEN_FLAGS, advect_scenes, density_of, flag_key, fluid_active, load_golden, swirl
 from oracle import refio
 from shiokaze_b200 import MacAdvection3, scenes
 
@@ -27,6 +27,27 @@ def need_ref(real="f32"):
 def same_bits(ours, ref64, on, what):
     diff = ours.astype(np.float64)[on] != ref64[on]
     assert not diff.any(), (what, int(diff.sum()), int(on.sum()), float(np.abs(ours.astype(np.float64)[on] - ref64[on]).max()))
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_against_the_committed_goldens(cuda_device, name):
+    """tests/golden/advect_<scene>.npz — outputs of the reference build, committed (tests/golden/make_golden_advect.py) — against the CUDA kernels through the
+    C-ABI: every flag combination, velocity and both scalars, bit for bit. Needs nothing but the repository."""
+    sc = SCENES[name]()
+    G = load_golden(name)
+    for flags in GOLDEN_FLAGS:
+        key = flag_key(flags)
+        A = MacAdvection3(sc.shape, sc.dx, **flags)
+        out = A.advect_vector(sc.vel, sc.vel_active, sc.fluid, sc.dt)
+        for d in range(3):
+            assert np.array_equal(out[d][sc.vel_active[d] != 0], G[f"{key}/vector{d}"]), (name, key, d)
+        q, qa = density_of(sc)
+        assert np.array_equal(A.advect_scalar(q, qa, sc.vel, sc.vel_active, sc.fluid, sc.dt)[qa != 0], G[f"{key}/density"]), (name, key)
+        if f"{key}/levelset" in G:
+            qa = fluid_active(sc)
+            q = A.advect_scalar(sc.fluid, qa, sc.vel, sc.vel_active, sc.fluid, sc.dt, background=float(np.float32(sc.band)))
+            assert np.array_equal(q[qa != 0], G[f"{key}/levelset"]), (name, key)
+        A.close()
 
 
 @pytest.mark.parametrize("flags", FLAGS, ids=IDS)
