@@ -91,6 +91,12 @@ template <class RealT, bool MASKED = true> HD RealT face_read(const Mac<RealT> &
 	return F.a[dim][n] ? v : (RealT)0;
 }
 HD int clampi(int v, int n) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); }
+// the same read at a flat index (the callers below form a base index once and add constant strides: the index products were a fifth of the instructions)
+template <class RealT, bool MASKED> HD RealT face_at(const Mac<RealT> &F, int dim, long long n) {
+	const RealT v = F.v[dim][n];
+	if (!MASKED) return v;
+	return F.a[dim][n] ? v : (RealT)0;
+}
 // std::min / std::max as the reference's library defines them (the first argument wins a tie: signed zeros keep their place)
 HD double std_min(double a, double b) { return b < a ? b : a; }
 HD double std_max(double a, double b) { return a < b ? b : a; }
@@ -201,21 +207,24 @@ template <class Read> HD double weno3d(int w, int h, int d, double px, double py
 // MASKED = false: the field holds zeros on its inactive faces (the forward result, written by this file), no mask lookups. DIM is a template parameter so
 // that no array of pointers is ever indexed at run time (that would move the kernel parameters into local memory: the first version ran at the speed of L1).
 template <class RealT, int DIM, bool MASKED> HD void face_full_velocity(const Mac<RealT> &F, const Grid &g, int i, int j, int k, RealT ur[3]) {
+	const int p[3] = {i - (DIM == 0), j - (DIM == 1), k - (DIM == 2)};
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
 		double u = 0.0;
 		if (c == DIM) u = (double)F.v[c][i + (long long)fw(g, c) * (long long)(j + fh(g, c) * k)];
 		else {
-			const int w = fw(g, c), h = fh(g, c), d = fd(g, c);
-			const int pi = i - (DIM == 0), pj = j - (DIM == 1), pk = k - (DIM == 2);
-#pragma unroll
-			for (int ii = 0; ii < 2; ++ii)
-#pragma unroll
-				for (int jj = 0; jj < 2; ++jj) {
-					const int qi = clampi(pi + ii * (DIM == 0) + jj * (c == 0), w), qj = clampi(pj + ii * (DIM == 1) + jj * (c == 1), h),
-					          qk = clampi(pk + ii * (DIM == 2) + jj * (c == 2), d);
-					u += (double)face_read<RealT, MASKED>(F, g, c, qi, qj, qk);
-				}
+			// the four faces differ by one step along DIM (outer, ii) and one along c (inner, jj); the third axis is fixed. Every coordinate is clamped into the
+			// component's grid on its own, so the flat index is a sum of three per-axis terms, each formed once.
+			const int T = 3 - DIM - c;
+			const int ext[3] = {fw(g, c), fh(g, c), fd(g, c)};
+			const long long stride[3] = {1, ext[0], (long long)ext[0] * ext[1]};
+			const long long a0 = clampi(p[DIM], ext[DIM]) * stride[DIM], a1 = clampi(p[DIM] + 1, ext[DIM]) * stride[DIM];
+			const long long b0 = clampi(p[c], ext[c]) * stride[c], b1 = clampi(p[c] + 1, ext[c]) * stride[c];
+			const long long t0 = clampi(p[T], ext[T]) * stride[T];
+			u += (double)face_at<RealT, MASKED>(F, c, t0 + a0 + b0);
+			u += (double)face_at<RealT, MASKED>(F, c, t0 + a0 + b1);
+			u += (double)face_at<RealT, MASKED>(F, c, t0 + a1 + b0);
+			u += (double)face_at<RealT, MASKED>(F, c, t0 + a1 + b1);
 			u /= 4.0;
 		}
 		ur[c] = (RealT)u;
@@ -265,6 +274,7 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
                     RealT *out, int i, int j, int k) {
 	constexpr bool MASKED = !COMBINE; // the backward pass reads the forward result, which carries zeros on inactive faces
 	const int w = fw(g, DIM), h = fh(g, DIM), d = fd(g, DIM);
+	const long long plane = (long long)w * h;
 	const long long n = i + (long long)w * (long long)(j + h * k);
 	RealT ur[3];
 	face_full_velocity<RealT, DIM, MASKED>(F, g, i, j, k, ur);
@@ -288,14 +298,14 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 			Stencil S;
 			make_stencil(w, h, d, px, py, pz, S);
 			ci = S.i; cj = S.j; ck = S.k;
+			const long long base = S.i + (long long)w * (long long)(S.j + h * S.k);
 #pragma unroll
-			for (int e = 0; e < 8; ++e) corner[e] = read(S.i + (e & 1), S.j + ((e >> 1) & 1), S.k + (e >> 2));
+			for (int e = 0; e < 8; ++e) corner[e] = face_at<RealT, MASKED>(F, DIM, base + (e & 1) + ((e >> 1) & 1) * (long long)w + (e >> 2) * plane);
 			value = trilinear_corners<RealT>(S, corner);
 		}
 	} else value = own;
 	if (RECORD) {
 		// (macadvection3.cpp:99-139) here u is read back as a vec3d: the position is formed in double throughout
-		auto fluid_read = [&](int a, int b, int c) -> RealT { return fluid[a + (long long)g.nx * (long long)(b + g.ny * c)]; };
 		double min_value, max_value;
 		double fx = (double)i + 0.5 * (DIM != 0), fy = (double)j + 0.5 * (DIM != 1), fz = (double)k + 0.5 * (DIM != 2);
 		if (!still) {
@@ -306,16 +316,23 @@ HD void advect_face(const Grid &g, const Mac<RealT> &F, double dt, const RealT *
 			const bool same = S.i == ci && S.j == cj && S.k == ck;
 			min_value = DBL_MAX;
 			max_value = DBL_MIN;
+			const long long base = S.i + (long long)w * (long long)(S.j + h * S.k);
 #pragma unroll
 			for (int e = 0; e < 8; ++e) {
-				const double v = (double)(same ? corner[e] : read(S.i + (e & 1), S.j + ((e >> 1) & 1), S.k + (e >> 2)));
+				const double v = (double)(same ? corner[e] : face_at<RealT, MASKED>(F, DIM, base + (e & 1) + ((e >> 1) & 1) * (long long)w + (e >> 2) * plane));
 				min_value = std_min(min_value, v);
 				max_value = std_max(max_value, v);
 			}
 		} else min_value = max_value = (double)own;
 		Stencil Sf;
 		make_stencil(g.nx, g.ny, g.nz, fx - 0.5, fy - 0.5, fz - 0.5, Sf);
-		const bool within_narrowband = (double)trilinear<RealT>(Sf, fluid_read) > band;
+		RealT fc[8];
+		{
+			const long long base = Sf.i + (long long)g.nx * (long long)(Sf.j + g.ny * Sf.k), cplane = (long long)g.nx * g.ny;
+#pragma unroll
+			for (int e = 0; e < 8; ++e) fc[e] = fluid[base + (e & 1) + ((e >> 1) & 1) * (long long)g.nx + (e >> 2) * cplane];
+		}
+		const bool within_narrowband = (double)trilinear_corners<RealT>(Sf, fc) > band;
 		R.mn[DIM][n] = (RealT)min_value;
 		R.mx[DIM][n] = (RealT)max_value;
 		R.nb[DIM][n] = within_narrowband ? 1 : 0;
@@ -381,17 +398,19 @@ HD void advect_cell(const Grid &g, const RealT *__restrict__ q, const uint8_t *_
 	RealT value;
 	Stencil S;
 	RealT corner[8];
+	const long long cplane = (long long)g.nx * g.ny;
+	long long cbase = 0;
 	if (!still) {
 		if (!WENO || RECORD) {
 			make_stencil(g.nx, g.ny, g.nz, p[0], p[1], p[2], S);
+			cbase = S.i + (long long)g.nx * (long long)(S.j + g.ny * S.k);
 #pragma unroll
-			for (int e = 0; e < 8; ++e) corner[e] = read(S.i + (e & 1), S.j + ((e >> 1) & 1), S.k + (e >> 2));
+			for (int e = 0; e < 8; ++e) corner[e] = q[cbase + (e & 1) + ((e >> 1) & 1) * (long long)g.nx + (e >> 2) * cplane];
 		}
 		if (WENO) value = (RealT)weno3d(g.nx, g.ny, g.nz, p[0], p[1], p[2], read);
 		else value = trilinear_corners<RealT>(S, corner);
 	} else value = q[n];
 	if (RECORD) {
-		auto fluid_read = [&](int a, int b, int c) -> RealT { return fluid[a + (long long)g.nx * (long long)(b + g.ny * c)]; };
 		double min_value, max_value;
 		bool within_narrowband;
 		if (!still) {
@@ -403,7 +422,10 @@ HD void advect_cell(const Grid &g, const RealT *__restrict__ q, const uint8_t *_
 				min_value = std_min(min_value, v);
 				max_value = std_max(max_value, v);
 			}
-			within_narrowband = (double)trilinear<RealT>(S, fluid_read) > band; // (same shape, same position: same weights)
+			RealT fc[8]; // (same shape, same position: same weights, same flat indices)
+#pragma unroll
+			for (int e = 0; e < 8; ++e) fc[e] = fluid[cbase + (e & 1) + ((e >> 1) & 1) * (long long)g.nx + (e >> 2) * cplane];
+			within_narrowband = (double)trilinear_corners<RealT>(S, fc) > band;
 		} else {
 			min_value = max_value = (double)q[n];
 			within_narrowband = (double)fluid[n] > band;

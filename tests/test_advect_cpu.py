@@ -135,3 +135,27 @@ def test_committed_goldens_are_what_the_reference_build_gives():
         for d in range(3):
             assert np.array_equal(r.vel[d][sc.vel_active[d] != 0].astype(np.float32), G[f"{flag_key(flags)}/vector{d}"])
 
+
+@pytest.mark.parametrize("shape", [(2, 3, 2), (5, 2, 3), (9, 4, 17)])
+def test_restatement_on_tiny_and_ragged_grids(shape):
+    """The smallest grids the reference's interpolation is defined on (every stencil clamped at a wall), ragged activity, displacements beyond the grid:
+    host build of the kernel source against the reference module run live."""
+    L = hostcheck()
+    from shiokaze_b200 import scenes
+    nx, ny, nz = shape
+    sc = scenes.random_blobs(nx, ny, nz, seed=2, with_solid=False)
+    rng = np.random.default_rng(5)
+    vel = [np.where(a != 0, rng.standard_normal(v.shape) * 3.0, 0).astype(np.float32) for v, a in zip(sc.vel, sc.vel_active)]
+    import dataclasses
+    sc = dataclasses.replace(sc, vel=vel, dt=0.37)
+    for flags in ({}, {"WENO": "Yes"}):
+        ref = refio.run_reference(sc, "f32", flags=flags, advect="vector")
+        u = [v.copy() for v in vel]
+        act = [np.ascontiguousarray(a, dtype=np.uint8) for a in sc.vel_active]
+        fluid = np.ascontiguousarray(sc.fluid, dtype=np.float32)
+        p = params(flags)
+        L.shkz_b200_hostcheck_advect_vector(nx, ny, nz, C.c_double(sc.dx), 0, C.c_double(sc.dt), ptrs(u), ptrs(act), C.c_void_p(fluid.ctypes.data), C.byref(p))
+        for d in range(3):
+            on = act[d] != 0
+            assert np.array_equal(u[d].astype(np.float64)[on], ref.vel[d][on]), (shape, flags, d)
+

@@ -217,6 +217,34 @@ def test_properties_at_a_size_the_reference_does_not_run_in_seconds(cuda_device)
     A.close()
 
 
+def test_edge_cases(cuda_device):
+    """No active face at all; a zero time step; the smallest grid the library takes (2 x 3 x 2, every stencil clamped at a wall), ragged extents."""
+    rng = np.random.default_rng(8)
+    for shape in ((2, 3, 2), (5, 2, 3), (33, 7, 65)):
+        nx, ny, nz = shape
+        A = MacAdvection3(shape, 1.0 / max(shape))
+        fs = [A.face_shape(d) for d in range(3)]
+        vel = [rng.standard_normal(f).astype(np.float32) for f in fs]
+        none = [np.zeros(f, np.uint8) for f in fs]
+        fluid = rng.standard_normal((nz, ny, nx)).astype(np.float32)
+        out = A.advect_vector(vel, none, fluid, 0.1)
+        assert all(np.array_equal(o, v) for o, v in zip(out, vel))                      # nothing active: nothing written
+        q = rng.standard_normal((nz, ny, nx)).astype(np.float32)
+        assert np.array_equal(A.advect_scalar(q, np.zeros((nz, ny, nx), np.uint8), vel, none, fluid, 0.1), q)
+        every = [np.ones(f, np.uint8) for f in fs]
+        out = A.advect_vector(vel, every, fluid, 0.0)                                   # dt = 0: every position is a grid point, weight 1 on itself
+        assert all(np.array_equal(o, v) for o, v in zip(out, vel))
+        assert np.array_equal(A.advect_scalar(q, np.ones((nz, ny, nx), np.uint8), vel, every, fluid, 0.0), q)
+        some = [(rng.random(f) < 0.6).astype(np.uint8) for f in fs]                     # ragged activity, displacements far beyond the grid: clamped, finite
+        out = A.advect_vector(vel, some, fluid, 50.0)
+        for d in range(3):
+            assert np.isfinite(out[d]).all()
+            assert np.array_equal(out[d][some[d] == 0], vel[d][some[d] == 0])
+            lo, hi = min(0.0, float(vel[d].min())), max(0.0, float(vel[d].max()))
+            assert lo <= float(out[d].min()) and float(out[d].max()) <= hi
+        A.close()
+
+
 def test_argument_errors(cuda_device):
     import ctypes as C
     from shiokaze_b200 import capi
