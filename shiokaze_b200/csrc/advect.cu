@@ -639,6 +639,59 @@ int scalar_device(shkz_b200_advect *A, double dt, void *q, const uint8_t *qact, 
 	return SHKZ_B200_OK;
 }
 
+// Face grids of a `_host` call -> device staging: the masks whole; the values whole through the copy engines, or — page-locked buffers, at most half of the
+// faces active, SHKZ_B200_HOST_COPIES != dense — only those of the active faces, by a kernel that reads the host buffers directly. *sparse tells which it was.
+int upload_faces(shkz_b200_advect *A, const void *const val[3], const uint8_t *const act[3], cudaStream_t s, void *dval[3], const uint8_t *dact[3], void *hmap[3],
+                 bool *sparse, uint64_t *n_active, uint64_t *h2d) {
+	const Grid &g = A->g;
+	const char *mode = getenv("SHKZ_B200_HOST_COPIES");
+	*sparse = !(mode && !strcmp(mode, "dense"));
+	for (int dim = 0; dim < 3; ++dim) {
+		hmap[dim] = mapped_host(val[dim]);
+		if (!hmap[dim]) *sparse = false;
+	}
+	for (int dim = 0; dim < 3; ++dim) {
+		const size_t nf = face_count(g, dim);
+		CKR(A->st_val[dim].need(nf * A->rb));
+		CKR(A->st_act[dim].need(nf));
+		CK(cudaMemcpyAsync(A->st_act[dim].p, act[dim], nf, cudaMemcpyHostToDevice, s));
+		dval[dim] = A->st_val[dim].p;
+		dact[dim] = static_cast<const uint8_t *>(A->st_act[dim].p);
+		*h2d += nf;
+	}
+	uint64_t n_faces = 0;
+	*n_active = 0;
+	if (*sparse) { // how many faces are active decides: above half of them the copy engines move whole arrays faster than kernels move the active entries
+		CKR(A->st_count.need(sizeof(unsigned long long)));
+		CK(cudaMemsetAsync(A->st_count.p, 0, sizeof(unsigned long long), s));
+		for (int dim = 0; dim < 3; ++dim) {
+			const long long nf = (long long)face_count(g, dim);
+			k_count_active<<<148 * 8, 256, 0, s>>>(nf, dact[dim], static_cast<unsigned long long *>(A->st_count.p));
+			n_faces += nf;
+		}
+		A->launches += 3;
+		unsigned long long c = 0;
+		CK(cudaMemcpyAsync(&c, A->st_count.p, sizeof c, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		*n_active = c;
+		if (2 * c > n_faces) *sparse = false;
+	}
+	for (int dim = 0; dim < 3; ++dim) {
+		const long long nf = (long long)face_count(g, dim);
+		if (*sparse) {
+			if (A->real == SHKZ_B200_REAL_F64) k_move_active<double><<<148 * 8, 256, 0, s>>>(nf, dact[dim], static_cast<const double *>(hmap[dim]), static_cast<double *>(dval[dim]));
+			else k_move_active<float><<<148 * 8, 256, 0, s>>>(nf, dact[dim], static_cast<const float *>(hmap[dim]), static_cast<float *>(dval[dim]));
+			++A->launches;
+		} else {
+			CK(cudaMemcpyAsync(dval[dim], val[dim], nf * A->rb, cudaMemcpyHostToDevice, s));
+			*h2d += nf * A->rb;
+		}
+	}
+	if (*sparse) *h2d += *n_active * A->rb;
+	CK(cudaGetLastError());
+	return SHKZ_B200_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -748,51 +801,10 @@ int shkz_b200_advect_vector_host(shkz_b200_advect *A, double dt, void *const u[3
 	const Grid &g = A->g;
 	void *du[3], *hmap[3];
 	const uint8_t *da[3];
-	uint64_t h2d = 0, d2h = 0;
-	const char *mode = getenv("SHKZ_B200_HOST_COPIES");
-	bool sparse = !(mode && !strcmp(mode, "dense"));
-	for (int dim = 0; dim < 3; ++dim) {
-		hmap[dim] = mapped_host(u[dim]);
-		if (!hmap[dim]) sparse = false;
-	}
+	uint64_t h2d = 0, d2h = 0, n_active = 0;
+	bool sparse = false;
 	CK(cudaEventRecord(A->ev[2], s));
-	for (int dim = 0; dim < 3; ++dim) {
-		const size_t nf = face_count(g, dim);
-		CKR(A->st_val[dim].need(nf * A->rb));
-		CKR(A->st_act[dim].need(nf));
-		CK(cudaMemcpyAsync(A->st_act[dim].p, u_active[dim], nf, cudaMemcpyHostToDevice, s));
-		du[dim] = A->st_val[dim].p;
-		da[dim] = static_cast<const uint8_t *>(A->st_act[dim].p);
-		h2d += nf;
-	}
-	uint64_t n_active = 0, n_faces = 0;
-	if (sparse) { // how many faces are active decides: above half of them the copy engines move whole arrays faster than kernels move the active entries
-		CKR(A->st_count.need(sizeof(unsigned long long)));
-		CK(cudaMemsetAsync(A->st_count.p, 0, sizeof(unsigned long long), s));
-		for (int dim = 0; dim < 3; ++dim) {
-			const long long nf = (long long)face_count(g, dim);
-			k_count_active<<<148 * 8, 256, 0, s>>>(nf, da[dim], static_cast<unsigned long long *>(A->st_count.p));
-			n_faces += nf;
-		}
-		A->launches += 3;
-		unsigned long long c = 0;
-		CK(cudaMemcpyAsync(&c, A->st_count.p, sizeof c, cudaMemcpyDeviceToHost, s));
-		CK(cudaStreamSynchronize(s));
-		n_active = c;
-		if (2 * n_active > n_faces) sparse = false;
-	}
-	for (int dim = 0; dim < 3; ++dim) {
-		const long long nf = (long long)face_count(g, dim);
-		if (sparse) {
-			if (A->real == SHKZ_B200_REAL_F64) k_move_active<double><<<148 * 8, 256, 0, s>>>(nf, da[dim], static_cast<const double *>(hmap[dim]), static_cast<double *>(du[dim]));
-			else k_move_active<float><<<148 * 8, 256, 0, s>>>(nf, da[dim], static_cast<const float *>(hmap[dim]), static_cast<float *>(du[dim]));
-			++A->launches;
-		} else {
-			CK(cudaMemcpyAsync(du[dim], u[dim], nf * A->rb, cudaMemcpyHostToDevice, s));
-			h2d += nf * A->rb;
-		}
-	}
-	if (sparse) h2d += n_active * A->rb;
+	CKR(upload_faces(A, u, u_active, s, du, da, hmap, &sparse, &n_active, &h2d));
 	if (fluid) {
 		CKR(A->st_fluid.need(cell_count(g) * A->rb));
 		CK(cudaMemcpyAsync(A->st_fluid.p, fluid, cell_count(g) * A->rb, cudaMemcpyHostToDevice, s));
@@ -840,20 +852,12 @@ int shkz_b200_advect_scalar_host(shkz_b200_advect *A, double dt, void *q, const 
 	cudaStream_t s = nullptr;
 	const Grid &g = A->g;
 	const size_t nc = cell_count(g);
-	void *dv[3];
+	void *dv[3], *hmap[3];
 	const uint8_t *da[3];
-	uint64_t h2d = 0;
+	uint64_t h2d = 0, n_active = 0;
+	bool sparse = false;
 	CK(cudaEventRecord(A->ev[2], s));
-	for (int dim = 0; dim < 3; ++dim) {
-		const size_t nf = face_count(g, dim);
-		CKR(A->st_val[dim].need(nf * A->rb));
-		CKR(A->st_act[dim].need(nf));
-		CK(cudaMemcpyAsync(A->st_val[dim].p, vel[dim], nf * A->rb, cudaMemcpyHostToDevice, s));
-		CK(cudaMemcpyAsync(A->st_act[dim].p, vel_active[dim], nf, cudaMemcpyHostToDevice, s));
-		dv[dim] = A->st_val[dim].p;
-		da[dim] = static_cast<const uint8_t *>(A->st_act[dim].p);
-		h2d += nf * (A->rb + 1);
-	}
+	CKR(upload_faces(A, vel, vel_active, s, dv, da, hmap, &sparse, &n_active, &h2d)); // (the velocity is only read: nothing of it travels back)
 	CKR(A->st_val[3].need(nc * A->rb));
 	CKR(A->st_act[3].need(nc));
 	CK(cudaMemcpyAsync(A->st_val[3].p, q, nc * A->rb, cudaMemcpyHostToDevice, s));
@@ -878,6 +882,8 @@ int shkz_b200_advect_scalar_host(shkz_b200_advect *A, double dt, void *q, const 
 	CK(cudaEventElapsedTime(&ms_d2h, A->ev[2], A->ev[3]));
 	if (stats) {
 		*stats = st;
+		stats->kernel_launches += sparse ? 6 : 0;
+		stats->host_copies = sparse ? 1 : 0;
 		stats->ms_h2d = ms_h2d; stats->ms_d2h = ms_d2h; stats->h2d_bytes = h2d; stats->d2h_bytes = nc * A->rb;
 	}
 	return SHKZ_B200_OK;

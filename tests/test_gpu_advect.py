@@ -143,6 +143,9 @@ def test_sparse_host_copies_equal_whole_array_copies(cuda_device, name, real, mo
         A = MacAdvection3(sc.shape, sc.dx, real=real)
         u = [P.like(v) for v in junk]
         act = [P.like(a.astype(np.uint8)) for a in sc.vel_active]
+        q0, qa = density_of(sc)
+        q_sparse = A.advect_scalar(q0.astype(dtype), qa, u, act, sc.fluid, sc.dt)          # the velocity of a scalar call travels the same way (and only one way)
+        st_scalar = dict(A.last_stats)
         st = A.advect_vector_inplace(u, act, sc.fluid, sc.dt)
         monkeypatch.setenv("SHKZ_B200_HOST_COPIES", "dense")
         w = [v.copy() for v in junk]
@@ -163,6 +166,8 @@ def test_sparse_host_copies_equal_whole_array_copies(cuda_device, name, real, mo
             assert np.array_equal(u[d][off], junk[d][off])
         ref = MacAdvection3(sc.shape, sc.dx, real=real)
         out = ref.advect_vector(sc.vel, sc.vel_active, sc.fluid, sc.dt)   # zeros on the inactive entries instead of junk: same active values
+        assert np.array_equal(ref.advect_scalar(q0.astype(dtype), qa, sc.vel, sc.vel_active, sc.fluid, sc.dt), q_sparse)
+        assert st_scalar["host_copies"] == (1 if 2 * active <= faces else 0) and ref.last_stats["host_copies"] == 0
         ref.close()
         for d in range(3):
             on = sc.vel_active[d] != 0
