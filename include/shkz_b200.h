@@ -87,7 +87,9 @@ typedef struct shkz_b200_params {
 	double mg_omega;              /* relaxation factor of the red-black sweeps, 0 < omega < 2 (1 = Gauss-Seidel; default 1.15) */
 	int32_t extrapolate_width;    /* > 0: project() ends with shkz_b200_extrapolate_constrain on the velocity it still holds on the device (default 0: the
 	                                 host's own macutility3::extrapolate_and_constrain_velocity call does it, as with the reference module) */
-	int32_t reserved;
+	int32_t velocity_masked;      /* nonzero: the ENTRIES of inactive faces in vel[] are unspecified on input and on output — the library reads an inactive face as 0, the
+	                                 background value of the simulators' velocity grids (what a dense array core hands over in place holds stale values there;
+	                                 default 0: every entry is what array3::operator() returns) */
 } shkz_b200_params;
 
 typedef struct shkz_b200_stats {

@@ -37,7 +37,7 @@ class Params(C.Structure):
                 ("mg_pre_sweeps", C.c_int32), ("mg_post_sweeps", C.c_int32), ("mg_coarse_sweeps", C.c_int32),
                 ("mg_min_size", C.c_int32), ("check_every", C.c_int32), ("mg_coarse_scale", C.c_double),
                 ("mg_gamma", C.c_int32), ("warm_start", C.c_int32), ("mg_omega", C.c_double),
-                ("extrapolate_width", C.c_int32), ("reserved", C.c_int32)]
+                ("extrapolate_width", C.c_int32), ("velocity_masked", C.c_int32)]
 
 
 class Stats(C.Structure):

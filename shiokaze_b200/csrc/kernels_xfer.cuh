@@ -45,40 +45,65 @@ __global__ void __launch_bounds__(TX * 4) k_flag_wet_slices(Dims d, XferGeom g, 
 	}
 }
 
-// rows [j0, j0+nj) x planes [k0, k0+nk) x columns [i0, i0+ni) of a W x H x * array: one row per warp at a time, lanes along x
+// rows [j0, j0+nj) x planes [k0, k0+nk) x columns [i0, i0+ni) of a W x H x * array: one row per warp at a time, lanes along x.
+// mask != nullptr (params.velocity_masked: the entries of inactive faces are unspecified): a face whose mask byte is 0 arrives as 0, the value an
+// inactive face of the simulators' velocity grids reads as.
 template <class T>
-__device__ __forceinline__ void copy_box(const T *__restrict__ src, T *__restrict__ dst, long long W, long long H, int i0, int j0, int k0, int ni, int nj, int nk) {
+__device__ __forceinline__ void copy_box(const T *__restrict__ src, T *__restrict__ dst, long long W, long long H, int i0, int j0, int k0, int ni, int nj, int nk,
+                                         const uint8_t *__restrict__ mask = nullptr) {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 	for (int row = warp; row < nj * nk; row += nwarps) {
 		const int jj = row % nj, kk = row / nj;
 		const long long base = i0 + W * ((j0 + jj) + H * (long long)(k0 + kk));
 		T v[3];
+		uint8_t m[3] = {1, 1, 1};
 #pragma unroll
 		for (int u = 0; u < 3; ++u) {
 			const int c = lane + 32 * u;
-			if (c < ni) v[u] = src[base + c];
+			if (c < ni) {
+				v[u] = src[base + c];
+				if (mask) m[u] = mask[base + c];
+			}
 		}
 #pragma unroll
 		for (int u = 0; u < 3; ++u) {
 			const int c = lane + 32 * u;
-			if (c < ni) dst[base + c] = v[u];
+			if (c < ni) dst[base + c] = m[u] ? v[u] : (T)0;
 		}
+	}
+}
+
+// v = 0 where the mask byte is 0 (params.velocity_masked on whole arrays already on the device; `act` may also be a mapped host pointer)
+template <class RealT>
+__global__ void __launch_bounds__(256) k_zero_inactive(long long n, RealT *__restrict__ v, const uint8_t *__restrict__ act) {
+	const bool vec_ok = (reinterpret_cast<unsigned long long>(act) & 3ull) == 0ull;
+	for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < (n + 3) >> 2; q += (long long)gridDim.x * blockDim.x) {
+		const long long f = q << 2;
+		if (vec_ok && f + 3 < n) {
+			const uchar4 m = *reinterpret_cast<const uchar4 *>(act + f);
+			if (!m.x) v[f] = (RealT)0;
+			if (!m.y) v[f + 1] = (RealT)0;
+			if (!m.z) v[f + 2] = (RealT)0;
+			if (!m.w) v[f + 3] = (RealT)0;
+		} else
+			for (long long e = f; e < n && e < f + 4; ++e)
+				if (!act[e]) v[e] = (RealT)0;
 	}
 }
 
 // the six faces and the eight nodes of every cell of the flagged blocks, host -> device staging (same dense layouts on both sides)
 template <class RealT>
 __global__ void __launch_bounds__(256) k_pull_slices(Dims d, XferGeom g, const int *__restrict__ list, const int *__restrict__ count, ConstFaceGrids<RealT> hvel,
-                                                      FaceGrids<RealT> dvel, const RealT *__restrict__ hsolid, RealT *__restrict__ dsolid) {
+                                                      FaceGrids<RealT> dvel, const RealT *__restrict__ hsolid, RealT *__restrict__ dsolid, FaceMasks hmask) {
 	static_assert(TX + 1 <= 96, "copy_box moves at most 96 columns");
 	const int n = *count;
 	for (int u = blockIdx.x; u < n; u += gridDim.x) {
 		const int s = list[u], tx = s % g.ntx, r = s / g.ntx;
 		const int i0 = tx * TX, j0 = (r % g.nty) * TY, k0 = (r / g.nty) * g.slice;
 		const int ni = min(TX, d.nx - i0), nj = min(TY, d.ny - j0), nk = min(g.slice, d.nzl - k0);
-		copy_box(hvel.p[0], dvel.p[0], d.nx + 1, d.ny, i0, j0, k0, ni + 1, nj, nk);
-		copy_box(hvel.p[1], dvel.p[1], d.nx, d.ny + 1, i0, j0, k0, ni, nj + 1, nk);
-		copy_box(hvel.p[2], dvel.p[2], d.nx, d.ny, i0, j0, k0, ni, nj, nk + 1);
+		copy_box(hvel.p[0], dvel.p[0], d.nx + 1, d.ny, i0, j0, k0, ni + 1, nj, nk, hmask.p[0]); // (hmask.p: the caller's masks, or null: values as they are)
+		copy_box(hvel.p[1], dvel.p[1], d.nx, d.ny + 1, i0, j0, k0, ni, nj + 1, nk, hmask.p[1]);
+		copy_box(hvel.p[2], dvel.p[2], d.nx, d.ny, i0, j0, k0, ni, nj, nk + 1, hmask.p[2]);
 		if (hsolid) copy_box(hsolid, dsolid, d.nx + 1, d.ny + 1, i0, j0, k0, ni + 1, nj + 1, nk + 1);
 	}
 }

@@ -1267,7 +1267,8 @@ static void *mapped_host(const void *p) {
 // they are most of the grid — pull velocity and solid nodes around them straight out of the caller's page-locked buffers and send the masks after them on
 // copy_stream. *sparse = false leaves everything but the level set to the whole-array copies. pulled = bytes read from host memory by k_pull_slices.
 template <class RealT>
-static int host_sparse_upload(shkz_b200_solver *S, void *const hvel[3], uint8_t *const vel_active[3], const void *hsolid, cudaStream_t stream, bool *sparse, uint64_t *pulled) {
+static int host_sparse_upload(shkz_b200_solver *S, void *const hvel[3], uint8_t *const vel_active[3], const void *hsolid, cudaStream_t stream, bool *sparse, uint64_t *pulled,
+                              void *const masked[3]) { // masked: device-visible addresses of the caller's masks when params.velocity_masked, else null
 	const Dims &d = S->d;
 	XferGeom g{};
 	g.ntx = (d.nx + TX - 1) / TX; g.nty = (d.ny + TY - 1) / TY;
@@ -1295,8 +1296,10 @@ static int host_sparse_upload(shkz_b200_solver *S, void *const hvel[3], uint8_t 
 			dv.p[dim] = static_cast<RealT *>(S->st_vel[dim].base);
 		}
 		const int pgrid = (int)(wet < 8ull * S->num_sms ? wet : 8ull * S->num_sms);
+		FaceMasks hm;
+		for (int dim = 0; dim < 3; ++dim) hm.p[dim] = masked ? static_cast<uint8_t *>(masked[dim]) : nullptr;
 		LAUNCH(S, "pull_slices", k_pull_slices<RealT>, pgrid, 256, stream, d, g, static_cast<const int *>(S->xf_list.base), static_cast<const int *>(S->xf_count.base), hv, dv,
-		       static_cast<const RealT *>(hsolid), static_cast<RealT *>(S->st_solid.base));
+		       static_cast<const RealT *>(hsolid), static_cast<RealT *>(S->st_solid.base), hm);
 	}
 	if (!S->whole_grid) {
 		// z-slab: the z faces of plane 0 and plane nzl are shared with the neighbouring slabs and finished by BOTH sides (the host keeps the upper slab's copy):
@@ -1308,6 +1311,11 @@ static int host_sparse_upload(shkz_b200_solver *S, void *const hvel[3], uint8_t 
 		CK(cudaMemcpyAsync(dw, hw, fplane * rbs, cudaMemcpyHostToDevice, stream));
 		CK(cudaMemcpyAsync(dw + fplane * d.nzl, hw + fplane * d.nzl, fplane * rbs, cudaMemcpyHostToDevice, stream));
 		*pulled += 2 * fplane * rbs;
+		if (masked) {
+			const uint8_t *hm = static_cast<const uint8_t *>(masked[2]);
+			LAUNCH(S, "zero_inactive", k_zero_inactive<RealT>, flat_blocks((long long)(fplane + 3) / 4), 256, stream, (long long)fplane, dw, hm);
+			LAUNCH(S, "zero_inactive", k_zero_inactive<RealT>, flat_blocks((long long)(fplane + 3) / 4), 256, stream, (long long)fplane, dw + fplane * d.nzl, hm + fplane * d.nzl);
+		}
 		if (hsolid) {
 			const RealT *hs = static_cast<const RealT *>(hsolid);
 			RealT *ds = static_cast<RealT *>(S->st_solid.base);
@@ -1318,6 +1326,7 @@ static int host_sparse_upload(shkz_b200_solver *S, void *const hvel[3], uint8_t 
 	}
 	const uint64_t per_block = (uint64_t)((TX + 1) * TY * g.slice + TX * (TY + 1) * g.slice + TX * TY * (g.slice + 1) + (hsolid ? (TX + 1) * (TY + 1) * (g.slice + 1) : 0));
 	*pulled += (uint64_t)wet * per_block * sizeof(RealT); // (blocks on the grid's upper edges are smaller: an upper bound by a few percent)
+	if (masked) *pulled += (uint64_t)wet * (uint64_t)((TX + 1) * TY * g.slice + TX * (TY + 1) * g.slice + TX * TY * (g.slice + 1)); // the mask bytes of the same faces
 	// the masks are first needed by the velocity update: they cross PCIe after the pull and behind assembly and solve
 	CK(cudaEventRecord(S->ev[10], stream));
 	CK(cudaStreamWaitEvent(S->copy_stream, S->ev[10], 0));
@@ -1504,6 +1513,16 @@ int shkz_b200_project_device(shkz_b200_solver *S, double dt, void *const vel[3],
 	if (!fn) return fail(SHKZ_B200_ERR_ARG, "unsupported real/precision combination");
 	if (stats) memset(stats, 0, sizeof *stats);
 	S->launches = 0;
+	if (P.velocity_masked && !S->xfer_sparse) {
+		// the entries of inactive faces are unspecified: make them what an inactive face reads as before anything looks at them (a sparse host call has done
+		// this while pulling the values it needs, kernels_xfer.cuh)
+		cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+		for (int dim = 0; dim < 3; ++dim) {
+			const long long nf = (long long)face_count(S->d, dim);
+			if (S->real == SHKZ_B200_REAL_F32) { LAUNCH(S, "zero_inactive", k_zero_inactive<float>, flat_blocks((nf + 3) / 4), 256, stream, nf, static_cast<float *>(vel[dim]), (const uint8_t *)vel_active[dim]); }
+			else { LAUNCH(S, "zero_inactive", k_zero_inactive<double>, flat_blocks((nf + 3) / 4), 256, stream, nf, static_cast<double *>(vel[dim]), (const uint8_t *)vel_active[dim]); }
+		}
+	}
 	const int rc = fn(S, dt, vel, vel_active, solid, fluid, fluid_levelset, P, pressure, pressure_active, stats, static_cast<cudaStream_t>(cuda_stream));
 	// a z-slab call that fails on this rank's host must not leave the other ranks' kernels spinning on planes that will never arrive
 	if (rc != SHKZ_B200_OK && rc != SHKZ_B200_ERR_COMM && !S->whole_grid && S->comm) S->comm->raise_abort();
@@ -1560,8 +1579,8 @@ static int project_host_impl(shkz_b200_solver *S, double dt, void *const vel[3],
 	CK(cudaMemcpyAsync(S->st_fluid.base, fluid, ncell * rb, cudaMemcpyHostToDevice, stream));
 	h2d += ncell * rb;
 	if (sparse) {
-		if (S->real == SHKZ_B200_REAL_F32) CKR((host_sparse_upload<float>(S, mvel, vel_active, msolid, stream, &sparse, &pulled)));
-		else CKR((host_sparse_upload<double>(S, mvel, vel_active, msolid, stream, &sparse, &pulled)));
+		if (S->real == SHKZ_B200_REAL_F32) CKR((host_sparse_upload<float>(S, mvel, vel_active, msolid, stream, &sparse, &pulled, P.velocity_masked ? mact : nullptr)));
+		else CKR((host_sparse_upload<double>(S, mvel, vel_active, msolid, stream, &sparse, &pulled, P.velocity_masked ? mact : nullptr)));
 	}
 	for (int dim = 0; dim < 3; ++dim) h2d += face_count(d, dim);
 	if (sparse) {

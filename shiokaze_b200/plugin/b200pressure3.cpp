@@ -92,10 +92,12 @@ protected:
 	// Zero-copy view of a grid whose core is b200array3 (`Array=b200array3`, plugin/b200array3.cpp): its value buffer and its one-byte-per-cell activity
 	// mask ARE the dense buffers the C-ABI takes, page-locked. Entries of inactive cells are first rewritten to what array3::operator() returns for them
 	// (fill value inside, background outside: array3.h:796-801) — a plain threaded sweep over memory instead of one std::function call per cell.
-	static bool dense_view( const array3<Real> &a, Real *&values, uint8_t *&active ) {
+	// as_they_are: hand the buffers over without that sweep (velocity grids with params.velocity_masked: the library reads an inactive face as 0 itself)
+	static bool dense_view( const array3<Real> &a, Real *&values, uint8_t *&active, bool as_they_are=false ) {
 		b200_dense_descriptor d;
 		if( ! a.const_send_message(B200_DENSE_MESSAGE,&d) || ! d.pinned || d.element_bytes != sizeof(Real) || ! d.values ) return false;
 		Real *v = static_cast<Real *>(d.values);
+		if( as_they_are ) { values = v; active = d.active; return true; }
 		const size_t plane = (size_t)d.nx*d.ny;
 		const Real background = a.get_background_value();
 		Real fill = background;
@@ -132,8 +134,17 @@ protected:
 		Real *vel[DIM3], *solid_dense (nullptr), *fluid_dense;
 		uint8_t *vel_active[DIM3], *unused (nullptr);
 		bool vel_in_place[DIM3];
+		// Velocity grids on the dense core whose background value is 0 (every simulator's) go over as they are: rewriting their inactive entries was a host
+		// sweep over three whole face grids per call — two thirds of this phase at 256^3 — for values the library can just as well read as 0 through the masks
+		// it gets anyway (params.velocity_masked). One device only: the z-slab path keeps the rewritten entries.
+		bool velocity_masked = m_slabs.empty();
 		for( int dim : DIMS3 ) {
-			vel_in_place[dim] = dense_view(velocity[dim],vel[dim],vel_active[dim]); // b200array3 grids are read and written where they live
+			b200_dense_descriptor probe;
+			velocity_masked = velocity_masked && velocity[dim].get_background_value() == Real(0) && velocity[dim].const_send_message(B200_DENSE_MESSAGE,&probe) &&
+				probe.pinned && probe.element_bytes == sizeof(Real) && probe.values;
+		}
+		for( int dim : DIMS3 ) {
+			vel_in_place[dim] = dense_view(velocity[dim],vel[dim],vel_active[dim],velocity_masked); // b200array3 grids are read and written where they live
 			if( ! vel_in_place[dim] ) {
 				const size_t nf = velocity[dim].shape().count();
 				vel[dim] = m_hvel[dim].ensure(nf);
@@ -162,6 +173,7 @@ protected:
 		params.surface_tension = surface_tension;
 		params.apply_rhs_correct = 0;
 		params.rhs_correct = 0.0;
+		params.velocity_masked = velocity_masked ? 1 : 0;
 		if( m_param.gain && m_target_volume ) {
 			timer.tick(); console::dump( "Computing volume correction...");
 			double x = (m_current_volume-m_target_volume)/m_target_volume;

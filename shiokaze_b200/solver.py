@@ -81,6 +81,7 @@ class MacPressureSolver3:
             elif key == "MGGamma": p.mg_gamma = int(value)
             elif key == "MGOmega": p.mg_omega = float(value)
             elif key == "ExtrapolateWidth": p.extrapolate_width = int(value)
+            elif key == "VelocityMasked": p.velocity_masked = int(bool(value))   # (library-level: the entries of inactive faces are unspecified, include/shkz_b200.h)
             else:
                 raise KeyError(f"unknown flag {key}")
 

@@ -148,3 +148,44 @@ def test_a_device_call_between_two_host_calls_does_not_leave_stale_pressure(cuda
         same(again, ref)
     finally:
         pin.free()
+
+
+@pytest.mark.parametrize("name", ["dambreak_solid", "flip", "smoke"])
+def test_velocity_masked_reads_inactive_faces_as_zero(cuda_device, name, monkeypatch):
+    """params.velocity_masked (what the Shiokaze module sets when it hands over velocity grids of the dense array core without rewriting their inactive entries):
+    junk on the inactive faces changes nothing — sparse host copies and whole-array host copies give the results of the clean input, bit for bit; without the
+    flag the junk is read (the flag is what is being tested)."""
+    sc = {"dambreak_solid": lambda: scenes.dambreak(40, True), "flip": lambda: scenes.flip_splash(48), "smoke": lambda: scenes.smoke_plume(24)}[name]()
+    rng = np.random.default_rng(11)
+    junk = [np.where(a != 0, v, 1e3 * rng.standard_normal(v.shape)).astype(np.float32) for v, a in zip(sc.vel, sc.vel_active)]
+
+    def run(vel, pinned, **flags):
+        S = MacPressureSolver3((sc.nx, sc.ny, sc.nz), sc.dx, **flags)
+        wrap = pinned.like if pinned else (lambda x: x.copy())
+        v, a = [wrap(x) for x in vel], [wrap(x) for x in sc.vel_active]
+        p, pa, res = S.project(sc.dt, v, a, None if sc.solid is None else wrap(sc.solid), wrap(sc.fluid), sc.fluid_levelset,
+                               pressure_out=wrap(np.zeros(sc.fluid.shape, np.float32)), pressure_active_out=wrap(np.zeros(sc.fluid.shape, np.uint8)))
+        S.close()
+        return [x.copy() for x in v], [x.copy() for x in a], p.copy(), res
+
+    clean_v, clean_a, clean_p, clean = run(sc.vel, None)
+    P = Pinned()
+    try:
+        for mode in ("sparse", "dense"):
+            if mode == "dense":
+                monkeypatch.setenv("SHKZ_B200_HOST_COPIES", "dense")
+            v, a, p, res = run(junk, P, VelocityMasked=1)
+            assert res.iterations == clean.iterations, mode
+            if mode == "dense" or not sc.fluid_levelset:
+                assert res.stats["host_copies"] == 0
+            assert np.array_equal(p, clean_p), mode
+            for d in range(3):
+                on = sc.vel_active[d] != 0
+                assert np.array_equal(a[d], clean_a[d]), (mode, d)
+                assert np.array_equal(v[d][on], clean_v[d][on]), (mode, d)
+        monkeypatch.delenv("SHKZ_B200_HOST_COPIES", raising=False)
+        if name != "smoke":   # (a smoke scene has no inactive face)
+            v, a, p, res = run(junk, None)
+            assert not np.array_equal(p, clean_p)
+    finally:
+        P.free()
