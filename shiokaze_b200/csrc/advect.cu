@@ -260,8 +260,7 @@ template <> struct Limits<double> {
 };
 
 // ---- faces ------------------------------------------------------------------------------------------------------------------------------------------
-// One thread per face of the three grids (blockIdx.y walks the planes of the x-, then y-, then z-faces); an inactive face only gets the zero a forward
-// result carries there.
+// advect_face: the work of ONE active face of direction DIM (k_advect_faces below maps threads to faces).
 //   COMBINE = false: advect_semiLagrangian_u(in = F, dt) -> out; RECORD: also the limiter's record (min, max over the eight corners, narrow-band flag)
 //   COMBINE = true : the backward pass (F = the forward result, called with -dt) and the limiter (macadvection3.cpp:163-178) in one go: out is the final
 //                    field; `orig` = the field before the advection (only this face of it is read, so `out` may be `orig`)
