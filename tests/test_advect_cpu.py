@@ -159,3 +159,55 @@ def test_restatement_on_tiny_and_ragged_grids(shape):
             on = act[d] != 0
             assert np.array_equal(u[d].astype(np.float64)[on], ref.vel[d][on]), (shape, flags, d)
 
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_restatement_on_random_grids_masks_flags_and_time_steps(seed):
+    """Random extents (2 .. 21 per axis), activity masks unrelated to the level set, values with exact zeros, time steps of either sign that carry the field
+    from a hundredth of a cell to far beyond the grid, every flag, Real = float and double, all three calls: host build of the kernel source against the
+    reference module run live."""
+    import dataclasses
+    from shiokaze_b200 import scenes
+    L = hostcheck()
+    rng = np.random.default_rng(seed)
+    for trial in range(6):
+        nx, ny, nz = (int(rng.integers(2, 22)) for _ in range(3))
+        sc = scenes.random_blobs(nx, ny, nz, seed=int(rng.integers(1, 1000)), with_solid=bool(rng.integers(0, 2)))
+        act = [(rng.random(a.shape) < rng.uniform(0.2, 1.0)).astype(np.uint8) for a in sc.vel_active]
+        vel = [np.where(a != 0, rng.standard_normal(a.shape) * rng.uniform(0.1, 5.0), 0).astype(np.float32) for a in act]
+        for v in vel:
+            v[rng.random(v.shape) < 0.05] = 0.0
+        dt = float(rng.choice([-1.0, 1.0]) * rng.uniform(0.01, 2.0))
+        sc = dataclasses.replace(sc, vel=vel, vel_active=act, dt=dt)
+        flags = {"TrimNarrowBand": int(rng.integers(0, 4))}
+        if rng.random() < 0.3:
+            flags["MacCormack"] = "No"
+        if rng.random() < 0.3:
+            flags["WENO"] = "Yes"
+        real = "f64" if rng.random() < 0.3 else "f32"
+        if not refio.ref_available(real):
+            continue
+        npdt = np.float64 if real == "f64" else np.float32
+        fa = fluid_active(sc)
+        fluid = np.ascontiguousarray(sc.fluid, dtype=npdt)
+        band = float(np.float32(sc.band))
+        if real == "f64":   # Real=double: fill / background of the level set are +-band in double, not the float32 values of the scene object
+            fluid = np.where(fa != 0, sc.fluid_raw.astype(np.float64), np.where(sc.fluid < 0, -sc.band, sc.band))
+            band = float(sc.band)
+        velr = [np.ascontiguousarray(v, dtype=npdt) for v in vel]
+        for mode in ("vector", "density", "levelset"):
+            ref = refio.run_reference(sc, real, flags=flags, advect=mode)
+            p = params(flags, band if mode == "levelset" else 0.0)
+            what = (seed, trial, (nx, ny, nz), mode, flags, real, dt)
+            if mode == "vector":
+                u = [v.copy() for v in velr]
+                L.shkz_b200_hostcheck_advect_vector(nx, ny, nz, C.c_double(sc.dx), int(real == "f64"), C.c_double(dt), ptrs(u), ptrs(act), C.c_void_p(fluid.ctypes.data), C.byref(p))
+                for d in range(3):
+                    assert np.array_equal(u[d].astype(np.float64)[act[d] != 0], ref.vel[d][act[d] != 0]), what
+            else:
+                q, qa = density_of(sc) if mode == "density" else (fluid.copy(), fa)
+                q, qa = np.ascontiguousarray(q, dtype=npdt).copy(), np.ascontiguousarray(qa)
+                L.shkz_b200_hostcheck_advect_scalar(nx, ny, nz, C.c_double(sc.dx), int(real == "f64"), C.c_double(dt), C.c_void_p(q.ctypes.data), C.c_void_p(qa.ctypes.data), ptrs(velr),
+                                                    ptrs(act), C.c_void_p(fluid.ctypes.data), C.byref(p))
+                assert np.array_equal(ref.pressure_active != 0, qa != 0), what
+                assert np.array_equal(q.astype(np.float64)[qa != 0], ref.pressure[qa != 0]), what
+
