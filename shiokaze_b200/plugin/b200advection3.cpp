@@ -102,8 +102,8 @@ protected:
 			});
 			return v;
 		}
-		std::fill(v.values,v.values+total,a.get_background_value());
-		if( v.active ) std::fill(v.active,v.active+total,(uint8_t)0);
+		b200_parallel_fill(v.values,total,a.get_background_value());
+		if( v.active ) b200_parallel_fill(v.active,total,(uint8_t)0);
 		a.const_parallel_actives([&]( int i, int j, int k, const auto &it ) {
 			const size_t n = i + sh.w * (j + sh.h * (size_t)k);
 			v.values[n] = it();

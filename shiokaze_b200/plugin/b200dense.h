@@ -22,7 +22,19 @@ typedef struct b200_dense_descriptor {
 } b200_dense_descriptor;
 
 #ifdef __cplusplus
+#include <algorithm>
 #include <cstdlib>
+#include <thread>
+#include <vector>
+// std::fill over a large page-locked buffer, split over the host threads (one thread fills ~8 GB/s: five whole grids at 256^3 took tens of milliseconds)
+template <class T> static void b200_parallel_fill( T *p, size_t count, T value ) {
+	const unsigned nthreads = (unsigned)std::max<size_t>(1,std::min<size_t>((size_t)NUM_THREAD,count/(1u<<20)));
+	if( nthreads <= 1 ) { std::fill(p,p+count,value); return; }
+	std::vector<std::thread> pool;
+	for( unsigned t=0; t<nthreads; ++t ) pool.emplace_back([=]() { std::fill(p+count*t/nthreads,p+count*(t+1)/nthreads,value); });
+	for( auto &t : pool ) t.join();
+}
+
 // Every Shiokaze module of this repository carries one of these. CUDA loads a kernel's code lazily, on its first launch, and that load takes a process-wide
 // driver lock and may wait for the launching context to drain. With `GPUs=N` the module drives N devices from N host threads of ONE process, and its kernels wait
 // for each other across devices: a thread that holds the loader lock while its device spins on a neighbour, whose host thread in turn needs that lock to launch

@@ -77,8 +77,8 @@ protected:
 			});
 			return;
 		}
-		std::fill(values,values+total,a.get_background_value());
-		if( active ) std::fill(active,active+total,(uint8_t)0);
+		b200_parallel_fill(values,total,a.get_background_value());
+		if( active ) b200_parallel_fill(active,total,(uint8_t)0);
 		a.const_parallel_actives([&]( int i, int j, int k, const auto &it ) {
 			const size_t n = i + s.w * (j + s.h * (size_t)k);
 			values[n] = it();
