@@ -26,6 +26,7 @@
 #include <shiokaze/advection/macadvection3_interface.h>
 #include <shiokaze/array/shared_array3.h>
 #include <shiokaze/utility/macutility3_interface.h>
+#include <shiokaze/utility/gridutility3_interface.h>
 #include <shiokaze/utility/utility.h>
 #include <cmath>
 #include <cstdint>
@@ -56,6 +57,7 @@ struct host : public recursive_configurable {
 	macproject3_driver proj{this,"macpressuresolver3"};
 	macutility3_driver util{this,"macutility3"};
 	macadvection3_driver adv{this,"macadvection3"};
+	gridutility3_driver grid{this,"gridutility3"};
 	shape3 shape;
 	double dx;
 	host( const scene_header &h ) {
@@ -105,6 +107,7 @@ int main( int argc, const char *argv[] ) {
 	bool dump_fractions (false), skip_project (false);
 	int extrapolate_constrain (-1);
 	std::string advect_mode;
+	int volume_repeat (0);
 	for( int i=1; i<argc; ++i ) {
 		if( ! std::strncmp(argv[i],"in=",3)) in_path = argv[i]+3;
 		if( ! std::strncmp(argv[i],"out=",4)) out_path = argv[i]+4;
@@ -123,6 +126,9 @@ int main( int argc, const char *argv[] ) {
 		//   levelset  advect_scalar(fluid, velocity, copy of fluid, dt)                         src/surfacetracker/maclevelsetsurfacetracker3.cpp:49-51
 		// The advected scalar is dumped in the result's pressure slot.
 		if( ! std::strncmp(argv[i],"RefAdvect=",10)) advect_mode = argv[i]+10;
+		// RefVolume=<n>: print gridutility3::get_volume(solid,fluid) (src/utility/gridutility3.cpp:318-346) n times — the value macliquid3 feeds
+		// set_target_volume with every step (DESIGN.md section 9 on why it cannot carry a parity bar)
+		if( ! std::strncmp(argv[i],"RefVolume=",10)) volume_repeat = std::atoi(argv[i]+10);
 	}
 	if( in_path.empty() || out_path.empty()) {
 		std::fprintf(stderr,"usage: ref_driver in=<scene> out=<result> [DumpFractions=1] [RecordDir=<dir>] [Projection=<module>] [flag=value ...]\n");
@@ -180,6 +186,7 @@ int main( int argc, const char *argv[] ) {
 	}
 	std::fclose(fp);
 	//
+	for( int n=0; n<volume_repeat; ++n ) std::printf("REFDRIVER volume=%.17g\n",H.grid->get_volume(H.solid,H.fluid));
 	double ms_last (0.0), ms_sum (0.0);
 	array3<Real> scalar; // RefAdvect=density
 	for( int rep=0; rep<repeat; ++rep ) {
