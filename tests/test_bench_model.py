@@ -26,6 +26,14 @@ def test_algorithmic_bytes_follow_design_md():
     assert ab("build_system") is None and ab("sweep@g0") is None
 
 
+def test_advection_bytes_follow_design_md():
+    # forward + record 19.3 B, backward + limiter 22 B per active face (Real = float), and the figure the document prints
+    assert abs(bench.ADVECT_BYTES_PER_ACTIVE_FACE - (4 + 1 + 4 / 3 + 4 + 9 + 4 + 1 + 9 + 4 + 4)) < 1e-12
+    assert round(bench.ADVECT_BYTES_PER_ACTIVE_FACE, 1) == 41.3
+    with open(os.path.join(ROOT, "DESIGN.md")) as f:
+        assert "= **41.3 B**" in f.read()
+
+
 def test_dominant_kernel_groups_the_sweep_variants():
     n = 1.0e6
     ab = lambda k: bench.algorithmic_bytes_per_launch(k, n, "mixed", "mg")
